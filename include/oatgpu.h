@@ -1,0 +1,229 @@
+/*
+ * oatgpu.h -- C ABI of liboatgpu.so, the B200 (sm_100a) implementation of Oat's per-frame
+ * tracking hot path:  framefilt mog -> framefilt col -C HSV -> posidet hsv  (+ framefilt bsub).
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces (paths relative to the Oat source tree).  A maintainer of the reference binds these
+ * from the `filter()` / `detectPosition()` overrides of `oat-framefilt` / `oat-posidet`; the
+ * stub to add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: opaque handles, plain pointers, sizes and pitches in BYTES, no C++/torch types;
+ *   - every call returns OAT_OK (0) or a negative oat_status; the message of the most recent
+ *     failure on the calling thread is oat_last_error() (the C++ host layer rethrows it as
+ *     std::runtime_error so that main() keeps the reference's "name: message, exit -1" contract,
+ *     src/framefilter/main.cpp:278-295);
+ *   - image pointers may be device memory, pinned host memory or pageable host memory; the
+ *     library inspects them (cudaPointerGetAttributes) and stages host buffers itself;
+ *   - images are 8-bit, 1 or 3 interleaved channels, row-major (lib/datatypes/Color.h:29-38);
+ *   - handles are NOT thread-safe; use one handle per thread/stream of frames, exactly like
+ *     the single-threaded reference components (lib/base/Component.cpp:50-76);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     OAT_ERR_CUDA.
+ */
+#ifndef OATGPU_H
+#define OATGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OATGPU_ABI_VERSION 1
+
+typedef enum oat_status {
+    OAT_OK = 0,
+    OAT_ERR_INVALID = -1,  /* bad argument (null handle, bad geometry, bad parameter range) */
+    OAT_ERR_CUDA = -2,     /* CUDA runtime error / no device */
+    OAT_ERR_NOMEM = -3,    /* allocation failed */
+    OAT_ERR_STATE = -4,    /* call sequence error (collect without submit, ring full, ...) */
+    OAT_ERR_UNSUPPORTED = -5
+} oat_status;
+
+/* ---- library ------------------------------------------------------------------------- */
+
+int oat_abi_version(void);
+/* Message of the last failure on this thread ("" if none). Never NULL. */
+const char *oat_last_error(void);
+/* Number of CUDA devices visible (0 if none / no driver). Never fails. */
+int oat_device_count(void);
+
+/* ---- context: one per (thread, device) ------------------------------------------------
+ * Replaces BackgroundSubtractorMOG::configureGPU(index)
+ * (src/framefilter/BackgroundSubtractorMOG.cpp:92-111): validates the index, selects the
+ * device, owns the CUDA streams the handles below run on. */
+typedef struct oat_ctx oat_ctx;
+int oat_ctx_create(int device_index, oat_ctx **out);
+int oat_ctx_destroy(oat_ctx *ctx);
+/* Block until everything queued through this context has finished. */
+int oat_ctx_sync(oat_ctx *ctx);
+/* The cudaStream_t (as void*) the synchronous entry points launch on; lets a harness time
+ * with CUDA events on the launching stream. */
+void *oat_ctx_stream(oat_ctx *ctx);
+/* Number of kernels of THIS library launched through ctx since creation. */
+uint64_t oat_ctx_kernel_launches(const oat_ctx *ctx);
+
+/* ---- framefilt mog --------------------------------------------------------------------
+ * Parameters of cv::BackgroundSubtractorMOG2; oat_mog_default_params() gives what
+ * cv::createBackgroundSubtractorMOG2() with no arguments gives, which is what the reference
+ * constructs (src/framefilter/BackgroundSubtractorMOG.cpp:83). */
+typedef struct oat_mog_params {
+    int history;              /* 500 */
+    int nmixtures;            /* 5 (1..5 supported) */
+    float var_threshold;      /* Tb 16 */
+    float var_threshold_gen;  /* Tg 9 */
+    float background_ratio;   /* TB 0.9 */
+    float var_init;           /* 15 */
+    float var_min;            /* 4 */
+    float var_max;            /* 75 */
+    float complexity_reduction_threshold; /* CT 0.05 */
+    int detect_shadows;       /* 1 */
+    int shadow_value;         /* 127 */
+    float shadow_threshold;   /* tau 0.5 */
+} oat_mog_params;
+void oat_mog_default_params(oat_mog_params *p);
+
+typedef struct oat_mog oat_mog;
+/* Replaces BackgroundSubtractorMOG::applyConfiguration (…MOG.cpp:69-89). params==NULL means
+ * defaults. The GMM state (fp32, mode-major planes) lives in HBM for the life of the handle. */
+int oat_mog_create(oat_ctx *ctx, int rows, int cols, const oat_mog_params *params, oat_mog **out);
+int oat_mog_destroy(oat_mog *mog);
+/* Forget the model (the next apply is "frame 1" again). */
+int oat_mog_reset(oat_mog *mog);
+/* Replaces BackgroundSubtractorMOG::filter, CPU branch (…MOG.cpp:124-125):
+ *     mog2->apply(frame, mask, learning_rate);  frame.setTo(0, mask == 0);
+ * bgr_in  : rows x cols x 3 BGR.     bgr_out : same geometry, may alias bgr_in, may be NULL.
+ * mask_out: rows x cols x 1 in {0 background, shadow_value, 255 foreground}, may be NULL.
+ * learning_rate is Oat's --adaptation-coeff (…MOG.cpp:56-59, :87-88); negative = automatic,
+ * >= 1 re-initialises the model, exactly as cv::BackgroundSubtractorMOG2::apply does.
+ * Synchronous: outputs are valid on return. */
+int oat_mog_apply(oat_mog *mog, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out,
+                  size_t out_pitch, uint8_t *mask_out, size_t mask_pitch, double learning_rate);
+/* Test/diagnostic egress of the GMM state in OpenCV's layout (host pointers, any may be NULL):
+ * modes_used u8[rows*cols]; weight,variance f32[rows*cols*K]; mean f32[rows*cols*K*3]. */
+int oat_mog_get_state(oat_mog *mog, uint8_t *modes_used, float *weight, float *variance,
+                      float *mean);
+/* Sum over pixels of live GMM modes after the last apply (m-bar = sum / (rows*cols)); this is
+ * the figure the algorithmic-bytes model 8 + 40*m-bar needs. */
+int oat_mog_live_modes(oat_mog *mog, uint64_t *sum_modes);
+
+/* ---- framefilt col -C HSV -------------------------------------------------------------
+ * Replaces ColorConvert::filter for BGR->HSV (src/framefilter/ColorConvert.cpp:101-107,
+ * lib/datatypes/Color.h:46-51): 8-bit cv::COLOR_BGR2HSV, H in [0,180). */
+int oat_bgr2hsv(oat_ctx *ctx, const uint8_t *bgr, size_t in_pitch, uint8_t *hsv, size_t out_pitch,
+                int rows, int cols);
+
+/* ---- framefilt bsub -------------------------------------------------------------------
+ * Replaces BackgroundSubtractor::filter (src/framefilter/BackgroundSubtractor.cpp:87-100):
+ * first frame becomes the background; alpha>0 runs accumulateWeighted + convertTo(8U); output
+ * is the saturating per-channel difference frame - background. channels is 1 or 3. */
+typedef struct oat_bsub oat_bsub;
+int oat_bsub_create(oat_ctx *ctx, int rows, int cols, int channels, double alpha, oat_bsub **out);
+int oat_bsub_destroy(oat_bsub *b);
+/* Optional explicit background image (BackgroundSubtractor.cpp:80-85). */
+int oat_bsub_set_background(oat_bsub *b, const uint8_t *img, size_t pitch);
+int oat_bsub_apply(oat_bsub *b, const uint8_t *in, size_t in_pitch, uint8_t *out, size_t out_pitch);
+
+/* ---- posidet hsv ----------------------------------------------------------------------
+ * Parameters of HSVDetector (src/positiondetector/HSVDetector.cpp:54-69, :87-140;
+ * HSVDetector.h:86-94). oat_hsv_default_params: H,S,V = [0,256], erode 0 (off), dilate 10,
+ * area = [0, DBL_MAX). */
+typedef struct oat_hsv_params {
+    int h_min, h_max; /* 0..256, inclusive band, 256 == 255 */
+    int s_min, s_max;
+    int v_min, v_max;
+    int erode_px;     /* <=0 : off */
+    int dilate_px;    /* <=0 : off */
+    double min_area;  /* keep contours with min_area <= m00 < max_area */
+    double max_area;
+} oat_hsv_params;
+void oat_hsv_default_params(oat_hsv_params *p);
+
+/* What detectPosition() + siftContours() produce (HSVDetector.cpp:142-173,
+ * DetectorFunc.cpp:31-66): Position2D::position / position_valid and the object area. */
+typedef struct oat_detection {
+    int32_t position_valid;
+    int32_t n_components; /* external contours found (diagnostic; not in the reference) */
+    double x;             /* m10 / m00 of the selected contour */
+    double y;             /* m01 / m00 */
+    double area;          /* m00 (0 if none selected) */
+} oat_detection;
+
+typedef struct oat_hsvdet oat_hsvdet;
+int oat_hsvdet_create(oat_ctx *ctx, int rows, int cols, oat_hsvdet **out);
+int oat_hsvdet_destroy(oat_hsvdet *det);
+/* Replaces HSVDetector::detectPosition (HSVDetector.cpp:142-173): inRange -> erode -> dilate ->
+ * findContours(RETR_EXTERNAL) -> moments -> largest area in [min,max).
+ * hsv: rows x cols x 3 HSV frame. Optional egress (each may be NULL; device or host):
+ *   thresh_out : rows x cols u8 {0,255}, the mask after inRange+erode+dilate;
+ *   labels_out : rows x cols int32, 8-connected component label of every foreground pixel of
+ *                that mask = linear index (y*cols+x) of the component's raster-first pixel,
+ *                -1 for background. */
+int oat_hsvdet_detect(oat_hsvdet *det, const uint8_t *hsv, size_t pitch, const oat_hsv_params *p,
+                      oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch,
+                      int32_t *labels_out);
+/* Same back-end on an already-thresholded binary mask (non-zero = foreground): the
+ * siftContours() entry (src/positiondetector/DetectorFunc.cpp:31-66) that `posidet thresh`
+ * and `posidet diff` also use. Morphology is applied first if erode_px/dilate_px > 0. */
+int oat_sift_contours(oat_hsvdet *det, const uint8_t *mask, size_t pitch, const oat_hsv_params *p,
+                      oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch,
+                      int32_t *labels_out);
+
+/* ---- fused tracker: mog -> col HSV -> hsv in one pass over HBM ------------------------
+ * One handle = one video stream (its own GMM state). Equivalent to the three reference
+ * components chained with no shared-memory hops in between. */
+typedef struct oat_tracker oat_tracker;
+int oat_tracker_create(oat_ctx *ctx, int rows, int cols, const oat_mog_params *mog_params,
+                       int ring_depth /* frames in flight for submit/collect, 0 = default */,
+                       oat_tracker **out);
+int oat_tracker_destroy(oat_tracker *t);
+int oat_tracker_reset(oat_tracker *t);
+/* Synchronous: one frame in, one detection out. Optional egress, each may be NULL:
+ * bgr_out (filtered frame = what framefilt mog publishes), fgmask_out (MOG2 mask),
+ * hsv_out (what framefilt col publishes), thresh_out (post-morphology mask). */
+int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                      const oat_hsv_params *p, oat_detection *out, uint8_t *bgr_out,
+                      size_t bgr_out_pitch, uint8_t *fgmask_out, size_t fgmask_pitch,
+                      uint8_t *hsv_out, size_t hsv_pitch, uint8_t *thresh_out,
+                      size_t thresh_pitch);
+/* Asynchronous pair: submit queues a frame (returns once the work is enqueued; host input
+ * buffers must stay valid and unchanged until the matching collect), collect returns the
+ * detections in submission order. bgr_out as in oat_tracker_track (may be NULL).
+ * OAT_ERR_STATE if more than ring_depth frames are outstanding / nothing is outstanding. */
+int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                       const oat_hsv_params *p, uint8_t *bgr_out, size_t bgr_out_pitch);
+int oat_tracker_collect(oat_tracker *t, oat_detection *out);
+int oat_tracker_live_modes(oat_tracker *t, uint64_t *sum_modes);
+/* Per-kernel device timing (CUDA events on the launching stream around the fused
+ * MOG+HSV+threshold kernel): enable, run frames, read the mean. Adds two event records per
+ * frame; off by default. */
+int oat_tracker_profile(oat_tracker *t, int enable);
+int oat_tracker_profile_read(oat_tracker *t, double *mean_mog_kernel_ms, uint64_t *launches);
+
+/* ---- synthetic frame source (measurement + parity) --------------------
+ * Deterministic counter-hash stream: static background 40..120, +-3 noise, a filled disc of
+ * colour BGR (40,220,60), radius rows/20, centre (cols/4 + 7t mod cols/2, rows/3 + 4t mod
+ * rows/3), absent at t=0. Bit-identical to oracle/synth.py and oracle/oat_oracle.c. Writes
+ * rows x cols x 3 BGR to dst (device or host). */
+int oat_synth_frame(oat_ctx *ctx, uint8_t *dst, size_t pitch, int rows, int cols, uint32_t seed,
+                    uint32_t t);
+
+/* ---- memory helpers for the pinned-host / device-resident Frame variants --------------- */
+int oat_alloc_device(oat_ctx *ctx, size_t bytes, void **out);
+int oat_free_device(oat_ctx *ctx, void *p);
+int oat_alloc_pinned(size_t bytes, void **out);
+int oat_free_pinned(void *p);
+/* Page-lock an existing mapping (e.g. a shmemdf segment) so copies from/to it are async DMA. */
+int oat_register_host(void *p, size_t bytes);
+int oat_unregister_host(void *p);
+/* Copy between any two of {device, pinned, pageable}; synchronous. */
+int oat_memcpy(oat_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* L2 flush for benchmarking: overwrites an internal buffer larger than L2. */
+int oat_flush_l2(oat_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OATGPU_H */
