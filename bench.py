@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the MOG + HSV-detect hot path on synthetic 1080p / 4K streams.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k] [--alpha A]
+  python bench.py --impl reference ...        # the reference's CPU path (OpenCV) on the host cores
+
+A "step" is ONE frame of ONE video stream through the whole path (framefilt mog -> framefilt col
+-C HSV -> posidet hsv: GMM update, zero background, BGR->HSV, inRange, dilate, contour moments,
+largest-blob centroid) -- the unit BASELINE.json's metric counts.  Three measurements per run:
+
+* value    : device-resident input frames (a ring of distinct synthetic frames in HBM), every
+             step timed with CUDA events on the library's stream, L2 flushed between steps;
+* e2e      : the same frames in pinned HOST memory through the public C-ABI (oat_tracker_submit /
+             collect): the H2D copy of every frame and the D2H read of every detection are inside
+             the timed region (wall clock, sync on both sides);
+* roofline : the fused MOG+HSV+threshold kernel alone (CUDA events around each launch),
+             algorithmic bytes (8 + 40*m) B/px with m = mean live GMM modes measured in this run
+             (SURVEY.md 8(d)), against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+
+N > 1 (torchrun): one independent stream per rank/GPU, no data-path collective ("weak" scaling);
+the job time is the max over ranks.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"1080p": (1080, 1920), "4k": (2160, 3840), "480p": (480, 640)}
+HSV_BAND = dict(h=(40, 80), s=(100, 256), v=(100, 256))
+SEED = 1000
+METRIC = "frames/s MOG+HSV detect"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS))
+    ap.add_argument("--alpha", type=float, default=0.01, help="framefilt mog --adaptation-coeff")
+    ap.add_argument("--ring", type=int, default=32, help="distinct synthetic frames cycled as input")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    r, c = WORKLOADS[args.workload]
+    return (f"{c}x{r} synthetic single-blob stream, framefilt mog -a {args.alpha:g} + col HSV + posidet hsv "
+            f"(H40-80 S100-256 V100-256, dilate 10)")
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own call sequence on the host cores (oracle/cv2ref.py runs the same
+# cv:: functions the reference calls, in its order; the reference cannot be compiled here).
+# ---------------------------------------------------------------------------------------------
+def cpu_pipeline_fps(args, nframes, warmup):
+    import numpy as np
+
+    import oracle
+    from oracle import cv2ref
+
+    rows, cols = WORKLOADS[args.workload]
+    ring = [oracle.synth_frame(rows, cols, SEED, t) for t in range(min(args.ring, 16))]
+    cores = os.cpu_count() or 1
+    if cv2ref.available():
+        import cv2
+
+        cv2.setNumThreads(cores)
+        pipe = cv2ref.Pipeline(args.alpha, **HSV_BAND)
+        step = lambda f: pipe.step(f)  # noqa: E731
+        kind_note = f"cv2 {cv2.__version__} calls in the reference's order (oracle/cv2ref.py), {cores} threads"
+    else:  # C restatement, single thread
+        cores = 1
+        trk = oracle.Tracker(rows, cols)
+        hp = oracle.HsvParams(**HSV_BAND)
+        step = lambda f: trk.track(f, args.alpha, hp)  # noqa: E731
+        kind_note = "C restatement oracle/oat_oracle.c, 1 thread (cv2 not importable)"
+    for i in range(warmup):
+        step(ring[i % len(ring)].copy())
+    frames = [ring[i % len(ring)].copy() for i in range(min(nframes, 64))]
+    t0 = time.perf_counter()
+    for i in range(nframes):
+        step(frames[i % len(frames)])
+    dt = time.perf_counter() - t0
+    return nframes / dt, dt, cores, kind_note
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows, cols = WORKLOADS[args.workload]
+    fps, dt, cores, note = cpu_pipeline_fps(args, args.steps, args.warmup)
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": fps,
+        "unit": "frames/s",
+        "mpix_per_s": fps * rows * cols / 1e6,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} frames, one frame per step; {note}"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(workload, alpha):
+    """Per-launch DRAM bytes of the fused kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return d.get(f"{workload}_a{alpha:g}")
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import torch
+
+    import oat_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available() or oat_b200.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    rows, cols = WORKLOADS[args.workload]
+    npx = rows * cols
+    K, W = args.steps, args.warmup
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    ctx = oat_b200.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    seed = SEED + rank  # one independent stream per rank
+
+    # ---- input ring: distinct synthetic frames, resident in HBM before timing starts --------
+    R = max(2, args.ring)
+    dev_frames = [ctx.alloc(npx * 3) for _ in range(R)]
+    # frame 0 is blob-free and becomes the first model; the ring then cycles t = 1..R
+    f0 = ctx.alloc(npx * 3)
+    ctx.synth_frame(rows, cols, seed, 0, out=f0)
+    for i, b in enumerate(dev_frames):
+        ctx.synth_frame(rows, cols, seed, i + 1, out=b)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- value: device-resident, per-step events, L2 flushed between steps -------------------
+    DEPTH = 4
+    trk = oat_b200.Tracker(ctx, rows, cols, args.alpha, hp, ring_depth=DEPTH)
+    trk.submit(f0)
+    trk.collect()
+    outstanding = 0
+    for i in range(W):
+        ctx.flush_l2()
+        trk.submit(dev_frames[i % R])
+        outstanding += 1
+        if outstanding == DEPTH:
+            trk.collect()
+            outstanding -= 1
+    while outstanding:
+        trk.collect()
+        outstanding -= 1
+    modes_before = trk.live_modes() / npx
+    trk.profile(True)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler.start()
+    wall0 = time.perf_counter()
+    last = None
+    for i in range(K):
+        ctx.flush_l2()
+        ev0[i].record(stream)
+        trk.submit(dev_frames[(W + i) % R])
+        ev1[i].record(stream)
+        outstanding += 1
+        if outstanding == DEPTH:
+            last = trk.collect()
+            outstanding -= 1
+        if i == K // 2:
+            sampler.sample()
+    while outstanding:
+        last = trk.collect()
+        outstanding -= 1
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = sum(step_ms)
+    kern_ms, kern_n = trk.profile_read()
+    trk.profile(False)
+    modes_after = trk.live_modes() / npx
+    mbar = 0.5 * (modes_before + modes_after)
+
+    # ---- pipelined (no flush, frames back to back; state may stay L2-resident) ---------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        trk.submit(dev_frames[i % R])
+        outstanding += 1
+        if outstanding == DEPTH:
+            trk.collect()
+            outstanding -= 1
+    while outstanding:
+        trk.collect()
+        outstanding -= 1
+    e1.record(stream)
+    barrier()
+    pipe_ms = e0.elapsed_time(e1)
+    trk.close()
+
+    # ---- e2e: pinned host frames through submit/collect, copies inside the timed region ------
+    HR = min(R, 8)
+    pin = oat_b200.PinnedArray((HR, rows, cols, 3))
+    for i in range(HR):
+        ctx.memcpy(pin.ptr + i * npx * 3, dev_frames[i], npx * 3)
+    trk2 = oat_b200.Tracker(ctx, rows, cols, args.alpha, hp, ring_depth=DEPTH)
+    trk2.submit(f0)
+    trk2.collect()
+    for i in range(min(W, 20)):
+        trk2.submit(pin.ptr + (i % HR) * npx * 3)
+        trk2.collect()
+    barrier()
+    t0 = time.perf_counter()
+    outstanding = 0
+    for i in range(K):
+        trk2.submit(pin.ptr + (i % HR) * npx * 3)
+        outstanding += 1
+        if outstanding == DEPTH:
+            trk2.collect()
+            outstanding -= 1
+    while outstanding:
+        trk2.collect()
+        outstanding -= 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    trk2.close()
+
+    # ---- reduce over ranks: the job took as long as its slowest rank -------------------------
+    if dist is not None:
+        t = torch.tensor([total_ms, pipe_ms, e2e_s, kern_ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, pipe_ms, e2e_s, kern_ms = [float(x) for x in t.tolist()]
+        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local}")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    if rank == 0:
+        peak, peak_src = load_peak()
+        fps = world * K / (total_ms * 1e-3)
+        b_alg = 8.0 + 40.0 * mbar  # bytes per pixel per frame, frame egress included
+        achieved = b_alg * npx / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        line = {
+            "metric": METRIC,
+            "value": fps,
+            "unit": "frames/s",
+            "mpix_per_s": fps * npx / 1e6,
+            "n_gpus": world,
+            "steps": K,
+            "warmup": W,
+            "ms_per_step": total_ms / K,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": workload_name(args),
+                "streams_per_gpu": 1,
+                "input": f"ring of {R} distinct device-resident frames",
+                "l2": "flushed (256 MiB overwrite) between timed steps; per-step CUDA events on the launching stream",
+                "mean_live_modes": mbar,
+                "parallelism": f"{world} independent stream(s), one per GPU, no collective",
+            },
+            "roofline": {
+                "bound": "hbm",
+                "kernel": "mog_fused_kernel<5,4>",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_px": b_alg,
+                "kernel_ms": kern_ms,
+                "kernel_launches_timed": kern_n,
+                "traffic": load_traffic(args.workload, args.alpha),
+            },
+            "e2e": {
+                "value": world * K / e2e_s,
+                "unit": "frames/s",
+                "h2d_bytes_per_step": npx * 3,
+                "d2h_bytes_per_step": 40,
+                "note": "pinned host frames via oat_tracker_submit/collect, ring depth 4, wall clock",
+            },
+            "pipelined": {"value": world * K / (pipe_ms * 1e-3), "unit": "frames/s",
+                          "note": "no L2 flush, frames back to back (GMM state may stay L2-resident)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": wall,
+            "last_detection": list(last.as_tuple()) if last is not None else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                nf = args.cpu_frames or (300 if args.workload != "4k" else 100)
+                cfps, cdt, cores, note = cpu_pipeline_fps(args, nf, 20)
+                line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                        "sample": f"{nf} frames of the same stream in {cdt:.1f} s; {note}"}
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
+                                        "sample": f"failed: {e!r}"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,12 @@ extern "C" {
 
 #define OATGPU_ABI_VERSION 1
 
+/* Every entry point below is exported with default visibility; everything else in the
+ * library (including the statically linked CUDA runtime) stays hidden. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 typedef enum oat_status {
     OAT_OK = 0,
     OAT_ERR_INVALID = -1,  /* bad argument (null handle, bad geometry, bad parameter range) */
@@ -196,6 +202,9 @@ int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, d
                        const oat_hsv_params *p, uint8_t *bgr_out, size_t bgr_out_pitch);
 int oat_tracker_collect(oat_tracker *t, oat_detection *out);
 int oat_tracker_live_modes(oat_tracker *t, uint64_t *sum_modes);
+/* GMM state egress, as oat_mog_get_state. */
+int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, float *variance,
+                          float *mean);
 /* Per-kernel device timing (CUDA events on the launching stream around the fused
  * MOG+HSV+threshold kernel): enable, run frames, read the mean. Adds two event records per
  * frame; off by default. */
@@ -222,6 +231,10 @@ int oat_unregister_host(void *p);
 int oat_memcpy(oat_ctx *ctx, void *dst, const void *src, size_t bytes);
 /* L2 flush for benchmarking: overwrites an internal buffer larger than L2. */
 int oat_flush_l2(oat_ctx *ctx);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,529 @@
+"""oat_b200 -- B200-native implementation of Oat's per-frame tracking hot path.
+
+This package is a thin ctypes binding of ``liboatgpu.so`` (C ABI in ``include/oatgpu.h``;
+kernels in ``oat_b200/csrc``) that mirrors the reference's operator interface for the path:
+
+* :class:`BackgroundSubtractorMOG`  -- ``framefilt mog``  (src/framefilter/BackgroundSubtractorMOG.cpp:114-127)
+* :func:`color_convert_hsv`        -- ``framefilt col -C HSV`` (src/framefilter/ColorConvert.cpp:101-107)
+* :class:`BackgroundSubtractor`     -- ``framefilt bsub`` (src/framefilter/BackgroundSubtractor.cpp:87-100)
+* :class:`HSVDetector`              -- ``posidet hsv``    (src/positiondetector/HSVDetector.cpp:142-173)
+* :class:`Tracker`                  -- the three chained, fused on the device
+
+There is NO CPU fallback: importing works without a GPU (so the build can be checked), but
+every compute call raises :class:`OatError` when the CUDA library or a device is missing.
+Nothing here imports ``oracle/`` (test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboatgpu.so")
+DBL_MAX = float(np.finfo(np.float64).max)
+
+OAT_OK = 0
+
+
+class OatError(RuntimeError):
+    """Raised for any non-zero oat_status (message = oat_last_error())."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"liboatgpu error {code}: {msg}")
+        self.code = code
+
+
+class MogParams(C.Structure):
+    _fields_ = [
+        ("history", C.c_int),
+        ("nmixtures", C.c_int),
+        ("var_threshold", C.c_float),
+        ("var_threshold_gen", C.c_float),
+        ("background_ratio", C.c_float),
+        ("var_init", C.c_float),
+        ("var_min", C.c_float),
+        ("var_max", C.c_float),
+        ("complexity_reduction_threshold", C.c_float),
+        ("detect_shadows", C.c_int),
+        ("shadow_value", C.c_int),
+        ("shadow_threshold", C.c_float),
+    ]
+
+
+class HsvParams(C.Structure):
+    """HSVDetector options (src/positiondetector/HSVDetector.cpp:54-69)."""
+
+    _fields_ = [
+        ("h_min", C.c_int), ("h_max", C.c_int),
+        ("s_min", C.c_int), ("s_max", C.c_int),
+        ("v_min", C.c_int), ("v_max", C.c_int),
+        ("erode_px", C.c_int),
+        ("dilate_px", C.c_int),
+        ("min_area", C.c_double),
+        ("max_area", C.c_double),
+    ]
+
+    @classmethod
+    def make(cls, h=(0, 256), s=(0, 256), v=(0, 256), erode=0, dilate=10, area=(0.0, DBL_MAX)):
+        return cls(h[0], h[1], s[0], s[1], v[0], v[1], erode, dilate, area[0], area[1])
+
+
+class Detection(C.Structure):
+    _fields_ = [
+        ("position_valid", C.c_int32),
+        ("n_components", C.c_int32),
+        ("x", C.c_double),
+        ("y", C.c_double),
+        ("area", C.c_double),
+    ]
+
+    def as_tuple(self):
+        return (bool(self.position_valid), self.x, self.y, self.area)
+
+
+_lib = None
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "oat_abi_version": (C.c_int, []),
+    "oat_last_error": (C.c_char_p, []),
+    "oat_device_count": (C.c_int, []),
+    "oat_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "oat_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "oat_ctx_sync": (C.c_int, [C.c_void_p]),
+    "oat_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "oat_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "oat_mog_default_params": (None, [C.POINTER(MogParams)]),
+    "oat_mog_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(MogParams), C.POINTER(C.c_void_p)]),
+    "oat_mog_destroy": (C.c_int, [C.c_void_p]),
+    "oat_mog_reset": (C.c_int, [C.c_void_p]),
+    "oat_mog_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                C.c_double]),
+    "oat_mog_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oat_mog_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "oat_bgr2hsv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    "oat_bsub_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
+    "oat_bsub_destroy": (C.c_int, [C.c_void_p]),
+    "oat_bsub_set_background": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "oat_bsub_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "oat_hsv_default_params": (None, [C.POINTER(HsvParams)]),
+    "oat_hsvdet_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "oat_hsvdet_destroy": (C.c_int, [C.c_void_p]),
+    "oat_hsvdet_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(HsvParams), C.POINTER(Detection),
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "oat_sift_contours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(HsvParams), C.POINTER(Detection),
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "oat_tracker_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(MogParams), C.c_int,
+                                     C.POINTER(C.c_void_p)]),
+    "oat_tracker_destroy": (C.c_int, [C.c_void_p]),
+    "oat_tracker_reset": (C.c_int, [C.c_void_p]),
+    "oat_tracker_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams),
+                                    C.POINTER(Detection), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.c_size_t, C.c_void_p, C.c_size_t]),
+    "oat_tracker_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams), C.c_void_p,
+                                     C.c_size_t]),
+    "oat_tracker_collect": (C.c_int, [C.c_void_p, C.POINTER(Detection)]),
+    "oat_tracker_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "oat_tracker_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oat_tracker_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "oat_tracker_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "oat_synth_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),
+    "oat_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "oat_free_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "oat_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "oat_free_pinned": (C.c_int, [C.c_void_p]),
+    "oat_register_host": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "oat_unregister_host": (C.c_int, [C.c_void_p]),
+    "oat_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "oat_flush_l2": (C.c_int, [C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def build(force: bool = False) -> str:
+    """Compile liboatgpu.so in-tree with nvcc for sm_100a (oat_b200/csrc/Makefile)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "oatgpu.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-s", "-C", csrc] + (["-B"] if force else []), check=True)
+    return LIB_PATH
+
+
+def lib():
+    """Load liboatgpu.so; raises OatError (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OatError(-2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ck(code: int):
+    if code != OAT_OK:
+        raise OatError(code, lib().oat_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return lib().oat_device_count()
+
+
+def _ptr(a):
+    """numpy array -> host pointer; int -> raw (device or pinned) pointer; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, DeviceBuffer):
+        return C.c_void_p(a.ptr)
+    return C.c_void_p(int(a))
+
+
+class Context:
+    """One per (thread, device); owns the CUDA streams (BackgroundSubtractorMOG::configureGPU,
+    src/framefilter/BackgroundSubtractorMOG.cpp:92-111)."""
+
+    def __init__(self, device_index: int = 0):
+        self._h = C.c_void_p()
+        _ck(lib().oat_ctx_create(device_index, C.byref(self._h)))
+        self.device_index = device_index
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _ck(lib().oat_ctx_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().oat_ctx_stream(self._h) or 0)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().oat_ctx_kernel_launches(self._h))
+
+    def flush_l2(self):
+        _ck(lib().oat_flush_l2(self._h))
+
+    def alloc(self, nbytes: int) -> "DeviceBuffer":
+        return DeviceBuffer(self, nbytes)
+
+    def memcpy(self, dst, src, nbytes: int):
+        _ck(lib().oat_memcpy(self._h, _ptr(dst), _ptr(src), nbytes))
+
+    def synth_frame(self, rows: int, cols: int, seed: int, t: int, out=None):
+        """Synthetic BGR frame; out = numpy array, DeviceBuffer or None (-> numpy)."""
+        ret = None
+        if out is None:
+            out = ret = np.empty((rows, cols, 3), np.uint8)
+        _ck(lib().oat_synth_frame(self._h, _ptr(out), cols * 3, rows, cols, seed, t))
+        return ret if ret is not None else out
+
+
+class DeviceBuffer:
+    """Device-resident Frame variant: raw HBM allocation handed to the C ABI by pointer."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx = ctx
+        self.nbytes = nbytes
+        p = C.c_void_p()
+        _ck(lib().oat_alloc_device(ctx._h, nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            lib().oat_free_device(self.ctx._h, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.ctx.memcpy(self, a, a.nbytes)
+        return self
+
+    def download(self, shape, dtype=np.uint8) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx.memcpy(out, self, out.nbytes)
+        return out
+
+
+class PinnedArray:
+    """Pinned-host Frame variant: page-locked numpy view (async DMA source/target)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _ck(lib().oat_alloc_pinned(n, C.byref(p)))
+        self.ptr = p.value
+        buf = (C.c_uint8 * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().oat_free_pinned(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def default_mog_params() -> MogParams:
+    p = MogParams()
+    lib().oat_mog_default_params(C.byref(p))
+    return p
+
+
+def _img(a, rows, cols, ch):
+    if isinstance(a, np.ndarray):
+        want = (rows, cols, ch) if ch > 1 else (rows, cols)
+        if a.dtype != np.uint8 or a.shape != want or not a.flags.c_contiguous:
+            raise ValueError(f"expected contiguous uint8 array of shape {want}, got {a.dtype} {a.shape}")
+    return a
+
+
+def _state_arrays(rows, cols, K):
+    return (np.empty((rows, cols), np.uint8), np.empty((rows, cols, K), np.float32),
+            np.empty((rows, cols, K), np.float32), np.empty((rows, cols, K, 3), np.float32))
+
+
+class BackgroundSubtractorMOG:
+    """``framefilt mog``: ``filter(frame)`` = MOG2 apply + zero the background
+    (src/framefilter/BackgroundSubtractorMOG.cpp:114-127).  ``adaptation_coeff`` is ``-a``."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, adaptation_coeff: float = 0.0,
+                 params: MogParams | None = None):
+        if not (0.0 <= adaptation_coeff <= 1.0):  # getNumericValue range check, ...MOG.cpp:87-88
+            raise ValueError("adaptation-coeff must be in [0, 1]")
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.learning_coeff = adaptation_coeff
+        self.params = params or default_mog_params()
+        self._h = C.c_void_p()
+        _ck(lib().oat_mog_create(ctx._h, rows, cols, C.byref(self.params), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_mog_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, frame, learning_rate=None, want_mask=True, want_frame=True):
+        """-> (filtered frame or None, mask or None) as numpy arrays (host in, host out)."""
+        _img(frame, self.rows, self.cols, 3)
+        out = np.empty((self.rows, self.cols, 3), np.uint8) if want_frame else None
+        mask = np.empty((self.rows, self.cols), np.uint8) if want_mask else None
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        _ck(lib().oat_mog_apply(self._h, _ptr(frame), self.cols * 3, _ptr(out), self.cols * 3, _ptr(mask), self.cols,
+                                lr))
+        return out, mask
+
+    def filter(self, frame: np.ndarray) -> np.ndarray:
+        """In place on a host frame, like FrameFilter::filter(cv::Mat&)."""
+        _img(frame, self.rows, self.cols, 3)
+        _ck(lib().oat_mog_apply(self._h, _ptr(frame), self.cols * 3, _ptr(frame), self.cols * 3, None, 0,
+                                self.learning_coeff))
+        return frame
+
+    def reset(self):
+        _ck(lib().oat_mog_reset(self._h))
+
+    def state(self):
+        K = self.params.nmixtures
+        m, w, v, mu = _state_arrays(self.rows, self.cols, K)
+        _ck(lib().oat_mog_get_state(self._h, _ptr(m), _ptr(w), _ptr(v), _ptr(mu)))
+        return m, w, v, mu
+
+    def live_modes(self) -> int:
+        s = C.c_uint64()
+        _ck(lib().oat_mog_live_modes(self._h, C.byref(s)))
+        return s.value
+
+
+def color_convert_hsv(ctx: Context, bgr: np.ndarray) -> np.ndarray:
+    """``framefilt col -C HSV`` on a host BGR frame."""
+    rows, cols = bgr.shape[:2]
+    _img(bgr, rows, cols, 3)
+    out = np.empty_like(bgr)
+    _ck(lib().oat_bgr2hsv(ctx._h, _ptr(bgr), cols * 3, _ptr(out), cols * 3, rows, cols))
+    return out
+
+
+class BackgroundSubtractor:
+    """``framefilt bsub`` (src/framefilter/BackgroundSubtractor.cpp:87-100)."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, channels: int = 3, adaptation_coeff: float = 0.0):
+        self.ctx, self.rows, self.cols, self.ch = ctx, rows, cols, channels
+        self._h = C.c_void_p()
+        _ck(lib().oat_bsub_create(ctx._h, rows, cols, channels, adaptation_coeff, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_bsub_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_background(self, img: np.ndarray):
+        _img(img, self.rows, self.cols, self.ch)
+        _ck(lib().oat_bsub_set_background(self._h, _ptr(img), self.cols * self.ch))
+
+    def filter(self, frame: np.ndarray) -> np.ndarray:
+        _img(frame, self.rows, self.cols, self.ch)
+        out = np.empty_like(frame)
+        pitch = self.cols * self.ch
+        _ck(lib().oat_bsub_apply(self._h, _ptr(frame), pitch, _ptr(out), pitch))
+        return out
+
+
+class HSVDetector:
+    """``posidet hsv``: ``detect(hsv)`` = inRange -> erode -> dilate -> siftContours
+    (src/positiondetector/HSVDetector.cpp:142-173, DetectorFunc.cpp:31-66)."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, params: HsvParams | None = None):
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.params = params or HsvParams.make()
+        self._h = C.c_void_p()
+        _ck(lib().oat_hsvdet_create(ctx._h, rows, cols, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_hsvdet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _run(self, fn, img, ch, want_thresh, want_labels):
+        _img(img, self.rows, self.cols, ch)
+        d = Detection()
+        thr = np.empty((self.rows, self.cols), np.uint8) if want_thresh else None
+        lab = np.empty((self.rows, self.cols), np.int32) if want_labels else None
+        _ck(fn(self._h, _ptr(img), self.cols * ch, C.byref(self.params), C.byref(d), _ptr(thr), self.cols, _ptr(lab)))
+        return d, thr, lab
+
+    def detect(self, hsv, want_thresh=False, want_labels=False):
+        """-> (Detection, thresh mask or None, labels or None)."""
+        return self._run(lib().oat_hsvdet_detect, hsv, 3, want_thresh, want_labels)
+
+    def sift_contours(self, mask, want_thresh=False, want_labels=False):
+        """siftContours on a binary mask (morphology per self.params applied first)."""
+        return self._run(lib().oat_sift_contours, mask, 1, want_thresh, want_labels)
+
+
+class Tracker:
+    """mog -> col HSV -> hsv fused on the device; one instance = one video stream."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, adaptation_coeff: float = 0.0,
+                 hsv: HsvParams | None = None, mog_params: MogParams | None = None, ring_depth: int = 0):
+        if not (0.0 <= adaptation_coeff <= 1.0):
+            raise ValueError("adaptation-coeff must be in [0, 1]")
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.learning_coeff = adaptation_coeff
+        self.hsv = hsv or HsvParams.make()
+        self.mog_params = mog_params or default_mog_params()
+        self._h = C.c_void_p()
+        _ck(lib().oat_tracker_create(ctx._h, rows, cols, C.byref(self.mog_params), ring_depth, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_tracker_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _ck(lib().oat_tracker_reset(self._h))
+
+    def track(self, bgr, egress=(), learning_rate=None):
+        """One frame in (numpy host array, DeviceBuffer or raw pointer), one Detection out.
+        egress: any of 'bgr', 'fgmask', 'hsv', 'thresh' -> returned as numpy arrays in a dict."""
+        _img(bgr, self.rows, self.cols, 3)
+        r, c = self.rows, self.cols
+        outs = {
+            "bgr": np.empty((r, c, 3), np.uint8) if "bgr" in egress else None,
+            "fgmask": np.empty((r, c), np.uint8) if "fgmask" in egress else None,
+            "hsv": np.empty((r, c, 3), np.uint8) if "hsv" in egress else None,
+            "thresh": np.empty((r, c), np.uint8) if "thresh" in egress else None,
+        }
+        d = Detection()
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        _ck(lib().oat_tracker_track(self._h, _ptr(bgr), c * 3, lr, C.byref(self.hsv), C.byref(d),
+                                    _ptr(outs["bgr"]), c * 3, _ptr(outs["fgmask"]), c, _ptr(outs["hsv"]), c * 3,
+                                    _ptr(outs["thresh"]), c))
+        return d, {k: v for k, v in outs.items() if v is not None}
+
+    def submit(self, bgr, bgr_out=None, learning_rate=None):
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        _ck(lib().oat_tracker_submit(self._h, _ptr(bgr), self.cols * 3, lr, C.byref(self.hsv), _ptr(bgr_out),
+                                     self.cols * 3))
+
+    def collect(self) -> Detection:
+        d = Detection()
+        _ck(lib().oat_tracker_collect(self._h, C.byref(d)))
+        return d
+
+    def live_modes(self) -> int:
+        s = C.c_uint64()
+        _ck(lib().oat_tracker_live_modes(self._h, C.byref(s)))
+        return s.value
+
+    def state(self):
+        K = self.mog_params.nmixtures
+        m, w, v, mu = _state_arrays(self.rows, self.cols, K)
+        _ck(lib().oat_tracker_get_state(self._h, _ptr(m), _ptr(w), _ptr(v), _ptr(mu)))
+        return m, w, v, mu
+
+    def profile(self, enable: bool):
+        _ck(lib().oat_tracker_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _ck(lib().oat_tracker_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

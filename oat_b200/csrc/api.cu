@@ -1,0 +1,1110 @@
+// api.cu -- the C ABI of liboatgpu.so (include/oatgpu.h).  Host-side orchestration only: pointer
+// classification + staging, per-frame constants, kernel launches on the context's stream.
+// There is NO CPU fallback anywhere in this file: without a CUDA device every compute entry
+// point fails with OAT_ERR_CUDA.
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "mog_fused.cuh"
+#include "pixel_ops.cuh"
+#include "tail.cuh"
+
+using namespace oat;
+
+// ---- errors --------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? OAT_ERR_NOMEM : OAT_ERR_CUDA,            \
+                        std::string(#call) + ": " + cudaGetErrorString(_e));                       \
+    } while (0)
+#define CKRET(expr)          \
+    do {                     \
+        int _r = (expr);     \
+        if (_r != OAT_OK) return _r; \
+    } while (0)
+#define REQUIRE(cond, msg) \
+    do {                   \
+        if (!(cond)) return fail(OAT_ERR_INVALID, msg); \
+    } while (0)
+
+// ---- context -------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return OAT_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return OAT_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct oat_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;   // compute
+    cudaStream_t h2d = nullptr;      // ingest copies (overlap with compute of the previous frame)
+    int *hsv_lut = nullptr;          // sdiv[256] | hdiv[256]
+    uint64_t launches = 0;
+    DevBuf flush;
+    DevBuf scratch_in, scratch_out;  // staging for the stateless entry points
+};
+
+extern "C" int oat_abi_version(void) { return OATGPU_ABI_VERSION; }
+extern "C" const char *oat_last_error(void) { return g_err.c_str(); }
+extern "C" int oat_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int bind(oat_ctx *c)
+{
+    if (!c) return fail(OAT_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    return OAT_OK;
+}
+
+extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
+{
+    REQUIRE(out, "oat_ctx_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(OAT_ERR_CUDA, std::string("no CUDA device available: ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    // reference: "Selected GPU index is invalid." (src/framefilter/BackgroundSubtractorMOG.cpp:94-100)
+    if (device_index < 0 || device_index >= n) return fail(OAT_ERR_INVALID, "Selected GPU index is invalid.");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_index));
+    if (prop.major != 10)
+        return fail(OAT_ERR_UNSUPPORTED, std::string("liboatgpu is built for sm_100a only; device is ") + prop.name);
+    oat_ctx *c = new (std::nothrow) oat_ctx();
+    if (!c) return fail(OAT_ERR_NOMEM, "out of host memory");
+    c->device = device_index;
+    CK(cudaSetDevice(device_index));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    int lut[512];
+    lut[0] = lut[256] = 0;
+    for (int i = 1; i < 256; ++i) {
+        lut[i] = (int)nearbyint((255 << 12) / (1.0 * i));
+        lut[256 + i] = (int)nearbyint((180 << 12) / (6.0 * i));
+    }
+    CK(cudaMalloc(&c->hsv_lut, sizeof(lut)));
+    CK(cudaMemcpy(c->hsv_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    *out = c;
+    return OAT_OK;
+}
+
+extern "C" int oat_ctx_destroy(oat_ctx *c)
+{
+    if (!c) return OAT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->h2d);
+    c->flush.release();
+    c->scratch_in.release();
+    c->scratch_out.release();
+    if (c->hsv_lut) cudaFree(c->hsv_lut);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->h2d);
+    delete c;
+    return OAT_OK;
+}
+
+extern "C" int oat_ctx_sync(oat_ctx *c)
+{
+    CKRET(bind(c));
+    CK(cudaStreamSynchronize(c->h2d));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+extern "C" void *oat_ctx_stream(oat_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t oat_ctx_kernel_launches(const oat_ctx *c) { return c ? c->launches : 0; }
+
+// ---- pointer classification + staging ------------------------------------------------------
+enum MemKind { MEM_PAGEABLE, MEM_PINNED, MEM_DEVICE };
+static MemKind mem_kind(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return MEM_PAGEABLE;
+    }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return MEM_DEVICE;
+    if (at.type == cudaMemoryTypeHost) return MEM_PINNED;
+    return MEM_PAGEABLE;
+}
+
+// Input image: returns a device view (ptr,pitch); host images are copied into `stage`.
+static int stage_in(oat_ctx *c, cudaStream_t s, DevBuf &stage, const void *src, size_t pitch, int rows,
+                    size_t rowbytes, const uint8_t **dptr, size_t *dpitch)
+{
+    if (mem_kind(src) == MEM_DEVICE) {
+        *dptr = (const uint8_t *)src;
+        *dpitch = pitch;
+        return OAT_OK;
+    }
+    const size_t tight = (rowbytes + 15) & ~(size_t)15;
+    CKRET(stage.ensure(tight * rows));
+    CK(cudaMemcpy2DAsync(stage.p, tight, src, pitch, rowbytes, rows, cudaMemcpyHostToDevice, s));
+    *dptr = (const uint8_t *)stage.p;
+    *dpitch = tight;
+    return OAT_OK;
+}
+// Output image: device view to write into; if the user pointer is host memory the view is
+// `stage` and finish_out() copies it back.
+struct OutView {
+    uint8_t *d = nullptr;
+    size_t dpitch = 0;
+    void *host = nullptr;
+    size_t hpitch = 0;
+    size_t rowbytes = 0;
+    int rows = 0;
+};
+static int stage_out(DevBuf &stage, void *dst, size_t pitch, int rows, size_t rowbytes, OutView *v)
+{
+    *v = OutView();
+    if (!dst) return OAT_OK;
+    v->rows = rows;
+    v->rowbytes = rowbytes;
+    if (mem_kind(dst) == MEM_DEVICE) {
+        v->d = (uint8_t *)dst;
+        v->dpitch = pitch;
+        return OAT_OK;
+    }
+    const size_t tight = (rowbytes + 15) & ~(size_t)15;
+    CKRET(stage.ensure(tight * rows));
+    v->d = (uint8_t *)stage.p;
+    v->dpitch = tight;
+    v->host = dst;
+    v->hpitch = pitch;
+    return OAT_OK;
+}
+static int finish_out(cudaStream_t s, const OutView &v)
+{
+    if (v.host)
+        CK(cudaMemcpy2DAsync(v.host, v.hpitch, v.d, v.dpitch, v.rowbytes, v.rows, cudaMemcpyDeviceToHost, s));
+    return OAT_OK;
+}
+
+static inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+#define LAUNCH_CHECK(c)                 \
+    do {                                \
+        ++(c)->launches;                \
+        CK(cudaGetLastError());         \
+    } while (0)
+
+// ---- GMM model -----------------------------------------------------------------------------
+extern "C" void oat_mog_default_params(oat_mog_params *p)
+{
+    if (!p) return;
+    p->history = 500;
+    p->nmixtures = 5;
+    p->var_threshold = 16.0f;
+    p->var_threshold_gen = 9.0f;
+    p->background_ratio = 0.9f;
+    p->var_init = 15.0f;
+    p->var_min = 4.0f;
+    p->var_max = 75.0f;
+    p->complexity_reduction_threshold = 0.05f;
+    p->detect_shadows = 1;
+    p->shadow_value = 127;
+    p->shadow_threshold = 0.5f;
+}
+
+struct MogModel {
+    BitGeom g{};
+    int K = 5;
+    oat_mog_params p{};
+    float *state = nullptr;
+    size_t plane = 0;
+    uint8_t *nmodes = nullptr;
+    int nframes = 0;
+    unsigned long long *d_sum = nullptr;
+
+    int create(int rows, int cols, const oat_mog_params *params)
+    {
+        if (params)
+            p = *params;
+        else
+            oat_mog_default_params(&p);
+        REQUIRE(rows > 0 && cols > 0 && rows <= 32768 && cols <= 32768, "MOG: bad frame geometry");
+        REQUIRE(p.nmixtures >= 1 && p.nmixtures <= 5, "MOG: nmixtures must be in 1..5");
+        REQUIRE(p.history >= 1, "MOG: history must be >= 1");
+        REQUIRE(p.shadow_value >= 0 && p.shadow_value <= 255, "MOG: shadow_value must be in 0..255");
+        g.rows = rows;
+        g.cols = cols;
+        g.wpr = div_up(cols, 32);
+        K = p.nmixtures;
+        plane = (size_t)rows * g.pitch_px();
+        CK(cudaMalloc(&state, plane * 5 * K * sizeof(float)));
+        CK(cudaMalloc(&nmodes, plane));
+        CK(cudaMalloc(&d_sum, sizeof(unsigned long long)));
+        CK(cudaMemset(nmodes, 0, plane));
+        nframes = 0;
+        return OAT_OK;
+    }
+    void destroy()
+    {
+        if (state) cudaFree(state);
+        if (nmodes) cudaFree(nmodes);
+        if (d_sum) cudaFree(d_sum);
+        state = nullptr;
+        nmodes = nullptr;
+        d_sum = nullptr;
+    }
+    // cv::BackgroundSubtractorMOG2Impl::apply: (re)initialise, count the frame, pick the rate.
+    void frame_consts(double learning_rate, MogConsts *c, int *reset)
+    {
+        const bool init = (nframes == 0) || (learning_rate >= 1);
+        if (init) nframes = 0;
+        ++nframes;
+        int d = 2 * nframes;
+        if (d > p.history) d = p.history;
+        const double lr = (learning_rate >= 0 && nframes > 1) ? learning_rate : 1.0 / d;
+        c->aT = (float)lr;
+        c->a1 = 1.0f - c->aT;
+        c->prune = (float)(-lr * (double)p.complexity_reduction_threshold);
+        c->Tb = p.var_threshold;
+        c->TB = p.background_ratio;
+        c->Tg = p.var_threshold_gen;
+        c->varInit = p.var_init;
+        c->varMin = p.var_min;
+        c->varMax = p.var_max;
+        c->tau = p.shadow_threshold;
+        c->detect_shadows = p.detect_shadows;
+        c->shadow_value = p.shadow_value;
+        *reset = init ? 1 : 0;
+    }
+};
+
+template <int PX>
+static void launch_fused_px(cudaStream_t s, int K, const FusedArgs &a)
+{
+    const long long threads = (long long)a.rows * a.wpr * (32 / PX);
+    const unsigned grid = nblocks(threads, 128);
+    switch (K) {
+    case 1: mog_fused_kernel<1, PX><<<grid, 128, 0, s>>>(a); break;
+    case 2: mog_fused_kernel<2, PX><<<grid, 128, 0, s>>>(a); break;
+    case 3: mog_fused_kernel<3, PX><<<grid, 128, 0, s>>>(a); break;
+    case 4: mog_fused_kernel<4, PX><<<grid, 128, 0, s>>>(a); break;
+    default: mog_fused_kernel<5, PX><<<grid, 128, 0, s>>>(a); break;
+    }
+}
+
+static bool aligned4(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 3u) == 0; }
+
+static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
+{
+    a.rows = m.g.rows;
+    a.cols = m.g.cols;
+    a.wpr = m.g.wpr;
+    a.state = m.state;
+    a.plane = m.plane;
+    a.nmodes = m.nmodes;
+    a.hsv_lut = c->hsv_lut;
+    const bool vec = (m.g.cols % 4 == 0) && aligned4(a.bgr, a.in_pitch) &&
+                     (!a.bgr_out || aligned4(a.bgr_out, a.bgr_out_pitch)) &&
+                     (!a.fg_out || aligned4(a.fg_out, a.fg_pitch)) && (!a.hsv_out || aligned4(a.hsv_out, a.hsv_pitch));
+    if (vec)
+        launch_fused_px<4>(c->stream, m.K, a);
+    else
+        launch_fused_px<1>(c->stream, m.K, a);
+    LAUNCH_CHECK(c);
+    return OAT_OK;
+}
+
+static int live_modes(oat_ctx *c, MogModel &m, uint64_t *sum)
+{
+    REQUIRE(sum, "live_modes: null output");
+    CK(cudaMemsetAsync(m.d_sum, 0, sizeof(unsigned long long), c->stream));
+    live_modes_kernel<<<nblocks((long long)m.plane, 256), 256, 0, c->stream>>>(m.nmodes, m.g, m.d_sum);
+    LAUNCH_CHECK(c);
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, m.d_sum, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *sum = h;
+    return OAT_OK;
+}
+
+// ---- framefilt mog -------------------------------------------------------------------------
+struct oat_mog {
+    oat_ctx *ctx;
+    MogModel m;
+    DevBuf in, out_bgr, out_mask;
+};
+
+extern "C" int oat_mog_create(oat_ctx *c, int rows, int cols, const oat_mog_params *params, oat_mog **out)
+{
+    REQUIRE(out, "oat_mog_create: out is null");
+    *out = nullptr;
+    CKRET(bind(c));
+    oat_mog *h = new (std::nothrow) oat_mog();
+    if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
+    h->ctx = c;
+    int r = h->m.create(rows, cols, params);
+    if (r != OAT_OK) {
+        h->m.destroy();
+        delete h;
+        return r;
+    }
+    *out = h;
+    return OAT_OK;
+}
+extern "C" int oat_mog_destroy(oat_mog *h)
+{
+    if (!h) return OAT_OK;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    h->m.destroy();
+    h->in.release();
+    h->out_bgr.release();
+    h->out_mask.release();
+    delete h;
+    return OAT_OK;
+}
+extern "C" int oat_mog_reset(oat_mog *h)
+{
+    REQUIRE(h, "null handle");
+    h->m.nframes = 0;
+    return OAT_OK;
+}
+
+extern "C" int oat_mog_apply(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out, size_t out_pitch,
+                             uint8_t *mask_out, size_t mask_pitch, double learning_rate)
+{
+    REQUIRE(h && bgr_in, "oat_mog_apply: null handle or input");
+    oat_ctx *c = h->ctx;
+    CKRET(bind(c));
+    const int rows = h->m.g.rows, cols = h->m.g.cols;
+    REQUIRE(in_pitch >= (size_t)3 * cols, "oat_mog_apply: input pitch too small");
+    REQUIRE(!bgr_out || out_pitch >= (size_t)3 * cols, "oat_mog_apply: output pitch too small");
+    REQUIRE(!mask_out || mask_pitch >= (size_t)cols, "oat_mog_apply: mask pitch too small");
+    FusedArgs a{};
+    CKRET(stage_in(c, c->stream, h->in, bgr_in, in_pitch, rows, (size_t)3 * cols, &a.bgr, &a.in_pitch));
+    OutView ob, om;
+    CKRET(stage_out(h->out_bgr, bgr_out, out_pitch, rows, (size_t)3 * cols, &ob));
+    CKRET(stage_out(h->out_mask, mask_out, mask_pitch, rows, (size_t)cols, &om));
+    h->m.frame_consts(learning_rate, &a.c, &a.reset);
+    a.do_hsv = 0;
+    a.thr_bits = nullptr;
+    a.bgr_out = ob.d;
+    a.bgr_out_pitch = ob.dpitch;
+    a.fg_out = om.d;
+    a.fg_pitch = om.dpitch;
+    CKRET(launch_fused(c, h->m, a));
+    CKRET(finish_out(c->stream, ob));
+    CKRET(finish_out(c->stream, om));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+
+extern "C" int oat_mog_live_modes(oat_mog *h, uint64_t *sum)
+{
+    REQUIRE(h, "null handle");
+    CKRET(bind(h->ctx));
+    return live_modes(h->ctx, h->m, sum);
+}
+
+static int get_state(oat_ctx *c, MogModel &m, uint8_t *modes_used, float *weight, float *variance, float *mean)
+{
+    const size_t n = (size_t)m.g.rows * m.g.cols;
+    const int K = m.K;
+    uint8_t *dm = nullptr;
+    float *dw = nullptr, *dv = nullptr, *dmean = nullptr;
+    if (modes_used) CK(cudaMalloc(&dm, n));
+    if (weight) CK(cudaMalloc(&dw, n * K * sizeof(float)));
+    if (variance) CK(cudaMalloc(&dv, n * K * sizeof(float)));
+    if (mean) CK(cudaMalloc(&dmean, n * K * 3 * sizeof(float)));
+    state_export_kernel<<<nblocks((long long)n, 256), 256, 0, c->stream>>>(m.state, m.plane, m.nmodes, m.g, K, dm, dw,
+                                                                           dv, dmean);
+    LAUNCH_CHECK(c);
+    CK(cudaStreamSynchronize(c->stream));
+    if (dm) CK(cudaMemcpy(modes_used, dm, n, cudaMemcpyDeviceToHost));
+    if (dw) CK(cudaMemcpy(weight, dw, n * K * sizeof(float), cudaMemcpyDeviceToHost));
+    if (dv) CK(cudaMemcpy(variance, dv, n * K * sizeof(float), cudaMemcpyDeviceToHost));
+    if (dmean) CK(cudaMemcpy(mean, dmean, n * K * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dm);
+    cudaFree(dw);
+    cudaFree(dv);
+    cudaFree(dmean);
+    return OAT_OK;
+}
+
+extern "C" int oat_mog_get_state(oat_mog *h, uint8_t *modes_used, float *weight, float *variance, float *mean)
+{
+    REQUIRE(h, "null handle");
+    CKRET(bind(h->ctx));
+    return get_state(h->ctx, h->m, modes_used, weight, variance, mean);
+}
+
+// ---- framefilt col -C HSV ------------------------------------------------------------------
+extern "C" int oat_bgr2hsv(oat_ctx *c, const uint8_t *bgr, size_t in_pitch, uint8_t *hsv, size_t out_pitch, int rows,
+                           int cols)
+{
+    CKRET(bind(c));
+    REQUIRE(bgr && hsv && rows > 0 && cols > 0, "oat_bgr2hsv: bad arguments");
+    REQUIRE(in_pitch >= (size_t)3 * cols && out_pitch >= (size_t)3 * cols, "oat_bgr2hsv: pitch too small");
+    const uint8_t *d;
+    size_t dp;
+    CKRET(stage_in(c, c->stream, c->scratch_in, bgr, in_pitch, rows, (size_t)3 * cols, &d, &dp));
+    OutView ov;
+    CKRET(stage_out(c->scratch_out, hsv, out_pitch, rows, (size_t)3 * cols, &ov));
+    bgr2hsv_kernel<<<nblocks((long long)rows * cols, 256), 256, 0, c->stream>>>(d, dp, ov.d, ov.dpitch, rows, cols,
+                                                                              c->hsv_lut);
+    LAUNCH_CHECK(c);
+    CKRET(finish_out(c->stream, ov));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+
+// ---- framefilt bsub ------------------------------------------------------------------------
+struct oat_bsub {
+    oat_ctx *ctx;
+    int rows, cols, ch;
+    double alpha;
+    bool set;
+    uint8_t *bg;
+    float *bgf;
+    DevBuf in, out;
+};
+
+extern "C" int oat_bsub_create(oat_ctx *c, int rows, int cols, int channels, double alpha, oat_bsub **out)
+{
+    REQUIRE(out, "oat_bsub_create: out is null");
+    *out = nullptr;
+    CKRET(bind(c));
+    REQUIRE(rows > 0 && cols > 0 && (channels == 1 || channels == 3), "oat_bsub_create: bad geometry");
+    // reference option range check: adaptation-coeff in [0,1] (BackgroundSubtractor.cpp:77)
+    REQUIRE(alpha >= 0.0 && alpha <= 1.0, "oat_bsub_create: alpha must be in [0,1]");
+    oat_bsub *b = new (std::nothrow) oat_bsub();
+    if (!b) return fail(OAT_ERR_NOMEM, "out of host memory");
+    b->ctx = c;
+    b->rows = rows;
+    b->cols = cols;
+    b->ch = channels;
+    b->alpha = alpha;
+    b->set = false;
+    b->bg = nullptr;
+    b->bgf = nullptr;
+    const size_t n = (size_t)rows * cols * channels;
+    if (cudaMalloc(&b->bg, n) != cudaSuccess || cudaMalloc(&b->bgf, n * sizeof(float)) != cudaSuccess) {
+        if (b->bg) cudaFree(b->bg);
+        delete b;
+        cudaGetLastError();
+        return fail(OAT_ERR_NOMEM, "oat_bsub_create: device allocation failed");
+    }
+    *out = b;
+    return OAT_OK;
+}
+extern "C" int oat_bsub_destroy(oat_bsub *b)
+{
+    if (!b) return OAT_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->bg);
+    cudaFree(b->bgf);
+    b->in.release();
+    b->out.release();
+    delete b;
+    return OAT_OK;
+}
+extern "C" int oat_bsub_set_background(oat_bsub *b, const uint8_t *img, size_t pitch)
+{
+    REQUIRE(b && img, "oat_bsub_set_background: null argument");
+    oat_ctx *c = b->ctx;
+    CKRET(bind(c));
+    const int rowbytes = b->cols * b->ch;
+    REQUIRE(pitch >= (size_t)rowbytes, "oat_bsub_set_background: pitch too small");
+    const uint8_t *d;
+    size_t dp;
+    CKRET(stage_in(c, c->stream, b->in, img, pitch, b->rows, rowbytes, &d, &dp));
+    bsub_set_bg_kernel<<<nblocks((long long)b->rows * rowbytes, 256), 256, 0, c->stream>>>(d, dp, b->bg, b->bgf,
+                                                                                         b->rows, rowbytes);
+    LAUNCH_CHECK(c);
+    CK(cudaStreamSynchronize(c->stream));
+    b->set = true;
+    return OAT_OK;
+}
+extern "C" int oat_bsub_apply(oat_bsub *b, const uint8_t *in, size_t in_pitch, uint8_t *out, size_t out_pitch)
+{
+    REQUIRE(b && in && out, "oat_bsub_apply: null argument");
+    oat_ctx *c = b->ctx;
+    CKRET(bind(c));
+    const int rowbytes = b->cols * b->ch;
+    REQUIRE(in_pitch >= (size_t)rowbytes && out_pitch >= (size_t)rowbytes, "oat_bsub_apply: pitch too small");
+    const uint8_t *d;
+    size_t dp;
+    CKRET(stage_in(c, c->stream, b->in, in, in_pitch, b->rows, rowbytes, &d, &dp));
+    OutView ov;
+    CKRET(stage_out(b->out, out, out_pitch, b->rows, rowbytes, &ov));
+    const float a = (float)b->alpha, bb = 1.0f - a;
+    bsub_kernel<<<nblocks((long long)b->rows * rowbytes, 256), 256, 0, c->stream>>>(
+        d, dp, ov.d, ov.dpitch, b->bg, b->bgf, b->rows, rowbytes, b->set ? 0 : 1, a, bb, b->alpha > 0.0 ? 1 : 0);
+    LAUNCH_CHECK(c);
+    b->set = true;
+    CKRET(finish_out(c->stream, ov));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+
+// ---- detect tail ---------------------------------------------------------------------------
+extern "C" void oat_hsv_default_params(oat_hsv_params *p)
+{
+    if (!p) return;
+    p->h_min = p->s_min = p->v_min = 0;
+    p->h_max = p->s_max = p->v_max = 256;
+    p->erode_px = 0;
+    p->dilate_px = 10;
+    p->min_area = 0.0;
+    p->max_area = DBL_MAX;
+}
+
+static int check_hsv_params(const oat_hsv_params *p)
+{
+    REQUIRE(p, "null hsv params");
+    // reference: thresholds are ints in 0..256 with min < max is NOT enforced for H/S/V
+    // (HSVDetector.cpp:87-110); area needs min < max (HSVDetector.cpp:130-137).
+    const int v[6] = {p->h_min, p->h_max, p->s_min, p->s_max, p->v_min, p->v_max};
+    for (int i = 0; i < 6; ++i) REQUIRE(v[i] >= 0 && v[i] <= 256, "HSV thresholds must be in 0..256");
+    REQUIRE(p->min_area < p->max_area, "area: min must be < max");
+    return OAT_OK;
+}
+
+struct Tail {
+    TailBuffers tb{};
+    uint32_t *bits0 = nullptr;  // threshold mask (input of the tail)
+    uint32_t *tmp = nullptr, *er = nullptr, *di = nullptr;
+    size_t nwords = 0;
+
+    int create(int rows, int cols)
+    {
+        REQUIRE(rows > 0 && cols > 0 && rows <= 32768 && cols <= 32768, "detector: bad frame geometry");
+        tb.g.rows = rows;
+        tb.g.cols = cols;
+        tb.g.wpr = div_up(cols, 32);
+        nwords = (size_t)rows * tb.g.wpr;
+        tb.nnodes = nwords * 32 + 1;
+        CK(cudaMalloc(&bits0, nwords * 4));
+        CK(cudaMalloc(&tmp, nwords * 4));
+        CK(cudaMalloc(&er, nwords * 4));
+        CK(cudaMalloc(&di, nwords * 4));
+        CK(cudaMalloc(&tb.G, nwords * 4));
+        CK(cudaMalloc(&tb.parent, tb.nnodes * sizeof(int)));
+        CK(cudaMalloc(&tb.acc, tb.nnodes * 3 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&tb.best, sizeof(unsigned long long)));
+        CK(cudaMalloc(&tb.count, sizeof(unsigned int)));
+        return OAT_OK;
+    }
+    void destroy()
+    {
+        cudaFree(bits0);
+        cudaFree(tmp);
+        cudaFree(er);
+        cudaFree(di);
+        cudaFree(tb.G);
+        cudaFree(tb.parent);
+        cudaFree(tb.acc);
+        cudaFree(tb.best);
+        cudaFree(tb.count);
+        *this = Tail();
+    }
+    // erode -> dilate -> labelling -> moments -> select; result to d_out (device memory)
+    int run(oat_ctx *c, const oat_hsv_params &p, oat_detection *d_out, uint8_t *thresh_dev, size_t thresh_pitch,
+            int32_t *labels_dev)
+    {
+        cudaStream_t s = c->stream;
+        const BitGeom g = tb.g;
+        const unsigned gw = nblocks((long long)nwords, 256);
+        const uint32_t *cur = bits0;
+        if (p.erode_px > 0) {
+            morph_h_kernel<false><<<gw, 256, 0, s>>>(cur, tmp, g, p.erode_px);
+            LAUNCH_CHECK(c);
+            morph_v_kernel<false><<<gw, 256, 0, s>>>(tmp, er, g, p.erode_px);
+            LAUNCH_CHECK(c);
+            cur = er;
+        }
+        if (p.dilate_px > 0) {
+            morph_h_kernel<true><<<gw, 256, 0, s>>>(cur, tmp, g, p.dilate_px);
+            LAUNCH_CHECK(c);
+            morph_v_kernel<true><<<gw, 256, 0, s>>>(tmp, di, g, p.dilate_px);
+            LAUNCH_CHECK(c);
+            cur = di;
+        }
+        if (thresh_dev) {
+            bits_to_mask_kernel<<<nblocks((long long)g.rows * g.pitch_px(), 256), 256, 0, s>>>(cur, g, thresh_dev,
+                                                                                             thresh_pitch);
+            LAUNCH_CHECK(c);
+        }
+        ccl_init_kernel<<<gw, 256, 0, s>>>(cur, tb);
+        LAUNCH_CHECK(c);
+        ccl_merge_kernel<<<gw, 256, 0, s>>>(cur, tb);
+        LAUNCH_CHECK(c);
+        if (labels_dev) {
+            ccl_labels_kernel<<<gw, 256, 0, s>>>(cur, tb, labels_dev);
+            LAUNCH_CHECK(c);
+        }
+        ccl_fill_kernel<<<gw, 256, 0, s>>>(cur, tb);
+        LAUNCH_CHECK(c);
+        if (g.rows > 1) {
+            ccl_moments_kernel<<<nblocks((long long)(g.rows - 1) * g.wpr, 256), 256, 0, s>>>(tb);
+            LAUNCH_CHECK(c);
+        }
+        ccl_select_kernel<<<gw, 256, 0, s>>>(cur, tb, p.min_area, p.max_area);
+        LAUNCH_CHECK(c);
+        ccl_finalize_kernel<<<1, 1, 0, s>>>(tb, d_out);
+        LAUNCH_CHECK(c);
+        return OAT_OK;
+    }
+};
+
+struct oat_hsvdet {
+    oat_ctx *ctx;
+    Tail tail;
+    oat_detection *d_res;
+    DevBuf in, out_thr, out_lab;
+};
+
+extern "C" int oat_hsvdet_create(oat_ctx *c, int rows, int cols, oat_hsvdet **out)
+{
+    REQUIRE(out, "oat_hsvdet_create: out is null");
+    *out = nullptr;
+    CKRET(bind(c));
+    oat_hsvdet *h = new (std::nothrow) oat_hsvdet();
+    if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
+    h->ctx = c;
+    h->d_res = nullptr;
+    int r = h->tail.create(rows, cols);
+    if (r == OAT_OK && cudaMalloc(&h->d_res, sizeof(oat_detection)) != cudaSuccess)
+        r = fail(OAT_ERR_NOMEM, "device allocation failed");
+    if (r != OAT_OK) {
+        h->tail.destroy();
+        delete h;
+        return r;
+    }
+    *out = h;
+    return OAT_OK;
+}
+extern "C" int oat_hsvdet_destroy(oat_hsvdet *h)
+{
+    if (!h) return OAT_OK;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    h->tail.destroy();
+    cudaFree(h->d_res);
+    h->in.release();
+    h->out_thr.release();
+    h->out_lab.release();
+    delete h;
+    return OAT_OK;
+}
+
+static int detect_common(oat_hsvdet *h, const uint8_t *img, size_t pitch, int channels, const oat_hsv_params *p,
+                         oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch, int32_t *labels_out)
+{
+    REQUIRE(h && img && out, "detect: null argument");
+    CKRET(check_hsv_params(p));
+    oat_ctx *c = h->ctx;
+    CKRET(bind(c));
+    const BitGeom g = h->tail.tb.g;
+    REQUIRE(pitch >= (size_t)channels * g.cols, "detect: input pitch too small");
+    REQUIRE(!thresh_out || thresh_pitch >= (size_t)g.cols, "detect: thresh pitch too small");
+    const uint8_t *d;
+    size_t dp;
+    CKRET(stage_in(c, c->stream, h->in, img, pitch, g.rows, (size_t)channels * g.cols, &d, &dp));
+    OutView ot;
+    CKRET(stage_out(h->out_thr, thresh_out, thresh_pitch, g.rows, (size_t)g.cols, &ot));
+    int32_t *lab_dev = nullptr;
+    const size_t lab_bytes = (size_t)g.rows * g.cols * sizeof(int32_t);
+    if (labels_out) {
+        if (mem_kind(labels_out) == MEM_DEVICE)
+            lab_dev = labels_out;
+        else {
+            CKRET(h->out_lab.ensure(lab_bytes));
+            lab_dev = (int32_t *)h->out_lab.p;
+        }
+    }
+    const unsigned gp = nblocks((long long)g.rows * g.pitch_px(), 256);
+    if (channels == 3)
+        inrange_bits_kernel<<<gp, 256, 0, c->stream>>>(d, dp, g, p->h_min, p->s_min, p->v_min, p->h_max, p->s_max,
+                                                       p->v_max, h->tail.bits0);
+    else
+        mask_to_bits_kernel<<<gp, 256, 0, c->stream>>>(d, dp, g, h->tail.bits0);
+    LAUNCH_CHECK(c);
+    CKRET(h->tail.run(c, *p, h->d_res, ot.d, ot.dpitch, lab_dev));
+    CKRET(finish_out(c->stream, ot));
+    if (labels_out && lab_dev != labels_out)
+        CK(cudaMemcpyAsync(labels_out, lab_dev, lab_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, h->d_res, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+
+extern "C" int oat_hsvdet_detect(oat_hsvdet *h, const uint8_t *hsv, size_t pitch, const oat_hsv_params *p,
+                                 oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch, int32_t *labels_out)
+{
+    return detect_common(h, hsv, pitch, 3, p, out, thresh_out, thresh_pitch, labels_out);
+}
+extern "C" int oat_sift_contours(oat_hsvdet *h, const uint8_t *mask, size_t pitch, const oat_hsv_params *p,
+                                 oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch, int32_t *labels_out)
+{
+    return detect_common(h, mask, pitch, 1, p, out, thresh_out, thresh_pitch, labels_out);
+}
+
+// ---- fused tracker -------------------------------------------------------------------------
+struct Slot {
+    DevBuf in;                      // staged input frame (host-fed streams)
+    oat_detection *h_res = nullptr; // pinned
+    oat_detection *d_res = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr;
+};
+
+struct oat_tracker {
+    oat_ctx *ctx;
+    MogModel m;
+    Tail tail;
+    std::vector<Slot> ring;
+    uint64_t head = 0, tailpos = 0;  // submitted / collected
+    DevBuf out_bgr, out_fg, out_hsv, out_thr;
+    // profiling of the fused kernel
+    int prof = 0;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+    double prof_ms = 0.0;
+    uint64_t prof_n = 0;
+};
+
+extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_params *mp, int ring_depth,
+                                  oat_tracker **out)
+{
+    REQUIRE(out, "oat_tracker_create: out is null");
+    *out = nullptr;
+    CKRET(bind(c));
+    REQUIRE(ring_depth >= 0 && ring_depth <= 64, "oat_tracker_create: ring_depth must be in 0..64");
+    if (ring_depth == 0) ring_depth = 4;
+    oat_tracker *t = new (std::nothrow) oat_tracker();
+    if (!t) return fail(OAT_ERR_NOMEM, "out of host memory");
+    t->ctx = c;
+    int r = t->m.create(rows, cols, mp);
+    if (r == OAT_OK) r = t->tail.create(rows, cols);
+    if (r == OAT_OK) {
+        t->ring.resize(ring_depth);
+        for (auto &s : t->ring) {
+            if (cudaHostAlloc(&s.h_res, sizeof(oat_detection), cudaHostAllocDefault) != cudaSuccess ||
+                cudaMalloc(&s.d_res, sizeof(oat_detection)) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+                r = fail(OAT_ERR_NOMEM, std::string("tracker ring allocation failed: ") +
+                                            cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
+    }
+    if (r != OAT_OK) {
+        oat_tracker_destroy(t);
+        return r;
+    }
+    *out = t;
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_destroy(oat_tracker *t)
+{
+    if (!t) return OAT_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->h2d);
+    cudaStreamSynchronize(t->ctx->stream);
+    t->m.destroy();
+    t->tail.destroy();
+    for (auto &s : t->ring) {
+        s.in.release();
+        if (s.h_res) cudaFreeHost(s.h_res);
+        if (s.d_res) cudaFree(s.d_res);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto &pr : t->prof_pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    t->out_bgr.release();
+    t->out_fg.release();
+    t->out_hsv.release();
+    t->out_thr.release();
+    delete t;
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_reset(oat_tracker *t)
+{
+    REQUIRE(t, "null handle");
+    REQUIRE(t->head == t->tailpos, "oat_tracker_reset: frames are still outstanding");
+    t->m.nframes = 0;
+    return OAT_OK;
+}
+
+static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                           const oat_hsv_params *p, OutView &ob, OutView &ofg, OutView &ohsv, OutView &othr)
+{
+    oat_ctx *c = t->ctx;
+    const int rows = t->m.g.rows, cols = t->m.g.cols;
+    Slot &s = t->ring[t->head % t->ring.size()];
+    FusedArgs a{};
+    if (mem_kind(bgr_in) == MEM_DEVICE) {
+        a.bgr = bgr_in;
+        a.in_pitch = in_pitch;
+    } else {
+        // ingest on the copy stream so the DMA of frame t+1 overlaps the kernels of frame t
+        CKRET(stage_in(c, c->h2d, s.in, bgr_in, in_pitch, rows, (size_t)3 * cols, &a.bgr, &a.in_pitch));
+        CK(cudaEventRecord(s.copied, c->h2d));
+        CK(cudaStreamWaitEvent(c->stream, s.copied, 0));
+    }
+    t->m.frame_consts(learning_rate, &a.c, &a.reset);
+    a.do_hsv = 1;
+    a.lo[0] = p->h_min;
+    a.lo[1] = p->s_min;
+    a.lo[2] = p->v_min;
+    a.hi[0] = p->h_max;
+    a.hi[1] = p->s_max;
+    a.hi[2] = p->v_max;
+    a.thr_bits = t->tail.bits0;
+    a.bgr_out = ob.d;
+    a.bgr_out_pitch = ob.dpitch;
+    a.fg_out = ofg.d;
+    a.fg_pitch = ofg.dpitch;
+    a.hsv_out = ohsv.d;
+    a.hsv_pitch = ohsv.dpitch;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (t->prof) {
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, c->stream));
+    }
+    CKRET(launch_fused(c, t->m, a));
+    if (t->prof) {
+        CK(cudaEventRecord(e1, c->stream));
+        t->prof_pending.emplace_back(e0, e1);
+    }
+    CKRET(t->tail.run(c, *p, s.d_res, othr.d, othr.dpitch, nullptr));
+    CKRET(finish_out(c->stream, ob));
+    CKRET(finish_out(c->stream, ofg));
+    CKRET(finish_out(c->stream, ohsv));
+    CKRET(finish_out(c->stream, othr));
+    CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(s.done, c->stream));
+    ++t->head;
+    return OAT_OK;
+}
+
+static int tracker_check(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, const oat_hsv_params *p)
+{
+    REQUIRE(t && bgr_in, "tracker: null handle or input");
+    CKRET(check_hsv_params(p));
+    REQUIRE(in_pitch >= (size_t)3 * t->m.g.cols, "tracker: input pitch too small");
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_collect(oat_tracker *t, oat_detection *out)
+{
+    REQUIRE(t && out, "oat_tracker_collect: null argument");
+    if (t->tailpos == t->head) return fail(OAT_ERR_STATE, "oat_tracker_collect: nothing outstanding");
+    CKRET(bind(t->ctx));
+    Slot &s = t->ring[t->tailpos % t->ring.size()];
+    CK(cudaEventSynchronize(s.done));
+    *out = *s.h_res;
+    ++t->tailpos;
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                                  const oat_hsv_params *p, uint8_t *bgr_out, size_t bgr_out_pitch)
+{
+    CKRET(tracker_check(t, bgr_in, in_pitch, p));
+    CKRET(bind(t->ctx));
+    if (t->head - t->tailpos >= t->ring.size())
+        return fail(OAT_ERR_STATE, "oat_tracker_submit: ring full (collect first)");
+    const int rows = t->m.g.rows, cols = t->m.g.cols;
+    REQUIRE(!bgr_out || bgr_out_pitch >= (size_t)3 * cols, "tracker: output pitch too small");
+    // async egress needs a stable device view: device pointers are written directly, host
+    // pointers go through a per-tracker staging buffer (one frame in flight for egress).
+    REQUIRE(!bgr_out || mem_kind(bgr_out) == MEM_DEVICE || t->head == t->tailpos,
+            "oat_tracker_submit: host bgr_out needs the previous frame collected first");
+    OutView ob, none1, none2, none3;
+    CKRET(stage_out(t->out_bgr, bgr_out, bgr_out_pitch, rows, (size_t)3 * cols, &ob));
+    return tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, none1, none2, none3);
+}
+
+extern "C" int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                                 const oat_hsv_params *p, oat_detection *out, uint8_t *bgr_out, size_t bgr_out_pitch,
+                                 uint8_t *fgmask_out, size_t fgmask_pitch, uint8_t *hsv_out, size_t hsv_pitch,
+                                 uint8_t *thresh_out, size_t thresh_pitch)
+{
+    CKRET(tracker_check(t, bgr_in, in_pitch, p));
+    REQUIRE(out, "oat_tracker_track: null output");
+    REQUIRE(t->head == t->tailpos, "oat_tracker_track: frames are still outstanding (collect first)");
+    CKRET(bind(t->ctx));
+    const int rows = t->m.g.rows, cols = t->m.g.cols;
+    REQUIRE(!bgr_out || bgr_out_pitch >= (size_t)3 * cols, "tracker: bgr_out pitch too small");
+    REQUIRE(!hsv_out || hsv_pitch >= (size_t)3 * cols, "tracker: hsv_out pitch too small");
+    REQUIRE(!fgmask_out || fgmask_pitch >= (size_t)cols, "tracker: fgmask pitch too small");
+    REQUIRE(!thresh_out || thresh_pitch >= (size_t)cols, "tracker: thresh pitch too small");
+    OutView ob, ofg, ohsv, othr;
+    CKRET(stage_out(t->out_bgr, bgr_out, bgr_out_pitch, rows, (size_t)3 * cols, &ob));
+    CKRET(stage_out(t->out_fg, fgmask_out, fgmask_pitch, rows, (size_t)cols, &ofg));
+    CKRET(stage_out(t->out_hsv, hsv_out, hsv_pitch, rows, (size_t)3 * cols, &ohsv));
+    CKRET(stage_out(t->out_thr, thresh_out, thresh_pitch, rows, (size_t)cols, &othr));
+    CKRET(tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, ofg, ohsv, othr));
+    return oat_tracker_collect(t, out);
+}
+
+extern "C" int oat_tracker_live_modes(oat_tracker *t, uint64_t *sum)
+{
+    REQUIRE(t, "null handle");
+    CKRET(bind(t->ctx));
+    return live_modes(t->ctx, t->m, sum);
+}
+
+extern "C" int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, float *variance,
+                                     float *mean)
+{
+    REQUIRE(t, "null handle");
+    CKRET(bind(t->ctx));
+    return get_state(t->ctx, t->m, modes_used, weight, variance, mean);
+}
+
+extern "C" int oat_tracker_profile(oat_tracker *t, int enable)
+{
+    REQUIRE(t, "null handle");
+    t->prof = enable ? 1 : 0;
+    return OAT_OK;
+}
+extern "C" int oat_tracker_profile_read(oat_tracker *t, double *mean_ms, uint64_t *launches)
+{
+    REQUIRE(t, "null handle");
+    CKRET(bind(t->ctx));
+    CK(cudaStreamSynchronize(t->ctx->stream));
+    for (auto &pr : t->prof_pending) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        t->prof_ms += ms;
+        ++t->prof_n;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    t->prof_pending.clear();
+    if (mean_ms) *mean_ms = t->prof_n ? t->prof_ms / (double)t->prof_n : 0.0;
+    if (launches) *launches = t->prof_n;
+    t->prof_ms = 0.0;
+    t->prof_n = 0;
+    return OAT_OK;
+}
+
+// ---- synthetic source ----------------------------------------------------------------------
+extern "C" int oat_synth_frame(oat_ctx *c, uint8_t *dst, size_t pitch, int rows, int cols, uint32_t seed, uint32_t t)
+{
+    CKRET(bind(c));
+    REQUIRE(dst && rows >= 20 && cols >= 4 && rows / 3 > 0 && cols / 2 > 0, "oat_synth_frame: bad arguments");
+    REQUIRE(pitch >= (size_t)3 * cols, "oat_synth_frame: pitch too small");
+    OutView ov;
+    CKRET(stage_out(c->scratch_out, dst, pitch, rows, (size_t)3 * cols, &ov));
+    const uint32_t kbg = fmix32_hd(seed ^ 0x9e3779b9u);
+    const uint32_t knz = fmix32_hd(seed + 0x7f4a7c15u * (t + 1u));
+    const int r = rows / 20;
+    const int cx = cols / 4 + (int)((7u * t) % (uint32_t)(cols / 2));
+    const int cy = rows / 3 + (int)((4u * t) % (uint32_t)(rows / 3));
+    synth_kernel<<<nblocks((long long)rows * cols, 256), 256, 0, c->stream>>>(ov.d, ov.dpitch, rows, cols, kbg, knz,
+                                                                            cx, cy, r, t != 0 ? 1 : 0);
+    LAUNCH_CHECK(c);
+    CKRET(finish_out(c->stream, ov));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+
+// ---- memory helpers ------------------------------------------------------------------------
+extern "C" int oat_alloc_device(oat_ctx *c, size_t bytes, void **out)
+{
+    CKRET(bind(c));
+    REQUIRE(out && bytes > 0, "oat_alloc_device: bad arguments");
+    CK(cudaMalloc(out, bytes));
+    return OAT_OK;
+}
+extern "C" int oat_free_device(oat_ctx *c, void *p)
+{
+    CKRET(bind(c));
+    if (p) CK(cudaFree(p));
+    return OAT_OK;
+}
+extern "C" int oat_alloc_pinned(size_t bytes, void **out)
+{
+    REQUIRE(out && bytes > 0, "oat_alloc_pinned: bad arguments");
+    CK(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return OAT_OK;
+}
+extern "C" int oat_free_pinned(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return OAT_OK;
+}
+extern "C" int oat_register_host(void *p, size_t bytes)
+{
+    REQUIRE(p && bytes > 0, "oat_register_host: bad arguments");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return OAT_OK;
+}
+extern "C" int oat_unregister_host(void *p)
+{
+    if (p) CK(cudaHostUnregister(p));
+    return OAT_OK;
+}
+extern "C" int oat_memcpy(oat_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    CKRET(bind(c));
+    REQUIRE(dst && src, "oat_memcpy: null pointer");
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+extern "C" int oat_flush_l2(oat_ctx *c)
+{
+    CKRET(bind(c));
+    const size_t bytes = (size_t)256 << 20;
+    CKRET(c->flush.ensure(bytes));
+    static uint32_t v = 0;
+    flush_kernel<<<148 * 8, 256, 0, c->stream>>>((uint4 *)c->flush.p, bytes / 16, ++v);
+    CK(cudaGetLastError());  // benchmark utility: not counted in oat_ctx_kernel_launches
+    return OAT_OK;
+}

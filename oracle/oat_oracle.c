@@ -237,8 +237,8 @@ ORC_API void orc_mog_apply(orc_mog *m, const uint8_t *bgr, size_t pitch, uint8_t
                         mean_m[1] -= k * d1;
                         mean_m[2] -= k * d2;
                         float varnew = var + k * (dist2 - var);
-                        varnew = varnew > varMin ? varnew : varMin; /* MAX(varnew, varMin) */
-                        varnew = varnew < varMax ? varnew : varMax; /* MIN(varnew, varMax) */
+                        varnew = (varnew < varMin) ? varMin : varnew; /* MAX(varnew, varMin) */
+                        varnew = (varnew > varMax) ? varMax : varnew; /* MIN(varnew, varMax) */
                         V[mode] = varnew;
                         for (int i = mode; i > 0; --i) {
                             if (weight < W[i - 1]) break;

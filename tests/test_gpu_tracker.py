@@ -1,0 +1,108 @@
+"""GPU parity of the fused tracker (mog -> col HSV -> hsv in one pass) vs the CPU oracle chain and
+vs the analytic known answer of the synthetic stream."""
+import numpy as np
+import pytest
+
+import oat_b200
+import oracle
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+HSV_BAND = dict(h=(40, 80), s=(100, 256), v=(100, 256))
+
+
+def test_synth_generator_matches_oracle(ctx):
+    for (rows, cols) in [(120, 160), (480, 640)]:
+        for t in (0, 1, 7, 33):
+            g = ctx.synth_frame(rows, cols, 1000, t)
+            assert np.array_equal(g, oracle.synth_frame(rows, cols, 1000, t))
+            assert np.array_equal(g, synth.frame(rows, cols, 1000, t))
+
+
+@pytest.mark.parametrize("shape", [(120, 160), (240, 320), (99, 150)])
+@pytest.mark.parametrize("lr", [0.0, 0.01])
+def test_tracker_matches_oracle_chain(ctx, shape, lr):
+    rows, cols = shape
+    trk = oat_b200.Tracker(ctx, rows, cols, adaptation_coeff=lr, hsv=oat_b200.HsvParams.make(**HSV_BAND))
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t in range(30):
+        f = oracle.synth_frame(rows, cols, 1000, t)
+        d, eg = trk.track(f, egress=("bgr", "fgmask", "hsv", "thresh"))
+        o, oeg = orc.track(f, lr, op)
+        for k in ("fgmask", "bgr", "hsv", "thresh"):
+            assert np.array_equal(eg[k], oeg[k]), f"{k} differs at t={t}: {(eg[k] != oeg[k]).sum()}"
+        assert bool(d.position_valid) == bool(o.position_valid)
+        assert d.n_components == o.n_components
+        assert abs(d.area - o.area) <= TOL and abs(d.x - o.x) <= TOL and abs(d.y - o.y) <= TOL
+        if lr == 0.0 and t >= 1:  # analytic known answer (A18)
+            cx, cy = synth.disc_centre(rows, cols, t)
+            assert d.n_components == 1 and d.x == cx + 0.5 and d.y == cy + 0.5
+    assert trk.live_modes() == int(orc.mog.state()[0].sum())
+    trk.close()
+
+
+def test_tracker_device_resident_and_async(ctx):
+    """Device-resident frames through submit/collect give the same detections as track()."""
+    rows, cols = 240, 320
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    a = oat_b200.Tracker(ctx, rows, cols, 0.01, hp)
+    b = oat_b200.Tracker(ctx, rows, cols, 0.01, hp, ring_depth=4)
+    frames = [ctx.alloc(rows * cols * 3) for _ in range(8)]
+    for t, buf in enumerate(frames):
+        ctx.synth_frame(rows, cols, 1001, t, out=buf)
+    want = [a.track(buf)[0].as_tuple() for buf in frames]
+    got = []
+    for i in range(0, 8, 4):
+        for buf in frames[i:i + 4]:
+            b.submit(buf)
+        with pytest.raises(oat_b200.OatError):
+            b.submit(frames[0])  # ring full
+        got += [b.collect().as_tuple() for _ in range(4)]
+    with pytest.raises(oat_b200.OatError):
+        b.collect()
+    assert got == want
+    # host (pageable + pinned) frames through the async path as well
+    c = oat_b200.Tracker(ctx, rows, cols, 0.01, hp, ring_depth=2)
+    pin = oat_b200.PinnedArray((2, rows, cols, 3))
+    got = []
+    for t in range(8):
+        pin.array[t % 2] = oracle.synth_frame(rows, cols, 1001, t)
+        c.submit(pin.ptr + (t % 2) * rows * cols * 3)
+        got.append(c.collect().as_tuple())
+    assert got == want
+    for x in (a, b, c):
+        x.close()
+
+
+@pytest.mark.parametrize("shape", [(1080, 1920)])
+def test_tracker_full_size_known_answer(ctx, shape):
+    """BASELINE config 1 size: analytic answer with -a 0 (A18) and size-independent properties
+    with -a 0.01: idempotent masks (thresh is {0,255}, fg in {0,127,255}) and live modes in 1..5."""
+    rows, cols = shape
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    trk = oat_b200.Tracker(ctx, rows, cols, 0.0, hp)
+    buf = ctx.alloc(rows * cols * 3)
+    for t in range(12):
+        ctx.synth_frame(rows, cols, 1000, t, out=buf)
+        d, _ = trk.track(buf)
+        if t >= 1:
+            cx, cy = synth.disc_centre(rows, cols, t)
+            assert d.position_valid and d.n_components == 1
+            assert d.x == cx + 0.5 and d.y == cy + 0.5
+    assert trk.live_modes() == rows * cols  # frozen one-mode model (A3)
+    trk.close()
+    trk = oat_b200.Tracker(ctx, rows, cols, 0.01, hp)
+    for t in range(12):
+        ctx.synth_frame(rows, cols, 1000, t, out=buf)
+        d, eg = trk.track(buf, egress=("fgmask", "thresh", "bgr"))
+        assert set(np.unique(eg["fgmask"])) <= {0, 127, 255}
+        assert set(np.unique(eg["thresh"])) <= {0, 255}
+        assert not eg["bgr"][eg["fgmask"] == 0].any()
+        if t >= 1:
+            cx, cy = synth.disc_centre(rows, cols, t)
+            assert d.position_valid and abs(d.x - cx - 0.5) < 8 and abs(d.y - cy - 0.5) < 8
+    m = trk.state()[0]
+    assert m.min() >= 1 and m.max() <= 5
+    trk.close()
