@@ -22,7 +22,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboatgpu.so")
+LIB_PATH = os.environ.get("OAT_B200_LIB") or os.path.join(_HERE, "liboatgpu.so")  # env override: kernel experiments
 DBL_MAX = float(np.finfo(np.float64).max)
 
 OAT_OK = 0

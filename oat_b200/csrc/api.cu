@@ -312,17 +312,17 @@ struct MogModel {
     }
 };
 
-template <int PX>
+template <int PX, bool TRACK>
 static void launch_fused_px(cudaStream_t s, int K, const FusedArgs &a)
 {
     const long long threads = (long long)a.rows * a.wpr * (32 / PX);
     const unsigned grid = nblocks(threads, 128);
     switch (K) {
-    case 1: mog_fused_kernel<1, PX><<<grid, 128, 0, s>>>(a); break;
-    case 2: mog_fused_kernel<2, PX><<<grid, 128, 0, s>>>(a); break;
-    case 3: mog_fused_kernel<3, PX><<<grid, 128, 0, s>>>(a); break;
-    case 4: mog_fused_kernel<4, PX><<<grid, 128, 0, s>>>(a); break;
-    default: mog_fused_kernel<5, PX><<<grid, 128, 0, s>>>(a); break;
+    case 1: mog_fused_kernel<1, PX, TRACK><<<grid, 128, 0, s>>>(a); break;
+    case 2: mog_fused_kernel<2, PX, TRACK><<<grid, 128, 0, s>>>(a); break;
+    case 3: mog_fused_kernel<3, PX, TRACK><<<grid, 128, 0, s>>>(a); break;
+    case 4: mog_fused_kernel<4, PX, TRACK><<<grid, 128, 0, s>>>(a); break;
+    default: mog_fused_kernel<5, PX, TRACK><<<grid, 128, 0, s>>>(a); break;
     }
 }
 
@@ -340,10 +340,15 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
     const bool vec = (m.g.cols % 4 == 0) && aligned4(a.bgr, a.in_pitch) &&
                      (!a.bgr_out || aligned4(a.bgr_out, a.bgr_out_pitch)) &&
                      (!a.fg_out || aligned4(a.fg_out, a.fg_pitch)) && (!a.hsv_out || aligned4(a.hsv_out, a.hsv_pitch));
-    if (vec)
-        launch_fused_px<4>(c->stream, m.K, a);
+    // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
+    // the state write-back; with a live rate every live mode changes every frame anyway.
+    const bool frozen = (a.c.aT == 0.0f) && !a.reset;
+    if (vec && frozen)
+        launch_fused_px<4, true>(c->stream, m.K, a);
+    else if (vec)
+        launch_fused_px<4, false>(c->stream, m.K, a);
     else
-        launch_fused_px<1>(c->stream, m.K, a);
+        launch_fused_px<1, true>(c->stream, m.K, a);
     LAUNCH_CHECK(c);
     return OAT_OK;
 }
@@ -610,6 +615,7 @@ struct Tail {
     uint32_t *bits0 = nullptr;  // threshold mask (input of the tail)
     uint32_t *tmp = nullptr, *er = nullptr, *di = nullptr;
     size_t nwords = 0;
+    size_t prep_smem_set = 48 * 1024;
 
     int create(int rows, int cols)
     {
@@ -628,6 +634,8 @@ struct Tail {
         CK(cudaMalloc(&tb.acc, tb.nnodes * 3 * sizeof(unsigned long long)));
         CK(cudaMalloc(&tb.best, sizeof(unsigned long long)));
         CK(cudaMalloc(&tb.count, sizeof(unsigned int)));
+        CK(cudaMalloc(&tb.ticket, sizeof(unsigned int)));
+        CK(cudaMalloc(&tb.rowext, (size_t)rows * sizeof(int2)));
         return OAT_OK;
     }
     void destroy()
@@ -641,37 +649,67 @@ struct Tail {
         cudaFree(tb.acc);
         cudaFree(tb.best);
         cudaFree(tb.count);
+        cudaFree(tb.ticket);
+        cudaFree(tb.rowext);
         *this = Tail();
     }
-    // erode -> dilate -> labelling -> moments -> select; result to d_out (device memory)
+    // [erode] -> [dilate] -> labelling -> moments -> select; result to d_out (device memory).
+    // 5 launches: prep (morphology + row extents + union-find init), merge, fill, moments, select.
     int run(oat_ctx *c, const oat_hsv_params &p, oat_detection *d_out, uint8_t *thresh_dev, size_t thresh_pitch,
             int32_t *labels_dev)
     {
         cudaStream_t s = c->stream;
         const BitGeom g = tb.g;
         const unsigned gw = nblocks((long long)nwords, 256);
-        const uint32_t *cur = bits0;
-        if (p.erode_px > 0) {
-            morph_h_kernel<false><<<gw, 256, 0, s>>>(cur, tmp, g, p.erode_px);
-            LAUNCH_CHECK(c);
-            morph_v_kernel<false><<<gw, 256, 0, s>>>(tmp, er, g, p.erode_px);
-            LAUNCH_CHECK(c);
-            cur = er;
+        int ke = p.erode_px > 0 ? p.erode_px : 0, kd = p.dilate_px > 0 ? p.dilate_px : 0;
+        const uint32_t *src = bits0;
+        const size_t smem_limit = 200 * 1024;
+        auto smem_for = [&](int R, int e, int d) {
+            const size_t nin = (size_t)R + (e > 0 ? e - 1 : 0) + (d > 0 ? d - 1 : 0);
+            return 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
+        };
+        int R = 8;
+        if (smem_for(R, ke, kd) > smem_limit) R = 1;
+        if (smem_for(R, ke, kd) > smem_limit) {
+            // very wide frame x very large kernel: separable passes through global memory instead
+            if (ke > 0) {
+                morph_h_kernel<false><<<gw, 256, 0, s>>>(src, tmp, g, ke);
+                LAUNCH_CHECK(c);
+                morph_v_kernel<false><<<gw, 256, 0, s>>>(tmp, er, g, ke);
+                LAUNCH_CHECK(c);
+                src = er;
+            }
+            if (kd > 0) {
+                morph_h_kernel<true><<<gw, 256, 0, s>>>(src, tmp, g, kd);
+                LAUNCH_CHECK(c);
+                morph_v_kernel<true><<<gw, 256, 0, s>>>(tmp, er == src ? bits0 : er, g, kd);
+                LAUNCH_CHECK(c);
+                src = (er == src) ? bits0 : er;
+            }
+            ke = kd = 0;
+            R = 8;
+            if (smem_for(R, 0, 0) > smem_limit) R = 1;
         }
-        if (p.dilate_px > 0) {
-            morph_h_kernel<true><<<gw, 256, 0, s>>>(cur, tmp, g, p.dilate_px);
-            LAUNCH_CHECK(c);
-            morph_v_kernel<true><<<gw, 256, 0, s>>>(tmp, di, g, p.dilate_px);
-            LAUNCH_CHECK(c);
-            cur = di;
+        PrepArgs pa;
+        pa.in = src;
+        pa.out = di;
+        pa.ke = ke;
+        pa.kd = kd;
+        pa.R = R;
+        pa.tb = tb;
+        const size_t smem = smem_for(R, ke, kd);
+        if (smem > prep_smem_set) {
+            CK(cudaFuncSetAttribute(tail_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+            prep_smem_set = smem_limit;
         }
+        tail_prep_kernel<<<div_up(g.rows, R), 256, smem, s>>>(pa);
+        LAUNCH_CHECK(c);
+        const uint32_t *cur = di;
         if (thresh_dev) {
             bits_to_mask_kernel<<<nblocks((long long)g.rows * g.pitch_px(), 256), 256, 0, s>>>(cur, g, thresh_dev,
                                                                                              thresh_pitch);
             LAUNCH_CHECK(c);
         }
-        ccl_init_kernel<<<gw, 256, 0, s>>>(cur, tb);
-        LAUNCH_CHECK(c);
         ccl_merge_kernel<<<gw, 256, 0, s>>>(cur, tb);
         LAUNCH_CHECK(c);
         if (labels_dev) {
@@ -684,9 +722,7 @@ struct Tail {
             ccl_moments_kernel<<<nblocks((long long)(g.rows - 1) * g.wpr, 256), 256, 0, s>>>(tb);
             LAUNCH_CHECK(c);
         }
-        ccl_select_kernel<<<gw, 256, 0, s>>>(cur, tb, p.min_area, p.max_area);
-        LAUNCH_CHECK(c);
-        ccl_finalize_kernel<<<1, 1, 0, s>>>(tb, d_out);
+        ccl_select_kernel<<<gw, 256, 0, s>>>(cur, tb, p.min_area, p.max_area, d_out);
         LAUNCH_CHECK(c);
         return OAT_OK;
     }

@@ -58,9 +58,10 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
+template <bool TRACK>
 __device__ __forceinline__ void upd(float &dst, float v, bool &dirty)
 {
-    dirty |= (__float_as_uint(dst) != __float_as_uint(v));
+    if (TRACK) dirty |= (__float_as_uint(dst) != __float_as_uint(v));
     dst = v;
 }
 __device__ __forceinline__ void fswap(float &a, float &b)
@@ -70,18 +71,20 @@ __device__ __forceinline__ void fswap(float &a, float &b)
     b = t;
 }
 
-// One pixel of cv::MOG2Invoker (modules/video/src/bgfg_gaussmix2.cpp), all K modes in
-// registers.  W/V/A/B/C = weight, variance, mean b/g/r, sorted by weight descending.
+// One pixel of cv::MOG2Invoker (modules/video/src/bgfg_gaussmix2.cpp); NA mode slots in
+// registers (n <= NA on entry and after a possible insertion), K = nmixtures (capacity).
+// TRACK: compare every state write with the old value so that an unchanged model (frozen
+// learning rate) is not written back.  W/V/A/B/C = weight, variance, mean b/g/r, sorted by weight descending.
 // Returns the mask value {0, shadow_value, 255}; `dirty` is set if any state bit changed.
-template <int K>
+template <int K, int NA, bool TRACK>
 __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, const float x2, int &n,
-                                               float (&W)[K], float (&V)[K], float (&A)[K], float (&B)[K],
-                                               float (&C)[K], const MogConsts &c, bool &dirty)
+                                               float (&W)[NA], float (&V)[NA], float (&A)[NA], float (&B)[NA],
+                                               float (&C)[NA], const MogConsts &c, bool &dirty)
 {
     bool bg = false, fits = false;
     float tot = 0.f;
 #pragma unroll
-    for (int m = 0; m < K; ++m) {
+    for (int m = 0; m < NA; ++m) {
         if (m < n) {  // n shrinks inside the loop when a mode is pruned, exactly like the reference
             float w = fadd(fmul(c.a1, W[m]), c.prune);
             int sc = 0;
@@ -94,13 +97,13 @@ __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, c
                     fits = true;
                     w = fadd(w, c.aT);
                     const float k = fdiv(c.aT, w);
-                    upd(A[m], fsub(A[m], fmul(k, d0)), dirty);
-                    upd(B[m], fsub(B[m], fmul(k, d1)), dirty);
-                    upd(C[m], fsub(C[m], fmul(k, d2)), dirty);
+                    upd<TRACK>(A[m], fsub(A[m], fmul(k, d0)), dirty);
+                    upd<TRACK>(B[m], fsub(B[m], fmul(k, d1)), dirty);
+                    upd<TRACK>(C[m], fsub(C[m], fmul(k, d2)), dirty);
                     float vn = fadd(var, fmul(k, fsub(dist2, var)));
                     vn = (vn < c.varMin) ? c.varMin : vn;  // MAX(varnew, varMin)
                     vn = (vn > c.varMax) ? c.varMax : vn;  // MIN(varnew, varMax)
-                    upd(V[m], vn, dirty);
+                    upd<TRACK>(V[m], vn, dirty);
                     bool go = true;
 #pragma unroll
                     for (int i = m; i > 0; --i) {
@@ -127,15 +130,15 @@ __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, c
             }
 #pragma unroll
             for (int j = 0; j <= m; ++j)
-                if (j == m - sc) upd(W[j], w, dirty);
+                if (j == m - sc) upd<TRACK>(W[j], w, dirty);
             tot = fadd(tot, w);
         }
     }
     float inv = 0.f;
     if (fabsf(tot) > FLT_EPSILON) inv = fdiv(1.f, tot);
 #pragma unroll
-    for (int m = 0; m < K; ++m)
-        if (m < n) upd(W[m], fmul(W[m], inv), dirty);
+    for (int m = 0; m < NA; ++m)
+        if (m < n) upd<TRACK>(W[m], fmul(W[m], inv), dirty);
 
     if (!fits && c.aT > 0.f) {
         const int mode = (n == K) ? K - 1 : n++;
@@ -145,11 +148,11 @@ __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, c
         } else {
             wn = c.aT;
 #pragma unroll
-            for (int i = 0; i < K - 1; ++i)
+            for (int i = 0; i < NA - 1; ++i)
                 if (i < n - 1) W[i] = fmul(W[i], c.a1);
         }
 #pragma unroll
-        for (int j = 0; j < K; ++j)
+        for (int j = 0; j < NA; ++j)
             if (j == mode) {
                 W[j] = wn;
                 V[j] = c.varInit;
@@ -159,7 +162,7 @@ __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, c
             }
         bool go = true;
 #pragma unroll
-        for (int i = K - 1; i > 0; --i) {
+        for (int i = NA - 1; i > 0; --i) {
             if (go && i <= n - 1) {
                 if (c.aT < W[i - 1]) {
                     go = false;
@@ -180,7 +183,7 @@ __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, c
         float tw = 0.f;
         bool done = false, shadow = false;
 #pragma unroll
-        for (int m = 0; m < K; ++m) {
+        for (int m = 0; m < NA; ++m) {
             if (!done && m < n) {
                 const float num = fadd(fadd(fadd(0.f, fmul(x0, A[m])), fmul(x1, B[m])), fmul(x2, C[m]));
                 const float den =
@@ -223,8 +226,151 @@ __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const int *lut, 
     h = hh < 0 ? hh + 180 : hh;
 }
 
-template <int K, int PX>
-__global__ void __launch_bounds__(128) mog_fused_kernel(const FusedArgs a)
+// Loads NL modes, runs the PX pixels of this thread, stores what changed.  NL (= the largest
+// live-mode count among the thread's pixels) is a template parameter so that the common case
+// (one or two live modes) is a compact, register-light code path; NA = modes held in registers
+// (one spare slot for a mode inserted this frame).
+template <int K, int NL, int PX, bool TRACK>
+__device__ __forceinline__ uint32_t mog_body(const FusedArgs &a, const int *lut, const int y, const int x,
+                                             const uint32_t (&px)[3 * PX], int (&n)[PX])
+{
+    constexpr int NA = (NL + 1 < K) ? NL + 1 : K;
+    const size_t pidx = (size_t)y * (a.wpr * 32) + x;
+    float S[NA][5][PX];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) {
+            if (m < NL && !a.reset) {
+                const float *p = a.state + (size_t)(m * 5 + cc) * a.plane + pidx;
+                if (PX == 4) {
+                    const float4 v = ld_state_f4(p);
+                    S[m][cc][0] = v.x;
+                    S[m][cc][PX > 1 ? 1 : 0] = v.y;
+                    S[m][cc][PX > 2 ? 2 : 0] = v.z;
+                    S[m][cc][PX > 3 ? 3 : 0] = v.w;
+                } else {
+                    S[m][cc][0] = ld_state_f1(p);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < PX; ++i) S[m][cc][i] = 0.f;
+            }
+        }
+    }
+
+    bool dirty = !TRACK || (a.reset != 0);
+    uint32_t nib = 0;
+    uint32_t fgm[PX], outb[3 * PX], outh[3 * PX];
+    int nnew_max = 0;
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        float W[NA], V[NA], A[NA], B[NA], C[NA];
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+            W[m] = S[m][0][i];
+            V[m] = S[m][1][i];
+            A[m] = S[m][2][i];
+            B[m] = S[m][3][i];
+            C[m] = S[m][4][i];
+        }
+        const int b = (int)px[3 * i], gch = (int)px[3 * i + 1], r = (int)px[3 * i + 2];
+        int ni = n[i];
+        const uint32_t mk = mog2_pixel<K, NA, TRACK>((float)b, (float)gch, (float)r, ni, W, V, A, B, C, a.c, dirty);
+        n[i] = ni;
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+            S[m][0][i] = W[m];
+            S[m][1][i] = V[m];
+            S[m][2][i] = A[m];
+            S[m][3][i] = B[m];
+            S[m][4][i] = C[m];
+        }
+        nnew_max = max(nnew_max, ni);
+        fgm[i] = mk;
+        const int ob = mk ? b : 0, og = mk ? gch : 0, orr = mk ? r : 0;
+        outb[3 * i] = ob;
+        outb[3 * i + 1] = og;
+        outb[3 * i + 2] = orr;
+        if (a.do_hsv) {
+            int h = 0, s = 0, v = 0;
+            if (mk) bgr2hsv_px(ob, og, orr, lut, h, s, v);
+            outh[3 * i] = h;
+            outh[3 * i + 1] = s;
+            outh[3 * i + 2] = v;
+            const bool in = (a.lo[0] <= h) & (h <= a.hi[0]) & (a.lo[1] <= s) & (s <= a.hi[1]) & (a.lo[2] <= v) &
+                            (v <= a.hi[2]);
+            nib |= (in ? 1u : 0u) << i;
+        }
+    }
+
+    if (dirty) {
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+            if (m < NL || m < nnew_max) {
+#pragma unroll
+                for (int cc = 0; cc < 5; ++cc) {
+                    float *p = a.state + (size_t)(m * 5 + cc) * a.plane + pidx;
+                    if (PX == 4)
+                        st_state_f4(p, make_float4(S[m][cc][0], S[m][cc][PX > 1 ? 1 : 0], S[m][cc][PX > 2 ? 2 : 0],
+                                                   S[m][cc][PX > 3 ? 3 : 0]));
+                    else
+                        st_state_f1(p, S[m][cc][0]);
+                }
+            }
+        }
+        if (PX == 4)
+            *reinterpret_cast<uint32_t *>(a.nmodes + pidx) = (uint32_t)n[0] | ((uint32_t)n[PX > 1 ? 1 : 0] << 8) |
+                                                             ((uint32_t)n[PX > 2 ? 2 : 0] << 16) |
+                                                             ((uint32_t)n[PX > 3 ? 3 : 0] << 24);
+        else
+            a.nmodes[pidx] = (uint8_t)n[0];
+    }
+    if (PX == 4) {
+        if (a.bgr_out) {
+            uint8_t *d = a.bgr_out + (size_t)y * a.bgr_out_pitch + 3 * x;
+#pragma unroll
+            for (int wd = 0; wd < 3; ++wd)
+                st_stream_u32(d + 4 * wd, outb[(4 * wd) % (3 * PX)] | (outb[(4 * wd + 1) % (3 * PX)] << 8) |
+                                              (outb[(4 * wd + 2) % (3 * PX)] << 16) |
+                                              (outb[(4 * wd + 3) % (3 * PX)] << 24));
+        }
+        if (a.hsv_out) {
+            uint8_t *d = a.hsv_out + (size_t)y * a.hsv_pitch + 3 * x;
+#pragma unroll
+            for (int wd = 0; wd < 3; ++wd)
+                st_stream_u32(d + 4 * wd, outh[(4 * wd) % (3 * PX)] | (outh[(4 * wd + 1) % (3 * PX)] << 8) |
+                                              (outh[(4 * wd + 2) % (3 * PX)] << 16) |
+                                              (outh[(4 * wd + 3) % (3 * PX)] << 24));
+        }
+        if (a.fg_out)
+            st_stream_u32(a.fg_out + (size_t)y * a.fg_pitch + x,
+                          fgm[0] | (fgm[PX > 1 ? 1 : 0] << 8) | (fgm[PX > 2 ? 2 : 0] << 16) |
+                              (fgm[PX > 3 ? 3 : 0] << 24));
+    } else {
+        if (a.bgr_out) {
+            uint8_t *d = a.bgr_out + (size_t)y * a.bgr_out_pitch + 3 * x;
+            d[0] = (uint8_t)outb[0];
+            d[1] = (uint8_t)outb[1];
+            d[2] = (uint8_t)outb[2];
+        }
+        if (a.hsv_out) {
+            uint8_t *d = a.hsv_out + (size_t)y * a.hsv_pitch + 3 * x;
+            d[0] = (uint8_t)outh[0];
+            d[1] = (uint8_t)outh[1];
+            d[2] = (uint8_t)outh[2];
+        }
+        if (a.fg_out) a.fg_out[(size_t)y * a.fg_pitch + x] = (uint8_t)fgm[0];
+    }
+    return nib;
+}
+
+#ifndef OAT_FUSED_MIN_BLOCKS
+#define OAT_FUSED_MIN_BLOCKS 4
+#endif
+
+template <int K, int PX, bool TRACK>
+__global__ void __launch_bounds__(128, OAT_FUSED_MIN_BLOCKS) mog_fused_kernel(const FusedArgs a)
 {
     __shared__ int lut[512];
     if (a.do_hsv) {
@@ -240,22 +386,20 @@ __global__ void __launch_bounds__(128) mog_fused_kernel(const FusedArgs a)
 
     if (active) {
         const size_t pidx = (size_t)y * (a.wpr * 32) + x;
-        // ---- loads: pixel bytes, mode counts, then the live planes --------------------------
         uint32_t px[3 * PX];
         int n[PX];
+        const uint8_t *src = a.bgr + (size_t)y * a.in_pitch + 3 * x;
         if (PX == 4) {
-            const uint8_t *src = a.bgr + (size_t)y * a.in_pitch + 3 * x;
             const uint32_t w0 = ld_stream_u32(src), w1 = ld_stream_u32(src + 4), w2 = ld_stream_u32(src + 8);
             const uint32_t nm = a.reset ? 0u : *reinterpret_cast<const uint32_t *>(a.nmodes + pidx);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                px[i] = (w0 >> (8 * i)) & 255u;
-                px[4 + i] = (w1 >> (8 * i)) & 255u;
-                px[8 + i] = (w2 >> (8 * i)) & 255u;
-                n[i] = (int)((nm >> (8 * i)) & 255u);
+                px[i % (3 * PX)] = (w0 >> (8 * i)) & 255u;
+                px[(4 + i) % (3 * PX)] = (w1 >> (8 * i)) & 255u;
+                px[(8 + i) % (3 * PX)] = (w2 >> (8 * i)) & 255u;
+                n[i % PX] = (int)((nm >> (8 * i)) & 255u);
             }
         } else {
-            const uint8_t *src = a.bgr + (size_t)y * a.in_pitch + 3 * x;
             px[0] = ld_stream_u8(src);
             px[1] = ld_stream_u8(src + 1);
             px[2] = ld_stream_u8(src + 2);
@@ -264,134 +408,17 @@ __global__ void __launch_bounds__(128) mog_fused_kernel(const FusedArgs a)
         int nmax = n[0];
 #pragma unroll
         for (int i = 1; i < PX; ++i) nmax = max(nmax, n[i]);
-
-        float S[K][5][PX];
-#pragma unroll
-        for (int m = 0; m < K; ++m) {
-            if (m < nmax) {
-#pragma unroll
-                for (int cc = 0; cc < 5; ++cc) {
-                    const float *p = a.state + (size_t)(m * 5 + cc) * a.plane + pidx;
-                    if (PX == 4) {
-                        const float4 v = ld_state_f4(p);
-                        S[m][cc][0] = v.x;
-                        S[m][cc][1] = v.y;
-                        S[m][cc][2] = v.z;
-                        S[m][cc][3] = v.w;
-                    } else {
-                        S[m][cc][0] = ld_state_f1(p);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int cc = 0; cc < 5; ++cc)
-#pragma unroll
-                    for (int i = 0; i < PX; ++i) S[m][cc][i] = 0.f;
-            }
-        }
-
-        // ---- per pixel: GMM update + classify, zero background, HSV, inRange ---------------
-        bool dirty = a.reset != 0;
-        uint32_t fgm[PX];
-        uint32_t outb[3 * PX], outh[3 * PX];
-        int nnew_max = 0;
-#pragma unroll
-        for (int i = 0; i < PX; ++i) {
-            float W[K], V[K], A[K], B[K], C[K];
-#pragma unroll
-            for (int m = 0; m < K; ++m) {
-                W[m] = S[m][0][i];
-                V[m] = S[m][1][i];
-                A[m] = S[m][2][i];
-                B[m] = S[m][3][i];
-                C[m] = S[m][4][i];
-            }
-            // bytes of pixel i: position 3*i .. 3*i+2 in the 12-byte group
-            const int b = (int)px[3 * i], gch = (int)px[3 * i + 1], r = (int)px[3 * i + 2];
-            const uint32_t mk = mog2_pixel<K>((float)b, (float)gch, (float)r, n[i], W, V, A, B, C, a.c, dirty);
-#pragma unroll
-            for (int m = 0; m < K; ++m) {
-                S[m][0][i] = W[m];
-                S[m][1][i] = V[m];
-                S[m][2][i] = A[m];
-                S[m][3][i] = B[m];
-                S[m][4][i] = C[m];
-            }
-            nnew_max = max(nnew_max, n[i]);
-            fgm[i] = mk;
-            const int ob = mk ? b : 0, og = mk ? gch : 0, orr = mk ? r : 0;
-            outb[3 * i] = ob;
-            outb[3 * i + 1] = og;
-            outb[3 * i + 2] = orr;
-            if (a.do_hsv) {
-                int h = 0, s = 0, v = 0;
-                if (mk) bgr2hsv_px(ob, og, orr, lut, h, s, v);
-                outh[3 * i] = h;
-                outh[3 * i + 1] = s;
-                outh[3 * i + 2] = v;
-                const bool in = (a.lo[0] <= h) & (h <= a.hi[0]) & (a.lo[1] <= s) & (s <= a.hi[1]) &
-                                (a.lo[2] <= v) & (v <= a.hi[2]);
-                nib |= (in ? 1u : 0u) << i;
-            }
-        }
-
-        // ---- stores --------------------------------------------------------------------------
-        if (dirty) {
-            const int nst = max(nmax, nnew_max);
-#pragma unroll
-            for (int m = 0; m < K; ++m) {
-                if (m < nst) {
-#pragma unroll
-                    for (int cc = 0; cc < 5; ++cc) {
-                        float *p = a.state + (size_t)(m * 5 + cc) * a.plane + pidx;
-                        if (PX == 4)
-                            st_state_f4(p, make_float4(S[m][cc][0], S[m][cc][1], S[m][cc][2], S[m][cc][3]));
-                        else
-                            st_state_f1(p, S[m][cc][0]);
-                    }
-                }
-            }
-            if (PX == 4)
-                *reinterpret_cast<uint32_t *>(a.nmodes + pidx) =
-                    (uint32_t)n[0] | ((uint32_t)n[PX > 1 ? 1 : 0] << 8) | ((uint32_t)n[PX > 2 ? 2 : 0] << 16) |
-                    ((uint32_t)n[PX > 3 ? 3 : 0] << 24);
-            else
-                a.nmodes[pidx] = (uint8_t)n[0];
-        }
-        if (PX == 4) {
-            if (a.bgr_out) {
-                uint8_t *d = a.bgr_out + (size_t)y * a.bgr_out_pitch + 3 * x;
-#pragma unroll
-                for (int wd = 0; wd < 3; ++wd)
-                    st_stream_u32(d + 4 * wd, outb[4 * wd] | (outb[4 * wd + 1] << 8) | (outb[4 * wd + 2] << 16) |
-                                                  (outb[4 * wd + 3] << 24));
-            }
-            if (a.hsv_out) {
-                uint8_t *d = a.hsv_out + (size_t)y * a.hsv_pitch + 3 * x;
-#pragma unroll
-                for (int wd = 0; wd < 3; ++wd)
-                    st_stream_u32(d + 4 * wd, outh[4 * wd] | (outh[4 * wd + 1] << 8) | (outh[4 * wd + 2] << 16) |
-                                                  (outh[4 * wd + 3] << 24));
-            }
-            if (a.fg_out)
-                st_stream_u32(a.fg_out + (size_t)y * a.fg_pitch + x,
-                              fgm[0] | (fgm[PX > 1 ? 1 : 0] << 8) | (fgm[PX > 2 ? 2 : 0] << 16) |
-                                  (fgm[PX > 3 ? 3 : 0] << 24));
-        } else {
-            if (a.bgr_out) {
-                uint8_t *d = a.bgr_out + (size_t)y * a.bgr_out_pitch + 3 * x;
-                d[0] = (uint8_t)outb[0];
-                d[1] = (uint8_t)outb[1];
-                d[2] = (uint8_t)outb[2];
-            }
-            if (a.hsv_out) {
-                uint8_t *d = a.hsv_out + (size_t)y * a.hsv_pitch + 3 * x;
-                d[0] = (uint8_t)outh[0];
-                d[1] = (uint8_t)outh[1];
-                d[2] = (uint8_t)outh[2];
-            }
-            if (a.fg_out) a.fg_out[(size_t)y * a.fg_pitch + x] = (uint8_t)fgm[0];
-        }
+        // thread-level dispatch on the number of live modes (spatially coherent in practice)
+        if (nmax <= 1 || K == 1)
+            nib = mog_body<K, 1, PX, TRACK>(a, lut, y, x, px, n);
+        else if (nmax == 2 || K == 2)
+            nib = mog_body<K, (K < 2 ? K : 2), PX, TRACK>(a, lut, y, x, px, n);
+        else if (nmax == 3 || K == 3)
+            nib = mog_body<K, (K < 3 ? K : 3), PX, TRACK>(a, lut, y, x, px, n);
+        else if (nmax == 4 || K == 4)
+            nib = mog_body<K, (K < 4 ? K : 4), PX, TRACK>(a, lut, y, x, px, n);
+        else
+            nib = mog_body<K, K, PX, TRACK>(a, lut, y, x, px, n);
     }
 
     // ---- threshold mask, 1 bit/pixel: 8 lanes x 4 px (or 32 lanes x 1 px) -> one word --------

@@ -34,9 +34,21 @@ struct TailBuffers {
     unsigned long long *acc;     // 3 planes of [rows*wpr*32 + 1]: 2*m00, 6*m10, 6*m01 (valid at roots)
     size_t nnodes;               // rows*wpr*32 + 1
     uint32_t *G;                 // [rows][wpr] hole-filled mask
+    int2 *rowext;                // [rows] first / last foreground x of the row (INT_MAX / -1 if none)
     unsigned long long *best;    // arg-max key  (s00 << 32 | id)
     unsigned int *count;         // number of external contours
+    unsigned int *ticket;        // last-block election of the select kernel
 };
+
+// Background pixels left of the first / right of the last foreground pixel of their row, and
+// the first and last image rows, reach the image border along their own row (or are on it):
+// they are exterior by construction and never become union-find nodes.  Only background
+// BETWEEN foreground pixels of a row ("candidates") has to be resolved by labelling.
+__device__ __forceinline__ uint32_t ones_below(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+__device__ __forceinline__ uint32_t range_mask(int j, int xmin, int xmax)
+{
+    return ones_below(xmax - 32 * j + 1) & ~ones_below(xmin - 32 * j);
+}
 
 // ---- bit helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t seg_mask(int s, int len) { return (len >= 32) ? 0xffffffffu : (((1u << len) - 1u) << s); }
@@ -65,6 +77,18 @@ __device__ __forceinline__ int uf_find(int *P, int x)
     }
     return x;
 }
+// find with path halving (monotone: parents only ever decrease, so atomicMin is safe)
+__device__ __forceinline__ int uf_find_halve(int *P, int x)
+{
+    int p = __ldcg(P + x);
+    while (p != x) {
+        const int gp = __ldcg(P + p);
+        if (gp != p) atomicMin(P + x, gp);
+        x = p;
+        p = gp;
+    }
+    return x;
+}
 __device__ __forceinline__ int uf_find_compress(int *P, int x)
 {
     const int r = uf_find(P, x);
@@ -74,8 +98,8 @@ __device__ __forceinline__ int uf_find_compress(int *P, int x)
 __device__ __forceinline__ void uf_union(int *P, int a, int b)
 {
     for (;;) {
-        a = uf_find(P, a);
-        b = uf_find(P, b);
+        a = uf_find_halve(P, a);
+        b = uf_find_halve(P, b);
         if (a == b) return;
         if (a < b) {
             const int t = a;
@@ -151,76 +175,179 @@ __global__ void morph_v_kernel(const uint32_t *__restrict__ in, uint32_t *__rest
 }
 
 // ---- union-find labelling -------------------------------------------------------------------
-// init: every segment start becomes its own root; background segments touching the image
-// border start out linked to EXT (node 0); accumulators of foreground starts are zeroed.
-__global__ void ccl_init_kernel(const uint32_t *__restrict__ bits, TailBuffers tb)
+__device__ __forceinline__ uint32_t cand_word(const uint32_t *bits, const int2 *rowext, const BitGeom &g, int y, int j)
 {
-    const BitGeom g = tb.g;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) {
-        tb.parent[0] = 0;
-        *tb.best = 0ull;
-        *tb.count = 0u;
+    if (y <= 0 || y >= g.rows - 1 || j < 0 || j >= g.wpr) return 0u;
+    const int2 e = rowext[y];
+    return ~bits[(size_t)y * g.wpr + j] & g.valid_mask(j) & range_mask(j, e.x, e.y);
+}
+// row-exterior background of word (y, j), rows 0 <= y < rows
+__device__ __forceinline__ uint32_t rowext_bg_word(const uint32_t *bits, const int2 *rowext, const BitGeom &g, int y, int j)
+{
+    const uint32_t bgw = ~bits[(size_t)y * g.wpr + j] & g.valid_mask(j);
+    if (y == 0 || y == g.rows - 1) return bgw;
+    const int2 e = rowext[y];
+    return bgw & ~range_mask(j, e.x, e.y);
+}
+
+// prep: [erode] -> [dilate] on a band of rows staged in shared memory, then per output row the
+// foreground extent and the union-find initialisation (every foreground / candidate-background
+// segment start becomes its own root, foreground accumulators are zeroed).
+struct PrepArgs {
+    const uint32_t *in;
+    uint32_t *out;
+    int ke, kd;  // erode / dilate kernel sizes (0 = off)
+    int R;       // output rows per CTA
+    TailBuffers tb;
+};
+
+template <bool DILATE>
+__device__ __forceinline__ uint32_t hpass_word(const uint32_t *row, int j, const BitGeom &g, int k)
+{
+    const uint32_t pad = DILATE ? 0u : 0xffffffffu;
+    auto word = [&](int jj) -> uint32_t {
+        if (jj < 0 || jj >= g.wpr) return pad;
+        return DILATE ? row[jj] : (row[jj] | ~g.valid_mask(jj));
+    };
+    const int a = k / 2;
+    uint32_t acc = pad;
+    int curq = INT_MIN;
+    uint32_t lo = 0, hi = 0;
+    for (int d = -a; d <= k - 1 - a; ++d) {
+        const int q = (d >= 0) ? (d >> 5) : -((-d + 31) >> 5);
+        const int r = d - 32 * q;
+        if (q != curq) {
+            lo = word(j + q);
+            hi = word(j + q + 1);
+            curq = q;
+        }
+        const uint32_t v = __funnelshift_r(lo, hi, r);
+        acc = DILATE ? (acc | v) : (acc & v);
     }
-    if (t >= g.rows * g.wpr) return;
-    const int y = t / g.wpr, j = t % g.wpr;
-    const uint32_t vm = g.valid_mask(j);
-    const uint32_t v = bits[t] & vm;
-#pragma unroll
-    for (int pol = 0; pol < 2; ++pol) {
-        const uint32_t w = pol ? v : (~v & vm);
-        for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-            const int s = __ffs(st) - 1;
-            const int id = node_id(g, y, j, s);
-            if (pol) {
-                tb.parent[id] = id;
-                tb.acc[id] = 0ull;
-                tb.acc[tb.nnodes + id] = 0ull;
-                tb.acc[2 * tb.nnodes + id] = 0ull;
-            } else {
-                const int len = run_len(w, s);
-                const int x0 = 32 * j + s, x1 = x0 + len - 1;
-                const bool border = (y == 0) || (y == g.rows - 1) || (x0 == 0) || (x1 == g.cols - 1);
-                tb.parent[id] = border ? 0 : id;
+    return acc & g.valid_mask(j);
+}
+
+__global__ void tail_prep_kernel(const PrepArgs a)
+{
+    extern __shared__ uint32_t sm[];
+    const BitGeom g = a.tb.g;
+    const int wpr = g.wpr, rows = g.rows;
+    const int y0 = blockIdx.x * a.R, y1 = min(y0 + a.R, rows) - 1;
+    const int ae = a.ke / 2, ad = a.kd / 2;
+    // rows of the eroded image the dilate needs, rows of the input the erode needs
+    const int e0 = max(a.kd > 0 ? y0 - ad : y0, 0), e1 = min(a.kd > 0 ? y1 - ad + a.kd - 1 : y1, rows - 1);
+    const int i0 = max(a.ke > 0 ? e0 - ae : e0, 0), i1 = min(a.ke > 0 ? e1 - ae + a.ke - 1 : e1, rows - 1);
+    const int nin = i1 - i0 + 1;
+    uint32_t *A = sm, *B = sm + (size_t)nin * wpr;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.tb.parent[0] = 0;
+        *a.tb.best = 0ull;
+        *a.tb.count = 0u;
+        *a.tb.ticket = 0u;
+    }
+    for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) {
+        const int r = t / wpr, j = t % wpr;
+        A[t] = a.in[(size_t)(i0 + r) * wpr + j] & g.valid_mask(j);
+    }
+    __syncthreads();
+    if (a.ke > 0) {
+        for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) B[t] = hpass_word<false>(A + (t / wpr) * wpr, t % wpr, g, a.ke);
+        __syncthreads();
+        const int ne = e1 - e0 + 1;
+        for (int t = threadIdx.x; t < ne * wpr; t += blockDim.x) {
+            const int y = e0 + t / wpr, j = t % wpr;
+            const int v0 = max(y - ae, 0), v1 = min(y - ae + a.ke - 1, rows - 1);
+            uint32_t acc = 0xffffffffu;
+            for (int yy = v0; yy <= v1; ++yy) acc &= B[(yy - i0) * wpr + j];
+            A[(y - i0) * wpr + j] = acc & g.valid_mask(j);
+        }
+        __syncthreads();
+    }
+    if (a.kd > 0) {
+        const int ne = e1 - e0 + 1;
+        for (int t = threadIdx.x; t < ne * wpr; t += blockDim.x) {
+            const int r = e0 - i0 + t / wpr;
+            B[r * wpr + t % wpr] = hpass_word<true>(A + r * wpr, t % wpr, g, a.kd);
+        }
+        __syncthreads();
+        const int no = y1 - y0 + 1;
+        for (int t = threadIdx.x; t < no * wpr; t += blockDim.x) {
+            const int y = y0 + t / wpr, j = t % wpr;
+            const int v0 = max(y - ad, 0), v1 = min(y - ad + a.kd - 1, rows - 1);
+            uint32_t acc = 0u;
+            for (int yy = v0; yy <= v1; ++yy) acc |= B[(yy - i0) * wpr + j];
+            A[(y - i0) * wpr + j] = acc;
+        }
+        __syncthreads();
+    }
+    // epilogue: one warp per output row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int y = y0 + warp; y <= y1; y += nwarps) {
+        const uint32_t *row = A + (size_t)(y - i0) * wpr;
+        int xmin = INT_MAX, xmax = -1;
+        for (int j = lane; j < wpr; j += 32) {
+            const uint32_t w = row[j];
+            a.out[(size_t)y * wpr + j] = w;
+            if (w) {
+                xmin = min(xmin, 32 * j + __ffs(w) - 1);
+                xmax = max(xmax, 32 * j + 31 - __clz(w));
+            }
+        }
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        if (lane == 0) a.tb.rowext[y] = make_int2(xmin, xmax);
+        if (xmax < 0) continue;  // no foreground in this row: nothing to initialise
+        const bool inner = (y > 0) && (y < rows - 1);
+        for (int j = lane; j < wpr; j += 32) {
+            const uint32_t w = row[j];
+            for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
+                const int id = node_id(g, y, j, __ffs(st) - 1);
+                a.tb.parent[id] = id;
+                a.tb.acc[id] = 0ull;
+                a.tb.acc[a.tb.nnodes + id] = 0ull;
+                a.tb.acc[2 * a.tb.nnodes + id] = 0ull;
+            }
+            if (inner) {
+                const uint32_t c = ~w & g.valid_mask(j) & range_mask(j, xmin, xmax);
+                for (uint32_t st = c & ~(c << 1); st; st &= st - 1) {
+                    const int id = node_id(g, y, j, __ffs(st) - 1);
+                    a.tb.parent[id] = id;
+                }
             }
         }
     }
 }
 
-// phase A: foreground 8-connected, background 4-connected.
+// phase A: foreground 8-connected; candidate background 4-connected, linked to EXT (node 0)
+// wherever it touches row-exterior background above or below.
 __global__ void ccl_merge_kernel(const uint32_t *__restrict__ bits, TailBuffers tb)
 {
     const BitGeom g = tb.g;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.rows * g.wpr) return;
     const int y = t / g.wpr, j = t % g.wpr;
+    const int2 ext = tb.rowext[y];
+    if (ext.y < 0 || 32 * j > ext.y || 32 * j + 31 < ext.x) return;  // nothing but exterior background here
     int *P = tb.parent;
-#pragma unroll
-    for (int pol = 0; pol < 2; ++pol) {
-        const bool fg = pol != 0;
-        const uint32_t w = pol_word(bits, g, y, j, fg);
-        if (!w) continue;
-        const uint32_t up = pol_word(bits, g, y - 1, j, fg);
-        const uint32_t left = pol_word(bits, g, y, j - 1, fg);
-        for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-            const int s = __ffs(st) - 1;
-            const int len = run_len(w, s);
-            const int e = s + len - 1;
-            const uint32_t sm = seg_mask(s, len);
-            const int id = node_id(g, y, j, s);
-            // same row, previous word
-            if (s == 0 && (left >> 31)) uf_union(P, id, node_id(g, y, j - 1, run_start(left, 31)));
-            // row above
-            const uint32_t ov = fg ? (sm | (sm << 1) | (sm >> 1)) : sm;
-            uint32_t m = up & ov;
-            while (m) {
-                const int b = __ffs(m) - 1;
-                const int us = run_start(up, b);
-                const int ul = run_len(up, us);
-                m &= ~seg_mask(us, ul);
-                uf_union(P, id, node_id(g, y - 1, j, us));
-            }
-            if (fg) {
+    {  // foreground
+        const uint32_t w = pol_word(bits, g, y, j, true);
+        if (w) {
+            const uint32_t up = pol_word(bits, g, y - 1, j, true);
+            const uint32_t left = pol_word(bits, g, y, j - 1, true);
+            for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
+                const int s = __ffs(st) - 1;
+                const int len = run_len(w, s);
+                const int e = s + len - 1;
+                const uint32_t sm = seg_mask(s, len);
+                const int id = node_id(g, y, j, s);
+                if (s == 0 && (left >> 31)) uf_union(P, id, node_id(g, y, j - 1, run_start(left, 31)));
+                uint32_t m = up & (sm | (sm << 1) | (sm >> 1));
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    const int us = run_start(up, b);
+                    m &= ~seg_mask(us, run_len(up, us));
+                    uf_union(P, id, node_id(g, y - 1, j, us));
+                }
                 if (s == 0) {
                     const uint32_t ul = pol_word(bits, g, y - 1, j - 1, true);
                     if (ul >> 31) uf_union(P, id, node_id(g, y - 1, j - 1, run_start(ul, 31)));
@@ -228,6 +355,30 @@ __global__ void ccl_merge_kernel(const uint32_t *__restrict__ bits, TailBuffers 
                 if (e == 31) {
                     const uint32_t ur = pol_word(bits, g, y - 1, j + 1, true);
                     if (ur & 1u) uf_union(P, id, node_id(g, y - 1, j + 1, 0));
+                }
+            }
+        }
+    }
+    {  // candidate background
+        const uint32_t w = cand_word(bits, tb.rowext, g, y, j);
+        if (w) {
+            const uint32_t up = cand_word(bits, tb.rowext, g, y - 1, j);
+            const uint32_t left = cand_word(bits, tb.rowext, g, y, j - 1);
+            const uint32_t ext_up = rowext_bg_word(bits, tb.rowext, g, y - 1, j);
+            const uint32_t ext_dn = rowext_bg_word(bits, tb.rowext, g, y + 1, j);
+            for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
+                const int s = __ffs(st) - 1;
+                const int len = run_len(w, s);
+                const uint32_t sm = seg_mask(s, len);
+                const int id = node_id(g, y, j, s);
+                if ((ext_up | ext_dn) & sm) uf_union(P, id, 0);
+                if (s == 0 && (left >> 31)) uf_union(P, id, node_id(g, y, j - 1, run_start(left, 31)));
+                uint32_t m = up & sm;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    const int us = run_start(up, b);
+                    m &= ~seg_mask(us, run_len(up, us));
+                    uf_union(P, id, node_id(g, y - 1, j, us));
                 }
             }
         }
@@ -256,7 +407,8 @@ __global__ void ccl_labels_kernel(const uint32_t *__restrict__ bits, TailBuffers
     }
 }
 
-// phase B: holes (background sets not linked to EXT) join the foreground beside them; writes G.
+// phase B: holes (candidate-background sets not linked to EXT) join the foreground beside them;
+// writes G = foreground + holes.
 __global__ void ccl_fill_kernel(const uint32_t *__restrict__ bits, TailBuffers tb)
 {
     const BitGeom g = tb.g;
@@ -264,18 +416,16 @@ __global__ void ccl_fill_kernel(const uint32_t *__restrict__ bits, TailBuffers t
     if (t >= g.rows * g.wpr) return;
     const int y = t / g.wpr, j = t % g.wpr;
     int *P = tb.parent;
-    const uint32_t vm = g.valid_mask(j);
-    const uint32_t f = bits[t] & vm;
-    const uint32_t bgw = ~f & vm;
+    const uint32_t f = bits[t] & g.valid_mask(j);
     uint32_t G = f;
-    for (uint32_t st = bgw & ~(bgw << 1); st; st &= st - 1) {
+    const uint32_t c = cand_word(bits, tb.rowext, g, y, j);
+    for (uint32_t st = c & ~(c << 1); st; st &= st - 1) {
         const int s = __ffs(st) - 1;
-        const int len = run_len(bgw, s);
+        const int len = run_len(c, s);
         const int id = node_id(g, y, j, s);
         if (uf_find_compress(P, id) == 0) continue;  // exterior
         G |= seg_mask(s, len);
-        // the pixel left of a hole segment is foreground or the same hole (previous word);
-        // a hole can never start at x == 0 (it would touch the border).
+        // the pixel left of a hole segment is foreground or the same hole (previous word)
         if (s > 0) {
             uf_union(P, id, node_id(g, y, j, run_start(f, s - 1)));
         } else {
@@ -352,9 +502,11 @@ __global__ void ccl_moments_kernel(TailBuffers tb)
     }
 }
 
-// select: arg-max over roots.
+// select: arg-max over roots; the last CTA to finish turns the winner into the detection
+// (cv::moments' contourMoments scaling: m00 = a00/2, m10 = a10/6, m01 = a01/6 in doubles, then
+// DetectorFunc.cpp:58-59 x = m10/m00, y = m01/m00).
 __global__ void ccl_select_kernel(const uint32_t *__restrict__ bits, TailBuffers tb, double min_area,
-                                  double max_area)
+                                  double max_area, oat_detection *out)
 {
     const BitGeom g = tb.g;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,7 +520,7 @@ __global__ void ccl_select_kernel(const uint32_t *__restrict__ bits, TailBuffers
             const int id = node_id(g, y, j, s);
             if (__ldcg(tb.parent + id) != id) continue;
             ++nroots;
-            const unsigned long long s00 = tb.acc[id];
+            const unsigned long long s00 = __ldcg(tb.acc + id);
             const double area = 0.5 * (double)s00;
             if (area >= min_area && area < max_area && s00 > 0ull) {
                 const unsigned long long k = (s00 << 32) | (unsigned long long)(unsigned)id;
@@ -379,29 +531,32 @@ __global__ void ccl_select_kernel(const uint32_t *__restrict__ bits, TailBuffers
     const unsigned tot = __reduce_add_sync(0xffffffffu, nroots);
     if (tot && (threadIdx.x & 31u) == 0) atomicAdd(tb.count, tot);
     if (key) atomicMax(tb.best, key);
-}
-
-__global__ void ccl_finalize_kernel(TailBuffers tb, oat_detection *out)
-{
-    const BitGeom g = tb.g;
-    const unsigned long long key = *tb.best;
-    oat_detection d;
-    d.position_valid = 0;
-    d.n_components = (int32_t)*tb.count;
-    d.x = d.y = d.area = 0.0;
-    if (key) {
-        const int id = (int)(key & 0xffffffffull);
-        // cv::moments' contourMoments: m00 = a00/2, m10 = a10/6, m01 = a01/6 in doubles
-        const double m00 = (double)tb.acc[id] * 0.5;
-        const double m10 = (double)tb.acc[tb.nnodes + id] * 0.16666666666666666666666666666667;
-        const double m01 = (double)tb.acc[2 * tb.nnodes + id] * 0.16666666666666666666666666666667;
-        d.position_valid = 1;
-        d.x = m10 / m00;
-        d.y = m01 / m00;
-        d.area = m00;
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(tb.ticket, 1u) == gridDim.x - 1);
     }
-    (void)g;
-    *out = d;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long best = __ldcg(tb.best);
+        oat_detection d;
+        d.position_valid = 0;
+        d.n_components = (int32_t)__ldcg(tb.count);
+        d.x = d.y = d.area = 0.0;
+        if (best) {
+            const int id = (int)(best & 0xffffffffull);
+            const double m00 = (double)__ldcg(tb.acc + id) * 0.5;
+            const double m10 = (double)__ldcg(tb.acc + tb.nnodes + id) * 0.16666666666666666666666666666667;
+            const double m01 = (double)__ldcg(tb.acc + 2 * tb.nnodes + id) * 0.16666666666666666666666666666667;
+            d.position_valid = 1;
+            d.x = m10 / m00;
+            d.y = m01 / m00;
+            d.area = m00;
+        }
+        *out = d;
+    }
 }
 
 }  // namespace oat
