@@ -6,6 +6,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -14,6 +15,7 @@
 
 #include "common.cuh"
 #include "mog_fused.cuh"
+#include "mog_pipe.cuh"
 #include "pixel_ops.cuh"
 #include "tail.cuh"
 
@@ -71,6 +73,8 @@ struct oat_ctx {
     cudaStream_t h2d = nullptr;      // ingest copies (overlap with compute of the previous frame)
     int *hsv_lut = nullptr;          // sdiv[256] | hdiv[256]
     uint64_t launches = 0;
+    int num_sms = 148;
+    bool pipe_attr_set = false;
     DevBuf flush;
     DevBuf scratch_in, scratch_out;  // staging for the stateless entry points
 };
@@ -114,6 +118,7 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     oat_ctx *c = new (std::nothrow) oat_ctx();
     if (!c) return fail(OAT_ERR_NOMEM, "out of host memory");
     c->device = device_index;
+    c->num_sms = prop.multiProcessorCount;
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
@@ -343,7 +348,35 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
     // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
     // the state write-back; with a live rate every live mode changes every frame anyway.
     const bool frozen = (a.c.aT == 0.0f) && !a.reset;
-    if (vec && frozen)
+    if (vec && !a.reset && m.K == 5 && !getenv("OAT_B200_NO_PIPE")) {
+        // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
+        // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
+        const size_t tight3 = (size_t)3 * m.g.cols;
+        const bool linear = (m.g.cols % 32 == 0) && a.in_pitch == tight3 && (!a.bgr_out || a.bgr_out_pitch == tight3) &&
+                            (!a.hsv_out || a.hsv_pitch == tight3) && (!a.fg_out || a.fg_pitch == (size_t)m.g.cols);
+        if (!c->pipe_attr_set) {
+            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+            c->pipe_attr_set = true;
+        }
+        PipeArgs pa;
+        pa.f = a;
+        pa.ntiles = (int)((m.plane + PIPE_TILE - 1) / PIPE_TILE);
+        pa.div_magic = 0xffffffffffffffffull / (unsigned long long)m.g.pitch_px() + 1ull;
+        pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
+        const int grid = pa.ntiles < 2 * c->num_sms ? pa.ntiles : 2 * c->num_sms;
+        pa.grid_tiles = grid;
+        if (frozen && linear)
+            mog_pipe_kernel<5, true, true><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+        else if (frozen)
+            mog_pipe_kernel<5, true, false><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+        else if (linear)
+            mog_pipe_kernel<5, false, true><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+        else
+            mog_pipe_kernel<5, false, false><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+    } else if (vec && frozen)
         launch_fused_px<4, true>(c->stream, m.K, a);
     else if (vec)
         launch_fused_px<4, false>(c->stream, m.K, a);

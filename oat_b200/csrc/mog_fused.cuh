@@ -51,6 +51,7 @@ struct FusedArgs {
     uint8_t *hsv_out;  // or NULL
     size_t hsv_pitch;
     const int *hsv_lut;  // sdiv[256] then hdiv[256]
+    unsigned int *slow_count;  // or NULL: += number of 4-pixel groups that are not "one mode, fits, background"
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
