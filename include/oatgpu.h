@@ -211,6 +211,11 @@ int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, fl
 int oat_tracker_profile(oat_tracker *t, int enable);
 int oat_tracker_profile_read(oat_tracker *t, double *mean_mog_kernel_ms, uint64_t *launches);
 
+/* Diagnostic: the detect tail of the most recently collected frame. out[12] = { status (0 = the
+ * one-launch tail sufficed, 1 = replayed through the unbounded path), run-table entries needed,
+ * replays so far, one-launch tail used, 8 SM-clock stamps of its labelling CTA }. */
+int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out);
+
 /* ---- synthetic frame source (measurement + parity) --------------------
  * Deterministic counter-hash stream: static background 40..120, +-3 noise, a filled disc of
  * colour BGR (40,220,60), radius rows/20, centre (cols/4 + 7t mod cols/2, rows/3 + 4t mod

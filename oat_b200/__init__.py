@@ -130,6 +130,7 @@ _SIGS = {
     "oat_tracker_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oat_tracker_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "oat_tracker_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "oat_tracker_tail_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "oat_synth_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),
     "oat_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "oat_free_device": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -519,6 +520,13 @@ class Tracker:
         m, w, v, mu = _state_arrays(self.rows, self.cols, K)
         _ck(lib().oat_tracker_get_state(self._h, _ptr(m), _ptr(w), _ptr(v), _ptr(mu)))
         return m, w, v, mu
+
+    def tail_stats(self):
+        """Diagnostics of the detect tail of the last collected frame (see oat_tracker_tail_stats)."""
+        a = (C.c_uint32 * 12)()
+        _ck(lib().oat_tracker_tail_stats(self._h, a))
+        v = list(a)
+        return {"status": v[0], "nodes": v[1], "replays": v[2], "fast": v[3], "cyc": v[4:]}
 
     def profile(self, enable: bool):
         _ck(lib().oat_tracker_profile(self._h, 1 if enable else 0))

@@ -18,6 +18,7 @@
 #include "mog_pipe.cuh"
 #include "pixel_ops.cuh"
 #include "tail.cuh"
+#include "tail_fast.cuh"
 
 using namespace oat;
 
@@ -71,10 +72,13 @@ struct oat_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t h2d = nullptr;      // ingest copies (overlap with compute of the previous frame)
+    static const int NTAIL = 4;
+    cudaStream_t tail[NTAIL] = {nullptr, nullptr, nullptr, nullptr};  // detect tails of in-flight frames (higher priority than compute)
     int *hsv_lut = nullptr;          // sdiv[256] | hdiv[256]
     uint64_t launches = 0;
     int num_sms = 148;
     bool pipe_attr_set = false;
+    unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel
     DevBuf flush;
     DevBuf scratch_in, scratch_out;  // staging for the stateless entry points
 };
@@ -122,12 +126,19 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;  // numerically lower = higher priority
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < oat_ctx::NTAIL; ++i) CK(cudaStreamCreateWithPriority(&c->tail[i], cudaStreamNonBlocking, hi));
+    }
     int lut[512];
     lut[0] = lut[256] = 0;
     for (int i = 1; i < 256; ++i) {
         lut[i] = (int)nearbyint((255 << 12) / (1.0 * i));
         lut[256 + i] = (int)nearbyint((180 << 12) / (6.0 * i));
     }
+    CK(cudaMalloc(&c->tile_counter, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(c->tile_counter, 0, 2 * sizeof(unsigned int)));
     CK(cudaMalloc(&c->hsv_lut, sizeof(lut)));
     CK(cudaMemcpy(c->hsv_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     *out = c;
@@ -140,10 +151,16 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->h2d);
+    for (int i = 0; i < oat_ctx::NTAIL; ++i)
+        if (c->tail[i]) {
+            cudaStreamSynchronize(c->tail[i]);
+            cudaStreamDestroy(c->tail[i]);
+        }
     c->flush.release();
     c->scratch_in.release();
     c->scratch_out.release();
     if (c->hsv_lut) cudaFree(c->hsv_lut);
+    if (c->tile_counter) cudaFree(c->tile_counter);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
     delete c;
@@ -155,6 +172,7 @@ extern "C" int oat_ctx_sync(oat_ctx *c)
     CKRET(bind(c));
     CK(cudaStreamSynchronize(c->h2d));
     CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < oat_ctx::NTAIL; ++i) CK(cudaStreamSynchronize(c->tail[i]));
     return OAT_OK;
 }
 extern "C" void *oat_ctx_stream(oat_ctx *c) { return c ? (void *)c->stream : nullptr; }
@@ -352,7 +370,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
         // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
         // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
         const size_t tight3 = (size_t)3 * m.g.cols;
-        const bool linear = (m.g.cols % 32 == 0) && a.in_pitch == tight3 && (!a.bgr_out || a.bgr_out_pitch == tight3) &&
+        const bool linear = (m.g.cols % 32 == 0) && a.in_pitch == tight3 && (((uintptr_t)a.bgr & 15u) == 0) && (!a.bgr_out || a.bgr_out_pitch == tight3) &&
                             (!a.hsv_out || a.hsv_pitch == tight3) && (!a.fg_out || a.fg_pitch == (size_t)m.g.cols);
         if (!c->pipe_attr_set) {
             CK(cudaFuncSetAttribute(mog_pipe_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
@@ -368,6 +386,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
         pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
         const int grid = pa.ntiles < 2 * c->num_sms ? pa.ntiles : 2 * c->num_sms;
         pa.grid_tiles = grid;
+        pa.tile_counter = c->tile_counter;  // launches on one context are stream-ordered, so one counter serves
         if (frozen && linear)
             mog_pipe_kernel<5, true, true><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
         else if (frozen)
@@ -643,12 +662,44 @@ static int check_hsv_params(const oat_hsv_params *p)
     return OAT_OK;
 }
 
+// Per-frame buffers of the one-launch tail (small: a 1080p set is ~270 KB), so the tails of
+// consecutive frames can run on different streams while the next fused kernel is in flight.
+struct FastBufs {
+    uint32_t *di = nullptr;      // post-morphology bits
+    int2 *rowext = nullptr;
+    int *bbox = nullptr;         // ymin, ymax
+    unsigned int *ticket = nullptr;
+    int create(size_t nwords, int rows)
+    {
+        CK(cudaMalloc(&di, nwords * 4));
+        CK(cudaMalloc(&rowext, (size_t)rows * sizeof(int2)));
+        CK(cudaMalloc(&bbox, 2 * sizeof(int)));
+        CK(cudaMalloc(&ticket, sizeof(unsigned int)));
+        const int init[2] = {INT_MAX, -1};
+        CK(cudaMemcpy(bbox, init, sizeof(init), cudaMemcpyHostToDevice));
+        CK(cudaMemset(ticket, 0, sizeof(unsigned int)));
+        return OAT_OK;
+    }
+    void destroy()
+    {
+        cudaFree(di);
+        cudaFree(rowext);
+        cudaFree(bbox);
+        cudaFree(ticket);
+        *this = FastBufs();
+    }
+};
+
 struct Tail {
     TailBuffers tb{};
     uint32_t *bits0 = nullptr;  // threshold mask (input of the tail)
     uint32_t *tmp = nullptr, *er = nullptr, *di = nullptr;
     size_t nwords = 0;
     size_t prep_smem_set = 48 * 1024;
+    FastBufs fb;                      // one-launch tail buffers for the synchronous entry points
+    size_t fast_smem = 0;             // dynamic shared memory of tail_fast_kernel (0: fast path unusable)
+    size_t fast_smem_set = 48 * 1024;
+    int fast_comps = 128;
 
     int create(int rows, int cols)
     {
@@ -669,6 +720,14 @@ struct Tail {
         CK(cudaMalloc(&tb.count, sizeof(unsigned int)));
         CK(cudaMalloc(&tb.ticket, sizeof(unsigned int)));
         CK(cudaMalloc(&tb.rowext, (size_t)rows * sizeof(int2)));
+        CKRET(fb.create(nwords, rows));
+        // label-phase budget (mask region + run table + accumulators in shared memory).  48 KB keeps a
+        // tail CTA co-resident with two CTAs of the fused kernel (2 x 74.1 KB) on one SM, which is what
+        // lets the tail of frame t overlap the fused kernel of frame t+1.  OAT_B200_TAIL_SMEM_KB overrides.
+        size_t kb = 48;
+        if (const char *e = getenv("OAT_B200_TAIL_SMEM_KB")) kb = (size_t)atoi(e);
+        if (kb > 200) kb = 200;
+        fast_smem = kb * 1024;
         return OAT_OK;
     }
     void destroy()
@@ -684,18 +743,73 @@ struct Tail {
         cudaFree(tb.count);
         cudaFree(tb.ticket);
         cudaFree(tb.rowext);
+        fb.destroy();
         *this = Tail();
     }
+    // Fast path: ONE launch (tail_fast.cuh).  Returns false (nothing enqueued) if this geometry /
+    // kernel size cannot use it; res->status == TAIL_OVERFLOW after completion means "replay with run()".
+    bool run_fast(oat_ctx *c, cudaStream_t stream, const FastBufs &b, const uint32_t *src, const oat_hsv_params &p,
+                  TailResult *d_res, uint8_t *thresh_dev, size_t thresh_pitch, int *err)
+    {
+        *err = OAT_OK;
+        const BitGeom g = tb.g;
+        if (fast_smem == 0 || g.rows < 2 || getenv("OAT_B200_NO_FAST_TAIL")) return false;
+        const int ke = p.erode_px > 0 ? p.erode_px : 0, kd = p.dilate_px > 0 ? p.dilate_px : 0;
+        const int R = 8;
+        const size_t nin = (size_t)R + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
+        const size_t stage = 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
+        if (stage > 200 * 1024) return false;
+        const size_t smem = stage > fast_smem ? stage : fast_smem;
+        if (smem + 2048 > fast_smem_set) {
+            cudaError_t e = cudaFuncSetAttribute(tail_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+            if (e != cudaSuccess) {
+                *err = fail(OAT_ERR_CUDA, std::string("cudaFuncSetAttribute(tail_fast_kernel): ") + cudaGetErrorString(e));
+                return true;
+            }
+            fast_smem_set = 200 * 1024;
+        }
+        FastArgs fa;
+        fa.in = src;
+        fa.out = b.di;
+        fa.ke = ke;
+        fa.kd = kd;
+        fa.R = R;
+        fa.g = g;
+        fa.rowext = b.rowext;
+        fa.bbox = b.bbox;
+        fa.ticket = b.ticket;
+        fa.min_area = p.min_area;
+        fa.max_area = p.max_area;
+        fa.res = d_res;
+        fa.smem_bytes = (int)smem;
+        fa.max_comps = fast_comps;
+        tail_fast_kernel<<<div_up(g.rows, R), 256, smem, stream>>>(fa);
+        ++c->launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            *err = fail(OAT_ERR_CUDA, std::string("tail_fast_kernel launch: ") + cudaGetErrorString(e));
+            return true;
+        }
+        if (thresh_dev) {
+            bits_to_mask_kernel<<<nblocks((long long)g.rows * g.pitch_px(), 256), 256, 0, stream>>>(b.di, g, thresh_dev,
+                                                                                                  thresh_pitch);
+            ++c->launches;
+        }
+        return true;
+    }
+
     // [erode] -> [dilate] -> labelling -> moments -> select; result to d_out (device memory).
     // 5 launches: prep (morphology + row extents + union-find init), merge, fill, moments, select.
-    int run(oat_ctx *c, const oat_hsv_params &p, oat_detection *d_out, uint8_t *thresh_dev, size_t thresh_pitch,
-            int32_t *labels_dev)
+    // Unbounded (every structure is in global memory): the fallback of run_fast and the path
+    // that can publish per-pixel labels.
+    int run(oat_ctx *c, const uint32_t *src_bits, const oat_hsv_params &p, oat_detection *d_out, uint8_t *thresh_dev,
+            size_t thresh_pitch, int32_t *labels_dev)
     {
         cudaStream_t s = c->stream;
         const BitGeom g = tb.g;
         const unsigned gw = nblocks((long long)nwords, 256);
         int ke = p.erode_px > 0 ? p.erode_px : 0, kd = p.dilate_px > 0 ? p.dilate_px : 0;
-        const uint32_t *src = bits0;
+        const uint32_t *src = src_bits;
         const size_t smem_limit = 200 * 1024;
         auto smem_for = [&](int R, int e, int d) {
             const size_t nin = (size_t)R + (e > 0 ? e - 1 : 0) + (d > 0 ? d - 1 : 0);
@@ -715,9 +829,10 @@ struct Tail {
             if (kd > 0) {
                 morph_h_kernel<true><<<gw, 256, 0, s>>>(src, tmp, g, kd);
                 LAUNCH_CHECK(c);
-                morph_v_kernel<true><<<gw, 256, 0, s>>>(tmp, er == src ? bits0 : er, g, kd);
+                uint32_t *dst = (er == src) ? tb.G : er;  // G is rewritten by the fill kernel later
+                morph_v_kernel<true><<<gw, 256, 0, s>>>(tmp, dst, g, kd);
                 LAUNCH_CHECK(c);
-                src = (er == src) ? bits0 : er;
+                src = dst;
             }
             ke = kd = 0;
             R = 8;
@@ -764,7 +879,7 @@ struct Tail {
 struct oat_hsvdet {
     oat_ctx *ctx;
     Tail tail;
-    oat_detection *d_res;
+    TailResult *d_res;
     DevBuf in, out_thr, out_lab;
 };
 
@@ -778,7 +893,7 @@ extern "C" int oat_hsvdet_create(oat_ctx *c, int rows, int cols, oat_hsvdet **ou
     h->ctx = c;
     h->d_res = nullptr;
     int r = h->tail.create(rows, cols);
-    if (r == OAT_OK && cudaMalloc(&h->d_res, sizeof(oat_detection)) != cudaSuccess)
+    if (r == OAT_OK && cudaMalloc(&h->d_res, sizeof(TailResult)) != cudaSuccess)
         r = fail(OAT_ERR_NOMEM, "device allocation failed");
     if (r != OAT_OK) {
         h->tail.destroy();
@@ -834,11 +949,29 @@ static int detect_common(oat_hsvdet *h, const uint8_t *img, size_t pitch, int ch
     else
         mask_to_bits_kernel<<<gp, 256, 0, c->stream>>>(d, dp, g, h->tail.bits0);
     LAUNCH_CHECK(c);
-    CKRET(h->tail.run(c, *p, h->d_res, ot.d, ot.dpitch, lab_dev));
+    // one-launch fast path unless per-pixel labels are wanted; replay through the unbounded
+    // path if the mask overflowed the shared-memory run table
+    bool need_generic = true;
+    if (!labels_out) {
+        int err = OAT_OK;
+        if (h->tail.run_fast(c, c->stream, h->tail.fb, h->tail.bits0, *p, h->d_res, ot.d, ot.dpitch, &err)) {
+            CKRET(err);
+            TailResult tr;
+            CK(cudaMemcpyAsync(&tr, h->d_res, sizeof(tr), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (tr.status == TAIL_OK) {
+                *out = tr.det;
+                need_generic = false;
+            }
+        }
+    }
+    if (need_generic) {
+        CKRET(h->tail.run(c, h->tail.bits0, *p, &h->d_res->det, ot.d, ot.dpitch, lab_dev));
+        CK(cudaMemcpyAsync(out, &h->d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
+    }
     CKRET(finish_out(c->stream, ot));
     if (labels_out && lab_dev != labels_out)
         CK(cudaMemcpyAsync(labels_out, lab_dev, lab_bytes, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(out, h->d_res, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return OAT_OK;
 }
@@ -857,8 +990,13 @@ extern "C" int oat_sift_contours(oat_hsvdet *h, const uint8_t *mask, size_t pitc
 // ---- fused tracker -------------------------------------------------------------------------
 struct Slot {
     DevBuf in;                      // staged input frame (host-fed streams)
-    oat_detection *h_res = nullptr; // pinned
-    oat_detection *d_res = nullptr;
+    TailResult *h_res = nullptr;    // pinned
+    TailResult *d_res = nullptr;
+    uint32_t *bits = nullptr;       // this frame's threshold mask (kept until collect: overflow replay)
+    FastBufs fb;                    // this frame's one-launch tail buffers
+    cudaEvent_t fused_done = nullptr;
+    oat_hsv_params hp{};
+    bool fast = false;              // the one-launch tail was used (status must be checked at collect)
     cudaEvent_t copied = nullptr, done = nullptr;
 };
 
@@ -868,6 +1006,7 @@ struct oat_tracker {
     Tail tail;
     std::vector<Slot> ring;
     uint64_t head = 0, tailpos = 0;  // submitted / collected
+    uint64_t replays = 0;            // frames whose tail had to be replayed through the unbounded path
     DevBuf out_bgr, out_fg, out_hsv, out_thr;
     // profiling of the fused kernel
     int prof = 0;
@@ -893,8 +1032,11 @@ extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_
     if (r == OAT_OK) {
         t->ring.resize(ring_depth);
         for (auto &s : t->ring) {
-            if (cudaHostAlloc(&s.h_res, sizeof(oat_detection), cudaHostAllocDefault) != cudaSuccess ||
-                cudaMalloc(&s.d_res, sizeof(oat_detection)) != cudaSuccess ||
+            if (cudaHostAlloc(&s.h_res, sizeof(TailResult), cudaHostAllocDefault) != cudaSuccess ||
+                cudaMalloc(&s.d_res, sizeof(TailResult)) != cudaSuccess ||
+                cudaMalloc(&s.bits, t->tail.nwords * 4) != cudaSuccess ||
+                s.fb.create(t->tail.nwords, rows) != OAT_OK ||
+                cudaEventCreateWithFlags(&s.fused_done, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
                 r = fail(OAT_ERR_NOMEM, std::string("tracker ring allocation failed: ") +
@@ -917,12 +1059,16 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->h2d);
     cudaStreamSynchronize(t->ctx->stream);
+    for (int i = 0; i < oat_ctx::NTAIL; ++i) cudaStreamSynchronize(t->ctx->tail[i]);
     t->m.destroy();
     t->tail.destroy();
     for (auto &s : t->ring) {
         s.in.release();
         if (s.h_res) cudaFreeHost(s.h_res);
         if (s.d_res) cudaFree(s.d_res);
+        if (s.bits) cudaFree(s.bits);
+        s.fb.destroy();
+        if (s.fused_done) cudaEventDestroy(s.fused_done);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -946,8 +1092,10 @@ extern "C" int oat_tracker_reset(oat_tracker *t)
     return OAT_OK;
 }
 
+// overlap: run this frame's detect tail on one of the context's tail streams so that it overlaps the
+// fused kernel of the next frame (submit/collect); otherwise everything stays on the compute stream.
 static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
-                           const oat_hsv_params *p, OutView &ob, OutView &ofg, OutView &ohsv, OutView &othr)
+                           const oat_hsv_params *p, OutView &ob, OutView &ofg, OutView &ohsv, OutView &othr, bool overlap)
 {
     oat_ctx *c = t->ctx;
     const int rows = t->m.g.rows, cols = t->m.g.cols;
@@ -970,7 +1118,8 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     a.hi[0] = p->h_max;
     a.hi[1] = p->s_max;
     a.hi[2] = p->v_max;
-    a.thr_bits = t->tail.bits0;
+    a.thr_bits = s.bits;
+    s.hp = *p;
     a.bgr_out = ob.d;
     a.bgr_out_pitch = ob.dpitch;
     a.fg_out = ofg.d;
@@ -988,13 +1137,27 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
         CK(cudaEventRecord(e1, c->stream));
         t->prof_pending.emplace_back(e0, e1);
     }
-    CKRET(t->tail.run(c, *p, s.d_res, othr.d, othr.dpitch, nullptr));
     CKRET(finish_out(c->stream, ob));
     CKRET(finish_out(c->stream, ofg));
     CKRET(finish_out(c->stream, ohsv));
-    CKRET(finish_out(c->stream, othr));
-    CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(s.done, c->stream));
+    cudaStream_t ts = c->stream;
+    if (overlap && !getenv("OAT_B200_NO_OVERLAP")) {
+        ts = c->tail[t->head % oat_ctx::NTAIL];
+        CK(cudaEventRecord(s.fused_done, c->stream));
+        CK(cudaStreamWaitEvent(ts, s.fused_done, 0));
+    }
+    {
+        int err = OAT_OK;
+        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err);
+        CKRET(err);
+        if (!s.fast) {
+            ts = c->stream;  // the unbounded path owns shared buffers: compute stream only
+            CKRET(t->tail.run(c, s.bits, *p, &s.d_res->det, othr.d, othr.dpitch, nullptr));
+        }
+    }
+    CKRET(finish_out(ts, othr));
+    CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(TailResult), cudaMemcpyDeviceToHost, ts));
+    CK(cudaEventRecord(s.done, ts));
     ++t->head;
     return OAT_OK;
 }
@@ -1014,7 +1177,16 @@ extern "C" int oat_tracker_collect(oat_tracker *t, oat_detection *out)
     CKRET(bind(t->ctx));
     Slot &s = t->ring[t->tailpos % t->ring.size()];
     CK(cudaEventSynchronize(s.done));
-    *out = *s.h_res;
+    if (s.fast && s.h_res->status != TAIL_OK) {
+        // the mask overflowed the one-launch tail's run table: replay this frame's mask through
+        // the unbounded path (its bits are still in the slot)
+        oat_ctx *c = t->ctx;
+        CKRET(t->tail.run(c, s.bits, s.hp, &s.d_res->det, nullptr, 0, nullptr));
+        CK(cudaMemcpyAsync(&s.h_res->det, &s.d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        ++t->replays;
+    }
+    *out = s.h_res->det;
     ++t->tailpos;
     return OAT_OK;
 }
@@ -1034,7 +1206,7 @@ extern "C" int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t 
             "oat_tracker_submit: host bgr_out needs the previous frame collected first");
     OutView ob, none1, none2, none3;
     CKRET(stage_out(t->out_bgr, bgr_out, bgr_out_pitch, rows, (size_t)3 * cols, &ob));
-    return tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, none1, none2, none3);
+    return tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, none1, none2, none3, true);
 }
 
 extern "C" int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
@@ -1056,7 +1228,7 @@ extern "C" int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t i
     CKRET(stage_out(t->out_fg, fgmask_out, fgmask_pitch, rows, (size_t)cols, &ofg));
     CKRET(stage_out(t->out_hsv, hsv_out, hsv_pitch, rows, (size_t)3 * cols, &ohsv));
     CKRET(stage_out(t->out_thr, thresh_out, thresh_pitch, rows, (size_t)cols, &othr));
-    CKRET(tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, ofg, ohsv, othr));
+    CKRET(tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, ofg, ohsv, othr, false));
     return oat_tracker_collect(t, out);
 }
 
@@ -1073,6 +1245,19 @@ extern "C" int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float 
     REQUIRE(t, "null handle");
     CKRET(bind(t->ctx));
     return get_state(t->ctx, t->m, modes_used, weight, variance, mean);
+}
+
+// Diagnostic: what the one-launch tail needed for the most recently collected frame.
+extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [12]: status, nodes, replays, fast, cyc[8] */)
+{
+    REQUIRE(t && out, "null argument");
+    const Slot &s = t->ring[(t->tailpos + t->ring.size() - 1) % t->ring.size()];
+    out[0] = (uint32_t)s.h_res->status;
+    out[1] = s.h_res->nodes;
+    out[2] = (uint32_t)t->replays;
+    out[3] = s.fast ? 1u : 0u;
+    for (int i = 0; i < 8; ++i) out[4 + i] = s.h_res->cyc[i];
+    return OAT_OK;
 }
 
 extern "C" int oat_tracker_profile(oat_tracker *t, int enable)

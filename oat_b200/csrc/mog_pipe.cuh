@@ -28,7 +28,7 @@ namespace oat {
 #define PIPE_CTHREADS_CFG 256
 #endif
 #ifndef PIPE_STAGES_CFG
-#define PIPE_STAGES_CFG 4
+#define PIPE_STAGES_CFG 3
 #endif
 #ifndef PIPE_MINBLOCKS_CFG
 #define PIPE_MINBLOCKS_CFG 2
@@ -108,6 +108,7 @@ struct PipeArgs {
     unsigned long long div_magic;  // ceil(2^64 / pitch_px): y = umul64hi(pidx, magic), exact for every pidx < 2^32
     int zero_in;                   // HSV (0,0,0) lies inside the inRange band
     int grid_tiles;                // tile stride between consecutive tiles of one CTA (= gridDim.x)
+    unsigned int *tile_counter;    // [2] dynamic tile scheduler (LINEAR frames): next tile, CTAs finished; zeroed once, self re-arming
 };
 
 // One pixel, n == 1: the m = 0 iteration of mog2_pixel() + normalisation, valid when the sample
@@ -149,7 +150,17 @@ __device__ __forceinline__ bool fast_px(const float x0, const float x1, const fl
 // loop, so the steady-state loop stays call-free and register-light).  Mode 0, the counts and the
 // BGR bytes live in the shared-memory stage `st`; modes >= 1 are read/written in global memory.
 // Does its own egress.  Returns the 4 threshold bits; sets dirty if any state changed.
-template <int K, bool TRACK>
+__device__ __forceinline__ float sel4(const float4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void set4(float4 &v, int i, float x)
+{
+    if (i == 0) v.x = x;
+    if (i == 1) v.y = x;
+    if (i == 2) v.z = x;
+    if (i == 3) v.w = x;
+}
+
+// NA = mode slots held in registers = min(largest live count among the 4 pixels + 1, K).
+template <int K, int NA, bool TRACK>
 __device__ __forceinline__ uint32_t pipe_slow(const PipeArgs &pa, const int *lut, uint8_t *st, const int tid,
                                               const size_t pidx, bool &dirty)
 {
@@ -162,19 +173,38 @@ __device__ __forceinline__ uint32_t pipe_slow(const PipeArgs &pa, const int *lut
         y = (int)__umul64hi((unsigned long long)pidx, pa.div_magic);
         x = (int)(pidx - (size_t)y * ((size_t)a.wpr * 32));
     }
+    // mode 1 of all four pixels in one round trip (the common multi-mode case is two modes);
+    // dead slots are unspecified, so loading / storing them back unchanged is harmless
+    const uint32_t nm4 = *reinterpret_cast<const uint32_t *>(smn);
+    const bool have1 = (NA > 2 || (NA == K && K > 1)) && (((nm4 + 0x7e7e7e7eu) & 0x80808080u) != 0u);  // any count >= 2
+    float4 M1[5];
+#pragma unroll
+    for (int cc = 0; cc < 5; ++cc) M1[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have1) {
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) M1[cc] = ld_state_f4(a.state + (size_t)(5 + cc) * a.plane + pidx);
+    }
+    bool store1 = false;
     uint32_t nib = 0;
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         int n = smn[i];
         const int n_old = n;
-        float W[K], V[K], A[K], B[K], C[K];
+        float W[NA], V[NA], A[NA], B[NA], C[NA];
         W[0] = sm0[i];
         V[0] = sm0[PIPE_TILE + i];
         A[0] = sm0[2 * PIPE_TILE + i];
         B[0] = sm0[3 * PIPE_TILE + i];
         C[0] = sm0[4 * PIPE_TILE + i];
+        if (NA > 1) {
+            W[NA > 1 ? 1 : 0] = sel4(M1[0], i);
+            V[NA > 1 ? 1 : 0] = sel4(M1[1], i);
+            A[NA > 1 ? 1 : 0] = sel4(M1[2], i);
+            B[NA > 1 ? 1 : 0] = sel4(M1[3], i);
+            C[NA > 1 ? 1 : 0] = sel4(M1[4], i);
+        }
 #pragma unroll
-        for (int m = 1; m < K; ++m) {
+        for (int m = 2; m < NA; ++m) {
             W[m] = V[m] = A[m] = B[m] = C[m] = 0.f;
             if (m < n) {
                 const float *g = a.state + (size_t)(m * 5) * a.plane + pidx + i;
@@ -187,7 +217,7 @@ __device__ __forceinline__ uint32_t pipe_slow(const PipeArgs &pa, const int *lut
         }
         const int b = smb[3 * i], g_ = smb[3 * i + 1], r = smb[3 * i + 2];
         bool d = !TRACK;
-        const uint32_t mk = mog2_pixel<K, K, TRACK>((float)b, (float)g_, (float)r, n, W, V, A, B, C, a.c, d);
+        const uint32_t mk = mog2_pixel<K, NA, TRACK>((float)b, (float)g_, (float)r, n, W, V, A, B, C, a.c, d);
         if (d) {
             dirty = true;
             sm0[i] = W[0];
@@ -197,8 +227,16 @@ __device__ __forceinline__ uint32_t pipe_slow(const PipeArgs &pa, const int *lut
             sm0[4 * PIPE_TILE + i] = C[0];
             smn[i] = (uint8_t)n;
             const int nw = max(n, n_old);
+            if (NA > 1 && nw > 1) {
+                set4(M1[0], i, W[NA > 1 ? 1 : 0]);
+                set4(M1[1], i, V[NA > 1 ? 1 : 0]);
+                set4(M1[2], i, A[NA > 1 ? 1 : 0]);
+                set4(M1[3], i, B[NA > 1 ? 1 : 0]);
+                set4(M1[4], i, C[NA > 1 ? 1 : 0]);
+                store1 = true;
+            }
 #pragma unroll
-            for (int m = 1; m < K; ++m) {
+            for (int m = 2; m < NA; ++m) {
                 if (m < nw) {
                     float *g = a.state + (size_t)(m * 5) * a.plane + pidx + i;
                     st_state_f1(g, W[m]);
@@ -231,6 +269,12 @@ __device__ __forceinline__ uint32_t pipe_slow(const PipeArgs &pa, const int *lut
         }
         if (a.fg_out) a.fg_out[(size_t)y * a.fg_pitch + x + i] = (uint8_t)mk;
     }
+    if (store1) {
+        // a pixel that gained its second mode this frame next to pixels without one: the dead lanes of
+        // the vector were never loaded (have1 false) and are stored as zeros -- still unspecified slots
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) st_state_f4(a.state + (size_t)(5 + cc) * a.plane + pidx, M1[cc]);
+    }
     return nib;
 }
 
@@ -248,7 +292,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < PIPE_STAGES; ++s) {
-            mbar_init(&full[s], 1 + PIPE_CTHREADS);
+            mbar_init(&full[s], LINEAR ? 1 : 1 + PIPE_CTHREADS);
             mbar_init(&done[s], PIPE_CTHREADS);
         }
         fence_mbar_init();
@@ -256,33 +300,75 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     if (tid < PIPE_STAGES) *reinterpret_cast<uint32_t *>(stage_mem + (size_t)tid * PIPE_STAGE_BYTES + PIPE_OFF_FLAG) = 0u;
     __syncthreads();
 
+    // Tile order.  LINEAR frames use a dynamic scheduler: the producer draws tile numbers from a
+    // global counter (tiles that hit the multi-mode slow path take several times longer than the
+    // rest, so a static split leaves the kernel waiting for its unluckiest CTA) and also brings the
+    // BGR bytes in with one more bulk copy.  Otherwise tile i of this CTA is blockIdx.x + i*gridDim.x
+    // and every compute thread copies its own 12 input bytes with cp.async.
+    constexpr bool DYN = LINEAR;
     const int first = blockIdx.x, stride = pa.grid_tiles;
-    const int my_n = first < pa.ntiles ? (pa.ntiles - first + stride - 1) / stride : 0;
+    const int my_n = DYN ? 0x7fffffff : (first < pa.ntiles ? (pa.ntiles - first + stride - 1) / stride : 0);
+    auto stage_tile = [&](int s) -> volatile int * {
+        return reinterpret_cast<volatile int *>(stage_mem + (size_t)s * PIPE_STAGE_BYTES + PIPE_OFF_FLAG + 4);
+    };
 
     if (tid >= PIPE_CTHREADS) {
         // ---- producer warp: one lane drives the bulk-copy engine -------------------------------
         if (tid != PIPE_CTHREADS) return;
-        auto tile_span = [&](int i, size_t &p0, uint32_t &npx) {
-            p0 = (size_t)(first + i * stride) * PIPE_TILE;
+        auto tile_span = [&](int tile, size_t &p0, uint32_t &npx) {
+            p0 = (size_t)tile * PIPE_TILE;
             const size_t rem = a.plane - p0;
             npx = rem < (size_t)PIPE_TILE ? (uint32_t)rem : (uint32_t)PIPE_TILE;
         };
-        auto issue_load = [&](int i) {
-            const int s = i % PIPE_STAGES;
+        auto issue_load = [&](int s, int tile) {
             size_t p0;
             uint32_t npx;
-            tile_span(i, p0, npx);
+            tile_span(tile, p0, npx);
             uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
-            mbar_expect_tx(&full[s], npx * 21u);
+            mbar_expect_tx(&full[s], npx * (DYN ? 24u : 21u));
 #pragma unroll
             for (int cc = 0; cc < 5; ++cc)
                 bulk_g2s(st + cc * (PIPE_TILE * 4), a.state + (size_t)cc * a.plane + p0, npx * 4u, &full[s]);
             bulk_g2s(st + PIPE_OFF_NM, a.nmodes + p0, npx, &full[s]);
+            if (DYN) bulk_g2s(st + PIPE_OFF_BGR, a.bgr + 3 * p0, npx * 3u, &full[s]);
         };
-        const int pre = my_n < PIPE_STAGES - 1 ? my_n : PIPE_STAGES - 1;
-        for (int i = 0; i < pre; ++i) issue_load(i);
-        for (int i = 0; i < my_n; ++i) {
+        // next tile of this CTA's sequence, or -1 when the frame is exhausted (DYN: every CTA draws
+        // exactly one number >= ntiles; the CTA that draws the last one re-arms the counter)
+        // DYN: the first PIPE_STAGES-1 tiles of a CTA are fixed (no atomic on the start-up path); later
+        // ones are drawn from the global counter one refill AHEAD of their use, so the L2 round trip
+        // of the atomic hides behind the wait for the stage.
+        int seq = 0, ahead = 0;
+        bool ended = false;
+        auto draw = [&]() -> int { return (int)atomicAdd(pa.tile_counter, 1u) + (PIPE_STAGES - 1) * (int)gridDim.x; };
+        auto next_tile = [&]() -> int {
+            int t;
+            if (DYN && seq >= PIPE_STAGES - 1) {
+                t = ahead;
+                if (t < pa.ntiles) ahead = draw();
+            } else {
+                t = first + seq * stride;
+                if (DYN && seq == PIPE_STAGES - 2) ahead = draw();
+            }
+            ++seq;
+            if (t >= pa.ntiles) {
+                ended = true;
+                return -1;
+            }
+            return t;
+        };
+        auto refill = [&](int s) {  // give stage s its next tile, or the end marker
+            const int t = next_tile();
+            *stage_tile(s) = t;
+            if (t >= 0)
+                issue_load(s, t);
+            else if (DYN)
+                mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
+        };
+        for (int k = 0; k < PIPE_STAGES - 1 && !ended; ++k) refill(k);
+        for (int i = 0;; ++i) {
             const int s = i % PIPE_STAGES;
+            const int tile = *stage_tile(s);
+            if (tile < 0) break;
             uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
             mbar_wait(&done[s], (uint32_t)(i / PIPE_STAGES) & 1u);
             bool store = true;
@@ -294,26 +380,35 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             if (store) {
                 size_t p0;
                 uint32_t npx;
-                tile_span(i, p0, npx);
+                tile_span(tile, p0, npx);
 #pragma unroll
                 for (int cc = 0; cc < 5; ++cc)
                     bulk_s2g(a.state + (size_t)cc * a.plane + p0, st + cc * (PIPE_TILE * 4), npx * 4u);
                 bulk_s2g(a.nmodes + p0, st + PIPE_OFF_NM, npx);
             }
             bulk_commit();
-            if (i + PIPE_STAGES - 1 < my_n) {
-                bulk_wait_read<1>();  // the stores of tile i-1 have finished reading their stage
-                issue_load(i + PIPE_STAGES - 1);
+            if (!ended) {
+                bulk_wait_read<1>();  // the stores of the previous tile have finished reading their stage
+                refill((i + PIPE_STAGES - 1) % PIPE_STAGES);
+            } else if (!DYN) {
+                *stage_tile((i + PIPE_STAGES - 1) % PIPE_STAGES) = -1;
             }
         }
         bulk_wait_read<0>();  // shared memory must outlive the last bulk stores
+        if (DYN) {  // the last producer to leave re-arms the scheduler for the next launch
+            const unsigned e = atomicAdd(pa.tile_counter + 1, 1u);
+            if (e == gridDim.x - 1) {
+                pa.tile_counter[0] = 0u;
+                pa.tile_counter[1] = 0u;
+            }
+        }
         return;
     }
 
     // ---- compute warps ---------------------------------------------------------------------------
     const unsigned pitch_px = (unsigned)a.wpr * 32u;
-    auto locate = [&](int i, size_t &pidx, int &y, int &x) -> bool {
-        pidx = (size_t)(first + i * stride) * PIPE_TILE + (size_t)tid * 4;
+    auto locate = [&](int tile, size_t &pidx, int &y, int &x) -> bool {
+        pidx = (size_t)tile * PIPE_TILE + (size_t)tid * 4;
         if (LINEAR) {
             y = 0;
             x = 0;
@@ -323,12 +418,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         x = (int)(pidx - (size_t)y * pitch_px);
         return (pidx < a.plane) && (x < a.cols);
     };
-    auto bgr_issue = [&](int i) {  // this thread's 12 input bytes of tile i -> its slot of the stage
+    auto bgr_issue = [&](int i) {  // (static order only) this thread's 12 input bytes of its i-th tile
         const int s = i % PIPE_STAGES;
         size_t pidx;
         int y, x;
-        if (locate(i, pidx, y, x)) {
-            const uint8_t *src = LINEAR ? a.bgr + 3 * pidx : a.bgr + (size_t)y * a.in_pitch + 3 * x;
+        if (locate(first + i * stride, pidx, y, x)) {
+            const uint8_t *src = a.bgr + (size_t)y * a.in_pitch + 3 * x;
             uint8_t *dst = stage_mem + (size_t)s * PIPE_STAGE_BYTES + PIPE_OFF_BGR + tid * 12;
             cp_async4(dst, src);
             cp_async4(dst + 4, src + 4);
@@ -336,7 +431,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         }
         cp_async_arrive_noinc(&full[s]);
     };
-    {
+    if (!DYN) {
         const int pre = my_n < PIPE_STAGES - 1 ? my_n : PIPE_STAGES - 1;
         for (int i = 0; i < pre; ++i) bgr_issue(i);
     }
@@ -345,14 +440,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
 
     for (int i = 0; i < my_n; ++i) {
         const int s = i % PIPE_STAGES;
-        if (i + PIPE_STAGES - 1 < my_n) bgr_issue(i + PIPE_STAGES - 1);
-        size_t pidx;
-        int y, x;
-        const bool active = locate(i, pidx, y, x);
+        if (!DYN && i + PIPE_STAGES - 1 < my_n) bgr_issue(i + PIPE_STAGES - 1);
         uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
         float *sm0 = reinterpret_cast<float *>(st) + tid * 4;
 
         mbar_wait(&full[s], (uint32_t)(i / PIPE_STAGES) & 1u);
+
+        const int tile = DYN ? *stage_tile(s) : first + i * stride;
+        if (DYN && tile < 0) break;
+        size_t pidx;
+        int y, x;
+        const bool active = locate(tile, pidx, y, x);
 
         bool dirty = !TRACK;
         uint32_t nib = 0;
@@ -406,7 +504,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             if (!fast) {
                 ++nslow;
                 bool d2 = false;
-                nib = pipe_slow<K, TRACK>(pa, lut, st, tid, pidx, d2);
+                const uint32_t nmax = max(max(nm & 255u, (nm >> 8) & 255u), max((nm >> 16) & 255u, nm >> 24));
+                if (nmax <= 1 || K <= 2)
+                    nib = pipe_slow<K, (K < 2 ? K : 2), TRACK>(pa, lut, st, tid, pidx, d2);
+                else if (nmax == 2 || K == 3)
+                    nib = pipe_slow<K, (K < 3 ? K : 3), TRACK>(pa, lut, st, tid, pidx, d2);
+                else
+                    nib = pipe_slow<K, K, TRACK>(pa, lut, st, tid, pidx, d2);
                 dirty |= d2 || !TRACK;
             }
         }

@@ -1,0 +1,566 @@
+// tail_fast.cuh -- the whole detect tail of `posidet hsv` in ONE launch for the common case
+// (a handful of blobs): morphology + row extents by all CTAs, then the LAST CTA to finish labels
+// the mask in shared memory and produces the detection.
+//
+//   cv::erode / cv::dilate, MORPH_RECT k x k      (src/positiondetector/HSVDetector.cpp:152-156, :253-273)
+//   siftContours()                                  (src/positiondetector/DetectorFunc.cpp:31-66)
+//
+// Same contour semantics as tail.cuh (external contours = 8-connected foreground + its 4-connected
+// holes; exact integer 2x2-cell moments; reverse-raster tie-break), different machinery: the
+// union-find nodes are whole row RUNS (foreground runs and "candidate" background runs between
+// the first and last foreground pixel of a row), extracted from the bit mask with warp scans and
+// kept -- together with the parent array and the per-contour accumulators -- in shared memory,
+// so every dependent pointer hop costs ~30 cycles instead of an L2 round trip, and nothing is
+// proportional to the frame size except one streaming pass over the mask.
+//
+// The run table is bounded by the shared-memory budget.  A mask that does not fit (more runs or
+// contours than the table holds: the first frame's whole-image blob, heavy noise) makes the
+// kernel report TAIL_OVERFLOW; the host then replays the frame through the unbounded
+// global-memory path of tail.cuh.  Results are identical either way.
+#pragma once
+#include "tail.cuh"
+
+namespace oat {
+
+enum { TAIL_OK = 0, TAIL_OVERFLOW = 1 };
+
+struct TailResult {
+    oat_detection det;
+    int32_t status;      // TAIL_OK / TAIL_OVERFLOW
+    uint32_t nodes;      // run-table entries the mask needed (diagnostic / sizing)
+    uint32_t slow_groups;  // fused kernel's slow-path census (filled by the host side from its counter)
+    uint32_t pad;
+    uint32_t cyc[8];     // SM-clock stamps of the labelling CTA (diagnostic): start, ticket, staged, counted, filled, merged, filled holes, end
+};
+
+struct FastArgs {
+    const uint32_t *in;  // threshold bits before morphology
+    uint32_t *out;       // post-morphology bits (what thresh egress publishes)
+    int ke, kd, R;
+    BitGeom g;
+    int2 *rowext;
+    int *bbox;               // ymin, ymax (reset by the last CTA for the next launch)
+    unsigned int *ticket;    // CTA completion counter (reset likewise)
+    double min_area, max_area;
+    TailResult *res;
+    int smem_bytes;          // dynamic shared memory per CTA
+    int max_comps;
+};
+
+// ---- shared-memory union-find (parents only ever decrease) ----------------------------------
+__device__ __forceinline__ uint32_t suf_find(volatile uint32_t *P, uint32_t x)
+{
+    uint32_t p = P[x];
+    while (p != x) {
+        const uint32_t gp = P[p];
+        if (gp != p) atomicMin(const_cast<uint32_t *>(P) + x, gp);
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void suf_union(volatile uint32_t *P, uint32_t a, uint32_t b)
+{
+    for (;;) {
+        a = suf_find(P, a);
+        b = suf_find(P, b);
+        if (a == b) return;
+        if (a < b) {
+            const uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        const uint32_t old = atomicMin(const_cast<uint32_t *>(P) + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// Region view of a bit image staged in shared memory: rows [y0, y1], words [j0, j1]; 0 elsewhere.
+struct RegionView {
+    const uint32_t *w;
+    int y0, y1, j0, j1, wd;
+    __device__ __forceinline__ uint32_t at(int y, int j) const
+    {
+        return (y < y0 || y > y1 || j < j0 || j > j1) ? 0u : w[(y - y0) * wd + (j - j0)];
+    }
+};
+// candidate background of an inner row: background between the row's first and last foreground pixel
+__device__ __forceinline__ uint32_t fast_candw(const RegionView &m, const BitGeom &g, int y, int j, int2 e)
+{
+    if (j < m.j0 || j > m.j1) return 0u;
+    return ~m.at(y, j) & g.valid_mask(j) & range_mask(j, e.x, e.y);
+}
+// any background pixel in columns [s, e] of row y ([s, e] lies inside the region's columns)
+__device__ __forceinline__ bool fast_any_bg(const RegionView &m, const BitGeom &g, int y, int s, int e)
+{
+    if (y < m.y0 || y > m.y1) return true;
+    for (int j = s >> 5; j <= (e >> 5); ++j)
+        if (~m.at(y, j) & g.valid_mask(j) & range_mask(j, s, e)) return true;
+    return false;
+}
+
+// The labelling phase, run by one CTA after every CTA has published its rows.  Everything it
+// touches repeatedly -- the mask's bounding region, row extents, run table, parents, accumulators
+// -- is staged in shared memory first (one coalesced pass over L2), so no step chases pointers
+// through global memory.
+__device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymin, const int ymax, const uint32_t a_t0)
+{
+    const BitGeom g = a.g;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    __shared__ uint32_t s_nF, s_nB, s_ncomp, s_fail;
+    __shared__ int s_xmin, s_xmax;
+    __shared__ unsigned long long s_best;
+    TailResult r;
+    r.det.position_valid = 0;
+    r.det.n_components = 0;
+    r.det.x = r.det.y = r.det.area = 0.0;
+    r.status = TAIL_OK;
+    r.nodes = 0;
+    r.slow_groups = 0;
+    r.pad = 0;
+    for (int i = 0; i < 8; ++i) r.cyc[i] = 0;
+    r.cyc[0] = a_t0;
+    r.cyc[1] = (uint32_t)clock64();
+    if (ymax < ymin) {  // empty mask
+        if (tid == 0) *a.res = r;
+        return;
+    }
+    const int H = ymax - ymin + 1;
+    const int C = a.max_comps;
+    // ---- 0. stage row extents, then the bounding region of the mask ---------------------------
+    // layout: ext[H] (int2) | offF[H+1] offB[H+1] (u32) | acc[3*C] (u64) | M[H*Wd] (u32) | node arrays
+    size_t used = 0;
+    int2 *ext = reinterpret_cast<int2 *>(smem);
+    used += (size_t)H * 8;
+    uint32_t *offF = reinterpret_cast<uint32_t *>(smem + used);
+    uint32_t *offB = offF + (H + 1);
+    used += (size_t)2 * (H + 1) * 4;
+    used = (used + 7) & ~(size_t)7;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(smem + used);
+    used += (size_t)3 * C * 8;
+    if (used + 1024 > (size_t)a.smem_bytes) {
+        if (tid == 0) {
+            r.status = TAIL_OVERFLOW;
+            *a.res = r;
+        }
+        return;
+    }
+    if (tid == 0) {
+        s_ncomp = 0;
+        s_fail = 0;
+        s_best = 0ull;
+        s_xmin = INT_MAX;
+        s_xmax = -1;
+    }
+    __syncthreads();
+    {
+        int xmin = INT_MAX, xmax = -1;
+        for (int y = tid; y < H; y += NT) {
+            const int2 e = __ldcg(a.rowext + ymin + y);
+            ext[y] = e;
+            if (e.y >= 0) {
+                xmin = min(xmin, e.x);
+                xmax = max(xmax, e.y);
+            }
+        }
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        if (lane == 0) {
+            atomicMin(&s_xmin, xmin);
+            atomicMax(&s_xmax, xmax);
+        }
+    }
+    __syncthreads();
+    const int jmin = s_xmin >> 5, jmax = s_xmax >> 5, Wd = jmax - jmin + 1;
+    const size_t RW = (size_t)H * Wd;
+    uint32_t *Ms = reinterpret_cast<uint32_t *>(smem + used);
+    uint32_t *Gs = Ms;  // holes are OR-ed into the same words once the merges (the last readers of the bare mask) are done
+    used += RW * 4;
+    const long long avail = (long long)a.smem_bytes - (long long)used;
+    const int N = avail > 0 ? (int)(avail / 12) : 0;  // start,end,row,comp: u16 x4 + parent u32 = 12 B
+    if (N < 16) {
+        if (tid == 0) {
+            r.status = TAIL_OVERFLOW;
+            *a.res = r;
+        }
+        return;
+    }
+    uint32_t *parent = reinterpret_cast<uint32_t *>(smem + used);
+    uint16_t *nstart = reinterpret_cast<uint16_t *>(parent + N);
+    uint16_t *nend = nstart + N;
+    uint16_t *nrow = nend + N;
+    uint16_t *ncomp = nrow + N;
+    for (size_t t = tid; t < RW; t += NT) {
+        const int y = (int)(t / Wd), j = jmin + (int)(t % Wd);
+        const uint32_t w = __ldcg(a.out + (size_t)(ymin + y) * g.wpr + j);
+        Ms[t] = w;
+    }
+    for (int c = tid; c < 3 * C; c += NT) acc[c] = 0ull;
+    __syncthreads();
+    r.cyc[2] = (uint32_t)clock64();
+    RegionView M{Ms, ymin, ymax, jmin, jmax, Wd};
+    RegionView G{Gs, ymin, ymax, jmin, jmax, Wd};
+
+    // ---- 1. runs per row (warp per row) ------------------------------------------------------
+    for (int y = ymin + warp; y <= ymax; y += nwarps) {
+        const int2 e = ext[y - ymin];
+        uint32_t cf = 0, cb = 0;
+        if (e.y >= 0) {
+            const bool inner = (y > 0) && (y < g.rows - 1);
+            for (int j = (e.x >> 5) + lane; j <= (e.y >> 5); j += 32) {
+                const uint32_t w = M.at(y, j), pw = M.at(y, j - 1);
+                cf += __popc(w & ~((w << 1) | (pw >> 31)));
+                if (inner) {
+                    const uint32_t c = fast_candw(M, g, y, j, e), pc = fast_candw(M, g, y, j - 1, e);
+                    cb += __popc(c & ~((c << 1) | (pc >> 31)));
+                }
+            }
+        }
+        cf = __reduce_add_sync(0xffffffffu, cf);
+        cb = __reduce_add_sync(0xffffffffu, cb);
+        if (lane == 0) {
+            offF[y - ymin] = cf;
+            offB[y - ymin] = cb;
+        }
+    }
+    __syncthreads();
+    r.cyc[3] = (uint32_t)clock64();
+    // ---- 2. exclusive scan over rows (one warp, chunked) ---------------------------------------
+    if (warp == 0) {
+        uint32_t baseF = 0, baseB = 0;
+        for (int y0 = 0; y0 < H; y0 += 32) {
+            const int y = y0 + lane;
+            const uint32_t vf = y < H ? offF[y] : 0u, vb = y < H ? offB[y] : 0u;
+            uint32_t sf = vf, sb = vb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tf = __shfl_up_sync(0xffffffffu, sf, d), tb = __shfl_up_sync(0xffffffffu, sb, d);
+                if (lane >= d) {
+                    sf += tf;
+                    sb += tb;
+                }
+            }
+            if (y < H) {
+                offF[y] = baseF + sf - vf;
+                offB[y] = baseB + sb - vb;
+            }
+            baseF += __shfl_sync(0xffffffffu, sf, 31);
+            baseB += __shfl_sync(0xffffffffu, sb, 31);
+        }
+        if (lane == 0) {
+            offF[H] = baseF;
+            offB[H] = baseB;
+            s_nF = baseF;
+            s_nB = baseB;
+        }
+    }
+    __syncthreads();
+    const uint32_t nF = s_nF, nB = s_nB;
+    r.nodes = nF + nB + 1;
+    if (nF + nB + 1 > (uint32_t)N) {
+        if (tid == 0) {
+            r.status = TAIL_OVERFLOW;
+            *a.res = r;
+        }
+        return;
+    }
+    // node ids: 0 = EXT, 1..nF foreground runs (raster order), nF+1..nF+nB candidate background runs
+    // ---- 3. fill the run table (warp per row) -------------------------------------------------
+    for (int y = ymin + warp; y <= ymax; y += nwarps) {
+        const int2 e = ext[y - ymin];
+        if (e.y < 0) continue;
+        const bool inner = (y > 0) && (y < g.rows - 1);
+        uint32_t bsF = 1 + offF[y - ymin], beF = bsF, bsB = 1 + nF + offB[y - ymin], beB = bsB;
+        for (int j0 = (e.x >> 5); j0 <= (e.y >> 5); j0 += 32) {
+            const int j = j0 + lane;
+            uint32_t sF = 0, eF = 0, sB = 0, eB = 0;
+            if (j <= (e.y >> 5)) {
+                const uint32_t w = M.at(y, j), pw = M.at(y, j - 1), nw = M.at(y, j + 1);
+                sF = w & ~((w << 1) | (pw >> 31));
+                eF = w & ~((w >> 1) | (nw << 31));
+                if (inner) {
+                    const uint32_t c = fast_candw(M, g, y, j, e), pc = fast_candw(M, g, y, j - 1, e),
+                                   nc = fast_candw(M, g, y, j + 1, e);
+                    sB = c & ~((c << 1) | (pc >> 31));
+                    eB = c & ~((c >> 1) | (nc << 31));
+                }
+            }
+            // exclusive warp scans of the four counts (packed 2 x 16 bit: a word holds <= 16 runs)
+            const uint32_t cnt1 = (uint32_t)__popc(sF) | ((uint32_t)__popc(eF) << 16);
+            const uint32_t cnt2 = (uint32_t)__popc(sB) | ((uint32_t)__popc(eB) << 16);
+            uint32_t x1 = cnt1, x2 = cnt2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t1 = __shfl_up_sync(0xffffffffu, x1, d), t2 = __shfl_up_sync(0xffffffffu, x2, d);
+                if (lane >= d) {
+                    x1 += t1;
+                    x2 += t2;
+                }
+            }
+            const uint32_t tot1 = __shfl_sync(0xffffffffu, x1, 31), tot2 = __shfl_sync(0xffffffffu, x2, 31);
+            x1 -= cnt1;
+            x2 -= cnt2;
+            uint32_t k;
+            k = bsF + (x1 & 0xffffu);
+            for (uint32_t m = sF; m; m &= m - 1, ++k) {
+                nstart[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+                nrow[k] = (uint16_t)y;
+                parent[k] = k;
+            }
+            k = beF + (x1 >> 16);
+            for (uint32_t m = eF; m; m &= m - 1, ++k) nend[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+            k = bsB + (x2 & 0xffffu);
+            for (uint32_t m = sB; m; m &= m - 1, ++k) {
+                nstart[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+                nrow[k] = (uint16_t)y;
+                parent[k] = k;
+            }
+            k = beB + (x2 >> 16);
+            for (uint32_t m = eB; m; m &= m - 1, ++k) nend[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+            bsF += tot1 & 0xffffu;
+            beF += tot1 >> 16;
+            bsB += tot2 & 0xffffu;
+            beB += tot2 >> 16;
+        }
+    }
+    if (tid == 0) parent[0] = 0;
+    __syncthreads();
+    volatile uint32_t *P = parent;
+    r.cyc[4] = (uint32_t)clock64();
+    // ---- 4. vertical merges (thread per run) --------------------------------------------------
+    for (uint32_t id = 1 + tid; id <= nF + nB; id += NT) {
+        const int y = nrow[id], s = nstart[id], e = nend[id];
+        const bool fg = id <= nF;
+        if (fg) {
+            if (y > ymin) {
+                const uint32_t lo0 = 1 + offF[y - 1 - ymin], hi0 = 1 + offF[y - ymin];
+                uint32_t lo = lo0, hi = hi0;  // first run of the previous row with end >= s - 1
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if ((int)nend[mid] < s - 1) lo = mid + 1; else hi = mid;
+                }
+                for (uint32_t k = lo; k < hi0 && (int)nstart[k] <= e + 1; ++k) suf_union(P, id, k);
+            }
+        } else {
+            // 4-connected to candidate background of the previous row
+            if (y > ymin) {
+                const uint32_t lo0 = 1 + nF + offB[y - 1 - ymin], hi0 = 1 + nF + offB[y - ymin];
+                uint32_t lo = lo0, hi = hi0;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if ((int)nend[mid] < s) lo = mid + 1; else hi = mid;
+                }
+                for (uint32_t k = lo; k < hi0 && (int)nstart[k] <= e; ++k) suf_union(P, id, k);
+            }
+            // exterior if it touches row-exterior background above or below: in rows 0 and
+            // rows-1 every background pixel is exterior; elsewhere the background outside the
+            // row's foreground extent is.
+            bool isext = false;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy += 2) {
+                const int yy = y + dy;  // candidate rows are inner rows, so 0 <= yy <= rows-1
+                if (yy == 0 || yy == g.rows - 1) {
+                    isext |= fast_any_bg(M, g, yy, s, e);
+                } else if (yy < ymin || yy > ymax) {
+                    isext = true;
+                } else {
+                    const int2 ee = ext[yy - ymin];
+                    isext |= (ee.y < 0) || (s < ee.x) || (e > ee.y);
+                }
+            }
+            if (isext) suf_union(P, id, 0u);
+        }
+    }
+    __syncthreads();
+    r.cyc[5] = (uint32_t)clock64();
+    // ---- 5. holes join the foreground beside them; G = foreground + holes -----------------------
+    for (uint32_t id = 1 + nF + tid; id <= nF + nB; id += NT) {
+        if (suf_find(P, id) == 0u) continue;  // exterior
+        const int y = nrow[id], s = nstart[id], e = nend[id];
+        // a candidate run lies strictly inside the row's foreground extent: runs end at s-1 and start at e+1
+        const uint32_t lo0 = 1 + offF[y - ymin], hi0 = 1 + offF[y - ymin + 1];
+        uint32_t lo = lo0, hi = hi0;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((int)nend[mid] < s - 1) lo = mid + 1; else hi = mid;
+        }
+        suf_union(P, id, lo);  // nend[lo] == s - 1
+        if (lo + 1 < hi0) suf_union(P, id, lo + 1);  // nstart[lo + 1] == e + 1
+        for (int j = s >> 5; j <= (e >> 5); ++j) atomicOr(Gs + (size_t)(y - ymin) * Wd + (j - jmin), range_mask(j, s, e));
+    }
+    __syncthreads();
+    r.cyc[6] = (uint32_t)clock64();
+    // ---- 6. contours = roots among the foreground runs: give them compact accumulator slots ----
+    for (uint32_t id = 1 + tid; id <= nF; id += NT) {
+        if (P[id] == id) {
+            const uint32_t c = atomicAdd(&s_ncomp, 1u);
+            ncomp[id] = (uint16_t)c;
+            if (c >= (uint32_t)C) s_fail = 1u;
+        }
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (tid == 0) {
+            r.status = TAIL_OVERFLOW;
+            *a.res = r;
+        }
+        return;
+    }
+    // ---- 7. exact 2x2-cell moments per run (cells are owned by their top row) ------------------
+    for (uint32_t id = 1 + tid; id <= nF + nB; id += NT) {
+        const uint32_t root = suf_find(P, id);
+        if (root == 0u) continue;  // exterior background owns nothing
+        const int y = nrow[id], s = nstart[id], e = nend[id];
+        if (y >= g.rows - 1) continue;
+        unsigned long long t00 = 0, t10 = 0, t01 = 0;
+        for (int j = s >> 5; j <= (e >> 5); ++j) {
+            const uint32_t T = G.at(y, j), Bw = G.at(y + 1, j);
+            const uint64_t T64 = (uint64_t)(G.at(y, j - 1) >> 31) | ((uint64_t)T << 1) | ((uint64_t)(G.at(y, j + 1) & 1u) << 33);
+            const uint64_t B64 = (uint64_t)(G.at(y + 1, j - 1) >> 31) | ((uint64_t)Bw << 1) |
+                                 ((uint64_t)(G.at(y + 1, j + 1) & 1u) << 33);
+            const uint64_t tl = T64, tr = T64 >> 1, bl = B64, br = B64 >> 1;
+            const uint32_t sm = range_mask(j, s, e);
+            const uint32_t F = (uint32_t)((tl & tr & bl & br) >> 1) & sm;
+            const uint32_t ma = (uint32_t)((tl & ~tr & bl & br) >> 1) & sm;
+            const uint32_t mb = (uint32_t)((tl & tr & ~bl & br) >> 1) & sm;
+            const uint32_t mc = (uint32_t)((tl & tr & bl & ~br) >> 1) & sm;
+            const uint32_t md = (uint32_t)(~tl & tr & bl & br) & sm;  // owner = top-right pixel, cell x = owner - 1
+            if (!(F | ma | mb | mc | md)) continue;
+            const uint32_t xb = 32u * (uint32_t)j;
+            const uint32_t nFc = __popc(F), na = __popc(ma), nb = __popc(mb), nc = __popc(mc), nd = __popc(md);
+            t00 += 2u * nFc + na + nb + nc + nd;
+            t10 += (unsigned long long)(6u * (sum_pos(F) + nFc * xb) + 3u * nFc + 3u * (sum_pos(ma) + na * xb) + na +
+                                        3u * (sum_pos(mb) + nb * xb) + 2u * nb + 3u * (sum_pos(mc) + nc * xb) + nc +
+                                        3u * (sum_pos(md) + nd * xb) - nd);
+            const uint32_t yy = (uint32_t)y;
+            t01 += (unsigned long long)(nFc * (6u * yy + 3u) + (na + nd) * (3u * yy + 2u) + (nb + nc) * (3u * yy + 1u));
+        }
+        if (t00 | t10 | t01) {
+            const uint32_t c = ncomp[root];
+            atomicAdd(acc + c, t00);
+            atomicAdd(acc + C + c, t10);
+            atomicAdd(acc + 2 * C + c, t01);
+        }
+    }
+    __syncthreads();
+    // ---- 8. select: largest area in [min, max); ties go to the raster-last contour ---------------
+    for (uint32_t id = 1 + tid; id <= nF; id += NT) {
+        if (P[id] != id) continue;
+        const unsigned long long s00 = acc[ncomp[id]];
+        const double area = 0.5 * (double)s00;
+        if (area >= a.min_area && area < a.max_area && s00 > 0ull) atomicMax(&s_best, (s00 << 32) | (unsigned long long)id);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        r.det.n_components = (int32_t)s_ncomp;
+        r.cyc[7] = (uint32_t)clock64();
+        if (s_best) {
+            const uint32_t id = (uint32_t)(s_best & 0xffffffffull);
+            const uint32_t c = ncomp[id];
+            const double m00 = (double)acc[c] * 0.5;
+            const double m10 = (double)acc[C + c] * 0.16666666666666666666666666666667;
+            const double m01 = (double)acc[2 * C + c] * 0.16666666666666666666666666666667;
+            r.det.position_valid = 1;
+            r.det.x = m10 / m00;
+            r.det.y = m01 / m00;
+            r.det.area = m00;
+        }
+        *a.res = r;
+    }
+}
+
+// One launch: [erode] -> [dilate] -> row extents on bands of R rows (all CTAs), then the last CTA
+// labels.  Dynamic shared memory: max(morphology staging, a.smem_bytes).
+__global__ void __launch_bounds__(256) tail_fast_kernel(const FastArgs a)
+{
+    extern __shared__ __align__(16) uint32_t sm[];
+    const uint32_t t_start = (uint32_t)clock64();
+    const BitGeom g = a.g;
+    const int wpr = g.wpr, rows = g.rows;
+    const int y0 = blockIdx.x * a.R, y1 = min(y0 + a.R, rows) - 1;
+    const int ae = a.ke / 2, ad = a.kd / 2;
+    const int e0 = max(a.kd > 0 ? y0 - ad : y0, 0), e1 = min(a.kd > 0 ? y1 - ad + a.kd - 1 : y1, rows - 1);
+    const int i0 = max(a.ke > 0 ? e0 - ae : e0, 0), i1 = min(a.ke > 0 ? e1 - ae + a.ke - 1 : e1, rows - 1);
+    const int nin = i1 - i0 + 1;
+    uint32_t *A = sm, *B = sm + (size_t)nin * wpr;
+    for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) {
+        const int r = t / wpr, j = t % wpr;
+        A[t] = a.in[(size_t)(i0 + r) * wpr + j] & g.valid_mask(j);
+    }
+    __syncthreads();
+    if (a.ke > 0) {
+        for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) B[t] = hpass_word<false>(A + (t / wpr) * wpr, t % wpr, g, a.ke);
+        __syncthreads();
+        const int ne = e1 - e0 + 1;
+        for (int t = threadIdx.x; t < ne * wpr; t += blockDim.x) {
+            const int y = e0 + t / wpr, j = t % wpr;
+            const int v0 = max(y - ae, 0), v1 = min(y - ae + a.ke - 1, rows - 1);
+            uint32_t accw = 0xffffffffu;
+            for (int yy = v0; yy <= v1; ++yy) accw &= B[(yy - i0) * wpr + j];
+            A[(y - i0) * wpr + j] = accw & g.valid_mask(j);
+        }
+        __syncthreads();
+    }
+    if (a.kd > 0) {
+        const int ne = e1 - e0 + 1;
+        for (int t = threadIdx.x; t < ne * wpr; t += blockDim.x) {
+            const int r = e0 - i0 + t / wpr;
+            B[r * wpr + t % wpr] = hpass_word<true>(A + r * wpr, t % wpr, g, a.kd);
+        }
+        __syncthreads();
+        const int no = y1 - y0 + 1;
+        for (int t = threadIdx.x; t < no * wpr; t += blockDim.x) {
+            const int y = y0 + t / wpr, j = t % wpr;
+            const int v0 = max(y - ad, 0), v1 = min(y - ad + a.kd - 1, rows - 1);
+            uint32_t accw = 0u;
+            for (int yy = v0; yy <= v1; ++yy) accw |= B[(yy - i0) * wpr + j];
+            A[(y - i0) * wpr + j] = accw;
+        }
+        __syncthreads();
+    }
+    // publish rows: mask, hole-fill seed, extents, vertical bounding range
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int bymin = INT_MAX, bymax = -1;
+    for (int y = y0 + warp; y <= y1; y += nwarps) {
+        const uint32_t *row = A + (size_t)(y - i0) * wpr;
+        int xmin = INT_MAX, xmax = -1;
+        for (int j = lane; j < wpr; j += 32) {
+            const uint32_t w = row[j];
+            a.out[(size_t)y * wpr + j] = w;
+            if (w) {
+                xmin = min(xmin, 32 * j + __ffs(w) - 1);
+                xmax = max(xmax, 32 * j + 31 - __clz(w));
+            }
+        }
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        if (lane == 0) a.rowext[y] = make_int2(xmin, xmax);
+        if (xmax >= 0) {
+            bymin = min(bymin, y);
+            bymax = max(bymax, y);
+        }
+    }
+    if (lane == 0 && bymax >= 0) {
+        atomicMin(a.bbox, bymin);
+        atomicMax(a.bbox + 1, bymax);
+    }
+    __shared__ bool s_last;
+    __shared__ int s_ymin, s_ymax;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        if (s_last) {
+            __threadfence();
+            s_ymin = atomicExch(a.bbox, INT_MAX);   // read + reset for the next launch
+            s_ymax = atomicExch(a.bbox + 1, -1);
+            *a.ticket = 0u;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    tail_label_phase(a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start);
+}
+
+}  // namespace oat

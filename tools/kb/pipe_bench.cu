@@ -47,35 +47,45 @@ int main(int argc, char **argv)
     auto kern = mog_pipe_kernel<5, false, true>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int mode = 0; mode < 2; ++mode) {  // 0: L2 flushed before every launch, 1: back to back
-        double tot = 0, best = 1e9;
+    std::vector<cudaEvent_t> E0(iters + 5), E1(iters + 5);
+    for (auto &e : E0) cudaEventCreate(&e);
+    for (auto &e : E1) cudaEventCreate(&e);
+    CK(cudaFuncSetAttribute(nullk, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+    if (getenv("CARVE")) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(flushk, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(nullk, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    for (int which = 0; which < 2; ++which)
+    for (int mode = 0; mode < 2; ++mode) {  // 0: L2 flushed before every launch, 1: back to back; all queued, one sync
         for (int it = 0; it < iters + 5; ++it) {
             a.bgr = bgr[1 + it % 8];
             if (mode == 0) flushk<<<1184, 256>>>(fl, fbytes / 16, it);
-            cudaEventRecord(e0);
-            kern<<<grid, PIPE_THREADS, PIPE_SMEM_BYTES>>>(pa);
-            cudaEventRecord(e1);
-            CK(cudaEventSynchronize(e1));
-            float ms; cudaEventElapsedTime(&ms, e0, e1);
-            if (it >= 5) { tot += ms; if (ms < best) best = ms; }
+            cudaEventRecord(E0[it]);
+            if (which == 0) kern<<<grid, PIPE_THREADS, PIPE_SMEM_BYTES>>>(pa); else nullk<<<grid, PIPE_THREADS, PIPE_SMEM_BYTES>>>(pa);
+            cudaEventRecord(E1[it]);
         }
+        CK(cudaDeviceSynchronize());
+        double tot = 0, best = 1e9;
+        for (int it = 5; it < iters + 5; ++it) { float ms; cudaEventElapsedTime(&ms, E0[it], E1[it]); tot += ms; if (ms < best) best = ms; }
         double us = 1e3 * tot / iters;
-        printf("%dx%d stages=%d tile=%d smem=%d cps=%d grid=%d %s: mean %.2f us best %.2f us -> %.0f GB/s (45 B/px)\n", cols, rows, PIPE_STAGES, PIPE_TILE,
-               PIPE_SMEM_BYTES, cps, grid, mode == 0 ? "flushed" : "hot", us, best * 1e3, 45.0 * plane / us / 1e3);
+        printf("%s %dx%d stages=%d cps=%d grid=%d %s (queued): mean %.2f us best %.2f us -> %.0f GB/s (45 B/px)\n", which ? "NULL " : "PIPE ", cols, rows, PIPE_STAGES, cps, grid,
+               mode == 0 ? "flushed" : "hot", us, best * 1e3, 45.0 * plane / us / 1e3);
     }
-    CK(cudaFuncSetAttribute(nullk, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
-    for (int mode = 0; mode < 2; ++mode) {
-        double tot = 0;
-        for (int it = 0; it < iters + 5; ++it) {
-            if (mode == 0) flushk<<<1184, 256>>>(fl, fbytes / 16, it);
+    {   // S states round-robin, back to back, ONE event pair: true HBM-fed steady state incl. launch gaps
+        const int S = 8;
+        std::vector<float *> st(S); std::vector<uint8_t *> nms(S);
+        for (int i = 0; i < S; ++i) { CK(cudaMalloc(&st[i], plane * 5 * 4)); CK(cudaMalloc(&nms[i], plane)); init_state<<<(plane + 255) / 256, 256>>>(st[i], plane, nms[i], bgr[0]); }
+        CK(cudaDeviceSynchronize());
+        for (int rep = 0; rep < 2; ++rep) {
+            const int n = 10 * S;
             cudaEventRecord(e0);
-            nullk<<<grid, PIPE_THREADS, PIPE_SMEM_BYTES>>>(pa);
+            for (int it = 0; it < n; ++it) { PipeArgs q = pa; q.f.state = st[it % S]; q.f.nmodes = nms[it % S]; q.f.bgr = bgr[1 + it % 8]; kern<<<grid, PIPE_THREADS, PIPE_SMEM_BYTES>>>(q); }
             cudaEventRecord(e1);
             CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1);
-            if (it >= 5) tot += ms;
+            printf("BACK2BACK %d states x %d launches, one event pair: %.2f us per launch -> %.0f GB/s (45 B/px)\n", S, n, 1e3 * ms / n, 45.0 * plane / (1e3 * ms / n) / 1e3);
         }
-        printf("null kernel, same launch config, %s: mean %.2f us\n", mode == 0 ? "after flush" : "back to back", 1e3 * tot / iters);
     }
     CK(cudaDeviceSynchronize());
     return 0;

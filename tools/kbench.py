@@ -16,6 +16,7 @@ ap.add_argument("--alpha", type=float, default=0.01)
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--noflush", action="store_true")
 ap.add_argument("--tag", default="")
+ap.add_argument("--static", action="store_true", help="blob-free frames only (every pixel takes the fast path)")
 args = ap.parse_args()
 rows, cols = {"1080p": (1080, 1920), "4k": (2160, 3840), "480p": (480, 640)}[args.res]
 ctx = oat_b200.Context(0)
@@ -24,7 +25,7 @@ hp = oat_b200.HsvParams.make(h=(40, 80), s=(100, 256), v=(100, 256))
 R = 32
 frames = [ctx.alloc(rows * cols * 3) for _ in range(R + 1)]
 for t, b in enumerate(frames):
-    ctx.synth_frame(rows, cols, 1000, t, out=b)
+    ctx.synth_frame(rows, cols, 1000, 0 if args.static else t, out=b)
 trk = oat_b200.Tracker(ctx, rows, cols, args.alpha, hp)
 trk.track(frames[0])
 for i in range(30):
@@ -40,6 +41,10 @@ for i in range(args.steps):
     trk.collect()
 ctx.sync()
 tot = sorted(a.elapsed_time(b) for a, b in ev)
+ts = trk.tail_stats()
+c = ts["cyc"]
+print("tail:", {k: ts[k] for k in ("status", "nodes", "replays", "fast")}, "label-CTA cycles since start:",
+      [(c[i] - c[0]) & 0xffffffff for i in range(1, 8)])
 kms, n = trk.profile_read()
 mbar = trk.live_modes() / (rows * cols)
 balg = 8 + 40 * mbar
