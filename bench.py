@@ -304,11 +304,11 @@ def run_b200(args):
     trk.close()
 
     # ---- roofline of the fused kernel: average launch duration over back-to-back launches ------------
-    # S independent streams of the same workload, one tracker each, submitted round-robin: the compute
-    # stream then carries S fused-kernel launches back to back (their detect tails run on the tail
-    # streams), bracketed by ONE CUDA-event pair per batch, so the ~5 us cost of an event bracket is
-    # shared by S launches; the S states (S * ~45 MB live) exceed L2, so every launch streams its
-    # planes from HBM without an explicit flush.
+    # S independent streams of the same workload, one tracker each.  A batch = the fused kernel of the
+    # next frame of every stream, launched back to back on the compute stream (fused kernel ONLY, via
+    # the diagnostic entry point, so nothing else runs on the GPU) between ONE CUDA-event pair: the
+    # ~5 us cost of an event bracket is shared by S launches, and the S states (S * ~45 MB live)
+    # exceed L2, so every launch streams its planes from HBM without an explicit flush.
     S = 8
     trks = [oat_b200.Tracker(ctx, rows, cols, args.alpha, hp, ring_depth=2) for _ in range(S)]
     for t_ in trks:
@@ -327,11 +327,9 @@ def run_b200(args):
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_.record(stream)
         for t_ in trks:
-            t_.submit(dev_frames[(W + i) % R])
+            t_.submit_fused_only(dev_frames[(W + i) % R])
         b_.record(stream)
         evs.append((a_, b_))
-        for t_ in trks:
-            t_.collect()
     barrier()
     m1 = sum(t_.live_modes() for t_ in trks) / (S * npx)
     kern_ms = sum(x.elapsed_time(y) for x, y in evs) / (NB * S)
@@ -424,8 +422,9 @@ def run_b200(args):
                 "algorithmic_bytes_per_px": b_alg,
                 "kernel_ms": kern_ms,
                 "kernel_launches_timed": kern_n,
-                "how": f"average over {kern_n} launches: {S} independent streams submitted round-robin, one CUDA-event pair on the "
-                       f"launching stream per batch of {S} back-to-back launches; {S} states ({S * 45 * npx / 1e6:.0f} MB live) > L2, no flush",
+                "how": f"average over {kern_n} launches: batches of {S} back-to-back launches (one per independent stream, fused "
+                       f"kernel only) between one CUDA-event pair on the launching stream; {S} states ({S * 45 * npx / 1e6:.0f} MB live) > L2, "
+                       "no flush",
                 "mean_live_modes": mbar_roof,
                 "single_launch_event_bracket_ms": single_ms,
                 "traffic": load_traffic(args.workload, args.alpha),

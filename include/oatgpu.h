@@ -211,6 +211,11 @@ int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, fl
 int oat_tracker_profile(oat_tracker *t, int enable);
 int oat_tracker_profile_read(oat_tracker *t, double *mean_mog_kernel_ms, uint64_t *launches);
 
+/* Diagnostic: enqueue only the fused MOG+HSV+threshold kernel for the next frame (device-resident
+ * frame; the model advances exactly as in oat_tracker_submit, no detection is produced, nothing
+ * to collect). For timing back-to-back launches of the dominant kernel in isolation. */
+int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch,
+                                  double learning_rate, const oat_hsv_params *p);
 /* Diagnostic: the detect tail of the most recently collected frame. out[12] = { status (0 = the
  * one-launch tail sufficed, 1 = replayed through the unbounded path), run-table entries needed,
  * replays so far, one-launch tail used, 8 SM-clock stamps of its labelling CTA }. */

@@ -130,6 +130,7 @@ _SIGS = {
     "oat_tracker_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oat_tracker_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "oat_tracker_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "oat_tracker_submit_fused_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams)]),
     "oat_tracker_tail_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "oat_synth_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),
     "oat_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -504,6 +505,11 @@ class Tracker:
         lr = self.learning_coeff if learning_rate is None else learning_rate
         _ck(lib().oat_tracker_submit(self._h, _ptr(bgr), self.cols * 3, lr, C.byref(self.hsv), _ptr(bgr_out),
                                      self.cols * 3))
+
+    def submit_fused_only(self, bgr, learning_rate=None):
+        """Diagnostic: only the fused kernel of the next frame (see oat_tracker_submit_fused_only)."""
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        _ck(lib().oat_tracker_submit_fused_only(self._h, _ptr(bgr), self.cols * 3, lr, C.byref(self.hsv)))
 
     def collect(self) -> Detection:
         d = Detection()

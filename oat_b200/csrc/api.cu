@@ -1170,6 +1170,33 @@ static int tracker_check(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch,
     return OAT_OK;
 }
 
+// Diagnostic: enqueue ONLY the fused MOG+HSV+threshold kernel of the next frame (the GMM state advances
+// exactly as in oat_tracker_submit; the detect tail is not run and there is nothing to collect).
+// Lets a harness time back-to-back launches of the dominant kernel in isolation.
+extern "C" int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch,
+                                             double learning_rate, const oat_hsv_params *p)
+{
+    CKRET(tracker_check(t, bgr_in, in_pitch, p));
+    CKRET(bind(t->ctx));
+    REQUIRE(t->head == t->tailpos, "oat_tracker_submit_fused_only: frames are still outstanding (collect first)");
+    REQUIRE(mem_kind(bgr_in) == MEM_DEVICE, "oat_tracker_submit_fused_only: device-resident frames only");
+    oat_ctx *c = t->ctx;
+    Slot &s = t->ring[t->head % t->ring.size()];
+    FusedArgs a{};
+    a.bgr = bgr_in;
+    a.in_pitch = in_pitch;
+    t->m.frame_consts(learning_rate, &a.c, &a.reset);
+    a.do_hsv = 1;
+    a.lo[0] = p->h_min;
+    a.lo[1] = p->s_min;
+    a.lo[2] = p->v_min;
+    a.hi[0] = p->h_max;
+    a.hi[1] = p->s_max;
+    a.hi[2] = p->v_max;
+    a.thr_bits = s.bits;
+    return launch_fused(c, t->m, a);
+}
+
 extern "C" int oat_tracker_collect(oat_tracker *t, oat_detection *out)
 {
     REQUIRE(t && out, "oat_tracker_collect: null argument");

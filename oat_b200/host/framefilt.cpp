@@ -1,0 +1,273 @@
+// oat-framefilt -- `oat framefilt TYPE SOURCE SINK [CONFIGURATION]` for the hot-path TYPEs, computing
+// on the B200 through the C ABI.  Mirrors src/framefilter/{main.cpp, FrameFilter.{h,cpp},
+// BackgroundSubtractorMOG.{h,cpp}, ColorConvert.{h,cpp}, BackgroundSubtractor.{h,cpp}}.
+//
+//   mog    cv::BackgroundSubtractorMOG2::apply + frame.setTo(0, mask == 0)   (...MOG.cpp:114-127)
+//   col    cv::cvtColor, BGR -> HSV                                           (ColorConvert.cpp:101-107)
+//   bsub   frame - background, saturating                                     (BackgroundSubtractor.cpp:87-100)
+//
+// Both shared-memory mappings (the SOURCE's frame and this SINK's frame) are page-locked once, so the
+// per-frame copies are asynchronous DMA straight from / into shared memory (HOST_PINNED variant);
+// the SOURCE is released as soon as its pixels are on the device, as in FrameFilter::process().
+#include <iostream>
+#include <memory>
+
+#include "gpu.h"
+#include "oat_cli.h"
+#include "oat_host.h"
+
+namespace oat {
+
+class FrameFilter : public Component {
+public:
+    FrameFilter(const std::string &source, const std::string &sink) : frame_source_address_(source), frame_sink_address_(sink) {}
+    std::string name() const override { return name_; }
+    virtual std::vector<config::OptionSpec> options() const = 0;
+    virtual void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) = 0;
+
+protected:
+    // FrameFilter::connectToNode (FrameFilter.cpp:37-57); sink_color lets `col` re-tag its output
+    bool connectToNode() override
+    {
+        frame_source_.touch(frame_source_address_);
+        if (frame_source_.connect() != SourceState::CONNECTED) return false;
+        in_ = frame_source_.parameters();
+        const PixelColor out_color = outputColor(in_.color);
+        const size_t out_bytes = in_.rows * in_.cols * (size_t)color_bytes(out_color);
+        frame_sink_.bind(frame_sink_address_, out_bytes);
+        shared_frame_ = frame_sink_.retrieve(in_.rows, in_.cols, color_bytes(out_color), out_color);
+        // HOST_PINNED: page-lock both mappings, stage buffers on the device
+        ctx_.reset(new gpu::Context(gpu_index_));
+        src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
+        dst_pin_.reset(new gpu::HostRegistration(frame_sink_.pixels(), out_bytes));
+        frame_sink_.set_memory(FrameMemory::HOST_PINNED, gpu_index_);
+        d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
+        d_out_.reset(new gpu::DeviceBuffer(*ctx_, out_bytes));
+        out_bytes_ = out_bytes;
+        setup();
+        return true;
+    }
+    // FrameFilter::process (FrameFilter.cpp:59-98), with the heap copies replaced by DMA
+    int process() override
+    {
+        if (frame_source_.wait() == NodeState::END) return 1;
+        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, frame_source_.pixels(), in_.bytes));
+        const Sample sample = frame_source_.retrieve()->sample();
+        frame_source_.post();
+
+        filter(d_in_->u8(), d_out_->u8());
+
+        frame_sink_.wait();
+        gpu::ck(oat_memcpy(ctx_->h, frame_sink_.pixels(), d_out_->p, out_bytes_));
+        shared_frame_.sample() = sample;  // filters never advance time
+        frame_sink_.post();
+        return 0;
+    }
+    virtual PixelColor outputColor(PixelColor in) const { return in; }
+    virtual void setup() {}
+    // device in -> device out
+    virtual void filter(const uint8_t *d_in, uint8_t *d_out) = 0;
+
+    std::string name_;
+    std::string frame_source_address_, frame_sink_address_;
+    Source<Frame> frame_source_;
+    Sink<Frame> frame_sink_;
+    Frame shared_frame_;
+    FrameParams in_;
+    size_t out_bytes_{0};
+    int gpu_index_{0};
+    std::unique_ptr<gpu::Context> ctx_;
+    std::unique_ptr<gpu::HostRegistration> src_pin_, dst_pin_;
+    std::unique_ptr<gpu::DeviceBuffer> d_in_, d_out_;
+};
+
+// ---- framefilt mog (BackgroundSubtractorMOG.{h,cpp}) -----------------------------------------------------
+class BackgroundSubtractorMOG : public FrameFilter {
+public:
+    BackgroundSubtractorMOG(const std::string &source, const std::string &sink) : FrameFilter(source, sink)
+    {
+        name_ = "mogfilt[" + source + "->" + sink + "]";
+    }
+    ~BackgroundSubtractorMOG() { oat_mog_destroy(mog_); }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"adaptation-coeff", 'a', true,
+                 "Value, 0 to 1.0, specifying how quickly the statistical model of the background image should be updated. Default is 0, specifying no adaptation."},
+                {"gpu-index", 0, true, "Index of the GPU to use for performing background subtraction."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        // ...MOG.cpp:87-88: range-checked [0, 1], default 0.0 (frozen model after the first frame)
+        config::getNumericValue<double>(vm, t, "adaptation-coeff", learning_coeff_, 0.0, 1.0);
+        // ...MOG.cpp:92-111: "Selected GPU index is invalid." comes back from oat_ctx_create
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override
+    {
+        if (in_.color != PIX_BGR) throw std::runtime_error("framefilt mog requires a BGR frame source.");
+        gpu::ck(oat_mog_create(ctx_->h, (int)in_.rows, (int)in_.cols, nullptr /* MOG2 defaults, ...MOG.cpp:83 */, &mog_));
+    }
+    void filter(const uint8_t *d_in, uint8_t *d_out) override
+    {
+        const size_t pitch = in_.cols * 3;
+        gpu::ck(oat_mog_apply(mog_, d_in, pitch, d_out, pitch, nullptr, 0, learning_coeff_));
+    }
+
+private:
+    double learning_coeff_{0.0};
+    oat_mog *mog_{nullptr};
+};
+
+// ---- framefilt col (ColorConvert.{h,cpp}) -----------------------------------------------------------------
+class ColorConvert : public FrameFilter {
+public:
+    ColorConvert(const std::string &source, const std::string &sink) : FrameFilter(source, sink)
+    {
+        name_ = "colorconvert[" + source + "->" + sink + "]";
+    }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"color", 'C', true, "Pixel color of the output frames. Values: GREY, BGR, HSV (only BGR -> HSV runs on the GPU path)."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        std::string c;
+        if (!config::getString(vm, t, "color", c)) throw std::runtime_error("A pixel color must be specified (-C).");
+        color_ = str_color(c);
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    PixelColor outputColor(PixelColor in) const override
+    {
+        // ColorConvert.cpp:78-86: a no-op conversion is an error
+        if (in == color_) throw std::runtime_error("Color conversion is not required: the source is already " + color_str(in) + ".");
+        if (!(in == PIX_BGR && color_ == PIX_HSV))
+            throw std::runtime_error("Only the BGR -> HSV conversion of the tracking path is implemented on the GPU.");
+        return color_;
+    }
+    void filter(const uint8_t *d_in, uint8_t *d_out) override
+    {
+        const size_t pitch = in_.cols * 3;
+        gpu::ck(oat_bgr2hsv(ctx_->h, d_in, pitch, d_out, pitch, (int)in_.rows, (int)in_.cols));
+    }
+
+private:
+    PixelColor color_{PIX_HSV};
+};
+
+// ---- framefilt bsub (BackgroundSubtractor.{h,cpp}) -----------------------------------------------------------
+class BackgroundSubtractor : public FrameFilter {
+public:
+    BackgroundSubtractor(const std::string &source, const std::string &sink) : FrameFilter(source, sink)
+    {
+        name_ = "bsub[" + source + "->" + sink + "]";
+    }
+    ~BackgroundSubtractor() { oat_bsub_destroy(bsub_); }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"adaptation-coeff", 'a', true, "Scalar value, 0 to 1.0, specifying how quickly the new frames are used to update the background image. Default is 0."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        config::getNumericValue<double>(vm, t, "adaptation-coeff", alpha_, 0.0, 1.0);
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override
+    {
+        gpu::ck(oat_bsub_create(ctx_->h, (int)in_.rows, (int)in_.cols, color_bytes(in_.color), alpha_, &bsub_));
+    }
+    void filter(const uint8_t *d_in, uint8_t *d_out) override
+    {
+        const size_t pitch = in_.cols * (size_t)color_bytes(in_.color);
+        gpu::ck(oat_bsub_apply(bsub_, d_in, pitch, d_out, pitch));
+    }
+
+private:
+    double alpha_{0.0};
+    oat_bsub *bsub_{nullptr};
+};
+
+}  // namespace oat
+
+static void printUsage(std::ostream &out)
+{
+    out << "Usage: framefilt [INFO]\n"
+           "   or: framefilt TYPE SOURCE SINK [CONFIGURATION]\n"
+           "Filter frames from SOURCE and published filtered frames to SINK.\n\n"
+           "TYPE\n"
+           "  bsub: Background subtraction\n"
+           "  col: Color conversion (BGR to HSV)\n"
+           "  mog: Mixture of Gaussians background segmentation\n\n"
+           "SOURCE:\n  User-supplied name of the memory segment to receive frames from (e.g. raw).\n\n"
+           "SINK:\n  User-supplied name of the memory segment to publish frames to (e.g. filt).\n\n"
+           "INFO:\n  --help                 Produce help message.\n  -v [ --version ]       Print version information.\n\n"
+           "CONFIGURATION:\n  -c [ --config ] FILE KEY   Configuration file/key pair.\n";
+}
+
+int main(int argc, char *argv[])
+{
+    using namespace oat;
+    std::string comp_name = "framefilt";
+    try {
+        for (int i = 1; i < argc; ++i) {
+            const std::string a = argv[i];
+            if (a == "--help" && argc == 2) { printUsage(std::cout); return 0; }
+            if (a == "-v" || a == "--version") { std::cout << "Oat Frame Filter (B200) version 0.1\n"; return 0; }
+        }
+        if (argc < 2) { printUsage(std::cout); return 0; }
+        const std::string type = argv[1];
+        // first pass: positional only, everything else left for the TYPE's own options (main.cpp:117-156)
+        std::vector<std::string> pos;
+        for (int i = 2; i < argc && pos.size() < 2; ++i) {
+            if (argv[i][0] == '-') break;
+            pos.push_back(argv[i]);
+        }
+        if (type != "mog" && type != "col" && type != "bsub") {
+            printUsage(std::cout);
+            std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
+            return -1;
+        }
+        if (pos.size() < 1) { printUsage(std::cout); std::cerr << whoError(comp_name, "Error: a SOURCE must be specified.\n"); return -1; }
+        if (pos.size() < 2) { printUsage(std::cout); std::cerr << whoError(comp_name, "Error: a SINK must be specified.\n"); return -1; }
+        std::shared_ptr<FrameFilter> filter;
+        if (type == "mog") filter = std::make_shared<BackgroundSubtractorMOG>(pos[0], pos[1]);
+        else if (type == "col") filter = std::make_shared<ColorConvert>(pos[0], pos[1]);
+        else filter = std::make_shared<BackgroundSubtractor>(pos[0], pos[1]);
+        comp_name = filter->name();
+
+        auto opts = filter->options();
+        opts.push_back({"config", 'c', true, "Configuration file/key pair."});
+        opts.push_back({"help", 0, false, ""});
+        const config::VariableMap vm = config::parse(argc, argv, 4, opts);
+        if (vm.count("help")) {
+            printUsage(std::cout);
+            for (const auto &o : filter->options()) std::cout << "  --" << o.long_name << "  " << o.help << "\n";
+            return 0;
+        }
+        config::OptionTable table;
+        if (vm.count("config")) {
+            table = config::getConfigTable(vm.values.at("config"), vm.values.at("config-key"));
+            config::checkKeys(filter->options(), table);
+        }
+        filter->applyConfiguration(vm, table);
+
+        std::cout << whoMessage(comp_name, "Listening to source " + pos[0] + ".\n")
+                  << whoMessage(comp_name, "Steaming to sink " + pos[1] + ".\n")
+                  << whoMessage(comp_name, "Press CTRL+C to exit.\n");
+        filter->run();
+        std::cout << whoMessage(comp_name, "Exiting.\n");
+        return 0;
+    } catch (const std::exception &ex) {
+        std::cerr << whoError(comp_name, ex.what()) << std::endl;
+    } catch (...) {
+        std::cerr << whoError(comp_name, "Unknown exception.") << std::endl;
+    }
+    return -1;
+}

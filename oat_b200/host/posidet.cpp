@@ -1,0 +1,263 @@
+// oat-posidet -- `oat posidet TYPE SOURCE SINK [CONFIGURATION]` for the hot-path TYPEs, computing on the
+// B200 through the C ABI.  Mirrors src/positiondetector/{main.cpp, PositionDetector.{h,cpp},
+// HSVDetector.{h,cpp}, DetectorFunc.{h,cpp}}.
+//
+//   hsv     inRange -> erode -> dilate -> siftContours on an HSV frame SOURCE (HSVDetector.cpp:142-173)
+//   track   (extension) the fused device path: takes the RAW BGR SOURCE and does framefilt mog ->
+//           framefilt col -C HSV -> posidet hsv in one pass, no shared-memory hops in between
+#include <cfloat>
+#include <iostream>
+#include <memory>
+
+#include "gpu.h"
+#include "oat_cli.h"
+#include "oat_host.h"
+
+namespace oat {
+
+class PositionDetector : public Component {
+public:
+    PositionDetector(const std::string &source, const std::string &sink) : frame_source_address_(source), position_sink_address_(sink) {}
+    std::string name() const override { return name_; }
+    virtual std::vector<config::OptionSpec> options() const = 0;
+    virtual void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) = 0;
+
+protected:
+    // PositionDetector::connectToNode (PositionDetector.cpp:40-56)
+    bool connectToNode() override
+    {
+        frame_source_.touch(frame_source_address_);
+        const SourceState rc = required_color_ == PIX_ANY ? frame_source_.connect() : frame_source_.connect(required_color_);
+        if (rc != SourceState::CONNECTED) return false;
+        in_ = frame_source_.parameters();
+        position_sink_.bind(position_sink_address_, position_sink_address_);
+        shared_position_ = position_sink_.retrieve();
+        ctx_.reset(new gpu::Context(gpu_index_));
+        src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
+        d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
+        setup();
+        return true;
+    }
+    // PositionDetector::process (PositionDetector.cpp:58-99)
+    int process() override
+    {
+        Position2D internal_pos("");
+        if (frame_source_.wait() == NodeState::END) return 1;
+        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, frame_source_.pixels(), in_.bytes));
+        internal_pos.set_sample(frame_source_.retrieve()->sample());  // propagate tick / usec (:80)
+        frame_source_.post();
+
+        detectPosition(d_in_->u8(), internal_pos);
+
+        position_sink_.wait();
+        *shared_position_ = internal_pos;  // everything but the label (Position2D.h:84-105)
+        position_sink_.post();
+        return 0;
+    }
+    virtual void setup() = 0;
+    // device frame in -> Position2D::position / position_valid
+    virtual void detectPosition(const uint8_t *d_frame, Position2D &position) = 0;
+
+    std::string name_;
+    std::string frame_source_address_, position_sink_address_;
+    PixelColor required_color_{PIX_ANY};
+    Source<Frame> frame_source_;
+    Sink<Position2D> position_sink_;
+    Position2D *shared_position_{nullptr};
+    FrameParams in_;
+    int gpu_index_{0};
+    std::unique_ptr<gpu::Context> ctx_;
+    std::unique_ptr<gpu::HostRegistration> src_pin_;
+    std::unique_ptr<gpu::DeviceBuffer> d_in_;
+};
+
+// options shared by `hsv` and `track` (HSVDetector.cpp:49-140)
+struct HSVOptions {
+    oat_hsv_params p;
+    HSVOptions() { oat_hsv_default_params(&p); }  // erode off, dilate 10 (:42-43), bands [0,256], area [0, DBL_MAX)
+    static std::vector<config::OptionSpec> options()
+    {
+        return {{"h-thresh", 'H', true, "Array of ints between 0 and 256, [min,max], specifying the hue passband."},
+                {"s-thresh", 'S', true, "Array of ints between 0 and 256, [min,max], specifying the saturation passband."},
+                {"v-thresh", 'V', true, "Array of ints between 0 and 256, [min,max], specifying the value passband."},
+                {"erode", 'e', true, "Contour erode kernel size in pixels (normalized box filter)."},
+                {"dilate", 'd', true, "Contour dilation kernel size in pixels (normalized box filter)."},
+                {"area", 'a', true, "Array of floats, [min,max], specifying the minimum and maximum object contour area in pixels^2."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void apply(const config::VariableMap &vm, const config::OptionTable &t)
+    {
+        std::vector<int> v;
+        auto band = [&](const char *key, int &lo, int &hi) {
+            if (config::getArray<int>(vm, t, key, v, 2)) {
+                lo = v[0];
+                hi = v[1];
+                if (lo < 0 || lo > 256 || hi < 0 || hi > 256)
+                    throw std::runtime_error(std::string("Values of ") + key + " should be between 0 and 256.");
+            }
+        };
+        band("h-thresh", p.h_min, p.h_max);
+        band("s-thresh", p.s_min, p.s_max);
+        band("v-thresh", p.v_min, p.v_max);
+        config::getNumericValue<int>(vm, t, "erode", p.erode_px, 0, 1 << 20);
+        config::getNumericValue<int>(vm, t, "dilate", p.dilate_px, 0, 1 << 20);
+        std::vector<double> area;
+        if (config::getArray<double>(vm, t, "area", area, 2)) {
+            p.min_area = area[0];
+            p.max_area = area[1];
+            if (p.min_area >= p.max_area) throw std::runtime_error("Max area should be larger than min area.");
+        }
+    }
+};
+
+static void fill(Position2D &position, const oat_detection &d)
+{
+    position.position_valid = d.position_valid != 0;  // DetectorFunc.cpp:46, :58-60
+    if (d.position_valid) {
+        position.position.x = d.x;
+        position.position.y = d.y;
+    }
+}
+
+// ---- posidet hsv ------------------------------------------------------------------------------------------
+class HSVDetector : public PositionDetector {
+public:
+    HSVDetector(const std::string &source, const std::string &sink) : PositionDetector(source, sink)
+    {
+        name_ = "hsvdetector[" + source + "->" + sink + "]";
+        required_color_ = PIX_HSV;  // HSVDetector.cpp:46
+    }
+    ~HSVDetector() { oat_hsvdet_destroy(det_); }
+    std::vector<config::OptionSpec> options() const override { return HSVOptions::options(); }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        o_.apply(vm, t);
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override { gpu::ck(oat_hsvdet_create(ctx_->h, (int)in_.rows, (int)in_.cols, &det_)); }
+    void detectPosition(const uint8_t *d_frame, Position2D &position) override
+    {
+        oat_detection d;
+        gpu::ck(oat_hsvdet_detect(det_, d_frame, in_.cols * 3, &o_.p, &d, nullptr, 0, nullptr));
+        fill(position, d);
+    }
+
+private:
+    HSVOptions o_;
+    oat_hsvdet *det_{nullptr};
+};
+
+// ---- posidet track: mog -> col HSV -> hsv fused on the device ----------------------------------------------
+class FusedTracker : public PositionDetector {
+public:
+    FusedTracker(const std::string &source, const std::string &sink) : PositionDetector(source, sink)
+    {
+        name_ = "tracker[" + source + "->" + sink + "]";
+        required_color_ = PIX_BGR;
+    }
+    ~FusedTracker() { oat_tracker_destroy(trk_); }
+    std::vector<config::OptionSpec> options() const override
+    {
+        auto o = HSVOptions::options();
+        o.push_back({"adaptation-coeff", 'A', true, "framefilt mog's adaptation coefficient, 0 to 1.0. Default 0."});
+        return o;
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        o_.apply(vm, t);
+        config::getNumericValue<double>(vm, t, "adaptation-coeff", learning_coeff_, 0.0, 1.0);
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override { gpu::ck(oat_tracker_create(ctx_->h, (int)in_.rows, (int)in_.cols, nullptr, 0, &trk_)); }
+    void detectPosition(const uint8_t *d_frame, Position2D &position) override
+    {
+        oat_detection d;
+        gpu::ck(oat_tracker_track(trk_, d_frame, in_.cols * 3, learning_coeff_, &o_.p, &d, nullptr, 0, nullptr, 0, nullptr, 0,
+                                  nullptr, 0));
+        fill(position, d);
+    }
+
+private:
+    HSVOptions o_;
+    double learning_coeff_{0.0};
+    oat_tracker *trk_{nullptr};
+};
+
+}  // namespace oat
+
+static void printUsage(std::ostream &out)
+{
+    out << "Usage: posidet [INFO]\n"
+           "   or: posidet TYPE SOURCE SINK [CONFIGURATION]\n"
+           "Perform object detection on frames from SOURCE. Publish detected object positions to SINK.\n\n"
+           "TYPE\n"
+           "  hsv: Object detection using color thresholding (requires an HSV frame SOURCE)\n"
+           "  track: fused mog + HSV conversion + hsv detection on a BGR frame SOURCE\n\n"
+           "SOURCE:\n  User-supplied name of the memory segment to receive frames from (e.g. raw).\n\n"
+           "SINK:\n  User-supplied name of the memory segment to publish detected positions to (e.g. pos).\n\n"
+           "INFO:\n  --help                 Produce help message.\n  -v [ --version ]       Print version information.\n\n"
+           "CONFIGURATION:\n  -c [ --config ] FILE KEY   Configuration file/key pair.\n";
+}
+
+int main(int argc, char *argv[])
+{
+    using namespace oat;
+    std::string comp_name = "posidet";
+    try {
+        for (int i = 1; i < argc; ++i) {
+            const std::string a = argv[i];
+            if (a == "--help" && argc == 2) { printUsage(std::cout); return 0; }
+            if (a == "-v" || a == "--version") { std::cout << "Oat Object Position Detector (B200) version 0.1\n"; return 0; }
+        }
+        if (argc < 2) { printUsage(std::cout); return 0; }
+        const std::string type = argv[1];
+        std::vector<std::string> pos;
+        for (int i = 2; i < argc && pos.size() < 2; ++i) {
+            if (argv[i][0] == '-') break;
+            pos.push_back(argv[i]);
+        }
+        if (type != "hsv" && type != "track") {
+            printUsage(std::cout);
+            std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
+            return -1;
+        }
+        if (pos.size() < 1) { printUsage(std::cout); std::cerr << whoError(comp_name, "Error: a SOURCE must be specified.\n"); return -1; }
+        if (pos.size() < 2) { printUsage(std::cout); std::cerr << whoError(comp_name, "Error: a SINK name must be specified.\n"); return -1; }
+        std::shared_ptr<PositionDetector> detector;
+        if (type == "hsv") detector = std::make_shared<HSVDetector>(pos[0], pos[1]);
+        else detector = std::make_shared<FusedTracker>(pos[0], pos[1]);
+        comp_name = detector->name();
+
+        auto opts = detector->options();
+        opts.push_back({"config", 'c', true, "Configuration file/key pair."});
+        opts.push_back({"help", 0, false, ""});
+        const config::VariableMap vm = config::parse(argc, argv, 4, opts);
+        if (vm.count("help")) {
+            printUsage(std::cout);
+            for (const auto &o : detector->options()) std::cout << "  --" << o.long_name << "  " << o.help << "\n";
+            return 0;
+        }
+        config::OptionTable table;
+        if (vm.count("config")) {
+            table = config::getConfigTable(vm.values.at("config"), vm.values.at("config-key"));
+            config::checkKeys(detector->options(), table);
+        }
+        detector->applyConfiguration(vm, table);
+
+        std::cout << whoMessage(comp_name, "Listening to source " + pos[0] + ".\n")
+                  << whoMessage(comp_name, "Steaming to sink " + pos[1] + ".\n")
+                  << whoMessage(comp_name, "Press CTRL+C to exit.\n");
+        detector->run();
+        std::cout << whoMessage(comp_name, "Exiting.\n");
+        return 0;
+    } catch (const std::exception &ex) {
+        std::cerr << whoError(comp_name, ex.what()) << std::endl;
+    } catch (...) {
+        std::cerr << whoError(comp_name, "Unknown exception.") << std::endl;
+    }
+    return -1;
+}

@@ -1,0 +1,100 @@
+"""End-to-end dataflow through real shared memory on the GPU box, one OS process per node exactly like an
+Oat graph (README.md:125-149):
+
+    oat frameserve synth raw | oat framefilt mog raw filt | oat framefilt col filt hsv -C HSV |
+    oat posidet hsv hsv pos -H .. -S .. -V .. | oat posisock std pos
+
+and the fused one-component form (oat posidet track raw pos).  Positions (JSON lines, the byte format of
+PositionCout + serializePosition) are compared with the CPU oracle on the same synthetic frames."""
+import json
+import os
+import subprocess
+import time
+
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oat_b200", "bin")
+ROWS, COLS, N = 240, 320, 14
+BAND = dict(h=(40, 80), s=(100, 256), v=(100, 256))
+HSV_ARGS = ["-H", "[40,80]", "-S", "[100,256]", "-V", "[100,256]"]
+
+
+def oracle_positions(lr):
+    trk = oracle.Tracker(ROWS, COLS)
+    hp = oracle.HsvParams(**BAND)
+    out = []
+    for t in range(N):
+        o, _ = trk.track(oracle.synth_frame(ROWS, COLS, 1000, t), lr, hp)
+        out.append(o)
+    return out
+
+
+def run_graph(tag, nodes):
+    """nodes: list of argv lists; consumers are started first, the frame server last (examples/*/*.sh)."""
+    names = [f"oatb200pipe_{tag}_{n}" for n in ("raw", "filt", "hsv", "pos")]
+    subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+    procs = []
+    try:
+        sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names[3]], stdout=subprocess.PIPE, text=True)
+        for argv in nodes(names):
+            procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                          text=True))
+        time.sleep(0.5)
+        serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(ROWS), "--cols", str(COLS),
+                                  "--num-samples", str(N), "--fps", "100"])
+        out, _ = sock.communicate(timeout=120)
+        assert serve.wait(timeout=30) == 0
+        for p in procs:
+            so, se = p.communicate(timeout=30)
+            assert p.returncode == 0, (p.args, so, se)  # END propagates downstream; every node exits 0
+        return [json.loads(line) for line in out.splitlines() if line.strip()]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+
+
+def check(positions, want):
+    assert len(positions) == N
+    for t, (p, o) in enumerate(zip(positions, want)):
+        assert p["tick"] == t + 1  # the frame server's Sample travels frame -> frame -> position
+        assert p["usec"] == 10000 * (t + 1)
+        assert p["pos_ok"] == bool(o.position_valid), t
+        if o.position_valid:
+            assert abs(p["pos_xy"][0] - o.x) < 1e-4 and abs(p["pos_xy"][1] - o.y) < 1e-4, (t, p, o.x, o.y)  # 5 decimals in JSON
+
+
+@pytest.mark.parametrize("lr", [0.0, 0.05])
+def test_three_component_chain(lr):
+    def nodes(n):
+        return [["oat-posidet", "hsv", n[2], n[3]] + HSV_ARGS,
+                ["oat-framefilt", "col", n[1], n[2], "-C", "HSV"],
+                ["oat-framefilt", "mog", n[0], n[1], "-a", str(lr)]]
+
+    check(run_graph(f"chain{int(lr * 100)}", nodes), oracle_positions(lr))
+
+
+def test_fused_tracker_component():
+    def nodes(n):
+        return [["oat-posidet", "track", n[0], n[3], "-A", "0.05"] + HSV_ARGS]
+
+    check(run_graph("fused", nodes), oracle_positions(0.05))
+
+
+def test_hsv_requires_hsv_source():
+    """posidet hsv on a BGR source: 'Maybe use oat-framefilt col?' and exit -1 (Source.h:300-313)."""
+    name = "oatb200pipe_color"
+    subprocess.run([os.path.join(BIN, "oat-clean"), name, name + "_pos"], capture_output=True)
+    det = subprocess.Popen([os.path.join(BIN, "oat-posidet"), "hsv", name, name + "_pos"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True)
+    time.sleep(0.3)
+    serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", name, "--rows", "60", "--cols", "80", "--num-samples", "3"])
+    so, se = det.communicate(timeout=60)
+    serve.wait(timeout=30)
+    assert det.returncode == 255 and "Maybe use oat-framefilt col?" in se
+    subprocess.run([os.path.join(BIN, "oat-clean"), name, name + "_pos"], capture_output=True)

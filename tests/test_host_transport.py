@@ -1,0 +1,86 @@
+"""Host side of the drop-in (oat_b200/host, C++17): the reference's shmemdf transport tests
+(test/shmemdf/*_test.cpp) re-expressed in oat_b200/host/shmemdf_test.cpp, and the CLI / configuration
+contract of the two hot-path executables (src/framefilter/main.cpp, src/positiondetector/main.cpp,
+lib/utility/TOMLSanitize.h).  None of this needs a GPU: option errors surface before the device is touched."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oat_b200", "bin")
+
+
+@pytest.fixture(scope="module")
+def host_bin():
+    # liboatgpu.so must exist for the link step of the two GPU executables
+    import oat_b200
+
+    oat_b200.build()
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oat_b200", "host")], check=True)
+    return BIN
+
+
+def run(args, **kw):
+    return subprocess.run(args, capture_output=True, text=True, timeout=60, **kw)
+
+
+def test_shmemdf_transport_suite(host_bin):
+    r = run([os.path.join(host_bin, "shmemdf_test"), os.path.join(host_bin, "oat-frameserve")])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failures" in r.stdout
+
+
+def test_dispatcher_and_usage(host_bin):
+    r = run([os.path.join(host_bin, "oat"), "framefilt", "--help"])
+    assert r.returncode == 0 and "framefilt TYPE SOURCE SINK" in r.stdout
+    r = run([os.path.join(host_bin, "oat"), "posidet", "--version"])
+    assert r.returncode == 0 and "Position Detector" in r.stdout
+    r = run([os.path.join(host_bin, "oat"), "nonsense"])
+    assert r.returncode != 0
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["oat-framefilt", "bogus", "a", "b"], "invalid TYPE"),
+    (["oat-framefilt", "mog", "a"], "a SINK must be specified"),
+    (["oat-framefilt", "mog"], "a SOURCE must be specified"),
+    (["oat-framefilt", "mog", "a", "b", "-a", "1.5"], "out of bounds"),       # getNumericValue range check, ...MOG.cpp:87-88
+    (["oat-framefilt", "mog", "a", "b", "--nonsense", "1"], "unrecognised option"),
+    (["oat-framefilt", "col", "a", "b"], "pixel color must be specified"),
+    (["oat-posidet", "hsv", "a", "b", "-H", "[40,300]"], "Values of h-thresh should be between 0 and 256."),
+    (["oat-posidet", "hsv", "a", "b", "-a", "[10,5]"], "Max area should be larger than min area."),
+    (["oat-posidet", "hsv", "a", "b", "-S", "[1,2,3]"], "2 elements"),
+    (["oat-posidet", "thresh", "a", "b"], "invalid TYPE"),
+])
+def test_cli_errors_exit_minus_one(host_bin, args, msg):
+    """Every exception is caught in main -> 'name: message' on stderr -> return -1 (main.cpp:278-295)."""
+    r = run([os.path.join(host_bin, args[0])] + args[1:])
+    assert r.returncode == 255, (r.returncode, r.stdout, r.stderr)
+    assert msg in r.stderr, r.stderr
+
+
+def test_toml_config_table(host_bin, tmp_path):
+    """-c FILE KEY selects a table; unknown keys are rejected (checkKeys); CLI beats TOML."""
+    cfg = tmp_path / "config.toml"
+    cfg.write_text('[hsv]\nh-thresh = [40, 80]\ns-thresh = [100, 256]\nerode = 0\ndilate = 10\n\n'
+                   '[stale]\nh_thresholds = [1, 2]\n\n[bad]\nh-thresh = [40, 999]\n')
+    exe = os.path.join(host_bin, "oat-posidet")
+    r = run([exe, "hsv", "a", "b", "-c", str(cfg), "stale"])
+    assert r.returncode == 255 and "Unknown configuration key 'h_thresholds'" in r.stderr
+    r = run([exe, "hsv", "a", "b", "-c", str(cfg), "missing"])
+    assert r.returncode == 255 and "No configuration table named 'missing'" in r.stderr
+    r = run([exe, "hsv", "a", "b", "-c", str(cfg), "bad"])
+    assert r.returncode == 255 and "between 0 and 256" in r.stderr
+    # CLI beats TOML (getValue, TOMLSanitize.h:175-183): with a good -H on the command line the bad table value
+    # is never used; the component then blocks in connect() waiting for a SINK, and SIGINT ends it cleanly (0)
+    import signal
+    import time
+
+    p = subprocess.Popen([exe, "hsv", "oatb200test_nosrc", "oatb200test_nosink", "-c", str(cfg), "bad", "-H", "[40,80]"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    time.sleep(0.5)
+    p.send_signal(signal.SIGINT)
+    out, err = p.communicate(timeout=10)
+    assert p.returncode == 0, (p.returncode, out, err)
+    assert "between 0 and 256" not in err
+    subprocess.run([os.path.join(host_bin, "oat-clean"), "oatb200test_nosrc", "oatb200test_nosink"], capture_output=True)
