@@ -209,6 +209,7 @@ def run_b200(args):
     import torch
 
     import oat_b200
+    from oat_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,7 +229,8 @@ def run_b200(args):
     hp = oat_b200.HsvParams.make(**HSV_BAND)
     ctx = oat_b200.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    seed = SEED + rank  # one independent stream per rank
+    # one independent stream per rank: stream s -> GPU s mod G, no data-path collective
+    seed = sharding.stream_seed(SEED, sharding.streams_for_rank(world, rank, world)[0])
 
     # ---- input ring: distinct synthetic frames, resident in HBM before timing starts --------
     R = max(2, args.ring)
@@ -375,13 +377,8 @@ def run_b200(args):
     trk2.close()
 
     # ---- reduce over ranks: the job took as long as its slowest rank -------------------------
-    if dist is not None:
-        t = torch.tensor([total_ms, cold_ms, e2e_s, kern_ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, cold_ms, e2e_s, kern_ms = [float(x) for x in t.tolist()]
-        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local}")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+    total_ms, cold_ms, e2e_s, kern_ms = sharding.max_over_ranks([total_ms, cold_ms, e2e_s, kern_ms], dist, f"cuda:{local}")
+    launches = sharding.sum_over_ranks(launches, dist, f"cuda:{local}")
     if rank == 0:
         peak, peak_src = load_peak()
         fps = world * K / (total_ms * 1e-3)
