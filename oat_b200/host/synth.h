@@ -1,5 +1,5 @@
-// synth.h -- the deterministic synthetic stream of SURVEY.md 8(d) on the host (bit-identical to
-// oracle/synth.py, oracle/oat_oracle.c and the device generator oat_synth_frame).
+// synth.h -- the deterministic synthetic stream of SURVEY.md 8(d) on the host (bit-identical to the
+// device generator oat_synth_frame and to the test suite's generators).
 #pragma once
 #include <cstdint>
 
