@@ -79,6 +79,7 @@ struct oat_ctx {
     int num_sms = 148;
     bool pipe_attr_set = false;
     unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel
+    unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
     DevBuf scratch_in, scratch_out;  // staging for the stateless entry points
 };
@@ -137,6 +138,8 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
         lut[i] = (int)nearbyint((255 << 12) / (1.0 * i));
         lut[256 + i] = (int)nearbyint((180 << 12) / (6.0 * i));
     }
+    CK(cudaMalloc(&c->slow_count, sizeof(unsigned int)));
+    CK(cudaMemset(c->slow_count, 0, sizeof(unsigned int)));
     CK(cudaMalloc(&c->tile_counter, 2 * sizeof(unsigned int)));
     CK(cudaMemset(c->tile_counter, 0, 2 * sizeof(unsigned int)));
     CK(cudaMalloc(&c->hsv_lut, sizeof(lut)));
@@ -161,6 +164,7 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     c->scratch_out.release();
     if (c->hsv_lut) cudaFree(c->hsv_lut);
     if (c->tile_counter) cudaFree(c->tile_counter);
+    if (c->slow_count) cudaFree(c->slow_count);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
     delete c;
@@ -360,6 +364,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
     a.plane = m.plane;
     a.nmodes = m.nmodes;
     a.hsv_lut = c->hsv_lut;
+    a.slow_count = c->slow_count;
     const bool vec = (m.g.cols % 4 == 0) && aligned4(a.bgr, a.in_pitch) &&
                      (!a.bgr_out || aligned4(a.bgr_out, a.bgr_out_pitch)) &&
                      (!a.fg_out || aligned4(a.fg_out, a.fg_pitch)) && (!a.hsv_out || aligned4(a.hsv_out, a.hsv_pitch));
@@ -384,7 +389,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
         pa.ntiles = (int)((m.plane + PIPE_TILE - 1) / PIPE_TILE);
         pa.div_magic = 0xffffffffffffffffull / (unsigned long long)m.g.pitch_px() + 1ull;
         pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
-        const int grid = pa.ntiles < 2 * c->num_sms ? pa.ntiles : 2 * c->num_sms;
+        const int grid = pa.ntiles < PIPE_CTAS_PER_SM * c->num_sms ? pa.ntiles : PIPE_CTAS_PER_SM * c->num_sms;
         pa.grid_tiles = grid;
         pa.tile_counter = c->tile_counter;  // launches on one context are stream-ordered, so one counter serves
         if (frozen && linear)
@@ -1284,6 +1289,11 @@ extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [12]: sta
     out[2] = (uint32_t)t->replays;
     out[3] = s.fast ? 1u : 0u;
     for (int i = 0; i < 8; ++i) out[4 + i] = s.h_res->cyc[i];
+    // cyc[7] is replaced by the context's cumulative slow-path census (read and reset)
+    unsigned int sc = 0;
+    CK(cudaMemcpy(&sc, t->ctx->slow_count, sizeof(sc), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(t->ctx->slow_count, 0, sizeof(sc)));
+    out[11] = sc;
     return OAT_OK;
 }
 

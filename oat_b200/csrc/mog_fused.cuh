@@ -215,6 +215,107 @@ __device__ __forceinline__ uint32_t mog2_pixel(const float x0, const float x1, c
     return 255u;
 }
 
+// The same algorithm as mog2_pixel(), written as ROLLED loops over mode arrays (which therefore live in
+// local memory).  Several times slower per pixel, but a fraction of the instruction footprint: the
+// pipelined kernel's slow path runs on a fraction of a percent of the pixels and its code is usually
+// cold, so what it costs is instruction fetch, not arithmetic.  Identical operation order.
+template <int K>
+__device__ __noinline__ uint32_t mog2_pixel_rolled(const float x0, const float x1, const float x2, int &n_io, float *W,
+                                                   float *V, float *A, float *B, float *C, const MogConsts &c)
+{
+    bool bg = false, fits = false;
+    float tot = 0.f;
+    int n = n_io;
+    const int n_in = n;
+#pragma unroll 1
+    for (int m = 0; m < n_in; ++m) {
+        if (m >= n) break;  // n shrinks inside the loop when a mode is pruned, exactly like the reference
+        float w = fadd(fmul(c.a1, W[m]), c.prune);
+        int sc = 0;
+        if (!fits) {
+            const float var = V[m];
+            const float d0 = fsub(A[m], x0), d1 = fsub(B[m], x1), d2 = fsub(C[m], x2);
+            const float dist2 = fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fmul(d2, d2));
+            if (tot < c.TB && dist2 < fmul(c.Tb, var)) bg = true;
+            if (dist2 < fmul(c.Tg, var)) {
+                fits = true;
+                w = fadd(w, c.aT);
+                const float k = fdiv(c.aT, w);
+                A[m] = fsub(A[m], fmul(k, d0));
+                B[m] = fsub(B[m], fmul(k, d1));
+                C[m] = fsub(C[m], fmul(k, d2));
+                float vn = fadd(var, fmul(k, fsub(dist2, var)));
+                vn = (vn < c.varMin) ? c.varMin : vn;
+                vn = (vn > c.varMax) ? c.varMax : vn;
+                V[m] = vn;
+#pragma unroll 1
+                for (int i = m; i > 0; --i) {
+                    if (w < W[i - 1]) break;
+                    ++sc;
+                    fswap(W[i], W[i - 1]);
+                    fswap(V[i], V[i - 1]);
+                    fswap(A[i], A[i - 1]);
+                    fswap(B[i], B[i - 1]);
+                    fswap(C[i], C[i - 1]);
+                }
+            }
+        }
+        if (w < -c.prune) {
+            w = 0.f;
+            --n;
+        }
+        W[m - sc] = w;
+        tot = fadd(tot, w);
+    }
+    float inv = 0.f;
+    if (fabsf(tot) > FLT_EPSILON) inv = fdiv(1.f, tot);
+#pragma unroll 1
+    for (int m = 0; m < n; ++m) W[m] = fmul(W[m], inv);
+    if (!fits && c.aT > 0.f) {
+        const int mode = (n == K) ? K - 1 : n++;
+        if (n == 1) {
+            W[mode] = 1.f;
+        } else {
+            W[mode] = c.aT;
+#pragma unroll 1
+            for (int i = 0; i < n - 1; ++i) W[i] = fmul(W[i], c.a1);
+        }
+        V[mode] = c.varInit;
+        A[mode] = x0;
+        B[mode] = x1;
+        C[mode] = x2;
+#pragma unroll 1
+        for (int i = n - 1; i > 0; --i) {
+            if (c.aT < W[i - 1]) break;
+            fswap(W[i], W[i - 1]);
+            fswap(V[i], V[i - 1]);
+            fswap(A[i], A[i - 1]);
+            fswap(B[i], B[i - 1]);
+            fswap(C[i], C[i - 1]);
+        }
+    }
+    n_io = n;
+    if (bg) return 0u;
+    if (c.detect_shadows) {
+        float tw = 0.f;
+#pragma unroll 1
+        for (int m = 0; m < n; ++m) {
+            const float num = fadd(fadd(fadd(0.f, fmul(x0, A[m])), fmul(x1, B[m])), fmul(x2, C[m]));
+            const float den = fadd(fadd(fadd(0.f, fmul(A[m], A[m])), fmul(B[m], B[m])), fmul(C[m], C[m]));
+            if (den == 0.f) break;
+            if (num <= den && num >= fmul(c.tau, den)) {
+                const float a = fdiv(num, den);
+                const float e0 = fsub(fmul(a, A[m]), x0), e1 = fsub(fmul(a, B[m]), x1), e2 = fsub(fmul(a, C[m]), x2);
+                const float dist2a = fadd(fadd(fadd(0.f, fmul(e0, e0)), fmul(e1, e1)), fmul(e2, e2));
+                if (dist2a < fmul(fmul(fmul(c.Tb, V[m]), a), a)) return (uint32_t)c.shadow_value;
+            }
+            tw = fadd(tw, W[m]);
+            if (tw > c.TB) break;
+        }
+    }
+    return 255u;
+}
+
 // 8-bit BGR -> HSV, OpenCV's integer RGB2HSV_b (hsv_shift 12, hrange 180); lut = sdiv|hdiv.
 __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const int *lut, int &h, int &s, int &v)
 {
@@ -224,6 +325,22 @@ __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const int *lut, 
     s = (diff * lut[v] + (1 << 11)) >> 12;
     int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
     hh = (hh * lut[256 + diff] + (1 << 11)) >> 12;
+    h = hh < 0 ? hh + 180 : hh;
+}
+
+// Same conversion without the table: sdiv[i] = round((255 << 12) / i) and hdiv[i] = round((180 << 12) / (6 i))
+// never hit a rounding tie (2N/i is never an odd integer for i <= 255), so round-half-up integer division
+// reproduces cvRound exactly.  Used where a table lookup would be a cold global load.
+__device__ __forceinline__ void bgr2hsv_px_div(int b, int g, int r, int &h, int &s, int &v)
+{
+    v = max(b, max(g, r));
+    const int vmin = min(b, min(g, r));
+    const int diff = v - vmin;
+    const int sdiv = v ? (2 * (255 << 12) + v) / (2 * v) : 0;
+    const int hdiv = diff ? (2 * 122880 + diff) / (2 * diff) : 0;
+    s = (diff * sdiv + (1 << 11)) >> 12;
+    int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
+    hh = (hh * hdiv + (1 << 11)) >> 12;
     h = hh < 0 ? hh + 180 : hh;
 }
 

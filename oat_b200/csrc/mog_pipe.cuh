@@ -37,10 +37,16 @@ constexpr int PIPE_CTHREADS = PIPE_CTHREADS_CFG;    // compute threads (8 warps)
 constexpr int PIPE_THREADS = PIPE_CTHREADS + 32;     // + one producer warp (bulk loads / stores)
 constexpr int PIPE_TILE = PIPE_CTHREADS * 4;        // pixels per tile
 constexpr int PIPE_STAGES = PIPE_STAGES_CFG;
+#ifndef PIPE_CTAS_PER_SM_CFG
+#define PIPE_CTAS_PER_SM_CFG PIPE_MINBLOCKS_CFG
+#endif
+constexpr int PIPE_CTAS_PER_SM = PIPE_CTAS_PER_SM_CFG;  // persistent grid = this x SM count
 constexpr int PIPE_OFF_NM = 5 * PIPE_TILE * 4;       // stage layout: 5 fp32 planes | mode counts | BGR | flag
 constexpr int PIPE_OFF_BGR = PIPE_OFF_NM + PIPE_TILE;
-constexpr int PIPE_OFF_FLAG = PIPE_OFF_BGR + 3 * PIPE_TILE;
-constexpr int PIPE_STAGE_BYTES = PIPE_OFF_FLAG + 128;  // 24704 B
+constexpr int PIPE_OFF_FLAG = PIPE_OFF_BGR + 3 * PIPE_TILE;   // +0 dirty flag, +4 tile number, +8 queue count, +12 queue head
+constexpr int PIPE_OFF_BITS = PIPE_OFF_FLAG + 128;            // threshold bits of the tile (PIPE_TILE / 8 bytes)
+constexpr int PIPE_OFF_QUEUE = PIPE_OFF_BITS + PIPE_TILE / 8;  // slow-pixel queue (u16 pixel-in-tile, 0xffff = empty)
+constexpr int PIPE_STAGE_BYTES = PIPE_OFF_QUEUE + 2 * PIPE_TILE;  // 26880 B
 constexpr int PIPE_SMEM_BYTES = PIPE_STAGES * PIPE_STAGE_BYTES;
 
 // ---- PTX wrappers: mbarrier + bulk async copies (sm_90+; SASS UBLKCP / SYNCS) ----------------
@@ -111,11 +117,14 @@ struct PipeArgs {
     unsigned int *tile_counter;    // [2] dynamic tile scheduler (LINEAR frames): next tile, CTAs finished; zeroed once, self re-arming
 };
 
-// One pixel, n == 1: the m = 0 iteration of mog2_pixel() + normalisation, valid when the sample
-// fits the mode, is background and the mode is not pruned (returns false otherwise: nothing stored).
+// One pixel with one or two live modes whose sample fits mode 0 (the heavier one): the m = 0
+// iteration of mog2_pixel(), the weight decay / pruning of mode 1 (the only thing the m = 1 iteration
+// does once a fit was found) and the normalisation -- the same operations in the same order.  Valid
+// when the sample fits mode 0, is background and mode 0 is not pruned (returns false otherwise:
+// nothing may be stored).  W1 is mode 1's weight (ignored when n == 1).
 template <bool TRACK>
 __device__ __forceinline__ bool fast_px(const float x0, const float x1, const float x2, float &W, float &V, float &A,
-                                        float &B, float &C, const MogConsts &c, bool &dirty)
+                                        float &B, float &C, float &W1, uint32_t &n, const MogConsts &c, bool &dirty)
 {
     const float w0 = fadd(fmul(c.a1, W), c.prune);
     const float d0 = fsub(A, x0), d1 = fsub(B, x1), d2 = fsub(C, x2);
@@ -129,10 +138,21 @@ __device__ __forceinline__ bool fast_px(const float x0, const float x1, const fl
     vn = (vn < c.varMin) ? c.varMin : vn;
     vn = (vn > c.varMax) ? c.varMax : vn;
     const bool pruned = w < -c.prune;
-    const float tot = fadd(0.f, w);
+    float tot = fadd(0.f, w);
+    float w1 = 0.f;
+    uint32_t nn = n;
+    if (n == 2u) {
+        w1 = fadd(fmul(c.a1, W1), c.prune);
+        if (w1 < -c.prune) {
+            w1 = 0.f;
+            nn = 1u;
+        }
+        tot = fadd(tot, w1);
+    }
     float inv = 0.f;
     if (fabsf(tot) > FLT_EPSILON) inv = fdiv(1.f, tot);
     const float nW = fmul(w, inv);
+    const float nW1 = (nn == 2u) ? fmul(w1, inv) : w1;
     const bool ok = bg && fits && !pruned;
     if (ok) {
         upd<TRACK>(W, nW, dirty);
@@ -140,16 +160,13 @@ __device__ __forceinline__ bool fast_px(const float x0, const float x1, const fl
         upd<TRACK>(A, nA, dirty);
         upd<TRACK>(B, nB, dirty);
         upd<TRACK>(C, nC, dirty);
+        if (n == 2u) upd<TRACK>(W1, nW1, dirty);
+        if (TRACK) dirty |= (nn != n);
+        n = nn;
     }
     return ok;
 }
 
-// Slow path (rare): any pixel of the thread has more than one live mode, does not fit its mode, is
-// foreground/shadow, or its mode is pruned.  The four pixels run one after the other through the
-// literal mog2_pixel() (all K mode slots in registers, a single inlined copy inside a rolled
-// loop, so the steady-state loop stays call-free and register-light).  Mode 0, the counts and the
-// BGR bytes live in the shared-memory stage `st`; modes >= 1 are read/written in global memory.
-// Does its own egress.  Returns the 4 threshold bits; sets dirty if any state changed.
 __device__ __forceinline__ float sel4(const float4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 __device__ __forceinline__ void set4(float4 &v, int i, float x)
 {
@@ -159,123 +176,101 @@ __device__ __forceinline__ void set4(float4 &v, int i, float x)
     if (i == 3) v.w = x;
 }
 
-// NA = mode slots held in registers = min(largest live count among the 4 pixels + 1, K).
-template <int K, int NA, bool TRACK>
-__device__ __forceinline__ uint32_t pipe_slow(const PipeArgs &pa, const int *lut, uint8_t *st, const int tid,
-                                              const size_t pidx, bool &dirty)
+// Slow path, ONE pixel (rare): more than two live modes, no fit on mode 0, foreground / shadow, or a pruned
+// mode.  Pixels that leave the fast path are queued per tile and drained by whichever lanes of the CTA
+// are free (a warp whose 128 pixels all sit on the blob would otherwise walk them 4 deep while the
+// other seven warps -- and the stage refill behind them -- wait), so this takes any pixel `e` of the
+// tile, not the caller's own.  Runs the rolled mog2_pixel_rolled(): cold code, small footprint.
+// Mode 0, the counts and the BGR bytes are in the shared-memory stage `st`; modes >= 1 in global memory.
+template <int K, bool TRACK>
+__device__ __forceinline__ void slow_pixel(const PipeArgs &pa, uint8_t *st, const int e, const size_t pidx)
 {
     const FusedArgs &a = pa.f;
-    float *sm0 = reinterpret_cast<float *>(st) + tid * 4;
-    uint8_t *smn = st + PIPE_OFF_NM + tid * 4;
-    const uint8_t *smb = st + PIPE_OFF_BGR + tid * 12;
-    int y = 0, x = 0;
-    if (a.bgr_out || a.hsv_out || a.fg_out) {
-        y = (int)__umul64hi((unsigned long long)pidx, pa.div_magic);
-        x = (int)(pidx - (size_t)y * ((size_t)a.wpr * 32));
-    }
-    // mode 1 of all four pixels in one round trip (the common multi-mode case is two modes);
-    // dead slots are unspecified, so loading / storing them back unchanged is harmless
-    const uint32_t nm4 = *reinterpret_cast<const uint32_t *>(smn);
-    const bool have1 = (NA > 2 || (NA == K && K > 1)) && (((nm4 + 0x7e7e7e7eu) & 0x80808080u) != 0u);  // any count >= 2
-    float4 M1[5];
-#pragma unroll
-    for (int cc = 0; cc < 5; ++cc) M1[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have1) {
-#pragma unroll
-        for (int cc = 0; cc < 5; ++cc) M1[cc] = ld_state_f4(a.state + (size_t)(5 + cc) * a.plane + pidx);
-    }
-    bool store1 = false;
-    uint32_t nib = 0;
+    float *sm0 = reinterpret_cast<float *>(st) + e;
+    uint8_t *smn = st + PIPE_OFF_NM + e;
+    const uint8_t *smb = st + PIPE_OFF_BGR + 3 * e;
+    int n = *smn;
+    const int n_old = n;
+    float W[K], V[K], A[K], B[K], C[K];
+    W[0] = sm0[0];
+    V[0] = sm0[PIPE_TILE];
+    A[0] = sm0[2 * PIPE_TILE];
+    B[0] = sm0[3 * PIPE_TILE];
+    C[0] = sm0[4 * PIPE_TILE];
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        int n = smn[i];
-        const int n_old = n;
-        float W[NA], V[NA], A[NA], B[NA], C[NA];
-        W[0] = sm0[i];
-        V[0] = sm0[PIPE_TILE + i];
-        A[0] = sm0[2 * PIPE_TILE + i];
-        B[0] = sm0[3 * PIPE_TILE + i];
-        C[0] = sm0[4 * PIPE_TILE + i];
-        if (NA > 1) {
-            W[NA > 1 ? 1 : 0] = sel4(M1[0], i);
-            V[NA > 1 ? 1 : 0] = sel4(M1[1], i);
-            A[NA > 1 ? 1 : 0] = sel4(M1[2], i);
-            B[NA > 1 ? 1 : 0] = sel4(M1[3], i);
-            C[NA > 1 ? 1 : 0] = sel4(M1[4], i);
+    for (int m = 1; m < n; ++m) {
+        const float *g = a.state + (size_t)(m * 5) * a.plane + pidx;
+        W[m] = ld_state_f1(g);
+        V[m] = ld_state_f1(g + a.plane);
+        A[m] = ld_state_f1(g + 2 * a.plane);
+        B[m] = ld_state_f1(g + 3 * a.plane);
+        C[m] = ld_state_f1(g + 4 * a.plane);
+    }
+    float oW[K], oV[K], oA[K], oB[K], oC[K];
+    if (TRACK) {
+#pragma unroll 1
+        for (int m = 0; m < n; ++m) {
+            oW[m] = W[m];
+            oV[m] = V[m];
+            oA[m] = A[m];
+            oB[m] = B[m];
+            oC[m] = C[m];
         }
-#pragma unroll
-        for (int m = 2; m < NA; ++m) {
-            W[m] = V[m] = A[m] = B[m] = C[m] = 0.f;
-            if (m < n) {
-                const float *g = a.state + (size_t)(m * 5) * a.plane + pidx + i;
-                W[m] = ld_state_f1(g);
-                V[m] = ld_state_f1(g + a.plane);
-                A[m] = ld_state_f1(g + 2 * a.plane);
-                B[m] = ld_state_f1(g + 3 * a.plane);
-                C[m] = ld_state_f1(g + 4 * a.plane);
-            }
+    }
+    const int b = smb[0], g_ = smb[1], r = smb[2];
+    const uint32_t mk = mog2_pixel_rolled<K>((float)b, (float)g_, (float)r, n, W, V, A, B, C, a.c);
+    const int nw = max(n, n_old);
+    bool d = true;
+    if (TRACK) {
+        d = (n != n_old);
+#pragma unroll 1
+        for (int m = 0; m < n_old && m < n; ++m)
+            d |= (__float_as_uint(oW[m]) != __float_as_uint(W[m])) | (__float_as_uint(oV[m]) != __float_as_uint(V[m])) |
+                 (__float_as_uint(oA[m]) != __float_as_uint(A[m])) | (__float_as_uint(oB[m]) != __float_as_uint(B[m])) |
+                 (__float_as_uint(oC[m]) != __float_as_uint(C[m]));
+    }
+    if (d) {
+        if (TRACK) *reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG) = 1u;
+        sm0[0] = W[0];
+        sm0[PIPE_TILE] = V[0];
+        sm0[2 * PIPE_TILE] = A[0];
+        sm0[3 * PIPE_TILE] = B[0];
+        sm0[4 * PIPE_TILE] = C[0];
+        *smn = (uint8_t)n;
+#pragma unroll 1
+        for (int m = 1; m < nw; ++m) {
+            float *g = a.state + (size_t)(m * 5) * a.plane + pidx;
+            st_state_f1(g, W[m]);
+            st_state_f1(g + a.plane, V[m]);
+            st_state_f1(g + 2 * a.plane, A[m]);
+            st_state_f1(g + 3 * a.plane, B[m]);
+            st_state_f1(g + 4 * a.plane, C[m]);
         }
-        const int b = smb[3 * i], g_ = smb[3 * i + 1], r = smb[3 * i + 2];
-        bool d = !TRACK;
-        const uint32_t mk = mog2_pixel<K, NA, TRACK>((float)b, (float)g_, (float)r, n, W, V, A, B, C, a.c, d);
-        if (d) {
-            dirty = true;
-            sm0[i] = W[0];
-            sm0[PIPE_TILE + i] = V[0];
-            sm0[2 * PIPE_TILE + i] = A[0];
-            sm0[3 * PIPE_TILE + i] = B[0];
-            sm0[4 * PIPE_TILE + i] = C[0];
-            smn[i] = (uint8_t)n;
-            const int nw = max(n, n_old);
-            if (NA > 1 && nw > 1) {
-                set4(M1[0], i, W[NA > 1 ? 1 : 0]);
-                set4(M1[1], i, V[NA > 1 ? 1 : 0]);
-                set4(M1[2], i, A[NA > 1 ? 1 : 0]);
-                set4(M1[3], i, B[NA > 1 ? 1 : 0]);
-                set4(M1[4], i, C[NA > 1 ? 1 : 0]);
-                store1 = true;
-            }
-#pragma unroll
-            for (int m = 2; m < NA; ++m) {
-                if (m < nw) {
-                    float *g = a.state + (size_t)(m * 5) * a.plane + pidx + i;
-                    st_state_f1(g, W[m]);
-                    st_state_f1(g + a.plane, V[m]);
-                    st_state_f1(g + 2 * a.plane, A[m]);
-                    st_state_f1(g + 3 * a.plane, B[m]);
-                    st_state_f1(g + 4 * a.plane, C[m]);
-                }
-            }
-        }
-        const int ob = mk ? b : 0, og = mk ? g_ : 0, orr = mk ? r : 0;
-        int h = 0, sa = 0, v = 0;
-        if (a.do_hsv) {
-            if (mk) bgr2hsv_px(ob, og, orr, lut, h, sa, v);
-            const bool in = (a.lo[0] <= h) & (h <= a.hi[0]) & (a.lo[1] <= sa) & (sa <= a.hi[1]) & (a.lo[2] <= v) &
-                            (v <= a.hi[2]);
-            nib |= (in ? 1u : 0u) << i;
-        }
+    }
+    const int ob = mk ? b : 0, og = mk ? g_ : 0, orr = mk ? r : 0;
+    int h = 0, sa = 0, v = 0;
+    if (a.do_hsv) {
+        if (mk) bgr2hsv_px_div(ob, og, orr, h, sa, v);
+        const bool in = (a.lo[0] <= h) & (h <= a.hi[0]) & (a.lo[1] <= sa) & (sa <= a.hi[1]) & (a.lo[2] <= v) & (v <= a.hi[2]);
+        if (in) atomicOr(reinterpret_cast<uint32_t *>(st + PIPE_OFF_BITS) + (e >> 5), 1u << (e & 31));
+    }
+    if (a.bgr_out || a.hsv_out || a.fg_out) {
+        const int y = (int)__umul64hi((unsigned long long)pidx, pa.div_magic);
+        const int x = (int)(pidx - (size_t)y * ((size_t)a.wpr * 32));
         if (a.bgr_out) {
-            uint8_t *dst = a.bgr_out + (size_t)y * a.bgr_out_pitch + 3 * (x + i);
+            uint8_t *dst = a.bgr_out + (size_t)y * a.bgr_out_pitch + 3 * x;
             dst[0] = (uint8_t)ob;
             dst[1] = (uint8_t)og;
             dst[2] = (uint8_t)orr;
         }
         if (a.hsv_out) {
-            uint8_t *dst = a.hsv_out + (size_t)y * a.hsv_pitch + 3 * (x + i);
+            uint8_t *dst = a.hsv_out + (size_t)y * a.hsv_pitch + 3 * x;
             dst[0] = (uint8_t)h;
             dst[1] = (uint8_t)sa;
             dst[2] = (uint8_t)v;
         }
-        if (a.fg_out) a.fg_out[(size_t)y * a.fg_pitch + x + i] = (uint8_t)mk;
+        if (a.fg_out) a.fg_out[(size_t)y * a.fg_pitch + x] = (uint8_t)mk;
     }
-    if (store1) {
-        // a pixel that gained its second mode this frame next to pixels without one: the dead lanes of
-        // the vector were never loaded (have1 false) and are stored as zeros -- still unspecified slots
-#pragma unroll
-        for (int cc = 0; cc < 5; ++cc) st_state_f4(a.state + (size_t)(5 + cc) * a.plane + pidx, M1[cc]);
-    }
-    return nib;
 }
 
 // LINEAR: cols % 32 == 0 and every image pitch is tight, so a pixel's byte offsets are plain
@@ -287,7 +282,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     __shared__ __align__(8) uint64_t full[PIPE_STAGES];  // stage loaded: 1 expect_tx arrive + 256 cp.async arrives
     __shared__ __align__(8) uint64_t done[PIPE_STAGES];  // stage updated in place by all compute threads
     const FusedArgs &a = pa.f;
-    const int *lut = a.hsv_lut;  // only the (rare) slow path converts to HSV: read through L1
     const int tid = threadIdx.x;
     if (tid == 0) {
 #pragma unroll
@@ -297,7 +291,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         }
         fence_mbar_init();
     }
-    if (tid < PIPE_STAGES) *reinterpret_cast<uint32_t *>(stage_mem + (size_t)tid * PIPE_STAGE_BYTES + PIPE_OFF_FLAG) = 0u;
+    for (int s = 0; s < PIPE_STAGES; ++s) {
+        uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
+        if (tid < 4) reinterpret_cast<uint32_t *>(st + PIPE_OFF_FLAG)[tid] = 0u;  // dirty, tile, queue count, queue head
+        for (int i = tid; i < PIPE_TILE; i += PIPE_THREADS) reinterpret_cast<uint16_t *>(st + PIPE_OFF_QUEUE)[i] = 0xffffu;
+    }
     __syncthreads();
 
     // Tile order.  LINEAR frames use a dynamic scheduler: the producer draws tile numbers from a
@@ -386,6 +384,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                     bulk_s2g(a.state + (size_t)cc * a.plane + p0, st + cc * (PIPE_TILE * 4), npx * 4u);
                 bulk_s2g(a.nmodes + p0, st + PIPE_OFF_NM, npx);
             }
+            if (a.thr_bits) {  // the tile's threshold bits: 128 B, one bulk store (word loop for a ragged last tile)
+                size_t p0;
+                uint32_t npx;
+                tile_span(tile, p0, npx);
+                if (npx == (uint32_t)PIPE_TILE) {
+                    bulk_s2g(a.thr_bits + (p0 >> 5), st + PIPE_OFF_BITS, PIPE_TILE / 8);
+                } else {
+                    const volatile uint32_t *bw = reinterpret_cast<const volatile uint32_t *>(st + PIPE_OFF_BITS);
+                    for (uint32_t w = 0; w < npx / 32u; ++w) a.thr_bits[(p0 >> 5) + w] = bw[w];
+                }
+            }
+            reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG)[2] = 0u;  // re-arm the slow-pixel queue
+            reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG)[3] = 0u;
             bulk_commit();
             if (!ended) {
                 bulk_wait_read<1>();  // the stores of the previous tile have finished reading their stage
@@ -452,12 +463,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         int y, x;
         const bool active = locate(tile, pidx, y, x);
 
-        bool dirty = !TRACK;
+        bool dirty = !TRACK, slow = false;
         uint32_t nib = 0;
         if (active) {
             const uint32_t nm = *(reinterpret_cast<const uint32_t *>(st + PIPE_OFF_NM) + tid);
             bool fast = false;
-            if (nm == 0x01010101u) {
+            const uint32_t two = nm - 0x01010101u;  // per pixel: 0 = one mode, 1 = two modes
+            if ((two & ~0x01010101u) == 0u && (K >= 2 || two == 0u)) {
+                // mode 1's weights first: the only global read of this path, in flight during the mode-0 maths
+                float4 W1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float *w1p = a.state + (size_t)5 * a.plane + pidx;
+                if (two != 0u) W1 = ld_state_f4(w1p);
                 const uint32_t *smb = reinterpret_cast<const uint32_t *>(st + PIPE_OFF_BGR) + tid * 3;
                 const uint32_t w0 = smb[0], w1 = smb[1], w2 = smb[2];
                 float4 W = *reinterpret_cast<const float4 *>(sm0);
@@ -465,15 +481,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                 float4 A = *reinterpret_cast<const float4 *>(sm0 + 2 * PIPE_TILE);
                 float4 B = *reinterpret_cast<const float4 *>(sm0 + 3 * PIPE_TILE);
                 float4 C = *reinterpret_cast<const float4 *>(sm0 + 4 * PIPE_TILE);
+                uint32_t n0 = nm & 255u, n1 = (nm >> 8) & 255u, n2 = (nm >> 16) & 255u, n3 = nm >> 24;
                 bool d2 = false;
                 bool ok = fast_px<TRACK>((float)(w0 & 255u), (float)((w0 >> 8) & 255u), (float)((w0 >> 16) & 255u), W.x,
-                                         V.x, A.x, B.x, C.x, a.c, d2);
+                                         V.x, A.x, B.x, C.x, W1.x, n0, a.c, d2);
                 ok &= fast_px<TRACK>((float)(w0 >> 24), (float)(w1 & 255u), (float)((w1 >> 8) & 255u), W.y, V.y, A.y, B.y,
-                                     C.y, a.c, d2);
+                                     C.y, W1.y, n1, a.c, d2);
                 ok &= fast_px<TRACK>((float)((w1 >> 16) & 255u), (float)(w1 >> 24), (float)(w2 & 255u), W.z, V.z, A.z, B.z,
-                                     C.z, a.c, d2);
+                                     C.z, W1.z, n2, a.c, d2);
                 ok &= fast_px<TRACK>((float)((w2 >> 8) & 255u), (float)((w2 >> 16) & 255u), (float)(w2 >> 24), W.w, V.w,
-                                     A.w, B.w, C.w, a.c, d2);
+                                     A.w, B.w, C.w, W1.w, n3, a.c, d2);
                 if (ok) {
                     fast = true;
                     if (!TRACK || d2) {
@@ -482,6 +499,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                         *reinterpret_cast<float4 *>(sm0 + 2 * PIPE_TILE) = A;
                         *reinterpret_cast<float4 *>(sm0 + 3 * PIPE_TILE) = B;
                         *reinterpret_cast<float4 *>(sm0 + 4 * PIPE_TILE) = C;
+                        if (two != 0u) {
+                            st_state_f4(w1p, W1);
+                            const uint32_t nnew = n0 | (n1 << 8) | (n2 << 16) | (n3 << 24);
+                            if (nnew != nm) *(reinterpret_cast<uint32_t *>(st + PIPE_OFF_NM) + tid) = nnew;
+                        }
                         dirty = true;
                     }
                     nib = zero_nib;
@@ -501,27 +523,54 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                     if (a.fg_out) st_stream_u32(LINEAR ? a.fg_out + pidx : a.fg_out + (size_t)y * a.fg_pitch + x, 0u);
                 }
             }
-            if (!fast) {
-                ++nslow;
-                bool d2 = false;
-                const uint32_t nmax = max(max(nm & 255u, (nm >> 8) & 255u), max((nm >> 16) & 255u, nm >> 24));
-                if (nmax <= 1 || K <= 2)
-                    nib = pipe_slow<K, (K < 2 ? K : 2), TRACK>(pa, lut, st, tid, pidx, d2);
-                else if (nmax == 2 || K == 3)
-                    nib = pipe_slow<K, (K < 3 ? K : 3), TRACK>(pa, lut, st, tid, pidx, d2);
-                else
-                    nib = pipe_slow<K, K, TRACK>(pa, lut, st, tid, pidx, d2);
-                dirty |= d2 || !TRACK;
-            }
+            slow = !fast;
         }
-        // threshold mask, 1 bit/pixel: 8 lanes x 4 px -> one word (word index = pidx / 32)
-        if (a.thr_bits) {
+        // threshold mask, 1 bit/pixel: 8 lanes x 4 px -> one word of the stage's bit block
+        uint32_t *sbits = reinterpret_cast<uint32_t *>(st + PIPE_OFF_BITS);
+        {
             const unsigned lane = tid & 31u;
             uint32_t wv = nib << (4 * (lane & 7u));
             wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
             wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
             wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
-            if ((lane & 7u) == 0 && pidx < a.plane) a.thr_bits[pidx >> 5] = wv;
+            if ((lane & 7u) == 0) sbits[tid >> 3] = wv;
+        }
+        __syncwarp();  // the words are in place before any of this warp's pixels can be claimed
+        // queue the pixels that left the fast path, then help drain the tile's queue
+        volatile uint32_t *qcnt = reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG) + 2;
+        volatile uint32_t *qhead = qcnt + 1;
+        volatile uint16_t *queue = reinterpret_cast<volatile uint16_t *>(st + PIPE_OFF_QUEUE);
+        if (slow) {
+            ++nslow;
+            const uint32_t base = atomicAdd(const_cast<uint32_t *>(qcnt), 4u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) queue[base + i] = (uint16_t)(tid * 4 + i);
+        }
+        __syncwarp();  // this warp's entries are published before any of its lanes starts claiming
+        for (;;) {     // warp-level claiming: lane 0 takes up to 32 queue slots, one pixel per lane
+            uint32_t h0 = 0, take = 0;
+            if ((tid & 31) == 0) {
+                const uint32_t h = *qhead, c = *qcnt;
+                if (h < c) {
+                    take = min(32u, c - h);
+                    if (atomicCAS(const_cast<uint32_t *>(qhead), h, h + take) == h)
+                        h0 = h;
+                    else
+                        take = 0xffffffffu;  // lost the race: look again
+                }
+            }
+            h0 = __shfl_sync(0xffffffffu, h0, 0);
+            take = __shfl_sync(0xffffffffu, take, 0);
+            if (take == 0u) break;
+            if (take == 0xffffffffu) continue;
+            if ((uint32_t)(tid & 31) < take) {
+                const uint32_t h = h0 + (uint32_t)(tid & 31);
+                uint32_t e;
+                while ((e = queue[h]) == 0xffffu) {}  // reserved by a pusher of another warp that is about to fill it
+                queue[h] = 0xffffu;
+                slow_pixel<K, TRACK>(pa, st, (int)e, (size_t)tile * PIPE_TILE + e);
+            }
+            __syncwarp();
         }
         if (TRACK && dirty) *reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG) = 1u;
         // hand the stage to the producer: generic-proxy writes -> async proxy, then arrive
