@@ -355,7 +355,7 @@ static void launch_fused_px(cudaStream_t s, int K, const FusedArgs &a)
 
 static bool aligned4(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 3u) == 0; }
 
-static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
+static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true)
 {
     a.rows = m.g.rows;
     a.cols = m.g.cols;
@@ -364,14 +364,14 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a)
     a.plane = m.plane;
     a.nmodes = m.nmodes;
     a.hsv_lut = c->hsv_lut;
-    a.slow_count = c->slow_count;
+    if (!a.slow_count) a.slow_count = c->slow_count;
     const bool vec = (m.g.cols % 4 == 0) && aligned4(a.bgr, a.in_pitch) &&
                      (!a.bgr_out || aligned4(a.bgr_out, a.bgr_out_pitch)) &&
                      (!a.fg_out || aligned4(a.fg_out, a.fg_pitch)) && (!a.hsv_out || aligned4(a.hsv_out, a.hsv_pitch));
     // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
     // the state write-back; with a live rate every live mode changes every frame anyway.
     const bool frozen = (a.c.aT == 0.0f) && !a.reset;
-    if (vec && !a.reset && m.K == 5 && !getenv("OAT_B200_NO_PIPE")) {
+    if (vec && !a.reset && m.K == 5 && allow_pipe && !getenv("OAT_B200_NO_PIPE")) {
         // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
         // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
         const size_t tight3 = (size_t)3 * m.g.cols;
@@ -754,7 +754,7 @@ struct Tail {
     // Fast path: ONE launch (tail_fast.cuh).  Returns false (nothing enqueued) if this geometry /
     // kernel size cannot use it; res->status == TAIL_OVERFLOW after completion means "replay with run()".
     bool run_fast(oat_ctx *c, cudaStream_t stream, const FastBufs &b, const uint32_t *src, const oat_hsv_params &p,
-                  TailResult *d_res, uint8_t *thresh_dev, size_t thresh_pitch, int *err)
+                  TailResult *d_res, uint8_t *thresh_dev, size_t thresh_pitch, int *err, unsigned int *slow_in = nullptr)
     {
         *err = OAT_OK;
         const BitGeom g = tb.g;
@@ -788,6 +788,7 @@ struct Tail {
         fa.res = d_res;
         fa.smem_bytes = (int)smem;
         fa.max_comps = fast_comps;
+        fa.slow_in = slow_in;
         tail_fast_kernel<<<div_up(g.rows, R), 256, smem, stream>>>(fa);
         ++c->launches;
         cudaError_t e = cudaGetLastError();
@@ -999,6 +1000,7 @@ struct Slot {
     TailResult *d_res = nullptr;
     uint32_t *bits = nullptr;       // this frame's threshold mask (kept until collect: overflow replay)
     FastBufs fb;                    // this frame's one-launch tail buffers
+    unsigned int *d_slow = nullptr; // fused kernel's slow-path census of this frame (re-armed by the tail)
     cudaEvent_t fused_done = nullptr;
     oat_hsv_params hp{};
     bool fast = false;              // the one-launch tail was used (status must be checked at collect)
@@ -1012,6 +1014,11 @@ struct oat_tracker {
     std::vector<Slot> ring;
     uint64_t head = 0, tailpos = 0;  // submitted / collected
     uint64_t replays = 0;            // frames whose tail had to be replayed through the unbounded path
+    // kernel choice: the pipelined fused kernel assumes most pixels take its fast path (<= 2 live modes, sample
+    // fits the heaviest); a stream where that fails (busy multi-modal scenes) is faster on the generic kernel
+    double slow_frac = 0.0;          // moving estimate of the fraction of 4-pixel groups leaving the fast path
+    bool use_generic = false;
+    uint64_t generic_frames = 0;
     DevBuf out_bgr, out_fg, out_hsv, out_thr;
     // profiling of the fused kernel
     int prof = 0;
@@ -1040,7 +1047,8 @@ extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_
             if (cudaHostAlloc(&s.h_res, sizeof(TailResult), cudaHostAllocDefault) != cudaSuccess ||
                 cudaMalloc(&s.d_res, sizeof(TailResult)) != cudaSuccess ||
                 cudaMalloc(&s.bits, t->tail.nwords * 4) != cudaSuccess ||
-                s.fb.create(t->tail.nwords, rows) != OAT_OK ||
+                s.fb.create(t->tail.nwords, rows) != OAT_OK || cudaMalloc(&s.d_slow, sizeof(unsigned int)) != cudaSuccess ||
+                cudaMemset(s.d_slow, 0, sizeof(unsigned int)) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.fused_done, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
@@ -1073,6 +1081,7 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
         if (s.d_res) cudaFree(s.d_res);
         if (s.bits) cudaFree(s.bits);
         s.fb.destroy();
+        if (s.d_slow) cudaFree(s.d_slow);
         if (s.fused_done) cudaEventDestroy(s.fused_done);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
@@ -1137,7 +1146,9 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, c->stream));
     }
-    CKRET(launch_fused(c, t->m, a));
+    a.slow_count = s.d_slow;
+    if (t->use_generic) ++t->generic_frames;
+    CKRET(launch_fused(c, t->m, a, !t->use_generic));
     if (t->prof) {
         CK(cudaEventRecord(e1, c->stream));
         t->prof_pending.emplace_back(e0, e1);
@@ -1153,7 +1164,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     }
     {
         int err = OAT_OK;
-        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err);
+        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err, s.d_slow);
         CKRET(err);
         if (!s.fast) {
             ts = c->stream;  // the unbounded path owns shared buffers: compute stream only
@@ -1217,6 +1228,12 @@ extern "C" int oat_tracker_collect(oat_tracker *t, oat_detection *out)
         CK(cudaMemcpyAsync(&s.h_res->det, &s.d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         ++t->replays;
+    }
+    if (s.fast) {  // the census rides on the one-launch tail's result
+        const double groups = (double)t->m.g.rows * t->m.g.cols / 4.0;
+        t->slow_frac = 0.75 * t->slow_frac + 0.25 * ((double)s.h_res->slow_groups / groups);
+        if (!t->use_generic && t->slow_frac > 0.30) t->use_generic = true;
+        else if (t->use_generic && t->slow_frac < 0.15) t->use_generic = false;
     }
     *out = s.h_res->det;
     ++t->tailpos;
@@ -1290,10 +1307,8 @@ extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [12]: sta
     out[3] = s.fast ? 1u : 0u;
     for (int i = 0; i < 8; ++i) out[4 + i] = s.h_res->cyc[i];
     // cyc[7] is replaced by the context's cumulative slow-path census (read and reset)
-    unsigned int sc = 0;
-    CK(cudaMemcpy(&sc, t->ctx->slow_count, sizeof(sc), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(t->ctx->slow_count, 0, sizeof(sc)));
-    out[11] = sc;
+    out[10] = (uint32_t)t->generic_frames;  // frames that ran the generic fused kernel (adaptive choice)
+    out[11] = s.h_res->slow_groups;          // census of that frame
     return OAT_OK;
 }
 

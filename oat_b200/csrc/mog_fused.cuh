@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(128, OAT_FUSED_MIN_BLOCKS) mog_fused_kernel(co
     const int x = (int)(g % gpr) * PX;
     const bool active = (y < a.rows) && (x < a.cols);  // PX==4 requires cols % 4 == 0
     uint32_t nib = 0;
+    bool multi = false;  // census: this thread's pixels carry more than one live mode
 
     if (active) {
         const size_t pidx = (size_t)y * (a.wpr * 32) + x;
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(128, OAT_FUSED_MIN_BLOCKS) mog_fused_kernel(co
         int nmax = n[0];
 #pragma unroll
         for (int i = 1; i < PX; ++i) nmax = max(nmax, n[i]);
+        multi = nmax >= 2;
         // thread-level dispatch on the number of live modes (spatially coherent in practice)
         if (nmax <= 1 || K == 1)
             nib = mog_body<K, 1, PX, TRACK>(a, lut, y, x, px, n);
@@ -539,6 +541,10 @@ __global__ void __launch_bounds__(128, OAT_FUSED_MIN_BLOCKS) mog_fused_kernel(co
             nib = mog_body<K, K, PX, TRACK>(a, lut, y, x, px, n);
     }
 
+    if (a.slow_count) {
+        const unsigned nm_ = __popc(__ballot_sync(0xffffffffu, multi));
+        if ((threadIdx.x & 31u) == 0 && nm_) atomicAdd(a.slow_count, (PX == 4 ? 1u : 0u) * nm_ + (PX == 4 ? 0u : (nm_ + 3u) / 4u));
+    }
     // ---- threshold mask, 1 bit/pixel: 8 lanes x 4 px (or 32 lanes x 1 px) -> one word --------
     if (a.thr_bits) {  // uniform
         const unsigned lane = threadIdx.x & 31u;

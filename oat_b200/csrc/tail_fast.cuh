@@ -28,7 +28,7 @@ struct TailResult {
     oat_detection det;
     int32_t status;      // TAIL_OK / TAIL_OVERFLOW
     uint32_t nodes;      // run-table entries the mask needed (diagnostic / sizing)
-    uint32_t slow_groups;  // fused kernel's slow-path census (filled by the host side from its counter)
+    uint32_t slow_groups;  // fused kernel's census: 4-pixel groups that left its fast path in this frame
     uint32_t pad;
     uint32_t cyc[8];     // SM-clock stamps of the labelling CTA (diagnostic): start, ticket, staged, counted, filled, merged, filled holes, end
 };
@@ -45,6 +45,7 @@ struct FastArgs {
     TailResult *res;
     int smem_bytes;          // dynamic shared memory per CTA
     int max_comps;
+    unsigned int *slow_in;   // or NULL: the fused kernel's slow-path census of this frame (read into the result, re-armed)
 };
 
 // ---- shared-memory union-find (parents only ever decrease) ----------------------------------
@@ -117,7 +118,7 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     r.det.x = r.det.y = r.det.area = 0.0;
     r.status = TAIL_OK;
     r.nodes = 0;
-    r.slow_groups = 0;
+    r.slow_groups = (tid == 0 && a.slow_in) ? atomicExch(a.slow_in, 0u) : 0u;
     r.pad = 0;
     for (int i = 0; i < 8; ++i) r.cyc[i] = 0;
     r.cyc[0] = a_t0;

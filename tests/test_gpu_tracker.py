@@ -106,3 +106,26 @@ def test_tracker_full_size_known_answer(ctx, shape):
     m = trk.state()[0]
     assert m.min() >= 1 and m.max() <= 5
     trk.close()
+
+
+def test_tracker_adaptive_kernel_choice_on_busy_stream(ctx):
+    """A multi-modal stream (heavy noise, fast adaptation) leaves the pipelined kernel's fast path on most
+    pixels: the tracker must switch to the generic fused kernel and stay bit-exact with the oracle throughout."""
+    from test_gpu_mog import noisy_stream
+
+    rows, cols, lr = 96, 128, 0.3
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    trk = oat_b200.Tracker(ctx, rows, cols, adaptation_coeff=lr, hsv=hp)
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t, f in enumerate(noisy_stream(rows, cols, 40, 20.0, seed=7)):
+        d, eg = trk.track(f, egress=("fgmask", "thresh"))
+        o, oeg = orc.track(f, lr, op)
+        assert np.array_equal(eg["fgmask"], oeg["fgmask"]), f"fgmask differs at t={t}"
+        assert np.array_equal(eg["thresh"], oeg["thresh"]), f"thresh differs at t={t}"
+        assert bool(d.position_valid) == bool(o.position_valid)
+        assert abs(d.x - o.x) <= TOL and abs(d.y - o.y) <= TOL and abs(d.area - o.area) <= TOL
+    st = trk.tail_stats()
+    assert st["cyc"][6] > 0, "the busy stream never switched to the generic kernel"
+    assert trk.live_modes() == int(orc.mog.state()[0].sum())
+    trk.close()

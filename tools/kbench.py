@@ -42,7 +42,7 @@ for i in range(args.steps):
 ctx.sync()
 tot = sorted(a.elapsed_time(b) for a, b in ev)
 ts = trk.tail_stats()
-print('slow groups (cumulative since last read):', ts['cyc'][7], 'over', args.steps + 31, 'frames ->', ts['cyc'][7] / (args.steps + 31) / (rows * cols / 4) * 100, '% of groups')
+print('slow groups in last frame:', ts['cyc'][7], '=', ts['cyc'][7] / (rows * cols / 4) * 100, '% of groups; generic-kernel frames:', ts['cyc'][6])
 c = ts["cyc"]
 print("tail:", {k: ts[k] for k in ("status", "nodes", "replays", "fast")}, "label-CTA cycles since start:",
       [(c[i] - c[0]) & 0xffffffff for i in range(1, 8)])
