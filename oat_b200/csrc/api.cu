@@ -207,7 +207,10 @@ static int stage_in(oat_ctx *c, cudaStream_t s, DevBuf &stage, const void *src, 
     }
     const size_t tight = (rowbytes + 15) & ~(size_t)15;
     CKRET(stage.ensure(tight * rows));
-    CK(cudaMemcpy2DAsync(stage.p, tight, src, pitch, rowbytes, rows, cudaMemcpyHostToDevice, s));
+    if (pitch == rowbytes && tight == rowbytes)  // contiguous frame: one linear DMA
+        CK(cudaMemcpyAsync(stage.p, src, rowbytes * rows, cudaMemcpyHostToDevice, s));
+    else
+        CK(cudaMemcpy2DAsync(stage.p, tight, src, pitch, rowbytes, rows, cudaMemcpyHostToDevice, s));
     *dptr = (const uint8_t *)stage.p;
     *dpitch = tight;
     return OAT_OK;
@@ -244,7 +247,12 @@ static int stage_out(DevBuf &stage, void *dst, size_t pitch, int rows, size_t ro
 static int finish_out(cudaStream_t s, const OutView &v)
 {
     if (v.host)
-        CK(cudaMemcpy2DAsync(v.host, v.hpitch, v.d, v.dpitch, v.rowbytes, v.rows, cudaMemcpyDeviceToHost, s));
+    {
+        if (v.hpitch == v.rowbytes && v.dpitch == v.rowbytes)
+            CK(cudaMemcpyAsync(v.host, v.d, v.rowbytes * v.rows, cudaMemcpyDeviceToHost, s));
+        else
+            CK(cudaMemcpy2DAsync(v.host, v.hpitch, v.d, v.dpitch, v.rowbytes, v.rows, cudaMemcpyDeviceToHost, s));
+    }
     return OAT_OK;
 }
 
