@@ -177,6 +177,23 @@ int oat_sift_contours(oat_hsvdet *det, const uint8_t *mask, size_t pitch, const 
                       oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch,
                       int32_t *labels_out);
 
+/* posidet thresh: replaces SimpleThreshold::detectPosition (src/positiondetector/SimpleThreshold.cpp:
+ * 130-143, :169-182): cv::inRange(grey, t_min, t_max) -> erode -> dilate -> siftContours on a 1-channel
+ * GREY frame; thresholds in 0..256 (256 == 255), erode/dilate/area from p. Egress as oat_hsvdet_detect. */
+int oat_thresh_detect(oat_hsvdet *det, const uint8_t *grey, size_t pitch, int t_min, int t_max,
+                      const oat_hsv_params *p, oat_detection *out, uint8_t *thresh_out,
+                      size_t thresh_pitch, int32_t *labels_out);
+
+/* framefilt thresh / framefilt mask: out = in where kept, 0 elsewhere (may alias in).
+ *   roi == NULL: replaces Threshold::filter (src/framefilter/Threshold.cpp:67-81): keep pixels whose
+ *                grey value (the frame itself if 1 channel, 8-bit cv::COLOR_BGR2GRAY if 3) lies in
+ *                [i_min, i_max], 0..256;
+ *   roi != NULL: replaces FrameMasker::filter (src/framefilter/FrameMasker.cpp:71-75):
+ *                frame.setTo(0, roi == 0), roi = rows x cols u8. */
+int oat_keep_where(oat_ctx *ctx, const uint8_t *in, size_t in_pitch, uint8_t *out, size_t out_pitch,
+                   int rows, int cols, int channels, const uint8_t *roi, size_t roi_pitch, int i_min,
+                   int i_max);
+
 /* ---- fused tracker: mog -> col HSV -> hsv in one pass over HBM ------------------------
  * One handle = one video stream (its own GMM state). Equivalent to the three reference
  * components chained with no shared-memory hops in between. */

@@ -116,6 +116,10 @@ _SIGS = {
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "oat_sift_contours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(HsvParams), C.POINTER(Detection),
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "oat_thresh_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(HsvParams),
+                                    C.POINTER(Detection), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "oat_keep_where": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "oat_tracker_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(MogParams), C.c_int,
                                      C.POINTER(C.c_void_p)]),
     "oat_tracker_destroy": (C.c_int, [C.c_void_p]),
@@ -386,6 +390,27 @@ def color_convert_hsv(ctx: Context, bgr: np.ndarray) -> np.ndarray:
     return out
 
 
+def threshold_filter(ctx: Context, frame: np.ndarray, i_min: int, i_max: int) -> np.ndarray:
+    """``framefilt thresh`` (src/framefilter/Threshold.cpp:67-81) on a host GREY or BGR frame."""
+    rows, cols = frame.shape[:2]
+    ch = 1 if frame.ndim == 2 else frame.shape[2]
+    _img(frame, rows, cols, ch)
+    out = np.empty_like(frame)
+    _ck(lib().oat_keep_where(ctx._h, _ptr(frame), cols * ch, _ptr(out), cols * ch, rows, cols, ch, None, 0, i_min, i_max))
+    return out
+
+
+def mask_filter(ctx: Context, frame: np.ndarray, roi: np.ndarray) -> np.ndarray:
+    """``framefilt mask`` (src/framefilter/FrameMasker.cpp:71-75): frame.setTo(0, roi == 0)."""
+    rows, cols = frame.shape[:2]
+    ch = 1 if frame.ndim == 2 else frame.shape[2]
+    _img(frame, rows, cols, ch)
+    _img(roi, rows, cols, 1)
+    out = np.empty_like(frame)
+    _ck(lib().oat_keep_where(ctx._h, _ptr(frame), cols * ch, _ptr(out), cols * ch, rows, cols, ch, _ptr(roi), cols, 0, 0))
+    return out
+
+
 class BackgroundSubtractor:
     """``framefilt bsub`` (src/framefilter/BackgroundSubtractor.cpp:87-100)."""
 
@@ -449,6 +474,16 @@ class HSVDetector:
     def detect(self, hsv, want_thresh=False, want_labels=False):
         """-> (Detection, thresh mask or None, labels or None)."""
         return self._run(lib().oat_hsvdet_detect, hsv, 3, want_thresh, want_labels)
+
+    def thresh_detect(self, grey, t_min, t_max, want_thresh=False, want_labels=False):
+        """``posidet thresh`` on a GREY frame (src/positiondetector/SimpleThreshold.cpp:169-182)."""
+        _img(grey, self.rows, self.cols, 1)
+        d = Detection()
+        thr = np.empty((self.rows, self.cols), np.uint8) if want_thresh else None
+        lab = np.empty((self.rows, self.cols), np.int32) if want_labels else None
+        _ck(lib().oat_thresh_detect(self._h, _ptr(grey), self.cols, t_min, t_max, C.byref(self.params), C.byref(d), _ptr(thr),
+                                    self.cols, _ptr(lab)))
+        return d, thr, lab
 
     def sift_contours(self, mask, want_thresh=False, want_labels=False):
         """siftContours on a binary mask (morphology per self.params applied first)."""

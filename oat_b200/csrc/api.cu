@@ -81,7 +81,7 @@ struct oat_ctx {
     unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
-    DevBuf scratch_in, scratch_out;  // staging for the stateless entry points
+    DevBuf scratch_in, scratch_out, scratch_roi;  // staging for the stateless entry points
 };
 
 extern "C" int oat_abi_version(void) { return OATGPU_ABI_VERSION; }
@@ -162,6 +162,7 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     c->flush.release();
     c->scratch_in.release();
     c->scratch_out.release();
+    c->scratch_roi.release();
     if (c->hsv_lut) cudaFree(c->hsv_lut);
     if (c->tile_counter) cudaFree(c->tile_counter);
     if (c->slow_count) cudaFree(c->slow_count);
@@ -931,8 +932,10 @@ extern "C" int oat_hsvdet_destroy(oat_hsvdet *h)
     return OAT_OK;
 }
 
+// channels 3: HSV frame + bands of p; 1 with t_min >= 0: grey frame + [t_min, t_max]; 1 with t_min < 0: binary mask
 static int detect_common(oat_hsvdet *h, const uint8_t *img, size_t pitch, int channels, const oat_hsv_params *p,
-                         oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch, int32_t *labels_out)
+                         oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch, int32_t *labels_out, int t_min = -1,
+                         int t_max = -1)
 {
     REQUIRE(h && img && out, "detect: null argument");
     CKRET(check_hsv_params(p));
@@ -960,6 +963,8 @@ static int detect_common(oat_hsvdet *h, const uint8_t *img, size_t pitch, int ch
     if (channels == 3)
         inrange_bits_kernel<<<gp, 256, 0, c->stream>>>(d, dp, g, p->h_min, p->s_min, p->v_min, p->h_max, p->s_max,
                                                        p->v_max, h->tail.bits0);
+    else if (t_min >= 0)
+        inrange1_bits_kernel<<<gp, 256, 0, c->stream>>>(d, dp, g, t_min, t_max, h->tail.bits0);
     else
         mask_to_bits_kernel<<<gp, 256, 0, c->stream>>>(d, dp, g, h->tail.bits0);
     LAUNCH_CHECK(c);
@@ -999,6 +1004,40 @@ extern "C" int oat_sift_contours(oat_hsvdet *h, const uint8_t *mask, size_t pitc
                                  oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch, int32_t *labels_out)
 {
     return detect_common(h, mask, pitch, 1, p, out, thresh_out, thresh_pitch, labels_out);
+}
+
+extern "C" int oat_thresh_detect(oat_hsvdet *h, const uint8_t *grey, size_t pitch, int t_min, int t_max,
+                                 const oat_hsv_params *p, oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch,
+                                 int32_t *labels_out)
+{
+    // SimpleThreshold.cpp:76-84: "Values of thresh should be between 0 and 256."
+    REQUIRE(t_min >= 0 && t_min <= 256 && t_max >= 0 && t_max <= 256, "Values of thresh should be between 0 and 256.");
+    return detect_common(h, grey, pitch, 1, p, out, thresh_out, thresh_pitch, labels_out, t_min, t_max);
+}
+
+// framefilt thresh / framefilt mask: zero the pixels outside an intensity band / a region-of-interest mask
+extern "C" int oat_keep_where(oat_ctx *c, const uint8_t *in, size_t in_pitch, uint8_t *out, size_t out_pitch, int rows, int cols,
+                              int channels, const uint8_t *roi, size_t roi_pitch, int i_min, int i_max)
+{
+    CKRET(bind(c));
+    REQUIRE(in && out && rows > 0 && cols > 0 && (channels == 1 || channels == 3), "oat_keep_where: bad arguments");
+    REQUIRE(in_pitch >= (size_t)channels * cols && out_pitch >= (size_t)channels * cols, "oat_keep_where: pitch too small");
+    REQUIRE(roi || (i_min >= 0 && i_min <= 256 && i_max >= 0 && i_max <= 256), "Values of intensity should be between 0 and 256.");
+    REQUIRE(!roi || roi_pitch >= (size_t)cols, "oat_keep_where: mask pitch too small");
+    const uint8_t *d;
+    size_t dp;
+    CKRET(stage_in(c, c->stream, c->scratch_in, in, in_pitch, rows, (size_t)channels * cols, &d, &dp));
+    OutView ov;
+    CKRET(stage_out(c->scratch_out, out, out_pitch, rows, (size_t)channels * cols, &ov));
+    const uint8_t *droi = nullptr;
+    size_t droi_pitch = 0;
+    if (roi) CKRET(stage_in(c, c->stream, c->scratch_roi, roi, roi_pitch, rows, (size_t)cols, &droi, &droi_pitch));
+    keep_where_kernel<<<nblocks((long long)rows * cols, 256), 256, 0, c->stream>>>(d, dp, ov.d, ov.dpitch, rows, cols, channels,
+                                                                                 droi, droi_pitch, i_min, i_max);
+    LAUNCH_CHECK(c);
+    CKRET(finish_out(c->stream, ov));
+    CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
 }
 
 // ---- fused tracker -------------------------------------------------------------------------

@@ -43,6 +43,43 @@ __global__ void inrange_bits_kernel(const uint8_t *__restrict__ img, size_t pitc
     if ((threadIdx.x & 31) == 0 && y < g.rows) bits[(size_t)y * g.wpr + (x >> 5)] = w;
 }
 
+// cv::inRange on a 1-channel frame -> bits (posidet thresh, src/positiondetector/SimpleThreshold.cpp:169-172)
+__global__ void inrange1_bits_kernel(const uint8_t *__restrict__ img, size_t pitch, BitGeom g, int lo, int hi,
+                                     uint32_t *__restrict__ bits)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ppx = g.pitch_px();
+    const int y = (int)(t / ppx), x = (int)(t % ppx);
+    bool in = false;
+    if (y < g.rows && x < g.cols) {
+        const int v = img[(size_t)y * pitch + x];
+        in = (lo <= v) & (v <= hi);
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && y < g.rows) bits[(size_t)y * g.wpr + (x >> 5)] = w;
+}
+
+// framefilt thresh (src/framefilter/Threshold.cpp:67-81): grey = cvtColor(BGR2GRAY) (8-bit fixed point:
+// (3735 b + 19235 g + 9798 r + 16384) >> 15), keep = inRange(grey, lo, hi), frame.setTo(0, keep == 0).
+// framefilt mask (src/framefilter/FrameMasker.cpp:71-75): frame.setTo(0, roi == 0).  One thread per pixel.
+__global__ void keep_where_kernel(const uint8_t *__restrict__ in, size_t in_pitch, uint8_t *__restrict__ out, size_t out_pitch,
+                                  int rows, int cols, int ch, const uint8_t *__restrict__ roi, size_t roi_pitch, int lo, int hi)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)rows * cols) return;
+    const int y = (int)(t / cols), x = (int)(t % cols);
+    const uint8_t *s = in + (size_t)y * in_pitch + (size_t)ch * x;
+    bool keep;
+    if (roi) {
+        keep = roi[(size_t)y * roi_pitch + x] != 0;
+    } else {
+        const int grey = ch == 3 ? ((3735 * s[0] + 19235 * s[1] + 9798 * s[2] + 16384) >> 15) : s[0];
+        keep = (lo <= grey) & (grey <= hi);
+    }
+    uint8_t *d = out + (size_t)y * out_pitch + (size_t)ch * x;
+    for (int c = 0; c < ch; ++c) d[c] = keep ? s[c] : 0;
+}
+
 // u8 mask (non-zero = foreground) -> bits
 __global__ void mask_to_bits_kernel(const uint8_t *__restrict__ mask, size_t pitch, BitGeom g,
                                     uint32_t *__restrict__ bits)

@@ -9,8 +9,10 @@
 // Both shared-memory mappings (the SOURCE's frame and this SINK's frame) are page-locked once, so the
 // per-frame copies are asynchronous DMA straight from / into shared memory (HOST_PINNED variant);
 // the SOURCE is released as soon as its pixels are on the device, as in FrameFilter::process().
+#include <cstdio>
 #include <iostream>
 #include <memory>
+#include <vector>
 
 #include "gpu.h"
 #include "oat_cli.h"
@@ -194,6 +196,91 @@ private:
     oat_bsub *bsub_{nullptr};
 };
 
+// ---- framefilt thresh (Threshold.{h,cpp}) ----------------------------------------------------------------------
+class Threshold : public FrameFilter {
+public:
+    Threshold(const std::string &source, const std::string &sink) : FrameFilter(source, sink) { name_ = "thresh[" + source + "->" + sink + "]"; }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"intensity", 'I', true, "Array of ints between 0 and 256, [min,max], specifying the intensity passband."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        std::vector<int> v;
+        if (config::getArray<int>(vm, t, "intensity", v, 2)) {
+            i_min_ = v[0];
+            i_max_ = v[1];
+            if (i_min_ < 0 || i_min_ > 256 || i_max_ < 0 || i_max_ > 256)
+                throw std::runtime_error("Values of intensity should be between 0 and 256.");  // Threshold.cpp:58-62
+        }
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void filter(const uint8_t *d_in, uint8_t *d_out) override
+    {
+        const int ch = color_bytes(in_.color);
+        gpu::ck(oat_keep_where(ctx_->h, d_in, in_.cols * ch, d_out, in_.cols * ch, (int)in_.rows, (int)in_.cols, ch, nullptr, 0, i_min_, i_max_));
+    }
+
+private:
+    int i_min_{0}, i_max_{256};
+};
+
+// ---- framefilt mask (FrameMasker.{h,cpp}); the mask image is a binary PGM (P5) file --------------------------------
+class FrameMasker : public FrameFilter {
+public:
+    FrameMasker(const std::string &source, const std::string &sink) : FrameFilter(source, sink) { name_ = "framemask[" + source + "->" + sink + "]"; }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"mask", 'm', true, "Path to a binary (P5) PGM image used to mask frames from SOURCE: pixels where the mask is 0 are set to 0."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        std::string path;
+        if (config::getString(vm, t, "mask", path)) {
+            FILE *f = std::fopen(path.c_str(), "rb");
+            int w = 0, h = 0, maxv = 0;
+            if (!f || std::fscanf(f, "P5 %d %d %d", &w, &h, &maxv) != 3 || maxv != 255 || std::fgetc(f) == EOF) {
+                if (f) std::fclose(f);
+                throw std::runtime_error("File \"" + path + "\" could not be read.");  // FrameMasker.cpp:64-65
+            }
+            roi_.resize((size_t)w * h);
+            const size_t got = std::fread(roi_.data(), 1, roi_.size(), f);
+            std::fclose(f);
+            if (got != roi_.size()) throw std::runtime_error("File \"" + path + "\" could not be read.");
+            roi_w_ = w;
+            roi_h_ = h;
+        }
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override
+    {
+        if (!roi_.empty()) {
+            if ((size_t)roi_w_ != in_.cols || (size_t)roi_h_ != in_.rows) throw std::runtime_error("Mask image and frames must have the same size.");
+            d_roi_.reset(new gpu::DeviceBuffer(*ctx_, roi_.size()));
+            gpu::ck(oat_memcpy(ctx_->h, d_roi_->p, roi_.data(), roi_.size()));
+        }
+    }
+    void filter(const uint8_t *d_in, uint8_t *d_out) override
+    {
+        const int ch = color_bytes(in_.color);
+        if (d_roi_)
+            gpu::ck(oat_keep_where(ctx_->h, d_in, in_.cols * ch, d_out, in_.cols * ch, (int)in_.rows, (int)in_.cols, ch, d_roi_->u8(), in_.cols, 0, 0));
+        else  // no mask configured: frames pass through (FrameMasker.cpp:73)
+            gpu::ck(oat_memcpy(ctx_->h, d_out, d_in, in_.bytes));
+    }
+
+private:
+    std::vector<uint8_t> roi_;
+    int roi_w_{0}, roi_h_{0};
+    std::unique_ptr<gpu::DeviceBuffer> d_roi_;
+};
+
 }  // namespace oat
 
 static void printUsage(std::ostream &out)
@@ -204,6 +291,8 @@ static void printUsage(std::ostream &out)
            "TYPE\n"
            "  bsub: Background subtraction\n"
            "  col: Color conversion (BGR to HSV)\n"
+           "  mask: Binary frame masking\n"
+           "  thresh: Simple intensity threshold\n"
            "  mog: Mixture of Gaussians background segmentation\n\n"
            "SOURCE:\n  User-supplied name of the memory segment to receive frames from (e.g. raw).\n\n"
            "SINK:\n  User-supplied name of the memory segment to publish frames to (e.g. filt).\n\n"
@@ -229,7 +318,7 @@ int main(int argc, char *argv[])
             if (argv[i][0] == '-') break;
             pos.push_back(argv[i]);
         }
-        if (type != "mog" && type != "col" && type != "bsub") {
+        if (type != "mog" && type != "col" && type != "bsub" && type != "thresh" && type != "mask") {
             printUsage(std::cout);
             std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
             return -1;
@@ -239,6 +328,8 @@ int main(int argc, char *argv[])
         std::shared_ptr<FrameFilter> filter;
         if (type == "mog") filter = std::make_shared<BackgroundSubtractorMOG>(pos[0], pos[1]);
         else if (type == "col") filter = std::make_shared<ColorConvert>(pos[0], pos[1]);
+        else if (type == "thresh") filter = std::make_shared<Threshold>(pos[0], pos[1]);
+        else if (type == "mask") filter = std::make_shared<FrameMasker>(pos[0], pos[1]);
         else filter = std::make_shared<BackgroundSubtractor>(pos[0], pos[1]);
         comp_name = filter->name();
 

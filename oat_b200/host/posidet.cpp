@@ -149,6 +149,51 @@ private:
     oat_hsvdet *det_{nullptr};
 };
 
+// ---- posidet thresh (SimpleThreshold.{h,cpp}) ---------------------------------------------------------------
+class SimpleThreshold : public PositionDetector {
+public:
+    SimpleThreshold(const std::string &source, const std::string &sink) : PositionDetector(source, sink)
+    {
+        name_ = "threshdetector[" + source + "->" + sink + "]";
+        required_color_ = PIX_GREY;  // SimpleThreshold.cpp:46
+    }
+    ~SimpleThreshold() { oat_hsvdet_destroy(det_); }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"thresh", 'T', true, "Array of ints between 0 and 256, [min,max], specifying the intensity passband."},
+                {"erode", 'e', true, "Contour erode kernel size in pixels (normalized box filter)."},
+                {"dilate", 'd', true, "Contour dilation kernel size in pixels (normalized box filter)."},
+                {"area", 'a', true, "Array of floats, [min,max], specifying the minimum and maximum object contour area in pixels^2."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        std::vector<int> v;
+        if (config::getArray<int>(vm, t, "thresh", v, 2)) {
+            t_min_ = v[0];
+            t_max_ = v[1];
+            if (t_min_ < 0 || t_min_ > 256 || t_max_ < 0 || t_max_ > 256)
+                throw std::runtime_error("Values of thresh should be between 0 and 256.");
+        }
+        o_.apply(vm, t);  // erode / dilate / area share HSVDetector's semantics (SimpleThreshold.cpp:86-110)
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override { gpu::ck(oat_hsvdet_create(ctx_->h, (int)in_.rows, (int)in_.cols, &det_)); }
+    void detectPosition(const uint8_t *d_frame, Position2D &position) override
+    {
+        oat_detection d;
+        gpu::ck(oat_thresh_detect(det_, d_frame, in_.cols, t_min_, t_max_, &o_.p, &d, nullptr, 0, nullptr));
+        fill(position, d);
+    }
+
+private:
+    HSVOptions o_;
+    int t_min_{0}, t_max_{256};
+    oat_hsvdet *det_{nullptr};
+};
+
 // ---- posidet track: mog -> col HSV -> hsv fused on the device ----------------------------------------------
 class FusedTracker : public PositionDetector {
 public:
@@ -196,6 +241,7 @@ static void printUsage(std::ostream &out)
            "Perform object detection on frames from SOURCE. Publish detected object positions to SINK.\n\n"
            "TYPE\n"
            "  hsv: Object detection using color thresholding (requires an HSV frame SOURCE)\n"
+           "  thresh: Object detection using intensity thresholding (requires a GREY frame SOURCE)\n"
            "  track: fused mog + HSV conversion + hsv detection on a BGR frame SOURCE\n\n"
            "SOURCE:\n  User-supplied name of the memory segment to receive frames from (e.g. raw).\n\n"
            "SINK:\n  User-supplied name of the memory segment to publish detected positions to (e.g. pos).\n\n"
@@ -220,7 +266,7 @@ int main(int argc, char *argv[])
             if (argv[i][0] == '-') break;
             pos.push_back(argv[i]);
         }
-        if (type != "hsv" && type != "track") {
+        if (type != "hsv" && type != "track" && type != "thresh") {
             printUsage(std::cout);
             std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
             return -1;
@@ -229,6 +275,7 @@ int main(int argc, char *argv[])
         if (pos.size() < 2) { printUsage(std::cout); std::cerr << whoError(comp_name, "Error: a SINK name must be specified.\n"); return -1; }
         std::shared_ptr<PositionDetector> detector;
         if (type == "hsv") detector = std::make_shared<HSVDetector>(pos[0], pos[1]);
+        else if (type == "thresh") detector = std::make_shared<SimpleThreshold>(pos[0], pos[1]);
         else detector = std::make_shared<FusedTracker>(pos[0], pos[1]);
         comp_name = detector->name();
 

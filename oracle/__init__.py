@@ -317,3 +317,46 @@ class Tracker:
         hsv = bgr2hsv(filt)
         det, thr = hsv_detect(hsv, p)
         return det, dict(fgmask=fg, bgr=filt, hsv=hsv, thresh=thr)
+
+
+# ---- posidet thresh / framefilt thresh / framefilt mask (numpy restatements; pinned against cv2 in tests) -------
+def inrange1(grey: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """cv::inRange on a 1-channel u8 image with Oat's 0..256 option range (src/positiondetector/
+    SimpleThreshold.cpp:169-172): inclusive both ends, bounds saturate to u8 so 256 == 255, lo > 255 passes nothing."""
+    g = grey.astype(np.int32)
+    return (((g >= lo) & (g <= hi)).astype(np.uint8)) * 255
+
+
+def bgr2grey(bgr: np.ndarray) -> np.ndarray:
+    """8-bit cv::COLOR_BGR2GRAY as the pinned OpenCV 4.13 computes it: 15-bit fixed point
+    (3735 b + 19235 g + 9798 r + 16384) >> 15 (OpenCV 3.x used 14-bit coefficients; +-1 on ~0.3 % of colours)."""
+    b = bgr[..., 0].astype(np.int32)
+    g = bgr[..., 1].astype(np.int32)
+    r = bgr[..., 2].astype(np.int32)
+    return ((3735 * b + 19235 * g + 9798 * r + 16384) >> 15).astype(np.uint8)
+
+
+def threshold_filter(frame: np.ndarray, i_min: int, i_max: int) -> np.ndarray:
+    """Threshold::filter (src/framefilter/Threshold.cpp:67-81): grey inRange, then frame.setTo(0, thresh == 0)."""
+    grey = bgr2grey(frame) if frame.ndim == 3 else frame
+    keep = inrange1(grey, i_min, i_max) != 0
+    out = frame.copy()
+    out[~keep] = 0
+    return out
+
+
+def mask_filter(frame: np.ndarray, roi: np.ndarray) -> np.ndarray:
+    """FrameMasker::filter (src/framefilter/FrameMasker.cpp:71-75): frame.setTo(0, roi == 0)."""
+    out = frame.copy()
+    out[roi == 0] = 0
+    return out
+
+
+def thresh_detect(grey: np.ndarray, t_min: int, t_max: int, p: "HsvParams"):
+    """SimpleThreshold::detectPosition: inRange -> erode -> dilate -> siftContours. Returns (Detection, mask)."""
+    m = inrange1(grey, t_min, t_max)
+    if p.erode > 0:
+        m = erode_rect(m, p.erode)
+    if p.dilate > 0:
+        m = dilate_rect(m, p.dilate)
+    return sift_contours(m, p.area[0], p.area[1]), m

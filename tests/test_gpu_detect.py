@@ -177,3 +177,35 @@ def test_bsub_parity(ctx):
                 f = rng.integers(0, 256, shape).astype(np.uint8)
                 assert np.array_equal(gpu.filter(f), orc.apply(f)), f"alpha={alpha} ch={ch} t={t}"
             gpu.close()
+
+
+@pytest.mark.parametrize("band", [(0, 256), (100, 200), (200, 100), (256, 256), (180, 256)])
+@pytest.mark.parametrize("morph", [(0, 0), (0, 10), (3, 5)])
+def test_posidet_thresh_parity(ctx, band, morph):
+    """posidet thresh (src/positiondetector/SimpleThreshold.cpp:169-182): GREY inRange -> erode -> dilate -> siftContours."""
+    rows, cols = 96, 140
+    rng = np.random.default_rng(band[0] * 7 + morph[1])
+    grey = np.clip(rng.normal(90, 30, (rows, cols)), 0, 255).astype(np.uint8)
+    yy, xx = np.mgrid[:rows, :cols]
+    for cy, cx, r in [(30, 40, 14), (60, 100, 9), (80, 20, 6)]:
+        grey[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 230
+    det = oat_b200.HSVDetector(ctx, rows, cols, oat_b200.HsvParams.make(erode=morph[0], dilate=morph[1]))
+    d, thr, lab = det.thresh_detect(grey, band[0], band[1], want_thresh=True, want_labels=True)
+    o, om = oracle.thresh_detect(grey, band[0], band[1], oracle.HsvParams(erode=morph[0], dilate=morph[1]))
+    assert np.array_equal(thr, om)
+    assert np.array_equal(lab, oracle.label8(om))
+    check_detection(d, o)
+    with pytest.raises(oat_b200.OatError):
+        det.thresh_detect(grey, 0, 300)
+    det.close()
+
+
+@pytest.mark.parametrize("shape", [(48, 64, 3), (37, 53, 3), (40, 72)])
+def test_framefilt_thresh_and_mask_parity(ctx, shape):
+    """framefilt thresh (Threshold.cpp:67-81) and framefilt mask (FrameMasker.cpp:71-75): bit-exact."""
+    rng = np.random.default_rng(shape[1])
+    frame = rng.integers(0, 256, shape, dtype=np.uint8)
+    for lo, hi in [(0, 256), (64, 192), (192, 64), (256, 256), (0, 0)]:
+        assert np.array_equal(oat_b200.threshold_filter(ctx, frame, lo, hi), oracle.threshold_filter(frame, lo, hi)), (lo, hi)
+    roi = (rng.random(shape[:2]) < 0.5).astype(np.uint8) * 255
+    assert np.array_equal(oat_b200.mask_filter(ctx, frame, roi), oracle.mask_filter(frame, roi))

@@ -204,3 +204,24 @@ def test_whole_chain_vs_cv2(lr):
         if lr == 0.0 and t >= 1:
             cx, cy = synth.disc_centre(rows, cols, t)
             assert (o.x, o.y) == (cx + 0.5, cy + 0.5) and o.n_components == 1
+
+
+def test_thresh_and_mask_restatements_match_cv2():
+    """posidet thresh / framefilt thresh / framefilt mask: the numpy restatements against the cv2 calls the
+    reference makes (SimpleThreshold.cpp:169-172, Threshold.cpp:67-81, FrameMasker.cpp:71-75)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (64, 96, 3), dtype=np.uint8)
+    grey = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(oracle.bgr2grey(bgr), grey)
+    # exhaustive check of the fixed-point grey formula on a colour cube slice
+    cube = np.stack(np.meshgrid(np.arange(0, 256, 5), np.arange(256), np.arange(0, 256, 3), indexing="ij"), -1).astype(np.uint8)
+    assert np.array_equal(oracle.bgr2grey(cube), cv2.cvtColor(cube.reshape(-1, 1, 3), cv2.COLOR_BGR2GRAY).reshape(cube.shape[:3]))
+    for lo, hi in [(0, 256), (100, 200), (200, 100), (256, 256), (0, 0), (255, 256), (37, 37)]:
+        want = cv2.inRange(grey, lo, hi)
+        assert np.array_equal(oracle.inrange1(grey, lo, hi), want), (lo, hi)
+        t = bgr.copy()
+        t[want == 0] = 0  # frame.setTo(0, thresh == 0)
+        assert np.array_equal(oracle.threshold_filter(bgr, lo, hi), t)
+    roi = (rng.random((64, 96)) < 0.6).astype(np.uint8) * 200
+    assert np.array_equal(oracle.mask_filter(bgr, roi), cv2.bitwise_and(bgr, bgr, mask=roi))
