@@ -78,6 +78,9 @@ struct oat_ctx {
     uint64_t launches = 0;
     int num_sms = 148;
     bool pipe_attr_set = false;
+    // development switches, read once at creation: OAT_B200_NO_PIPE / _NO_FAST_TAIL / _NO_OVERLAP force the generic
+    // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
+    bool no_pipe = false, no_fast_tail = false, no_overlap = false;
     unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
@@ -124,6 +127,9 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     if (!c) return fail(OAT_ERR_NOMEM, "out of host memory");
     c->device = device_index;
     c->num_sms = prop.multiProcessorCount;
+    c->no_pipe = getenv("OAT_B200_NO_PIPE") != nullptr;
+    c->no_fast_tail = getenv("OAT_B200_NO_FAST_TAIL") != nullptr;
+    c->no_overlap = getenv("OAT_B200_NO_OVERLAP") != nullptr;
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
@@ -380,7 +386,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
     // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
     // the state write-back; with a live rate every live mode changes every frame anyway.
     const bool frozen = (a.c.aT == 0.0f) && !a.reset;
-    if (vec && !a.reset && m.K == 5 && allow_pipe && !getenv("OAT_B200_NO_PIPE")) {
+    if (vec && !a.reset && m.K == 5 && allow_pipe && !c->no_pipe) {
         // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
         // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
         const size_t tight3 = (size_t)3 * m.g.cols;
@@ -767,7 +773,7 @@ struct Tail {
     {
         *err = OAT_OK;
         const BitGeom g = tb.g;
-        if (fast_smem == 0 || g.rows < 2 || getenv("OAT_B200_NO_FAST_TAIL")) return false;
+        if (fast_smem == 0 || g.rows < 2 || c->no_fast_tail) return false;
         const int ke = p.erode_px > 0 ? p.erode_px : 0, kd = p.dilate_px > 0 ? p.dilate_px : 0;
         const int R = 8;
         const size_t nin = (size_t)R + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
@@ -1204,7 +1210,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     CKRET(finish_out(c->stream, ofg));
     CKRET(finish_out(c->stream, ohsv));
     cudaStream_t ts = c->stream;
-    if (overlap && !getenv("OAT_B200_NO_OVERLAP")) {
+    if (overlap && !c->no_overlap) {
         ts = c->tail[t->head % oat_ctx::NTAIL];
         CK(cudaEventRecord(s.fused_done, c->stream));
         CK(cudaStreamWaitEvent(ts, s.fused_done, 0));

@@ -81,6 +81,22 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// same, with an L2 eviction-priority hint (createpolicy): the input frame is read exactly once, so it
+// must not displace the GMM planes, which the next frame of the stream re-reads from L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
@@ -165,6 +181,52 @@ __device__ __forceinline__ bool fast_px(const float x0, const float x1, const fl
         n = nn;
     }
     return ok;
+}
+
+// Frozen model (learning rate 0 -- Oat's default -a 0 -- where nothing is ever inserted), one live mode:
+// the whole of mog2_pixel() for that case inline, classification included, so that foreground pixels do
+// not leave the fast path: returns the mask value {0, shadow, 255}, or 0xffffffff if the mode would be
+// pruned (left to the slow path).  Same operations in the same order as mog2_pixel().
+__device__ __forceinline__ uint32_t frozen_px(const float x0, const float x1, const float x2, float &W, float &V, float &A,
+                                              float &B, float &C, const MogConsts &c, bool &dirty)
+{
+    float w = fadd(fmul(c.a1, W), c.prune);
+    const float d0 = fsub(A, x0), d1 = fsub(B, x1), d2 = fsub(C, x2);
+    const float dist2 = fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fmul(d2, d2));
+    const bool bg = (0.f < c.TB) && (dist2 < fmul(c.Tb, V));
+    float nA = A, nB = B, nC = C, vn = V;
+    if (dist2 < fmul(c.Tg, V)) {
+        w = fadd(w, c.aT);
+        const float k = fdiv(c.aT, w);
+        nA = fsub(A, fmul(k, d0));
+        nB = fsub(B, fmul(k, d1));
+        nC = fsub(C, fmul(k, d2));
+        vn = fadd(V, fmul(k, fsub(dist2, V)));
+        vn = (vn < c.varMin) ? c.varMin : vn;
+        vn = (vn > c.varMax) ? c.varMax : vn;
+    }
+    if (w < -c.prune) return 0xffffffffu;
+    const float tot = fadd(0.f, w);
+    float inv = 0.f;
+    if (fabsf(tot) > FLT_EPSILON) inv = fdiv(1.f, tot);
+    const float nW = fmul(w, inv);
+    upd<true>(W, nW, dirty);
+    upd<true>(V, vn, dirty);
+    upd<true>(A, nA, dirty);
+    upd<true>(B, nB, dirty);
+    upd<true>(C, nC, dirty);
+    if (bg) return 0u;
+    if (c.detect_shadows) {  // detectShadowGMM over the single mode
+        const float num = fadd(fadd(fadd(0.f, fmul(x0, nA)), fmul(x1, nB)), fmul(x2, nC));
+        const float den = fadd(fadd(fadd(0.f, fmul(nA, nA)), fmul(nB, nB)), fmul(nC, nC));
+        if (den != 0.f && num <= den && num >= fmul(c.tau, den)) {
+            const float a = fdiv(num, den);
+            const float e0 = fsub(fmul(a, nA), x0), e1 = fsub(fmul(a, nB), x1), e2 = fsub(fmul(a, nC), x2);
+            const float dist2a = fadd(fadd(fadd(0.f, fmul(e0, e0)), fmul(e1, e1)), fmul(e2, e2));
+            if (dist2a < fmul(fmul(fmul(c.Tb, vn), a), a)) return (uint32_t)c.shadow_value;
+        }
+    }
+    return 255u;
 }
 
 __device__ __forceinline__ float sel4(const float4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
@@ -313,6 +375,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     if (tid >= PIPE_CTHREADS) {
         // ---- producer warp: one lane drives the bulk-copy engine -------------------------------
         if (tid != PIPE_CTHREADS) return;
+        const uint64_t pol_first = l2_policy_evict_first();
         auto tile_span = [&](int tile, size_t &p0, uint32_t &npx) {
             p0 = (size_t)tile * PIPE_TILE;
             const size_t rem = a.plane - p0;
@@ -328,7 +391,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             for (int cc = 0; cc < 5; ++cc)
                 bulk_g2s(st + cc * (PIPE_TILE * 4), a.state + (size_t)cc * a.plane + p0, npx * 4u, &full[s]);
             bulk_g2s(st + PIPE_OFF_NM, a.nmodes + p0, npx, &full[s]);
-            if (DYN) bulk_g2s(st + PIPE_OFF_BGR, a.bgr + 3 * p0, npx * 3u, &full[s]);
+            if (DYN) bulk_g2s_hint(st + PIPE_OFF_BGR, a.bgr + 3 * p0, npx * 3u, &full[s], pol_first);
         };
         // next tile of this CTA's sequence, or -1 when the frame is exhausted (DYN: every CTA draws
         // exactly one number >= ntiles; the CTA that draws the last one re-arms the counter)
@@ -469,7 +532,45 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             const uint32_t nm = *(reinterpret_cast<const uint32_t *>(st + PIPE_OFF_NM) + tid);
             bool fast = false;
             const uint32_t two = nm - 0x01010101u;  // per pixel: 0 = one mode, 1 = two modes
-            if ((two & ~0x01010101u) == 0u && (K >= 2 || two == 0u)) {
+            if (TRACK && two == 0u && a.c.aT == 0.f && !a.bgr_out && !a.hsv_out && !a.fg_out) {
+                // frozen one-mode model: classify in place, foreground included
+                const uint32_t *smb = reinterpret_cast<const uint32_t *>(st + PIPE_OFF_BGR) + tid * 3;
+                const uint32_t w0 = smb[0], w1 = smb[1], w2 = smb[2];
+                float4 W = *reinterpret_cast<const float4 *>(sm0);
+                float4 V = *reinterpret_cast<const float4 *>(sm0 + PIPE_TILE);
+                float4 A = *reinterpret_cast<const float4 *>(sm0 + 2 * PIPE_TILE);
+                float4 B = *reinterpret_cast<const float4 *>(sm0 + 3 * PIPE_TILE);
+                float4 C = *reinterpret_cast<const float4 *>(sm0 + 4 * PIPE_TILE);
+                const uint32_t b0 = w0 & 255u, g0 = (w0 >> 8) & 255u, r0 = (w0 >> 16) & 255u, b1 = w0 >> 24, g1 = w1 & 255u,
+                               r1 = (w1 >> 8) & 255u, b2 = (w1 >> 16) & 255u, g2 = w1 >> 24, r2 = w2 & 255u, b3 = (w2 >> 8) & 255u,
+                               g3 = (w2 >> 16) & 255u, r3 = w2 >> 24;
+                bool d2 = false;
+                const uint32_t m0 = frozen_px((float)b0, (float)g0, (float)r0, W.x, V.x, A.x, B.x, C.x, a.c, d2);
+                const uint32_t m1 = frozen_px((float)b1, (float)g1, (float)r1, W.y, V.y, A.y, B.y, C.y, a.c, d2);
+                const uint32_t m2 = frozen_px((float)b2, (float)g2, (float)r2, W.z, V.z, A.z, B.z, C.z, a.c, d2);
+                const uint32_t m3 = frozen_px((float)b3, (float)g3, (float)r3, W.w, V.w, A.w, B.w, C.w, a.c, d2);
+                if ((m0 | m1 | m2 | m3) != 0xffffffffu) {
+                    fast = true;
+                    if (d2) {
+                        *reinterpret_cast<float4 *>(sm0) = W;
+                        *reinterpret_cast<float4 *>(sm0 + PIPE_TILE) = V;
+                        *reinterpret_cast<float4 *>(sm0 + 2 * PIPE_TILE) = A;
+                        *reinterpret_cast<float4 *>(sm0 + 3 * PIPE_TILE) = B;
+                        *reinterpret_cast<float4 *>(sm0 + 4 * PIPE_TILE) = C;
+                        dirty = true;
+                    }
+                    nib = zero_nib;
+                    if ((m0 | m1 | m2 | m3) != 0u && a.do_hsv) {  // some pixel keeps its colour: threshold it
+                        auto bit = [&](uint32_t mk, uint32_t b, uint32_t g, uint32_t r) -> uint32_t {
+                            if (!mk) return zero_nib & 1u;
+                            int h, sa, v;
+                            bgr2hsv_px_div((int)b, (int)g, (int)r, h, sa, v);
+                            return ((a.lo[0] <= h) & (h <= a.hi[0]) & (a.lo[1] <= sa) & (sa <= a.hi[1]) & (a.lo[2] <= v) & (v <= a.hi[2])) ? 1u : 0u;
+                        };
+                        nib = bit(m0, b0, g0, r0) | (bit(m1, b1, g1, r1) << 1) | (bit(m2, b2, g2, r2) << 2) | (bit(m3, b3, g3, r3) << 3);
+                    }
+                }
+            } else if ((two & ~0x01010101u) == 0u && (K >= 2 || two == 0u)) {
                 // mode 1's weights first: the only global read of this path, in flight during the mode-0 maths
                 float4 W1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float *w1p = a.state + (size_t)5 * a.plane + pidx;
