@@ -255,6 +255,13 @@ int oat_free_pinned(void *p);
 /* Page-lock an existing mapping (e.g. a shmemdf segment) so copies from/to it are async DMA. */
 int oat_register_host(void *p, size_t bytes);
 int oat_unregister_host(void *p);
+/* Device-resident Frame variant across processes (SharedFrameHeader memory kind DEVICE): export a device
+ * allocation made with oat_alloc_device as a 64-byte handle (cudaIpcMemHandle_t) that travels in the
+ * shared frame header; another process on the same GPU opens it and passes the pointer to any entry
+ * point above. The exporter must outlive the importers' use. */
+int oat_ipc_export(oat_ctx *ctx, const void *dev_ptr, unsigned char handle[64]);
+int oat_ipc_open(oat_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int oat_ipc_close(oat_ctx *ctx, void *dev_ptr);
 /* Copy between any two of {device, pinned, pageable}; synchronous. */
 int oat_memcpy(oat_ctx *ctx, void *dst, const void *src, size_t bytes);
 /* L2 flush for benchmarking: overwrites an internal buffer larger than L2. */

@@ -143,6 +143,9 @@ _SIGS = {
     "oat_free_pinned": (C.c_int, [C.c_void_p]),
     "oat_register_host": (C.c_int, [C.c_void_p, C.c_size_t]),
     "oat_unregister_host": (C.c_int, [C.c_void_p]),
+    "oat_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    "oat_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "oat_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "oat_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "oat_flush_l2": (C.c_int, [C.c_void_p]),
 }

@@ -1449,6 +1449,31 @@ extern "C" int oat_unregister_host(void *p)
     if (p) CK(cudaHostUnregister(p));
     return OAT_OK;
 }
+extern "C" int oat_ipc_export(oat_ctx *c, const void *dev_ptr, unsigned char handle[64])
+{
+    CKRET(bind(c));
+    REQUIRE(dev_ptr && handle, "oat_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return OAT_OK;
+}
+extern "C" int oat_ipc_open(oat_ctx *c, const unsigned char handle[64], void **dev_ptr)
+{
+    CKRET(bind(c));
+    REQUIRE(dev_ptr && handle, "oat_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return OAT_OK;
+}
+extern "C" int oat_ipc_close(oat_ctx *c, void *dev_ptr)
+{
+    CKRET(bind(c));
+    if (dev_ptr) CK(cudaIpcCloseMemHandle(dev_ptr));
+    return OAT_OK;
+}
 extern "C" int oat_memcpy(oat_ctx *c, void *dst, const void *src, size_t bytes)
 {
     CKRET(bind(c));

@@ -38,14 +38,25 @@ protected:
         const size_t out_bytes = in_.rows * in_.cols * (size_t)color_bytes(out_color);
         frame_sink_.bind(frame_sink_address_, out_bytes);
         shared_frame_ = frame_sink_.retrieve(in_.rows, in_.cols, color_bytes(out_color), out_color);
-        // HOST_PINNED: page-lock both mappings, stage buffers on the device
         ctx_.reset(new gpu::Context(gpu_index_));
-        src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
-        dst_pin_.reset(new gpu::HostRegistration(frame_sink_.pixels(), out_bytes));
-        frame_sink_.set_memory(FrameMemory::HOST_PINNED, gpu_index_);
         d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
         d_out_.reset(new gpu::DeviceBuffer(*ctx_, out_bytes));
         out_bytes_ = out_bytes;
+        // SOURCE side: a DEVICE frame is imported through its IPC handle (device -> device hand-off);
+        // a host frame's mapping is page-locked once (HOST_PINNED) so the per-frame copy is plain DMA
+        if (frame_source_.header()->memory == FrameMemory::DEVICE)
+            src_dev_.reset(new gpu::IpcImport(*ctx_, frame_source_.header()->ipc_handle));
+        else
+            src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
+        // SINK side: --device-sink publishes the output buffer itself (no copy back to the host)
+        if (device_sink_) {
+            unsigned char handle[64];
+            gpu::ck(oat_ipc_export(ctx_->h, d_out_->p, handle));
+            frame_sink_.publish_device(handle, gpu_index_);
+        } else {
+            dst_pin_.reset(new gpu::HostRegistration(frame_sink_.pixels(), out_bytes));
+            frame_sink_.set_memory(FrameMemory::HOST_PINNED, gpu_index_);
+        }
         setup();
         return true;
     }
@@ -53,14 +64,19 @@ protected:
     int process() override
     {
         if (frame_source_.wait() == NodeState::END) return 1;
-        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, frame_source_.pixels(), in_.bytes));
+        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? src_dev_->p : frame_source_.pixels(), in_.bytes));
         const Sample sample = frame_source_.retrieve()->sample();
         frame_source_.post();
 
-        filter(d_in_->u8(), d_out_->u8());
-
-        frame_sink_.wait();
-        gpu::ck(oat_memcpy(ctx_->h, frame_sink_.pixels(), d_out_->p, out_bytes_));
+        if (device_sink_) {
+            // the published buffer IS d_out_: it may only change while no SOURCE is reading it
+            frame_sink_.wait();
+            filter(d_in_->u8(), d_out_->u8());
+        } else {
+            filter(d_in_->u8(), d_out_->u8());
+            frame_sink_.wait();
+            gpu::ck(oat_memcpy(ctx_->h, frame_sink_.pixels(), d_out_->p, out_bytes_));
+        }
         shared_frame_.sample() = sample;  // filters never advance time
         frame_sink_.post();
         return 0;
@@ -78,9 +94,14 @@ protected:
     FrameParams in_;
     size_t out_bytes_{0};
     int gpu_index_{0};
+    bool device_sink_{false};  // --device-sink: publish frames in device memory (SharedFrameHeader memory kind DEVICE)
     std::unique_ptr<gpu::Context> ctx_;
     std::unique_ptr<gpu::HostRegistration> src_pin_, dst_pin_;
+    std::unique_ptr<gpu::IpcImport> src_dev_;
     std::unique_ptr<gpu::DeviceBuffer> d_in_, d_out_;
+
+public:
+    void set_device_sink(bool v) { device_sink_ = v; }
 };
 
 // ---- framefilt mog (BackgroundSubtractorMOG.{h,cpp}) -----------------------------------------------------
@@ -334,6 +355,7 @@ int main(int argc, char *argv[])
         comp_name = filter->name();
 
         auto opts = filter->options();
+        opts.push_back({"device-sink", 0, false, "Publish filtered frames in GPU memory (zero-copy hand-off to GPU components on the same device)."});
         opts.push_back({"config", 'c', true, "Configuration file/key pair."});
         opts.push_back({"help", 0, false, ""});
         const config::VariableMap vm = config::parse(argc, argv, 4, opts);
@@ -348,6 +370,7 @@ int main(int argc, char *argv[])
             config::checkKeys(filter->options(), table);
         }
         filter->applyConfiguration(vm, table);
+        filter->set_device_sink(vm.count("device-sink"));
 
         std::cout << whoMessage(comp_name, "Listening to source " + pos[0] + ".\n")
                   << whoMessage(comp_name, "Steaming to sink " + pos[1] + ".\n")

@@ -5,6 +5,9 @@
 #include <iostream>
 #include <thread>
 
+#include <memory>
+
+#include "gpu.h"
 #include "oat_cli.h"
 #include "oat_host.h"
 #include "synth.h"
@@ -15,7 +18,7 @@ int main(int argc, char *argv[])
     const std::string comp_name = "frameserve";
     try {
         if (argc < 3 || std::string(argv[1]) != "synth") {
-            std::cout << "Usage: frameserve synth SINK [--rows R --cols C --num-samples N --fps F --seed S]\n";
+            std::cout << "Usage: frameserve synth SINK [--rows R --cols C --num-samples N --fps F --seed S --device --gpu-index I]\n";
             return argc < 2 ? 0 : -1;
         }
         struct Server : Component {
@@ -25,7 +28,8 @@ int main(int argc, char *argv[])
         } sig_owner;  // installs the SIGINT handler
         const std::string sink_addr = argv[2];
         const std::vector<config::OptionSpec> opts = {{"rows", 0, true, ""}, {"cols", 0, true, ""}, {"num-samples", 'n', true, ""},
-                                                      {"fps", 'r', true, ""}, {"seed", 0, true, ""}};
+                                                      {"fps", 'r', true, ""}, {"seed", 0, true, ""}, {"device", 0, false, ""},
+                                                      {"gpu-index", 0, true, ""}};
         const config::VariableMap vm = config::parse(argc, argv, 3, opts);
         config::OptionTable none;
         int rows = 480, cols = 640, seed = 1000;
@@ -37,16 +41,31 @@ int main(int argc, char *argv[])
         config::getNumericValue<double>(vm, none, "fps", fps, 0.0, 1e6);
         config::getNumericValue<int>(vm, none, "seed", seed, 0, 1 << 30);
 
+        int gpu_index = 0;
+        config::getNumericValue<int>(vm, none, "gpu-index", gpu_index, 0, 1 << 20);
+        const bool device = vm.count("device");  // frames are generated on the GPU and published in device memory
         Sink<Frame> frame_sink;
         frame_sink.bind(sink_addr, (size_t)rows * cols * 3);
         Frame shared_frame = frame_sink.retrieve(rows, cols, 3, PIX_BGR);
         if (fps > 0.0) shared_frame.set_rate_hz(fps);
+        std::unique_ptr<gpu::Context> ctx;
+        std::unique_ptr<gpu::DeviceBuffer> d_frame;
+        if (device) {
+            ctx.reset(new gpu::Context(gpu_index));
+            d_frame.reset(new gpu::DeviceBuffer(*ctx, (size_t)rows * cols * 3));
+            unsigned char handle[64];
+            gpu::ck(oat_ipc_export(ctx->h, d_frame->p, handle));
+            frame_sink.publish_device(handle, gpu_index);
+        }
         std::vector<uint8_t> next((size_t)rows * cols * 3);
         auto tick = std::chrono::steady_clock::now();
         for (uint64_t t = 0; t < n && !quit; ++t) {
-            synth::frame(next.data(), rows, cols, (uint32_t)seed, (uint32_t)t);  // outside the critical section
+            if (!device) synth::frame(next.data(), rows, cols, (uint32_t)seed, (uint32_t)t);  // outside the critical section
             frame_sink.wait();
-            std::memcpy(shared_frame.data(), next.data(), next.size());
+            if (device)
+                gpu::ck(oat_synth_frame(ctx->h, d_frame->u8(), (size_t)cols * 3, rows, cols, (uint32_t)seed, (uint32_t)t));
+            else
+                std::memcpy(shared_frame.data(), next.data(), next.size());
             shared_frame.incrementSampleCount();  // only pure SINKs advance time (TestFrame.cpp:114)
             frame_sink.post();
             if (fps > 0.0) {

@@ -44,5 +44,15 @@ struct HostRegistration {
     HostRegistration &operator=(const HostRegistration &) = delete;
 };
 
+// a device frame published by another process (SharedFrameHeader memory kind DEVICE)
+struct IpcImport {
+    oat_ctx *ctx;
+    void *p{nullptr};
+    IpcImport(Context &c, const unsigned char handle[64]) : ctx(c.h) { ck(oat_ipc_open(ctx, handle, &p)); }
+    ~IpcImport() { oat_ipc_close(ctx, p); }
+    IpcImport(const IpcImport &) = delete;
+    IpcImport &operator=(const IpcImport &) = delete;
+};
+
 }  // namespace gpu
 }  // namespace oat

@@ -578,6 +578,14 @@ public:
     // the pixel region of the segment (for page-locking: HOST_PINNED variant)
     void *pixels() const { return obj_shmem_.base() + sh_object_->data_offset; }
     void set_memory(FrameMemory m, int device = -1) { sh_object_->memory = m; sh_object_->device_index = device; }
+    // DEVICE variant: the pixels live in a device allocation exported through a CUDA IPC handle; the shm
+    // pixel area stays unused.  Call before the first post().
+    void publish_device(const unsigned char handle[64], int device)
+    {
+        std::memcpy(sh_object_->ipc_handle, handle, 64);
+        sh_object_->device_index = device;
+        sh_object_->memory = FrameMemory::DEVICE;
+    }
     SharedFrameHeader *header() { return sh_object_; }
 
 private:

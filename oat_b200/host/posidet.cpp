@@ -33,7 +33,10 @@ protected:
         position_sink_.bind(position_sink_address_, position_sink_address_);
         shared_position_ = position_sink_.retrieve();
         ctx_.reset(new gpu::Context(gpu_index_));
-        src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
+        if (frame_source_.header()->memory == FrameMemory::DEVICE)  // device -> device hand-off
+            src_dev_.reset(new gpu::IpcImport(*ctx_, frame_source_.header()->ipc_handle));
+        else
+            src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
         d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
         setup();
         return true;
@@ -43,7 +46,7 @@ protected:
     {
         Position2D internal_pos("");
         if (frame_source_.wait() == NodeState::END) return 1;
-        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, frame_source_.pixels(), in_.bytes));
+        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? src_dev_->p : frame_source_.pixels(), in_.bytes));
         internal_pos.set_sample(frame_source_.retrieve()->sample());  // propagate tick / usec (:80)
         frame_source_.post();
 
@@ -68,6 +71,7 @@ protected:
     int gpu_index_{0};
     std::unique_ptr<gpu::Context> ctx_;
     std::unique_ptr<gpu::HostRegistration> src_pin_;
+    std::unique_ptr<gpu::IpcImport> src_dev_;
     std::unique_ptr<gpu::DeviceBuffer> d_in_;
 };
 

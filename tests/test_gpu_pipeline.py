@@ -33,7 +33,7 @@ def oracle_positions(lr):
     return out
 
 
-def run_graph(tag, nodes):
+def run_graph(tag, nodes, serve_args=()):
     """nodes: list of argv lists; consumers are started first, the frame server last (examples/*/*.sh)."""
     names = [f"oatb200pipe_{tag}_{n}" for n in ("raw", "filt", "hsv", "pos")]
     subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
@@ -45,7 +45,7 @@ def run_graph(tag, nodes):
                                           text=True))
         time.sleep(0.5)
         serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(ROWS), "--cols", str(COLS),
-                                  "--num-samples", str(N), "--fps", "100"])
+                                  "--num-samples", str(N), "--fps", "100"] + list(serve_args))
         out, _ = sock.communicate(timeout=120)
         assert serve.wait(timeout=30) == 0
         for p in procs:
@@ -77,6 +77,18 @@ def test_three_component_chain(lr):
                 ["oat-framefilt", "mog", n[0], n[1], "-a", str(lr)]]
 
     check(run_graph(f"chain{int(lr * 100)}", nodes), oracle_positions(lr))
+
+
+def test_device_resident_chain():
+    """The north star's device-resident Frame variant: the frame server generates frames ON the GPU and
+    publishes them through a CUDA IPC handle in the shared frame header (memory kind DEVICE); mog and col
+    publish device frames too (--device-sink), so pixels never touch host memory between the four processes."""
+    def nodes(n):
+        return [["oat-posidet", "hsv", n[2], n[3]] + HSV_ARGS,
+                ["oat-framefilt", "col", n[1], n[2], "-C", "HSV", "--device-sink"],
+                ["oat-framefilt", "mog", n[0], n[1], "-a", "0.05", "--device-sink"]]
+
+    check(run_graph("devchain", nodes, serve_args=("--device",)), oracle_positions(0.05))
 
 
 def test_fused_tracker_component():
