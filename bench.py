@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--alpha", type=float, default=0.01, help="framefilt mog --adaptation-coeff")
     ap.add_argument("--ring", type=int, default=32, help="distinct synthetic frames cycled as input")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="extra measurement: aggregate frames/s of this many independent streams on each GPU (BASELINE configs 3-4)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -347,7 +349,38 @@ def run_b200(args):
     trks[0].profile(False)
     for t_ in trks:
         t_.close()
-    pipe_ms = total_ms
+    # ---- optional: many independent streams per GPU (each its own GMM state), submitted round-robin ----------
+    multi = None
+    if args.streams > 1:
+        S2 = args.streams
+        mt = [oat_b200.Tracker(ctx, rows, cols, args.alpha, hp, ring_depth=2) for _ in range(S2)]
+        for t_ in mt:
+            t_.submit(f0)
+            t_.collect()
+        for i in range(10):
+            for t_ in mt:
+                t_.submit(dev_frames[i % R])
+            for t_ in mt:
+                t_.collect()
+        rounds = max(4, K // S2)
+        m0_, m1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        m0_.record(stream)
+        for t_ in mt:
+            t_.submit(dev_frames[10 % R])
+        for i in range(1, rounds):  # one frame of every stream stays in flight while the next round is submitted
+            for t_ in mt:
+                t_.collect()
+                t_.submit(dev_frames[(10 + i) % R])
+        for t_ in mt:
+            t_.collect()
+        m1_.record(stream)
+        barrier()
+        multi_ms = sharding.max_over_ranks([m0_.elapsed_time(m1_)], dist, f"cuda:{local}")[0]
+        multi = {"streams_per_gpu": S2, "value": world * S2 * rounds / (multi_ms * 1e-3), "unit": "frames/s",
+                 "note": f"{S2} independent streams per GPU ({S2 * 45 * npx / 1e6:.0f} MB of live GMM state per GPU), round-robin submit/collect"}
+        for t_ in mt:
+            t_.close()
 
     # ---- e2e: pinned host frames through submit/collect, copies inside the timed region ------
     HR = min(R, 8)
@@ -435,6 +468,7 @@ def run_b200(args):
             },
             "cold_frame": {"latency_ms": cold_ms, "note": "median submit->collect of one frame in flight, L2 flushed before it "
                                                           "(fused kernel + detect tail + result read-back, serialised)"},
+            "multi_stream": multi,
             "tail": {"one_launch": bool(tail["fast"]), "run_table_entries": tail["nodes"], "replays": tail["replays"]},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
