@@ -687,12 +687,14 @@ static int check_hsv_params(const oat_hsv_params *p)
 struct FastBufs {
     uint32_t *di = nullptr;      // post-morphology bits
     int2 *rowext = nullptr;
+    int2 *rowcnt = nullptr;      // per-row run counts
     int *bbox = nullptr;         // ymin, ymax
     unsigned int *ticket = nullptr;
     int create(size_t nwords, int rows)
     {
         CK(cudaMalloc(&di, nwords * 4));
         CK(cudaMalloc(&rowext, (size_t)rows * sizeof(int2)));
+        CK(cudaMalloc(&rowcnt, (size_t)rows * sizeof(int2)));
         CK(cudaMalloc(&bbox, 2 * sizeof(int)));
         CK(cudaMalloc(&ticket, sizeof(unsigned int)));
         const int init[2] = {INT_MAX, -1};
@@ -704,6 +706,7 @@ struct FastBufs {
     {
         cudaFree(di);
         cudaFree(rowext);
+        cudaFree(rowcnt);
         cudaFree(bbox);
         cudaFree(ticket);
         *this = FastBufs();
@@ -796,6 +799,7 @@ struct Tail {
         fa.R = R;
         fa.g = g;
         fa.rowext = b.rowext;
+        fa.rowcnt = b.rowcnt;
         fa.bbox = b.bbox;
         fa.ticket = b.ticket;
         fa.min_area = p.min_area;

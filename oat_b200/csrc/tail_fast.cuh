@@ -39,6 +39,7 @@ struct FastArgs {
     int ke, kd, R;
     BitGeom g;
     int2 *rowext;
+    int2 *rowcnt;            // per row: foreground runs, candidate-background runs (counted by the CTA that made the row)
     int *bbox;               // ymin, ymax (reset by the last CTA for the next launch)
     unsigned int *ticket;    // CTA completion counter (reset likewise)
     double min_area, max_area;
@@ -160,6 +161,9 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
         for (int y = tid; y < H; y += NT) {
             const int2 e = __ldcg(a.rowext + ymin + y);
             ext[y] = e;
+            const int2 cnt = __ldcg(a.rowcnt + ymin + y);  // run counts, made by the CTA that produced the row
+            offF[y] = (uint32_t)cnt.x;
+            offB[y] = (uint32_t)cnt.y;
             if (e.y >= 0) {
                 xmin = min(xmin, e.x);
                 xmax = max(xmax, e.y);
@@ -203,29 +207,6 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     RegionView M{Ms, ymin, ymax, jmin, jmax, Wd};
     RegionView G{Gs, ymin, ymax, jmin, jmax, Wd};
 
-    // ---- 1. runs per row (warp per row) ------------------------------------------------------
-    for (int y = ymin + warp; y <= ymax; y += nwarps) {
-        const int2 e = ext[y - ymin];
-        uint32_t cf = 0, cb = 0;
-        if (e.y >= 0) {
-            const bool inner = (y > 0) && (y < g.rows - 1);
-            for (int j = (e.x >> 5) + lane; j <= (e.y >> 5); j += 32) {
-                const uint32_t w = M.at(y, j), pw = M.at(y, j - 1);
-                cf += __popc(w & ~((w << 1) | (pw >> 31)));
-                if (inner) {
-                    const uint32_t c = fast_candw(M, g, y, j, e), pc = fast_candw(M, g, y, j - 1, e);
-                    cb += __popc(c & ~((c << 1) | (pc >> 31)));
-                }
-            }
-        }
-        cf = __reduce_add_sync(0xffffffffu, cf);
-        cb = __reduce_add_sync(0xffffffffu, cb);
-        if (lane == 0) {
-            offF[y - ymin] = cf;
-            offB[y - ymin] = cb;
-        }
-    }
-    __syncthreads();
     r.cyc[3] = (uint32_t)clock64();
     // ---- 2. exclusive scan over rows (one warp, chunked) ---------------------------------------
     if (warp == 0) {
@@ -267,62 +248,76 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
         return;
     }
     // node ids: 0 = EXT, 1..nF foreground runs (raster order), nF+1..nF+nB candidate background runs
-    // ---- 3. fill the run table (warp per row) -------------------------------------------------
-    for (int y = ymin + warp; y <= ymax; y += nwarps) {
-        const int2 e = ext[y - ymin];
-        if (e.y < 0) continue;
-        const bool inner = (y > 0) && (y < g.rows - 1);
-        uint32_t bsF = 1 + offF[y - ymin], beF = bsF, bsB = 1 + nF + offB[y - ymin], beB = bsB;
-        for (int j0 = (e.x >> 5); j0 <= (e.y >> 5); j0 += 32) {
-            const int j = j0 + lane;
-            uint32_t sF = 0, eF = 0, sB = 0, eB = 0;
-            if (j <= (e.y >> 5)) {
-                const uint32_t w = M.at(y, j), pw = M.at(y, j - 1), nw = M.at(y, j + 1);
-                sF = w & ~((w << 1) | (pw >> 31));
-                eF = w & ~((w >> 1) | (nw << 31));
-                if (inner) {
-                    const uint32_t c = fast_candw(M, g, y, j, e), pc = fast_candw(M, g, y, j - 1, e),
-                                   nc = fast_candw(M, g, y, j + 1, e);
-                    sB = c & ~((c << 1) | (pc >> 31));
-                    eB = c & ~((c >> 1) | (nc << 31));
+    // ---- 3. fill the run table: G lanes per row (G = region width in words rounded up to a power of two,
+    //         so a narrow blob puts 32/G rows in flight per warp), one word per lane, segmented warp scans ----
+    {
+        int G = 1;
+        while (G < Wd && G < 32) G <<= 1;
+        const int rpw = 32 / G, gl = lane & (G - 1), gi = lane / G;
+        for (int yb = ymin + warp * rpw; yb <= ymax; yb += nwarps * rpw) {
+            const int y = yb + gi;
+            const bool row_ok = y <= ymax;
+            const int2 e = row_ok ? ext[y - ymin] : make_int2(INT_MAX, -1);
+            const bool live = row_ok && e.y >= 0;
+            const bool inner = (y > 0) && (y < g.rows - 1);
+            uint32_t bsF = 0, beF = 0, bsB = 0, beB = 0;
+            if (live) {
+                bsF = beF = 1 + offF[y - ymin];
+                bsB = beB = 1 + nF + offB[y - ymin];
+            }
+            // G == 32: one row per warp, as many 32-word chunks as the row needs (warp-uniform trip count);
+            // G < 32: every row of the region fits one chunk
+            const int nchunk = (G == 32) ? (live ? ((e.y >> 5) - (e.x >> 5)) / 32 + 1 : 0) : 1;
+            for (int ch = 0; ch < nchunk; ++ch) {
+                const int j = (live ? (e.x >> 5) : 0) + ch * 32 + gl;
+                uint32_t sF = 0, eF = 0, sB = 0, eB = 0;
+                if (live && j <= (e.y >> 5)) {
+                    const uint32_t w = M.at(y, j), pw = M.at(y, j - 1), nw = M.at(y, j + 1);
+                    sF = w & ~((w << 1) | (pw >> 31));
+                    eF = w & ~((w >> 1) | (nw << 31));
+                    if (inner) {
+                        const uint32_t c = fast_candw(M, g, y, j, e), pc = fast_candw(M, g, y, j - 1, e),
+                                       nc = fast_candw(M, g, y, j + 1, e);
+                        sB = c & ~((c << 1) | (pc >> 31));
+                        eB = c & ~((c >> 1) | (nc << 31));
+                    }
                 }
-            }
-            // exclusive warp scans of the four counts (packed 2 x 16 bit: a word holds <= 16 runs)
-            const uint32_t cnt1 = (uint32_t)__popc(sF) | ((uint32_t)__popc(eF) << 16);
-            const uint32_t cnt2 = (uint32_t)__popc(sB) | ((uint32_t)__popc(eB) << 16);
-            uint32_t x1 = cnt1, x2 = cnt2;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t1 = __shfl_up_sync(0xffffffffu, x1, d), t2 = __shfl_up_sync(0xffffffffu, x2, d);
-                if (lane >= d) {
-                    x1 += t1;
-                    x2 += t2;
+                // exclusive scans of the four counts inside each group of G lanes (packed 2 x 16 bit)
+                const uint32_t cnt1 = (uint32_t)__popc(sF) | ((uint32_t)__popc(eF) << 16);
+                const uint32_t cnt2 = (uint32_t)__popc(sB) | ((uint32_t)__popc(eB) << 16);
+                uint32_t x1 = cnt1, x2 = cnt2;
+                for (int d = 1; d < G; d <<= 1) {
+                    const uint32_t t1 = __shfl_up_sync(0xffffffffu, x1, d, G), t2 = __shfl_up_sync(0xffffffffu, x2, d, G);
+                    if (gl >= d) {
+                        x1 += t1;
+                        x2 += t2;
+                    }
                 }
+                const uint32_t tot1 = __shfl_sync(0xffffffffu, x1, G - 1, G), tot2 = __shfl_sync(0xffffffffu, x2, G - 1, G);
+                x1 -= cnt1;
+                x2 -= cnt2;
+                uint32_t k;
+                k = bsF + (x1 & 0xffffu);
+                for (uint32_t m = sF; m; m &= m - 1, ++k) {
+                    nstart[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+                    nrow[k] = (uint16_t)y;
+                    parent[k] = k;
+                }
+                k = beF + (x1 >> 16);
+                for (uint32_t m = eF; m; m &= m - 1, ++k) nend[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+                k = bsB + (x2 & 0xffffu);
+                for (uint32_t m = sB; m; m &= m - 1, ++k) {
+                    nstart[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+                    nrow[k] = (uint16_t)y;
+                    parent[k] = k;
+                }
+                k = beB + (x2 >> 16);
+                for (uint32_t m = eB; m; m &= m - 1, ++k) nend[k] = (uint16_t)(32 * j + __ffs(m) - 1);
+                bsF += tot1 & 0xffffu;
+                beF += tot1 >> 16;
+                bsB += tot2 & 0xffffu;
+                beB += tot2 >> 16;
             }
-            const uint32_t tot1 = __shfl_sync(0xffffffffu, x1, 31), tot2 = __shfl_sync(0xffffffffu, x2, 31);
-            x1 -= cnt1;
-            x2 -= cnt2;
-            uint32_t k;
-            k = bsF + (x1 & 0xffffu);
-            for (uint32_t m = sF; m; m &= m - 1, ++k) {
-                nstart[k] = (uint16_t)(32 * j + __ffs(m) - 1);
-                nrow[k] = (uint16_t)y;
-                parent[k] = k;
-            }
-            k = beF + (x1 >> 16);
-            for (uint32_t m = eF; m; m &= m - 1, ++k) nend[k] = (uint16_t)(32 * j + __ffs(m) - 1);
-            k = bsB + (x2 & 0xffffu);
-            for (uint32_t m = sB; m; m &= m - 1, ++k) {
-                nstart[k] = (uint16_t)(32 * j + __ffs(m) - 1);
-                nrow[k] = (uint16_t)y;
-                parent[k] = k;
-            }
-            k = beB + (x2 >> 16);
-            for (uint32_t m = eB; m; m &= m - 1, ++k) nend[k] = (uint16_t)(32 * j + __ffs(m) - 1);
-            bsF += tot1 & 0xffffu;
-            beF += tot1 >> 16;
-            bsB += tot2 & 0xffffu;
-            beB += tot2 >> 16;
         }
     }
     if (tid == 0) parent[0] = 0;
@@ -473,7 +468,7 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
 
 // One launch: [erode] -> [dilate] -> row extents on bands of R rows (all CTAs), then the last CTA
 // labels.  Dynamic shared memory: max(morphology staging, a.smem_bytes).
-__global__ void __launch_bounds__(256) tail_fast_kernel(const FastArgs a)
+__global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
 {
     extern __shared__ __align__(16) uint32_t sm[];
     const uint32_t t_start = (uint32_t)clock64();
@@ -536,7 +531,27 @@ __global__ void __launch_bounds__(256) tail_fast_kernel(const FastArgs a)
         }
         xmin = __reduce_min_sync(0xffffffffu, xmin);
         xmax = __reduce_max_sync(0xffffffffu, xmax);
-        if (lane == 0) a.rowext[y] = make_int2(xmin, xmax);
+        // run counts of the row (the labelling CTA only has to scan them): foreground runs, and candidate
+        // background runs = background between the row's first and last foreground pixel (inner rows only)
+        int cf = 0, cb = 0;
+        if (xmax >= 0) {
+            const bool inner = (y > 0) && (y < rows - 1);
+            for (int j = (xmin >> 5) + lane; j <= (xmax >> 5); j += 32) {
+                const uint32_t w = row[j], pw = j > 0 ? row[j - 1] : 0u;
+                cf += __popc(w & ~((w << 1) | (pw >> 31)));
+                if (inner) {
+                    const uint32_t c = ~w & g.valid_mask(j) & range_mask(j, xmin, xmax);
+                    const uint32_t pc = j > 0 ? (~row[j - 1] & g.valid_mask(j - 1) & range_mask(j - 1, xmin, xmax)) : 0u;
+                    cb += __popc(c & ~((c << 1) | (pc >> 31)));
+                }
+            }
+        }
+        cf = __reduce_add_sync(0xffffffffu, cf);
+        cb = __reduce_add_sync(0xffffffffu, cb);
+        if (lane == 0) {
+            a.rowext[y] = make_int2(xmin, xmax);
+            a.rowcnt[y] = make_int2(cf, cb);
+        }
         if (xmax >= 0) {
             bymin = min(bymin, y);
             bymax = max(bymax, y);

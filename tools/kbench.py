@@ -45,7 +45,7 @@ ts = trk.tail_stats()
 print('slow groups in last frame:', ts['cyc'][7], '=', ts['cyc'][7] / (rows * cols / 4) * 100, '% of groups; generic-kernel frames:', ts['cyc'][6])
 c = ts["cyc"]
 print("tail:", {k: ts[k] for k in ("status", "nodes", "replays", "fast")}, "label-CTA cycles since start:",
-      [(c[i] - c[0]) & 0xffffffff for i in range(1, 8)])
+      [(c[i] - c[0]) & 0xffffffff for i in range(1, 6)])
 kms, n = trk.profile_read()
 mbar = trk.live_modes() / (rows * cols)
 balg = 8 + 40 * mbar
