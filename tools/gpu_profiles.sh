@@ -8,10 +8,12 @@ SMI=$!
 python bench.py > gpurun_out/${TAG}_bench_1080p.json 2> gpurun_out/${TAG}_bench_1080p.err
 python bench.py --workload 4k --steps 600 > gpurun_out/${TAG}_bench_4k.json 2> gpurun_out/${TAG}_bench_4k.err
 python bench.py --alpha 0 --steps 1000 --no-cpu-baseline > gpurun_out/${TAG}_bench_1080p_a0.json 2> gpurun_out/${TAG}_bench_1080p_a0.err
+python bench.py --workload 4k --steps 400 --streams 8 --no-cpu-baseline > gpurun_out/${TAG}_bench_4k_8streams.json 2> gpurun_out/${TAG}_bench_4k_8streams.err
+python bench.py --steps 1000 --streams 8 --no-cpu-baseline > gpurun_out/${TAG}_bench_1080p_8streams.json 2> gpurun_out/${TAG}_bench_1080p_8streams.err
 python bench.py --impl reference --steps 100 --warmup 10 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 kill $SMI
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mog_pipe -s 40 -c 1 -f -o gpurun_out/${TAG}_fused_1080p python tools/kbench.py --res 1080p --steps 20 > gpurun_out/${TAG}_ncu_fused_1080p.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mog_pipe -s 40 -c 1 -f -o gpurun_out/${TAG}_fused_4k python tools/kbench.py --res 4k --steps 20 > gpurun_out/${TAG}_ncu_fused_4k.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tail_fast -s 40 -c 1 -f -o gpurun_out/${TAG}_tail_1080p python tools/kbench.py --res 1080p --steps 20 > gpurun_out/${TAG}_ncu_tail_1080p.log 2>&1
-for f in 1080p 4k 1080p_a0 reference; do echo "== $f"; cat gpurun_out/${TAG}_bench_$f.json | cut -c1-600; done
+for f in 1080p 4k 1080p_a0 4k_8streams 1080p_8streams reference; do echo "== $f"; cat gpurun_out/${TAG}_bench_$f.json | cut -c1-600; done
