@@ -395,20 +395,20 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         };
         // next tile of this CTA's sequence, or -1 when the frame is exhausted (DYN: every CTA draws
         // exactly one number >= ntiles; the CTA that draws the last one re-arms the counter)
-        // DYN: the first PIPE_STAGES-1 tiles of a CTA are fixed (no atomic on the start-up path); later
+        // DYN: the first PIPE_STAGES tiles of a CTA are fixed (no atomic on the start-up path); later
         // ones are drawn from the global counter one refill AHEAD of their use, so the L2 round trip
         // of the atomic hides behind the wait for the stage.
         int seq = 0, ahead = 0;
         bool ended = false;
-        auto draw = [&]() -> int { return (int)atomicAdd(pa.tile_counter, 1u) + (PIPE_STAGES - 1) * (int)gridDim.x; };
+        auto draw = [&]() -> int { return (int)atomicAdd(pa.tile_counter, 1u) + PIPE_STAGES * (int)gridDim.x; };
         auto next_tile = [&]() -> int {
             int t;
-            if (DYN && seq >= PIPE_STAGES - 1) {
+            if (DYN && seq >= PIPE_STAGES) {
                 t = ahead;
                 if (t < pa.ntiles) ahead = draw();
             } else {
                 t = first + seq * stride;
-                if (DYN && seq == PIPE_STAGES - 2) ahead = draw();
+                if (DYN && seq == PIPE_STAGES - 1) ahead = draw();
             }
             ++seq;
             if (t >= pa.ntiles) {
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             else if (DYN)
                 mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
         };
-        for (int k = 0; k < PIPE_STAGES - 1 && !ended; ++k) refill(k);
+        for (int k = 0; k < PIPE_STAGES && !ended; ++k) refill(k);  // every stage starts loaded
         for (int i = 0;; ++i) {
             const int s = i % PIPE_STAGES;
             const int tile = *stage_tile(s);
@@ -461,11 +461,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG)[2] = 0u;  // re-arm the slow-pixel queue
             reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG)[3] = 0u;
             bulk_commit();
+            // refill THIS stage as soon as its stores have read it (not one tile later): its next tile is
+            // then in flight for PIPE_STAGES-1 tile times instead of one
             if (!ended) {
-                bulk_wait_read<1>();  // the stores of the previous tile have finished reading their stage
-                refill((i + PIPE_STAGES - 1) % PIPE_STAGES);
+                bulk_wait_read<0>();
+                refill(s);
             } else if (!DYN) {
-                *stage_tile((i + PIPE_STAGES - 1) % PIPE_STAGES) = -1;
+                *stage_tile(s) = -1;
             }
         }
         bulk_wait_read<0>();  // shared memory must outlive the last bulk stores

@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 
+def pytest_sessionstart(session):
+    """Native artefacts are git-ignored: build whatever is missing (nvcc cross-compiles without a GPU) so the
+    suite does not depend on __graft_entry__.build() having run first."""
+    import oat_b200
+    import oracle
+
+    if not os.path.exists(oat_b200.LIB_PATH):
+        oat_b200.build()
+    oracle.build()
+
+
 @pytest.fixture(scope="session")
 def ctx():
     import oat_b200
