@@ -81,7 +81,8 @@ struct oat_ctx {
     // development switches, read once at creation: OAT_B200_NO_PIPE / _NO_FAST_TAIL / _NO_OVERLAP force the generic
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false;
-    unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel
+    unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel ([2], ping-pong)
+    uint64_t pipe_launches = 0;
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
     DevBuf scratch_in, scratch_out, scratch_roi;  // staging for the stateless entry points
@@ -406,7 +407,10 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
         const int grid = pa.ntiles < PIPE_CTAS_PER_SM * c->num_sms ? pa.ntiles : PIPE_CTAS_PER_SM * c->num_sms;
         pa.grid_tiles = grid;
-        pa.tile_counter = c->tile_counter;  // launches on one context are stream-ordered, so one counter serves
+        // launches on one context are stream-ordered: two counters ping-pong, each launch arms the next one's
+        pa.tile_counter = c->tile_counter + (c->pipe_launches & 1u);
+        pa.tile_counter_next = c->tile_counter + ((c->pipe_launches + 1u) & 1u);
+        ++c->pipe_launches;
         if (frozen && linear)
             mog_pipe_kernel<5, true, true><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
         else if (frozen)

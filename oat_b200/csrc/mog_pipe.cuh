@@ -130,7 +130,8 @@ struct PipeArgs {
     unsigned long long div_magic;  // ceil(2^64 / pitch_px): y = umul64hi(pidx, magic), exact for every pidx < 2^32
     int zero_in;                   // HSV (0,0,0) lies inside the inRange band
     int grid_tiles;                // tile stride between consecutive tiles of one CTA (= gridDim.x)
-    unsigned int *tile_counter;    // [2] dynamic tile scheduler (LINEAR frames): next tile, CTAs finished; zeroed once, self re-arming
+    unsigned int *tile_counter;    // dynamic tile scheduler (LINEAR frames): next tile number of THIS launch (starts at 0)
+    unsigned int *tile_counter_next;  // the counter the NEXT launch on this context will use: zeroed by this launch
 };
 
 // One pixel with one or two live modes whose sample fits mode 0 (the heavier one): the m = 0
@@ -346,6 +347,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     const FusedArgs &a = pa.f;
     const int tid = threadIdx.x;
     if (tid == 0) {
+        // the two scheduler counters ping-pong between launches (stream-ordered): arm the other one
+        if (LINEAR && blockIdx.x == 0) *pa.tile_counter_next = 0u;
 #pragma unroll
         for (int s = 0; s < PIPE_STAGES; ++s) {
             mbar_init(&full[s], LINEAR ? 1 : 1 + PIPE_CTHREADS);
@@ -471,13 +474,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             }
         }
         bulk_wait_read<0>();  // shared memory must outlive the last bulk stores
-        if (DYN) {  // the last producer to leave re-arms the scheduler for the next launch
-            const unsigned e = atomicAdd(pa.tile_counter + 1, 1u);
-            if (e == gridDim.x - 1) {
-                pa.tile_counter[0] = 0u;
-                pa.tile_counter[1] = 0u;
-            }
-        }
         return;
     }
 
