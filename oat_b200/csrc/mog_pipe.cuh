@@ -642,8 +642,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         if (slow) {
             ++nslow;
             const uint32_t base = atomicAdd(const_cast<uint32_t *>(qcnt), 4u);
+            __threadfence_block();  // release: this warp's threshold words are visible before its pixels can be claimed
 #pragma unroll
-            for (int i = 0; i < 4; ++i) queue[base + i] = (uint16_t)(tid * 4 + i);
+            for (int i = 0; i < 4; ++i) queue[base + i] = (uint16_t)(tid * 4 + i);  // relaxed (volatile) flag-style publish
         }
         __syncwarp();  // this warp's entries are published before any of its lanes starts claiming
         for (;;) {     // warp-level claiming: lane 0 takes up to 32 queue slots, one pixel per lane
@@ -666,6 +667,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                 const uint32_t h = h0 + (uint32_t)(tid & 31);
                 uint32_t e;
                 while ((e = queue[h]) == 0xffffu) {}  // reserved by a pusher of another warp that is about to fill it
+                __threadfence_block();                // acquire: pairs with the pusher's fence
                 queue[h] = 0xffffu;
                 slow_pixel<K, TRACK>(pa, st, (int)e, (size_t)tile * PIPE_TILE + e);
             }
