@@ -386,7 +386,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
                      (!a.fg_out || aligned4(a.fg_out, a.fg_pitch)) && (!a.hsv_out || aligned4(a.hsv_out, a.hsv_pitch));
     // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
     // the state write-back; with a live rate every live mode changes every frame anyway.
-    const bool frozen = (a.c.aT == 0.0f) && !a.reset;
+    const bool frozen = (a.c.aT == 0.0f) && !a.reset && !getenv("OAT_B200_NO_TRACK");
     if (vec && !a.reset && m.K == 5 && allow_pipe && !c->no_pipe) {
         // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
         // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index

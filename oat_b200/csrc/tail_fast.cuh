@@ -403,40 +403,69 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
         }
         return;
     }
-    // ---- 7. exact 2x2-cell moments per run (cells are owned by their top row) ------------------
-    for (uint32_t id = 1 + tid; id <= nF + nB; id += NT) {
-        const uint32_t root = suf_find(P, id);
-        if (root == 0u) continue;  // exterior background owns nothing
-        const int y = nrow[id], s = nstart[id], e = nend[id];
-        if (y >= g.rows - 1) continue;
-        unsigned long long t00 = 0, t10 = 0, t01 = 0;
-        for (int j = s >> 5; j <= (e >> 5); ++j) {
-            const uint32_t T = G.at(y, j), Bw = G.at(y + 1, j);
-            const uint64_t T64 = (uint64_t)(G.at(y, j - 1) >> 31) | ((uint64_t)T << 1) | ((uint64_t)(G.at(y, j + 1) & 1u) << 33);
-            const uint64_t B64 = (uint64_t)(G.at(y + 1, j - 1) >> 31) | ((uint64_t)Bw << 1) |
-                                 ((uint64_t)(G.at(y + 1, j + 1) & 1u) << 33);
-            const uint64_t tl = T64, tr = T64 >> 1, bl = B64, br = B64 >> 1;
-            const uint32_t sm = range_mask(j, s, e);
-            const uint32_t F = (uint32_t)((tl & tr & bl & br) >> 1) & sm;
-            const uint32_t ma = (uint32_t)((tl & ~tr & bl & br) >> 1) & sm;
-            const uint32_t mb = (uint32_t)((tl & tr & ~bl & br) >> 1) & sm;
-            const uint32_t mc = (uint32_t)((tl & tr & bl & ~br) >> 1) & sm;
-            const uint32_t md = (uint32_t)(~tl & tr & bl & br) & sm;  // owner = top-right pixel, cell x = owner - 1
-            if (!(F | ma | mb | mc | md)) continue;
-            const uint32_t xb = 32u * (uint32_t)j;
-            const uint32_t nFc = __popc(F), na = __popc(ma), nb = __popc(mb), nc = __popc(mc), nd = __popc(md);
-            t00 += 2u * nFc + na + nb + nc + nd;
-            t10 += (unsigned long long)(6u * (sum_pos(F) + nFc * xb) + 3u * nFc + 3u * (sum_pos(ma) + na * xb) + na +
-                                        3u * (sum_pos(mb) + nb * xb) + 2u * nb + 3u * (sum_pos(mc) + nc * xb) + nc +
-                                        3u * (sum_pos(md) + nd * xb) - nd);
-            const uint32_t yy = (uint32_t)y;
-            t01 += (unsigned long long)(nFc * (6u * yy + 3u) + (na + nd) * (3u * yy + 2u) + (nb + nc) * (3u * yy + 1u));
-        }
-        if (t00 | t10 | t01) {
-            const uint32_t c = ncomp[root];
-            atomicAdd(acc + c, t00);
-            atomicAdd(acc + C + c, t10);
-            atomicAdd(acc + 2 * C + c, t01);
+    // ---- 7. exact 2x2-cell moments (cells are owned by their top row).  Four lanes share a run, each
+    //         taking every fourth word of it; a warp whose lanes all feed the same contour (the usual
+    //         single-blob mask) folds its sums with shuffles and issues ONE set of atomics ------------
+    {
+        const uint32_t nwork = (nF + nB) * 4u;
+        const uint32_t nround = (nwork + NT - 1) / NT;
+        for (uint32_t rd = 0; rd < nround; ++rd) {
+            const uint32_t wk = rd * NT + tid;
+            uint32_t root = 0u;
+            unsigned long long t00 = 0, t10 = 0, t01 = 0;
+            if (wk < nwork) {
+                const uint32_t id = 1u + (wk >> 2);
+                root = suf_find(P, id);
+                const int y = nrow[id], s = nstart[id], e = nend[id];
+                if (root != 0u && y < g.rows - 1) {  // exterior background owns nothing; the last row owns no cells
+                    for (int j = (s >> 5) + (int)(wk & 3u); j <= (e >> 5); j += 4) {
+                        const uint32_t T = G.at(y, j), Bw = G.at(y + 1, j);
+                        const uint64_t T64 = (uint64_t)(G.at(y, j - 1) >> 31) | ((uint64_t)T << 1) | ((uint64_t)(G.at(y, j + 1) & 1u) << 33);
+                        const uint64_t B64 = (uint64_t)(G.at(y + 1, j - 1) >> 31) | ((uint64_t)Bw << 1) |
+                                             ((uint64_t)(G.at(y + 1, j + 1) & 1u) << 33);
+                        const uint64_t tl = T64, tr = T64 >> 1, bl = B64, br = B64 >> 1;
+                        const uint32_t sm = range_mask(j, s, e);
+                        const uint32_t F = (uint32_t)((tl & tr & bl & br) >> 1) & sm;
+                        const uint32_t ma = (uint32_t)((tl & ~tr & bl & br) >> 1) & sm;
+                        const uint32_t mb = (uint32_t)((tl & tr & ~bl & br) >> 1) & sm;
+                        const uint32_t mc = (uint32_t)((tl & tr & bl & ~br) >> 1) & sm;
+                        const uint32_t md = (uint32_t)(~tl & tr & bl & br) & sm;  // owner = top-right pixel, cell x = owner - 1
+                        if (!(F | ma | mb | mc | md)) continue;
+                        const uint32_t xb = 32u * (uint32_t)j;
+                        const uint32_t nFc = __popc(F), na = __popc(ma), nb = __popc(mb), nc = __popc(mc), nd = __popc(md);
+                        t00 += 2u * nFc + na + nb + nc + nd;
+                        t10 += (unsigned long long)(6u * (sum_pos(F) + nFc * xb) + 3u * nFc + 3u * (sum_pos(ma) + na * xb) + na +
+                                                    3u * (sum_pos(mb) + nb * xb) + 2u * nb + 3u * (sum_pos(mc) + nc * xb) + nc +
+                                                    3u * (sum_pos(md) + nd * xb) - nd);
+                        const uint32_t yy = (uint32_t)y;
+                        t01 += (unsigned long long)(nFc * (6u * yy + 3u) + (na + nd) * (3u * yy + 2u) + (nb + nc) * (3u * yy + 1u));
+                    }
+                }
+            }
+            const bool have = (t00 | t10 | t01) != 0ull;
+            // one contour for the whole warp?  (lanes with nothing to add do not count)
+            const unsigned contrib = __ballot_sync(0xffffffffu, have);
+            if (contrib == 0u) continue;
+            const uint32_t root0 = __shfl_sync(0xffffffffu, root, __ffs(contrib) - 1);
+            if (__all_sync(0xffffffffu, !have || root == root0)) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    t00 += __shfl_xor_sync(0xffffffffu, t00, d);
+                    t10 += __shfl_xor_sync(0xffffffffu, t10, d);
+                    t01 += __shfl_xor_sync(0xffffffffu, t01, d);
+                }
+                if (lane == 0) {
+                    const uint32_t c = ncomp[root0];
+                    atomicAdd(acc + c, t00);
+                    atomicAdd(acc + C + c, t10);
+                    atomicAdd(acc + 2 * C + c, t01);
+                }
+            } else if (have) {
+                const uint32_t c = ncomp[root];
+                atomicAdd(acc + c, t00);
+                atomicAdd(acc + C + c, t10);
+                atomicAdd(acc + 2 * C + c, t01);
+            }
         }
     }
     __syncthreads();
