@@ -728,7 +728,9 @@ struct Tail {
     size_t fast_smem_set = 48 * 1024;
     int fast_comps = 128;
 
-    int create(int rows, int cols)
+    // smem_kb: shared-memory budget of the one-launch tail (stand-alone detectors can afford a whole SM's worth;
+    // the tracker keeps it small enough to co-reside with the fused kernel)
+    int create(int rows, int cols, size_t smem_kb = 48)
     {
         REQUIRE(rows > 0 && cols > 0 && rows <= 32768 && cols <= 32768, "detector: bad frame geometry");
         tb.g.rows = rows;
@@ -751,7 +753,7 @@ struct Tail {
         // label-phase budget (mask region + run table + accumulators in shared memory).  48 KB keeps a
         // tail CTA co-resident with two CTAs of the fused kernel (2 x 74.1 KB) on one SM, which is what
         // lets the tail of frame t overlap the fused kernel of frame t+1.  OAT_B200_TAIL_SMEM_KB overrides.
-        size_t kb = 48;
+        size_t kb = smem_kb;
         if (const char *e = getenv("OAT_B200_TAIL_SMEM_KB")) kb = (size_t)atoi(e);
         if (kb > 200) kb = 200;
         fast_smem = kb * 1024;
@@ -921,7 +923,7 @@ extern "C" int oat_hsvdet_create(oat_ctx *c, int rows, int cols, oat_hsvdet **ou
     if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
     h->ctx = c;
     h->d_res = nullptr;
-    int r = h->tail.create(rows, cols);
+    int r = h->tail.create(rows, cols, 160);
     if (r == OAT_OK && cudaMalloc(&h->d_res, sizeof(TailResult)) != cudaSuccess)
         r = fail(OAT_ERR_NOMEM, "device allocation failed");
     if (r != OAT_OK) {

@@ -45,7 +45,8 @@ def blobs(rows, cols, n, rmax, seed, holes=True):
 def run_sift(ctx, mask, erode=0, dilate=0, area=(0.0, oat_b200.DBL_MAX)):
     rows, cols = mask.shape
     det = oat_b200.HSVDetector(ctx, rows, cols, oat_b200.HsvParams.make(erode=erode, dilate=dilate, area=area))
-    d, thr, lab = det.sift_contours(mask, want_thresh=True, want_labels=True)
+    d, thr, lab = det.sift_contours(mask, want_thresh=True, want_labels=True)  # labels: the unbounded multi-launch tail
+    d_fast, thr_fast, _ = det.sift_contours(mask, want_thresh=True)            # no labels: the one-launch tail (or its replay)
     det.close()
     # oracle: same morphology, then sift
     om = (mask != 0).astype(np.uint8) * 255
@@ -57,6 +58,8 @@ def run_sift(ctx, mask, erode=0, dilate=0, area=(0.0, oat_b200.DBL_MAX)):
     assert np.array_equal(thr, om), "post-morphology mask differs"
     assert np.array_equal(lab, oracle.label8(om)), "component labels differ"
     check_detection(d, o)
+    assert np.array_equal(thr_fast, om), "post-morphology mask of the one-launch tail differs"
+    check_detection(d_fast, o)
     return d, o
 
 
@@ -209,3 +212,11 @@ def test_framefilt_thresh_and_mask_parity(ctx, shape):
         assert np.array_equal(oat_b200.threshold_filter(ctx, frame, lo, hi), oracle.threshold_filter(frame, lo, hi)), (lo, hi)
     roi = (rng.random(shape[:2]) < 0.5).astype(np.uint8) * 255
     assert np.array_equal(oat_b200.mask_filter(ctx, frame, roi), oracle.mask_filter(frame, roi))
+
+
+@pytest.mark.parametrize("shape,n,rmax,dilate", [((1080, 1920), 6, 90, 10), ((1080, 1920), 60, 40, 0), ((2160, 3840), 5, 300, 10),
+                                                 ((720, 1000), 25, 60, 4), ((1080, 1920), 400, 12, 0)])
+def test_sift_full_size_masks(ctx, shape, n, rmax, dilate):
+    """Frame-sized masks with holes, islands in holes and many blobs: one-launch tail (wide and narrow regions,
+    the run table filling up, overflow -> replay) and the multi-launch tail, both against the oracle."""
+    run_sift(ctx, blobs(shape[0], shape[1], n, rmax, seed=n + rmax), dilate=dilate)
