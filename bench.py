@@ -463,7 +463,7 @@ def run_b200(args):
                 "value": world * K / e2e_s,
                 "unit": "frames/s",
                 "h2d_bytes_per_step": npx * 3,
-                "d2h_bytes_per_step": 40,
+                "d2h_bytes_per_step": 88,
                 "note": "pinned host frames via oat_tracker_submit/collect, ring depth 4, wall clock",
             },
             "cold_frame": {"latency_ms": cold_ms, "note": "median submit->collect of one frame in flight, L2 flushed before it "

@@ -184,6 +184,20 @@ int oat_thresh_detect(oat_hsvdet *det, const uint8_t *grey, size_t pitch, int t_
                       const oat_hsv_params *p, oat_detection *out, uint8_t *thresh_out,
                       size_t thresh_pitch, int32_t *labels_out);
 
+/* posidet diff: replaces DifferenceDetector::detectPosition (src/positiondetector/DifferenceDetector.cpp:118-173):
+ * cv::absdiff(frame, last) -> cv::threshold(> diff_threshold, THRESH_BINARY) -> cv::blur(blur_px x blur_px) ->
+ * siftContours (a blurred pixel counts as foreground when it is non-zero), last <- frame. GREY frames. The first
+ * call has no previous image and, like the reference, sifts the raw frame. blur_px 0 = off; 1..22 supported
+ * (OAT_ERR_UNSUPPORTED above: one set pixel then no longer survives the box average). thresh_out (optional): 255
+ * where the sifted image is non-zero. */
+typedef struct oat_diffdet oat_diffdet;
+int oat_diffdet_create(oat_ctx *ctx, int rows, int cols, oat_diffdet **out);
+int oat_diffdet_destroy(oat_diffdet *det);
+int oat_diffdet_reset(oat_diffdet *det);
+int oat_diffdet_detect(oat_diffdet *det, const uint8_t *grey, size_t pitch, int diff_threshold, int blur_px,
+                       double min_area, double max_area, oat_detection *out, uint8_t *thresh_out,
+                       size_t thresh_pitch);
+
 /* framefilt thresh / framefilt mask: out = in where kept, 0 elsewhere (may alias in).
  *   roi == NULL: replaces Threshold::filter (src/framefilter/Threshold.cpp:67-81): keep pixels whose
  *                grey value (the frame itself if 1 channel, 8-bit cv::COLOR_BGR2GRAY if 3) lies in

@@ -118,6 +118,11 @@ _SIGS = {
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "oat_thresh_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(HsvParams),
                                     C.POINTER(Detection), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "oat_diffdet_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "oat_diffdet_destroy": (C.c_int, [C.c_void_p]),
+    "oat_diffdet_reset": (C.c_int, [C.c_void_p]),
+    "oat_diffdet_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_double,
+                                     C.POINTER(Detection), C.c_void_p, C.c_size_t]),
     "oat_keep_where": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "oat_tracker_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(MogParams), C.c_int,
@@ -491,6 +496,36 @@ class HSVDetector:
     def sift_contours(self, mask, want_thresh=False, want_labels=False):
         """siftContours on a binary mask (morphology per self.params applied first)."""
         return self._run(lib().oat_sift_contours, mask, 1, want_thresh, want_labels)
+
+
+class DifferenceDetector:
+    """``posidet diff`` (src/positiondetector/DifferenceDetector.cpp:118-173): motion by frame differencing."""
+
+    def __init__(self, ctx: Context, rows: int, cols: int, diff_threshold: int = 10, blur: int = 2,
+                 area=(0.0, DBL_MAX)):
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.diff_threshold, self.blur, self.area = diff_threshold, blur, tuple(area)
+        self._h = C.c_void_p()
+        _ck(lib().oat_diffdet_create(ctx._h, rows, cols, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_diffdet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def detect(self, grey, want_thresh=False):
+        _img(grey, self.rows, self.cols, 1)
+        d = Detection()
+        thr = np.empty((self.rows, self.cols), np.uint8) if want_thresh else None
+        _ck(lib().oat_diffdet_detect(self._h, _ptr(grey), self.cols, self.diff_threshold, self.blur, self.area[0], self.area[1],
+                                     C.byref(d), _ptr(thr), self.cols))
+        return d, thr
 
 
 class Tracker:

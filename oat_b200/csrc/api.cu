@@ -1031,6 +1031,125 @@ extern "C" int oat_thresh_detect(oat_hsvdet *h, const uint8_t *grey, size_t pitc
     return detect_common(h, grey, pitch, 1, p, out, thresh_out, thresh_pitch, labels_out, t_min, t_max);
 }
 
+// ---- posidet diff ------------------------------------------------------------------------------
+struct oat_diffdet {
+    oat_ctx *ctx;
+    Tail tail;
+    TailResult *d_res;
+    uint8_t *last;  // previous frame (tight rows x cols)
+    bool have_last;
+    DevBuf in, out_thr;
+};
+extern "C" int oat_diffdet_create(oat_ctx *c, int rows, int cols, oat_diffdet **out)
+{
+    REQUIRE(out, "oat_diffdet_create: out is null");
+    *out = nullptr;
+    CKRET(bind(c));
+    oat_diffdet *h = new (std::nothrow) oat_diffdet();
+    if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
+    h->ctx = c;
+    h->d_res = nullptr;
+    h->last = nullptr;
+    h->have_last = false;
+    int r = h->tail.create(rows, cols, 160);
+    if (r == OAT_OK && (cudaMalloc(&h->d_res, sizeof(TailResult)) != cudaSuccess || cudaMalloc(&h->last, (size_t)rows * cols) != cudaSuccess))
+        r = fail(OAT_ERR_NOMEM, "device allocation failed");
+    if (r != OAT_OK) {
+        h->tail.destroy();
+        cudaFree(h->d_res);
+        cudaFree(h->last);
+        delete h;
+        return r;
+    }
+    *out = h;
+    return OAT_OK;
+}
+extern "C" int oat_diffdet_destroy(oat_diffdet *h)
+{
+    if (!h) return OAT_OK;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    h->tail.destroy();
+    cudaFree(h->d_res);
+    cudaFree(h->last);
+    h->in.release();
+    h->out_thr.release();
+    delete h;
+    return OAT_OK;
+}
+extern "C" int oat_diffdet_reset(oat_diffdet *h)
+{
+    REQUIRE(h, "null handle");
+    h->have_last = false;
+    return OAT_OK;
+}
+extern "C" int oat_diffdet_detect(oat_diffdet *h, const uint8_t *grey, size_t pitch, int diff_threshold, int blur_px, double min_area,
+                                  double max_area, oat_detection *out, uint8_t *thresh_out, size_t thresh_pitch)
+{
+    REQUIRE(h && grey && out, "oat_diffdet_detect: null argument");
+    REQUIRE(diff_threshold >= 0 && blur_px >= 0, "diff-threshold and blur must be >= 0");
+    REQUIRE(min_area < max_area, "area: min must be < max");
+    oat_ctx *c = h->ctx;
+    CKRET(bind(c));
+    const BitGeom g = h->tail.tb.g;
+    // cv::blur of a 0/255 image is non-zero wherever ONE set pixel falls in the box only while 255/k^2 rounds up
+    if (blur_px > 22 || blur_px > g.rows || blur_px > g.cols)
+        return fail(OAT_ERR_UNSUPPORTED, "posidet diff: blur sizes above 22 (or above the frame size) are not implemented");
+    REQUIRE(pitch >= (size_t)g.cols, "detect: input pitch too small");
+    REQUIRE(!thresh_out || thresh_pitch >= (size_t)g.cols, "detect: thresh pitch too small");
+    const uint8_t *d;
+    size_t dp;
+    CKRET(stage_in(c, c->stream, h->in, grey, pitch, g.rows, (size_t)g.cols, &d, &dp));
+    OutView ot;
+    CKRET(stage_out(h->out_thr, thresh_out, thresh_pitch, g.rows, (size_t)g.cols, &ot));
+    cudaStream_t s = c->stream;
+    const unsigned gp = nblocks((long long)g.rows * g.pitch_px(), 256), gw = nblocks((long long)h->tail.nwords, 256);
+    absdiff_bits_kernel<<<gp, 256, 0, s>>>(d, dp, h->last, g, diff_threshold, h->have_last ? 0 : 1, h->tail.bits0);
+    LAUNCH_CHECK(c);
+    const uint32_t *cur = h->tail.bits0;
+    if (h->have_last && blur_px > 0) {  // (blurred != 0) == box dilation with cv::blur's anchor and reflected border
+        const int a = blur_px / 2;
+        morph_h_kernel<true><<<gw, 256, 0, s>>>(h->tail.bits0, h->tail.tmp, g, blur_px);
+        LAUNCH_CHECK(c);
+        if (blur_px % 2 == 0) {
+            reflect_even_fix_kernel<<<nblocks(g.rows, 256), 256, 0, s>>>(h->tail.bits0, h->tail.tmp, g, a, 0);
+            LAUNCH_CHECK(c);
+        }
+        morph_v_kernel<true><<<gw, 256, 0, s>>>(h->tail.tmp, h->tail.er, g, blur_px);
+        LAUNCH_CHECK(c);
+        if (blur_px % 2 == 0) {
+            reflect_even_fix_kernel<<<nblocks(g.wpr, 256), 256, 0, s>>>(h->tail.tmp, h->tail.er, g, a, 1);
+            LAUNCH_CHECK(c);
+        }
+        cur = h->tail.er;
+    }
+    h->have_last = true;
+    oat_hsv_params p;
+    oat_hsv_default_params(&p);
+    p.erode_px = p.dilate_px = 0;
+    p.min_area = min_area;
+    p.max_area = max_area;
+    bool need_generic = true;
+    int err = OAT_OK;
+    if (h->tail.run_fast(c, s, h->tail.fb, cur, p, h->d_res, ot.d, ot.dpitch, &err)) {
+        CKRET(err);
+        TailResult tr;
+        CK(cudaMemcpyAsync(&tr, h->d_res, sizeof(tr), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (tr.status == TAIL_OK) {
+            *out = tr.det;
+            need_generic = false;
+        }
+    }
+    if (need_generic) {
+        CKRET(h->tail.run(c, cur, p, &h->d_res->det, ot.d, ot.dpitch, nullptr));
+        CK(cudaMemcpyAsync(out, &h->d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, s));
+    }
+    CKRET(finish_out(s, ot));
+    CK(cudaStreamSynchronize(s));
+    return OAT_OK;
+}
+
 // framefilt thresh / framefilt mask: zero the pixels outside an intensity band / a region-of-interest mask
 extern "C" int oat_keep_where(oat_ctx *c, const uint8_t *in, size_t in_pitch, uint8_t *out, size_t out_pitch, int rows, int cols,
                               int channels, const uint8_t *roi, size_t roi_pitch, int i_min, int i_max)

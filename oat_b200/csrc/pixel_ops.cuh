@@ -80,6 +80,42 @@ __global__ void keep_where_kernel(const uint8_t *__restrict__ in, size_t in_pitc
     for (int c = 0; c < ch; ++c) d[c] = keep ? s[c] : 0;
 }
 
+// posidet diff (src/positiondetector/DifferenceDetector.cpp:154-173): bit = |frame - last| > threshold (cv::absdiff +
+// cv::threshold THRESH_BINARY), last <- frame.  first != 0: the reference's first call has no previous image and sifts
+// the raw frame itself (threshold_frame_ = frame.clone()): bit = frame != 0.
+__global__ void absdiff_bits_kernel(const uint8_t *__restrict__ img, size_t pitch, uint8_t *__restrict__ last, BitGeom g,
+                                    int thresh, int first, uint32_t *__restrict__ bits)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ppx = g.pitch_px();
+    const int y = (int)(t / ppx), x = (int)(t % ppx);
+    bool in = false;
+    if (y < g.rows && x < g.cols) {
+        const int v = img[(size_t)y * pitch + x];
+        uint8_t *l = last + (size_t)y * g.cols + x;
+        const int d = v > *l ? v - *l : *l - v;
+        in = first ? (v != 0) : (d > thresh);
+        *l = (uint8_t)v;
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && y < g.rows) bits[(size_t)y * g.wpr + (x >> 5)] = w;
+}
+// cv::blur's BORDER_REFLECT_101 with an EVEN k x k box (anchor k/2): at x = 0 (y = 0) the mirrored sample -k/2 -> +k/2
+// falls outside the plain window, so column 0 (row 0) additionally sees column (row) k/2.  vertical == 0: fix column 0
+// of `out` from `in` (the un-dilated rows); vertical != 0: fix row 0 of `out` from row k/2 of `in`.
+__global__ void reflect_even_fix_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, BitGeom g, int a, int vertical)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!vertical) {
+        if (t >= g.rows || a >= g.cols) return;
+        const uint32_t bit = (in[(size_t)t * g.wpr + (a >> 5)] >> (a & 31)) & 1u;
+        if (bit) out[(size_t)t * g.wpr] |= 1u;
+    } else {
+        if (t >= g.wpr || a >= g.rows) return;
+        out[t] |= in[(size_t)a * g.wpr + t];
+    }
+}
+
 // u8 mask (non-zero = foreground) -> bits
 __global__ void mask_to_bits_kernel(const uint8_t *__restrict__ mask, size_t pitch, BitGeom g,
                                     uint32_t *__restrict__ bits)

@@ -198,6 +198,50 @@ private:
     oat_hsvdet *det_{nullptr};
 };
 
+// ---- posidet diff (DifferenceDetector.{h,cpp}) ----------------------------------------------------------------
+class DifferenceDetector : public PositionDetector {
+public:
+    DifferenceDetector(const std::string &source, const std::string &sink) : PositionDetector(source, sink)
+    {
+        name_ = "diffdetector[" + source + "->" + sink + "]";
+        required_color_ = PIX_GREY;  // DifferenceDetector.cpp:44
+    }
+    ~DifferenceDetector() { oat_diffdet_destroy(det_); }
+    std::vector<config::OptionSpec> options() const override
+    {
+        return {{"diff-threshold", 'd', true, "Intensity difference threshold to consider an object contour."},
+                {"blur", 'b', true, "Blurring kernel size in pixels (normalized box filter)."},
+                {"area", 'a', true, "Array of floats, [min,max], specifying the minimum and maximum object contour area in pixels^2."},
+                {"gpu-index", 0, true, "Index of the GPU to use."}};
+    }
+    void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
+    {
+        config::getNumericValue<int>(vm, t, "diff-threshold", diff_threshold_, 0, 1 << 20);
+        config::getNumericValue<int>(vm, t, "blur", blur_, 0, 1 << 20);
+        std::vector<double> area;
+        if (config::getArray<double>(vm, t, "area", area, 2)) {
+            min_area_ = area[0];
+            max_area_ = area[1];
+            if (min_area_ >= max_area_) throw std::runtime_error("Max area should be larger than min area.");
+        }
+        config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+    }
+
+protected:
+    void setup() override { gpu::ck(oat_diffdet_create(ctx_->h, (int)in_.rows, (int)in_.cols, &det_)); }
+    void detectPosition(const uint8_t *d_frame, Position2D &position) override
+    {
+        oat_detection d;
+        gpu::ck(oat_diffdet_detect(det_, d_frame, in_.cols, diff_threshold_, blur_, min_area_, max_area_, &d, nullptr, 0));
+        fill(position, d);
+    }
+
+private:
+    int diff_threshold_{10}, blur_{2};  // DifferenceDetector.h:74, .cpp:41
+    double min_area_{0.0}, max_area_{DBL_MAX};
+    oat_diffdet *det_{nullptr};
+};
+
 // ---- posidet track: mog -> col HSV -> hsv fused on the device ----------------------------------------------
 class FusedTracker : public PositionDetector {
 public:
@@ -246,6 +290,7 @@ static void printUsage(std::ostream &out)
            "TYPE\n"
            "  hsv: Object detection using color thresholding (requires an HSV frame SOURCE)\n"
            "  thresh: Object detection using intensity thresholding (requires a GREY frame SOURCE)\n"
+           "  diff: Difference detector (grey-scale, motion)\n"
            "  track: fused mog + HSV conversion + hsv detection on a BGR frame SOURCE\n\n"
            "SOURCE:\n  User-supplied name of the memory segment to receive frames from (e.g. raw).\n\n"
            "SINK:\n  User-supplied name of the memory segment to publish detected positions to (e.g. pos).\n\n"
@@ -270,7 +315,7 @@ int main(int argc, char *argv[])
             if (argv[i][0] == '-') break;
             pos.push_back(argv[i]);
         }
-        if (type != "hsv" && type != "track" && type != "thresh") {
+        if (type != "hsv" && type != "track" && type != "thresh" && type != "diff") {
             printUsage(std::cout);
             std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
             return -1;
@@ -280,6 +325,7 @@ int main(int argc, char *argv[])
         std::shared_ptr<PositionDetector> detector;
         if (type == "hsv") detector = std::make_shared<HSVDetector>(pos[0], pos[1]);
         else if (type == "thresh") detector = std::make_shared<SimpleThreshold>(pos[0], pos[1]);
+        else if (type == "diff") detector = std::make_shared<DifferenceDetector>(pos[0], pos[1]);
         else detector = std::make_shared<FusedTracker>(pos[0], pos[1]);
         comp_name = detector->name();
 

@@ -360,3 +360,35 @@ def thresh_detect(grey: np.ndarray, t_min: int, t_max: int, p: "HsvParams"):
     if p.dilate > 0:
         m = dilate_rect(m, p.dilate)
     return sift_contours(m, p.area[0], p.area[1]), m
+
+
+def blur_nonzero(mask: np.ndarray, k: int) -> np.ndarray:
+    """(cv::blur(mask, k x k) != 0) for a 0/255 mask: box average with anchor k/2, BORDER_REFLECT_101, rounded to
+    u8 -- non-zero iff the (multiplicity-counted) number c of set samples in the box has 510 c > k^2."""
+    a = k // 2
+    rows, cols = mask.shape
+    p = np.pad((mask != 0).astype(np.int64), ((a, k - 1 - a), (a, k - 1 - a)), mode="reflect")
+    cnt = np.zeros(mask.shape, np.int64)
+    for dy in range(k):
+        for dx in range(k):
+            cnt += p[dy:dy + rows, dx:dx + cols]
+    return ((510 * cnt > k * k).astype(np.uint8)) * 255
+
+
+class DifferenceDetector:
+    """DifferenceDetector::detectPosition (src/positiondetector/DifferenceDetector.cpp:118-173)."""
+
+    def __init__(self, diff_threshold=10, blur=2, area=(0.0, DBL_MAX)):
+        self.thr, self.blur, self.area = diff_threshold, blur, tuple(area)
+        self.last = None
+
+    def detect(self, grey: np.ndarray):
+        if self.last is None:  # threshold_frame_ = frame.clone(): the raw frame is sifted (non-zero = object)
+            m = ((grey != 0).astype(np.uint8)) * 255
+        else:
+            d = np.abs(grey.astype(np.int32) - self.last.astype(np.int32))
+            m = ((d > self.thr).astype(np.uint8)) * 255
+            if self.blur > 0:
+                m = blur_nonzero(m, self.blur)
+        self.last = grey.copy()
+        return sift_contours(m, self.area[0], self.area[1]), m

@@ -220,3 +220,29 @@ def test_sift_full_size_masks(ctx, shape, n, rmax, dilate):
     """Frame-sized masks with holes, islands in holes and many blobs: one-launch tail (wide and narrow regions,
     the run table filling up, overflow -> replay) and the multi-launch tail, both against the oracle."""
     run_sift(ctx, blobs(shape[0], shape[1], n, rmax, seed=n + rmax), dilate=dilate)
+
+
+@pytest.mark.parametrize("blur", [0, 1, 2, 3, 4, 7, 10, 22])
+@pytest.mark.parametrize("shape", [(60, 83), (64, 128)])
+def test_posidet_diff_parity(ctx, blur, shape):
+    """posidet diff (src/positiondetector/DifferenceDetector.cpp:118-173): absdiff -> threshold -> blur -> siftContours,
+    with the raw-first-frame quirk and cv::blur's even-box reflected border (activity in the corner)."""
+    rows, cols = shape
+    rng = np.random.default_rng(blur * 31 + rows)
+    det = oat_b200.DifferenceDetector(ctx, rows, cols, diff_threshold=10, blur=blur)
+    orc = oracle.DifferenceDetector(diff_threshold=10, blur=blur)
+    for t in range(7):
+        grey = np.clip(rng.normal(100, 3, (rows, cols)), 0, 255).astype(np.uint8)
+        if t == 0:
+            grey[rng.random((rows, cols)) < 0.3] = 0
+        y0, x0 = int(rng.integers(0, rows - 8)), int(rng.integers(0, cols - 8))
+        grey[y0:y0 + 8, x0:x0 + 8] = 220
+        if t % 2:
+            grey[0:3, 0:2] = 250
+        d, thr = det.detect(grey, want_thresh=True)
+        o, om = orc.detect(grey)
+        assert np.array_equal(thr, om), f"sifted mask differs at t={t}: {(thr != om).sum()} px"
+        check_detection(d, o, f"t={t}")
+    det.close()
+    with pytest.raises(oat_b200.OatError):
+        oat_b200.DifferenceDetector(ctx, rows, cols, blur=23).detect(np.zeros((rows, cols), np.uint8))

@@ -50,7 +50,8 @@ def test_dispatcher_and_usage(host_bin):
     (["oat-posidet", "hsv", "a", "b", "-H", "[40,300]"], "Values of h-thresh should be between 0 and 256."),
     (["oat-posidet", "hsv", "a", "b", "-a", "[10,5]"], "Max area should be larger than min area."),
     (["oat-posidet", "hsv", "a", "b", "-S", "[1,2,3]"], "2 elements"),
-    (["oat-posidet", "diff", "a", "b"], "invalid TYPE"),
+    (["oat-posidet", "kalman", "a", "b"], "invalid TYPE"),
+    (["oat-posidet", "diff", "a", "b", "-a", "[9,3]"], "Max area should be larger than min area."),
     (["oat-posidet", "thresh", "a", "b", "-T", "[10,999]"], "Values of thresh should be between 0 and 256."),
     (["oat-framefilt", "thresh", "a", "b", "-I", "[-1,5]"], "Values of intensity should be between 0 and 256."),
     (["oat-framefilt", "mask", "a", "b", "-m", "/nonexistent.pgm"], "could not be read"),

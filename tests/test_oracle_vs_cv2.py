@@ -225,3 +225,37 @@ def test_thresh_and_mask_restatements_match_cv2():
         assert np.array_equal(oracle.threshold_filter(bgr, lo, hi), t)
     roi = (rng.random((64, 96)) < 0.6).astype(np.uint8) * 200
     assert np.array_equal(oracle.mask_filter(bgr, roi), cv2.bitwise_and(bgr, bgr, mask=roi))
+
+
+def test_difference_detector_restatement_matches_cv2():
+    """posidet diff: the numpy restatement against the reference's cv2 call sequence
+    (src/positiondetector/DifferenceDetector.cpp:154-173 + DetectorFunc.cpp:31-66), incl. the even-kernel
+    anchor / reflected border of cv::blur and the raw-first-frame quirk."""
+    rng = np.random.default_rng(11)
+    rows, cols = 60, 83
+    for k in (0, 1, 2, 3, 4, 5, 8, 10, 15, 22):
+        det = oracle.DifferenceDetector(diff_threshold=10, blur=k)
+        last = None
+        for t in range(6):
+            grey = np.clip(rng.normal(100, 3, (rows, cols)), 0, 255).astype(np.uint8)
+            if t == 0:
+                grey[rng.random((rows, cols)) < 0.3] = 0  # so that the raw first frame is not one big blob
+            y0, x0 = int(rng.integers(0, rows - 8)), int(rng.integers(0, cols - 8))
+            grey[y0:y0 + 8, x0:x0 + 8] = 220
+            if t % 2:
+                grey[0:3, 0:2] = 250  # activity in the corner: the reflected border of an even box matters there
+            # reference sequence
+            if last is None:
+                thr = grey.copy()
+            else:
+                thr = cv2.absdiff(grey, last)
+                _, thr = cv2.threshold(thr, 10, 255, cv2.THRESH_BINARY)
+                if k > 0:
+                    thr = cv2.blur(thr, (k, k))
+            last = grey.copy()
+            want = cv2ref.sift_contours(thr)
+            got, m = det.detect(grey)
+            assert np.array_equal(m != 0, thr != 0), (k, t)
+            assert bool(got.position_valid) == bool(want[0]), (k, t)
+            if want[0]:
+                assert abs(got.x - want[1]) < 1e-9 and abs(got.y - want[2]) < 1e-9 and abs(got.area - want[3]) < 1e-9, (k, t)
