@@ -23,8 +23,25 @@ int main(int argc, char *argv[])
             int process() override { return 1; }
         } sig_owner;
         const config::VariableMap vm = config::parse(argc, argv, 3, {{"npy", 0, true, ""}});
-        std::ofstream npy;
-        if (vm.count("npy")) npy.open(vm.values.at("npy"), std::ios::binary);
+        // .npy exactly as the reference's recorder writes it (src/recorder/Format.cpp:35-72, PositionWriter.cpp:80-82):
+        // v1.0 header with a 10-digit shape placeholder that is patched at exit (emplaceNumpyShape, Format.cpp:74-93)
+        static const char NPY_DTYPE[] =
+            "[('tick', '<u8'),('usec', '<u8'),('unit', '<i4'),('pos_ok', '<i1'),('pos_xy', 'f8', (2)),('vel_ok', '<i1'),"
+            "('vel_xy', 'f8', (2)),('head_ok', '<i1'),('head_xy', 'f8', (2)),('reg_ok', '<i1'),('reg', 'a10')]";
+        std::fstream npy;
+        uint64_t nrec = 0;
+        if (vm.count("npy")) {
+            npy.open(vm.values.at("npy"), std::ios::binary | std::ios::out | std::ios::trunc);
+            std::string dict = std::string("{'shape': (0000000000, ), 'fortran_order': False, 'descr': ") + NPY_DTYPE + "}";
+            const size_t rem = 16 - ((dict.size() + 10) % 16);
+            dict.append(rem, ' ');
+            dict.back() = '\n';
+            std::string hdr = std::string("\x93NUMPY") + '\x01' + '\x00';
+            hdr.push_back((char)(dict.size() & 0xff));
+            hdr.push_back((char)((dict.size() >> 8) & 0xff));
+            hdr += dict;
+            npy.write(hdr.data(), (std::streamsize)hdr.size());
+        }
         Source<Position2D> source;
         source.touch(argv[2]);
         if (source.connect() != SourceState::CONNECTED) return 0;
@@ -37,9 +54,19 @@ int main(int argc, char *argv[])
                 char rec[Position2D::NPY_DTYPE_BYTES];
                 packPosition(p, rec);
                 npy.write(rec, sizeof(rec));
+                ++nrec;
             } else {
                 std::cout << serializePosition(p) << "\n" << std::flush;
             }
+        }
+        if (npy.is_open()) {  // emplaceNumpyShape
+            const std::string n = std::to_string(nrec);
+            if (n.size() <= 10) {
+                const std::string shape = "'shape': " + std::string(10 - n.size(), ' ') + "(" + n + ", ), ";
+                npy.seekp(11);
+                npy.write(shape.data(), (std::streamsize)shape.size());
+            }
+            npy.close();
         }
         return 0;
     } catch (const std::exception &ex) {

@@ -293,8 +293,43 @@ static void test_pipeline(const std::string &frameserve)
     scrub(addr);
 }
 
+// helper mode for the position egress test: publish N positions on ADDR (what a posidet SINK does)
+static int emit_positions(const std::string &addr, int n)
+{
+    Sink<Position2D> sink;  // the consumer may already have created the node: do not scrub it away
+    sink.bind(addr, addr);
+    Position2D *shared = sink.retrieve();
+    Sample clock;
+    clock.set_rate_hz(50.0);
+    // wait for a reader so that nothing is published into the void
+    for (int i = 0; i < 3000; ++i) {
+        bool attached = false;
+        {
+            Shmem probe;
+            probe.open(addr + "_node", sizeof(Node), Shmem::OPEN_OR_CREATE);
+            attached = reinterpret_cast<Node *>(probe.base())->source_ref_count() > 0;
+        }
+        if (attached) break;
+        usleep(1000);
+    }
+    for (int t = 0; t < n; ++t) {
+        Position2D p("");
+        clock.incrementCount();
+        p.set_sample(clock);
+        p.position_valid = (t % 3) != 0;
+        p.position.x = 10.5 + t;
+        p.position.y = 0.125 * t;
+        sink.wait();
+        *shared = p;
+        sink.post();
+    }
+    sink.wait();
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 3 && std::string(argv[1]) == "emit-positions") return emit_positions(argv[2], std::atoi(argv[3]));
     test_node();
     test_sink();
     test_source();

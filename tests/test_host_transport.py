@@ -88,3 +88,35 @@ def test_toml_config_table(host_bin, tmp_path):
     assert p.returncode == 0, (p.returncode, out, err)
     assert "between 0 and 256" not in err
     subprocess.run([os.path.join(host_bin, "oat-clean"), "oatb200test_nosrc", "oatb200test_nosink"], capture_output=True)
+
+
+def test_position_egress_formats(host_bin, tmp_path):
+    """posisock std: JSON lines with serializePosition's keys (lib/datatypes/Position2D.h:169-233) and a .npy file
+    with the recorder's header + 82-byte packed records (lib/datatypes/Position2D.cpp:24-96, src/recorder/Format.cpp:35-93)
+    that numpy loads with the reference's dtype."""
+    import json
+
+    import numpy as np
+
+    for mode in ("json", "npy"):
+        addr = f"oatb200test_pos_{mode}"
+        npy = tmp_path / "pos.npy"
+        sock_args = [os.path.join(host_bin, "oat-posisock"), "std", addr] + (["--npy", str(npy)] if mode == "npy" else [])
+        sock = subprocess.Popen(sock_args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        emit = subprocess.Popen([os.path.join(host_bin, "shmemdf_test"), "emit-positions", addr, "7"])
+        out, err = sock.communicate(timeout=60)
+        assert emit.wait(timeout=30) == 0 and sock.returncode == 0, err
+        if mode == "json":
+            recs = [json.loads(ln) for ln in out.splitlines() if ln.strip()]
+            assert [r["tick"] for r in recs] == list(range(1, 8))
+            assert [r["usec"] for r in recs] == [20000 * k for k in range(1, 8)]
+            assert all(list(r) [:4] == ["tick", "usec", "unit", "pos_ok"] for r in recs)
+            assert recs[1]["pos_ok"] is True and recs[1]["pos_xy"] == [11.5, 0.125]
+            assert recs[0]["pos_ok"] is False and "pos_xy" not in recs[0]
+        else:
+            a = np.load(npy)
+            assert a.shape == (7,) and a.dtype.itemsize == 82
+            assert a["tick"].tolist() == list(range(1, 8)) and a["usec"].tolist() == [20000 * k for k in range(1, 8)]
+            assert a["pos_ok"].tolist() == [0, 1, 1, 0, 1, 1, 0]
+            assert np.allclose(a["pos_xy"][:, 0], 10.5 + np.arange(7)) and np.allclose(a["pos_xy"][:, 1], 0.125 * np.arange(7))
+        subprocess.run([os.path.join(host_bin, "oat-clean"), addr], capture_output=True)
