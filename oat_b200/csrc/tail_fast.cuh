@@ -509,11 +509,23 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
     const int i0 = max(a.ke > 0 ? e0 - ae : e0, 0), i1 = min(a.ke > 0 ? e1 - ae + a.ke - 1 : e1, rows - 1);
     const int nin = i1 - i0 + 1;
     uint32_t *A = sm, *B = sm + (size_t)nin * wpr;
+    uint32_t any = 0;
     for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) {
         const int r = t / wpr, j = t % wpr;
-        A[t] = a.in[(size_t)(i0 + r) * wpr + j] & g.valid_mask(j);
+        const uint32_t w = a.in[(size_t)(i0 + r) * wpr + j] & g.valid_mask(j);
+        A[t] = w;
+        any |= w;
     }
-    __syncthreads();
+    // Most bands of a tracking mask are empty: nothing to erode or dilate, no extents, no runs.  (An empty input
+    // band gives an empty output band for dilation, and for erosion a fortiori.)
+    const bool band_empty = __syncthreads_or(any != 0u) == 0;
+    if (band_empty) {
+        for (int t = threadIdx.x; t < (y1 - y0 + 1) * wpr; t += blockDim.x) a.out[(size_t)y0 * wpr + t] = 0u;
+        for (int y = y0 + (int)threadIdx.x; y <= y1; y += blockDim.x) {
+            a.rowext[y] = make_int2(INT_MAX, -1);
+            a.rowcnt[y] = make_int2(0, 0);
+        }
+    } else {
     if (a.ke > 0) {
         for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) B[t] = hpass_word<false>(A + (t / wpr) * wpr, t % wpr, g, a.ke);
         __syncthreads();
@@ -590,6 +602,7 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
         atomicMin(a.bbox, bymin);
         atomicMax(a.bbox + 1, bymax);
     }
+    }  // !band_empty
     __shared__ bool s_last;
     __shared__ int s_ymin, s_ymax;
     __threadfence();
