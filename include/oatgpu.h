@@ -247,9 +247,9 @@ int oat_tracker_profile_read(oat_tracker *t, double *mean_mog_kernel_ms, uint64_
  * to collect). For timing back-to-back launches of the dominant kernel in isolation. */
 int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch,
                                   double learning_rate, const oat_hsv_params *p);
-/* Diagnostic: the detect tail of the most recently collected frame. out[12] = { status (0 = the
+/* Diagnostic: the detect tail of the most recently collected frame. out[14] = { status (0 = the
  * one-launch tail sufficed, 1 = replayed through the unbounded path), run-table entries needed,
- * replays so far, one-launch tail used, 6 SM-clock stamps of its labelling CTA, frames run on the generic fused
+ * replays so far, one-launch tail used, 8 SM-clock stamps of its labelling CTA, frames run on the generic fused
  * kernel so far (adaptive kernel choice), 4-pixel groups that left the fused kernel's fast path in that frame }. */
 int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out);
 

@@ -602,10 +602,11 @@ class Tracker:
 
     def tail_stats(self):
         """Diagnostics of the detect tail of the last collected frame (see oat_tracker_tail_stats)."""
-        a = (C.c_uint32 * 12)()
+        a = (C.c_uint32 * 14)()
         _ck(lib().oat_tracker_tail_stats(self._h, a))
         v = list(a)
-        return {"status": v[0], "nodes": v[1], "replays": v[2], "fast": v[3], "cyc": v[4:]}
+        return {"status": v[0], "nodes": v[1], "replays": v[2], "fast": v[3], "cyc": v[4:12], "generic_frames": v[12],
+                "slow_groups": v[13]}
 
     def profile(self, enable: bool):
         _ck(lib().oat_tracker_profile(self._h, 1 if enable else 0))

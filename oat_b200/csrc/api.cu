@@ -72,8 +72,8 @@ struct oat_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t h2d = nullptr;      // ingest copies (overlap with compute of the previous frame)
-    static const int NTAIL = 4;
-    cudaStream_t tail[NTAIL] = {nullptr, nullptr, nullptr, nullptr};  // detect tails of in-flight frames (higher priority than compute)
+    static const int NTAIL = 8;
+    cudaStream_t tail[NTAIL] = {};  // detect tails of in-flight frames (higher priority than compute)
     int *hsv_lut = nullptr;          // sdiv[256] | hdiv[256]
     uint64_t launches = 0;
     int num_sms = 148;
@@ -1479,7 +1479,7 @@ extern "C" int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float 
 }
 
 // Diagnostic: what the one-launch tail needed for the most recently collected frame.
-extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [12]: status, nodes, replays, fast, cyc[8] */)
+extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [14]: status, nodes, replays, fast, cyc[8], generic frames, slow groups */)
 {
     REQUIRE(t && out, "null argument");
     const Slot &s = t->ring[(t->tailpos + t->ring.size() - 1) % t->ring.size()];
@@ -1488,9 +1488,8 @@ extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [12]: sta
     out[2] = (uint32_t)t->replays;
     out[3] = s.fast ? 1u : 0u;
     for (int i = 0; i < 8; ++i) out[4 + i] = s.h_res->cyc[i];
-    // cyc[7] is replaced by the context's cumulative slow-path census (read and reset)
-    out[10] = (uint32_t)t->generic_frames;  // frames that ran the generic fused kernel (adaptive choice)
-    out[11] = s.h_res->slow_groups;          // census of that frame
+    out[12] = (uint32_t)t->generic_frames;  // frames that ran the generic fused kernel (adaptive choice)
+    out[13] = s.h_res->slow_groups;          // census of that frame
     return OAT_OK;
 }
 

@@ -42,10 +42,10 @@ for i in range(args.steps):
 ctx.sync()
 tot = sorted(a.elapsed_time(b) for a, b in ev)
 ts = trk.tail_stats()
-print('slow groups in last frame:', ts['cyc'][7], '=', ts['cyc'][7] / (rows * cols / 4) * 100, '% of groups; generic-kernel frames:', ts['cyc'][6])
+print('slow groups in last frame:', ts['slow_groups'], '=', ts['slow_groups'] / (rows * cols / 4) * 100, '% of groups; generic-kernel frames:', ts['generic_frames'])
 c = ts["cyc"]
 print("tail:", {k: ts[k] for k in ("status", "nodes", "replays", "fast")}, "label-CTA cycles since start:",
-      [(c[i] - c[0]) & 0xffffffff for i in range(1, 6)])
+      [(c[i] - c[0]) & 0xffffffff for i in range(1, 8)])
 kms, n = trk.profile_read()
 mbar = trk.live_modes() / (rows * cols)
 balg = 8 + 40 * mbar
