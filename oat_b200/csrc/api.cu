@@ -80,7 +80,7 @@ struct oat_ctx {
     bool pipe_attr_set = false;
     // development switches, read once at creation: OAT_B200_NO_PIPE / _NO_FAST_TAIL / _NO_OVERLAP force the generic
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
-    bool no_pipe = false, no_fast_tail = false, no_overlap = false;
+    bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
     unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel ([2], ping-pong)
     uint64_t pipe_launches = 0;
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
@@ -131,6 +131,7 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->no_pipe = getenv("OAT_B200_NO_PIPE") != nullptr;
     c->no_fast_tail = getenv("OAT_B200_NO_FAST_TAIL") != nullptr;
     c->no_overlap = getenv("OAT_B200_NO_OVERLAP") != nullptr;
+    c->pdl = getenv("OAT_B200_NO_PDL") == nullptr;
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
@@ -411,14 +412,27 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         pa.tile_counter = c->tile_counter + (c->pipe_launches & 1u);
         pa.tile_counter_next = c->tile_counter + ((c->pipe_launches + 1u) & 1u);
         ++c->pipe_launches;
+        // programmatic dependent launch: the next frame's CTAs become resident (and run their prologue:
+        // mbarrier + queue initialisation) while this frame's last CTAs drain; the kernel orders its
+        // first global access behind the previous grid with griddepcontrol.wait
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)grid);
+        lc.blockDim = dim3(PIPE_THREADS);
+        lc.dynamicSmemBytes = PIPE_SMEM_BYTES;
+        lc.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = c->pdl ? 1u : 0u;
         if (frozen && linear)
-            mog_pipe_kernel<5, true, true><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, true, true>, pa));
         else if (frozen)
-            mog_pipe_kernel<5, true, false><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, true, false>, pa));
         else if (linear)
-            mog_pipe_kernel<5, false, true><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, false, true>, pa));
         else
-            mog_pipe_kernel<5, false, false><<<grid, PIPE_THREADS, PIPE_SMEM_BYTES, c->stream>>>(pa);
+            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, false, false>, pa));
     } else if (vec && frozen)
         launch_fused_px<4, true>(c->stream, m.K, a);
     else if (vec)

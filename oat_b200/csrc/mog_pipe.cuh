@@ -346,9 +346,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     __shared__ __align__(8) uint64_t done[PIPE_STAGES];  // stage updated in place by all compute threads
     const FusedArgs &a = pa.f;
     const int tid = threadIdx.x;
+    // let the next launch on this stream (programmatic dependent launch) become resident as CTAs of
+    // this one retire; it parks in griddepcontrol.wait below until this grid has completed and flushed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
-        // the two scheduler counters ping-pong between launches (stream-ordered): arm the other one
-        if (LINEAR && blockIdx.x == 0) *pa.tile_counter_next = 0u;
 #pragma unroll
         for (int s = 0; s < PIPE_STAGES; ++s) {
             mbar_init(&full[s], LINEAR ? 1 : 1 + PIPE_CTHREADS);
@@ -362,6 +363,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         for (int i = tid; i < PIPE_TILE; i += PIPE_THREADS) reinterpret_cast<uint16_t *>(st + PIPE_OFF_QUEUE)[i] = 0xffffu;
     }
     __syncthreads();
+    // everything above touched shared memory only; global memory (GMM state, scheduler counters) is
+    // ordered behind the previous grid on the stream from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the two scheduler counters ping-pong between launches (stream-ordered): arm the other one
+    if (LINEAR && blockIdx.x == 0 && tid == 0) *pa.tile_counter_next = 0u;
 
     // Tile order.  LINEAR frames use a dynamic scheduler: the producer draws tile numbers from a
     // global counter (tiles that hit the multi-mode slow path take several times longer than the
