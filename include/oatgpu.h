@@ -233,6 +233,42 @@ int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, d
                        const oat_hsv_params *p, uint8_t *bgr_out, size_t bgr_out_pitch);
 int oat_tracker_collect(oat_tracker *t, oat_detection *out);
 int oat_tracker_live_modes(oat_tracker *t, uint64_t *sum_modes);
+
+/* ---- posifilt kalman + posicom mean: the O(1) epilogue behind the detectors ----
+ * The Position2D fields those components touch (lib/datatypes/Position2D.h:112-155). */
+typedef struct oat_position {
+    int32_t position_valid, velocity_valid, heading_valid;
+    int32_t reserved;
+    double x, y;   /* Position2D::position */
+    double vx, vy; /* Position2D::velocity */
+    double hx, hy; /* Position2D::heading (unit vector) */
+} oat_position;
+/* KalmanFilter2D's options (src/positionfilter/KalmanFilter2D.cpp:40-92; defaults
+ * KalmanFilter2D.h:66-83: dt 0.02 s, timeout 0 s, sigma-accel 5, sigma-noise 0).  NOTE the reference's
+ * semantics: not_found_threshold = int(timeout / dt), and a position is valid only while
+ * not_found_count < threshold -- with the default timeout 0 no output is ever valid. */
+typedef struct oat_kalman_params {
+    double dt, timeout, sigma_accel, sigma_noise;
+} oat_kalman_params;
+void oat_kalman_default_params(oat_kalman_params *p);
+typedef struct oat_posfilt oat_posfilt;
+/* n_sources position streams (1..8); kalman != NULL: each goes through its own KalmanFilter2D
+ * (replaces KalmanFilter2D::filter, KalmanFilter2D.cpp:95-145); combine_mean != 0: the (filtered)
+ * sources are merged by MeanPosition::combine (src/positioncombiner/MeanPosition.cpp:60-118) with
+ * heading_anchor = --heading-anchor (negative: headings are averaged instead of generated).
+ * The filter state lives on the device; one apply = one kernel launch. */
+int oat_posfilt_create(oat_ctx *ctx, int n_sources, const oat_kalman_params *kalman, int combine_mean,
+                       int heading_anchor, oat_posfilt **out);
+int oat_posfilt_destroy(oat_posfilt *f);
+int oat_posfilt_reset(oat_posfilt *f);
+/* sources: n_sources raw positions (host memory); out: 1 position if combine_mean else n_sources. */
+int oat_posfilt_apply(oat_posfilt *f, const oat_position *sources, oat_position *out);
+/* Fuse a single-source filter behind a tracker: every frame's detection feeds it on the device, in
+ * frame order (also when detect tails of consecutive frames overlap), and
+ * oat_tracker_collect_position returns the filtered position next to the raw detection.
+ * Pass NULL to detach. */
+int oat_tracker_attach_posfilt(oat_tracker *t, oat_posfilt *f);
+int oat_tracker_collect_position(oat_tracker *t, oat_detection *det, oat_position *pos);
 /* GMM state egress, as oat_mog_get_state. */
 int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, float *variance,
                           float *mean);

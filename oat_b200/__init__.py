@@ -71,6 +71,27 @@ class HsvParams(C.Structure):
         return cls(h[0], h[1], s[0], s[1], v[0], v[1], erode, dilate, area[0], area[1])
 
 
+class Position(C.Structure):
+    """oat_position: the Position2D fields the position filters/combiners touch (Position2D.h:112-155)."""
+    _fields_ = [
+        ("position_valid", C.c_int32),
+        ("velocity_valid", C.c_int32),
+        ("heading_valid", C.c_int32),
+        ("reserved", C.c_int32),
+        ("x", C.c_double),
+        ("y", C.c_double),
+        ("vx", C.c_double),
+        ("vy", C.c_double),
+        ("hx", C.c_double),
+        ("hy", C.c_double),
+    ]
+
+
+class KalmanParams(C.Structure):
+    """oat_kalman_params: oat posifilt kalman --dt/--timeout/--sigma-accel/--sigma-noise (KalmanFilter2D.cpp:40-92)."""
+    _fields_ = [("dt", C.c_double), ("timeout", C.c_double), ("sigma_accel", C.c_double), ("sigma_noise", C.c_double)]
+
+
 class Detection(C.Structure):
     _fields_ = [
         ("position_valid", C.c_int32),
@@ -136,6 +157,13 @@ _SIGS = {
                                      C.c_size_t]),
     "oat_tracker_collect": (C.c_int, [C.c_void_p, C.POINTER(Detection)]),
     "oat_tracker_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "oat_kalman_default_params": (None, [C.POINTER(KalmanParams)]),
+    "oat_posfilt_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(KalmanParams), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "oat_posfilt_destroy": (C.c_int, [C.c_void_p]),
+    "oat_posfilt_reset": (C.c_int, [C.c_void_p]),
+    "oat_posfilt_apply": (C.c_int, [C.c_void_p, C.POINTER(Position), C.POINTER(Position)]),
+    "oat_tracker_attach_posfilt": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "oat_tracker_collect_position": (C.c_int, [C.c_void_p, C.POINTER(Detection), C.POINTER(Position)]),
     "oat_tracker_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oat_tracker_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "oat_tracker_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -528,6 +556,49 @@ class DifferenceDetector:
         return d, thr
 
 
+class PositionFilter:
+    """`oat posifilt kalman` (KalmanFilter2D, src/positionfilter/KalmanFilter2D.cpp:95-200) per source and/or
+    `oat posicom mean` (MeanPosition::combine, src/positioncombiner/MeanPosition.cpp:60-118) over the sources,
+    one kernel launch per sample; the filter state lives on the device."""
+
+    def __init__(self, ctx: Context, n_sources: int = 1, kalman: KalmanParams | dict | None = None,
+                 combine_mean: bool = False, heading_anchor: int = -1):
+        self.ctx, self.n, self.combine = ctx, n_sources, combine_mean
+        kp = None
+        if kalman is not None:
+            kp = KalmanParams()
+            lib().oat_kalman_default_params(C.byref(kp))
+            if isinstance(kalman, dict):
+                for k, v in kalman.items():
+                    setattr(kp, k, v)
+            else:
+                kp = kalman
+        self._h = C.c_void_p()
+        _ck(lib().oat_posfilt_create(ctx._h, n_sources, C.byref(kp) if kp is not None else None, int(combine_mean),
+                                     heading_anchor, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oat_posfilt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _ck(lib().oat_posfilt_reset(self._h))
+
+    def apply(self, sources):
+        """sources: n Position structs -> one Position (combine_mean) or a list of n."""
+        arr = (Position * self.n)(*sources)
+        out = (Position * (1 if self.combine else self.n))()
+        _ck(lib().oat_posfilt_apply(self._h, arr, out))
+        return out[0] if self.combine else list(out)
+
+
 class Tracker:
     """mog -> col HSV -> hsv fused on the device; one instance = one video stream."""
 
@@ -588,6 +659,16 @@ class Tracker:
         d = Detection()
         _ck(lib().oat_tracker_collect(self._h, C.byref(d)))
         return d
+
+    def attach_posfilt(self, f: "PositionFilter | None"):
+        """Fuse a single-source position filter behind this tracker (device-side epilogue, frame order)."""
+        _ck(lib().oat_tracker_attach_posfilt(self._h, f._h if f is not None else None))
+        self._pf = f
+
+    def collect_position(self):
+        d, p = Detection(), Position()
+        _ck(lib().oat_tracker_collect_position(self._h, C.byref(d), C.byref(p)))
+        return d, p
 
     def live_modes(self) -> int:
         s = C.c_uint64()

@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
 #include <new>
 #include <string>
 #include <vector>
@@ -19,6 +21,7 @@
 #include "pixel_ops.cuh"
 #include "tail.cuh"
 #include "tail_fast.cuh"
+#include "posfilt.cuh"
 
 using namespace oat;
 
@@ -81,7 +84,15 @@ struct oat_ctx {
     // development switches, read once at creation: OAT_B200_NO_PIPE / _NO_FAST_TAIL / _NO_OVERLAP force the generic
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
-    unsigned int *tile_counter = nullptr;  // dynamic tile scheduler of the pipelined fused kernel ([2], ping-pong)
+    cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
+    // dynamic tile scheduler of the pipelined fused kernel: 4 monotonic draw counters used round-robin by
+    // consecutive launches (at most two launches overlap); the host knows how many draws each launch makes
+    unsigned int *tile_counter = nullptr;
+    unsigned int tile_base[4] = {0, 0, 0, 0};
+    // model whose pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the next
+    // launch on the same model may chain to it tile by tile instead of waiting for the whole grid
+    unsigned long long chain_uid = 0;
+    bool no_chain = false;
     uint64_t pipe_launches = 0;
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
@@ -132,9 +143,11 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->no_fast_tail = getenv("OAT_B200_NO_FAST_TAIL") != nullptr;
     c->no_overlap = getenv("OAT_B200_NO_OVERLAP") != nullptr;
     c->pdl = getenv("OAT_B200_NO_PDL") == nullptr;
+    c->no_chain = getenv("OAT_B200_NO_CHAIN") != nullptr;
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->post, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;  // numerically lower = higher priority
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -148,8 +161,8 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     }
     CK(cudaMalloc(&c->slow_count, sizeof(unsigned int)));
     CK(cudaMemset(c->slow_count, 0, sizeof(unsigned int)));
-    CK(cudaMalloc(&c->tile_counter, 2 * sizeof(unsigned int)));
-    CK(cudaMemset(c->tile_counter, 0, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->tile_counter, 4 * sizeof(unsigned int)));
+    CK(cudaMemset(c->tile_counter, 0, 4 * sizeof(unsigned int)));
     CK(cudaMalloc(&c->hsv_lut, sizeof(lut)));
     CK(cudaMemcpy(c->hsv_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     *out = c;
@@ -162,6 +175,10 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->h2d);
+    if (c->post) {
+        cudaStreamSynchronize(c->post);
+        cudaStreamDestroy(c->post);
+    }
     for (int i = 0; i < oat_ctx::NTAIL; ++i)
         if (c->tail[i]) {
             cudaStreamSynchronize(c->tail[i]);
@@ -269,6 +286,7 @@ static inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs 
 #define LAUNCH_CHECK(c)                 \
     do {                                \
         ++(c)->launches;                \
+        (c)->chain_uid = 0;             \
         CK(cudaGetLastError());         \
     } while (0)
 
@@ -299,6 +317,9 @@ struct MogModel {
     uint8_t *nmodes = nullptr;
     int nframes = 0;
     unsigned long long *d_sum = nullptr;
+    unsigned int *tile_seq = nullptr;  // per tile of the pipelined kernel: sequence number of the last launch that finished it
+    unsigned int seq = 0;              // sequence number the next pipelined launch expects (and publishes + 1)
+    unsigned long long uid = 0;
 
     int create(int rows, int cols, const oat_mog_params *params)
     {
@@ -319,6 +340,12 @@ struct MogModel {
         CK(cudaMalloc(&nmodes, plane));
         CK(cudaMalloc(&d_sum, sizeof(unsigned long long)));
         CK(cudaMemset(nmodes, 0, plane));
+        const size_t ntiles = (plane + PIPE_TILE - 1) / PIPE_TILE;
+        CK(cudaMalloc(&tile_seq, ntiles * sizeof(unsigned int)));
+        CK(cudaMemset(tile_seq, 0, ntiles * sizeof(unsigned int)));
+        static std::atomic<unsigned long long> next_uid{1};
+        uid = next_uid++;
+        seq = 0;
         nframes = 0;
         return OAT_OK;
     }
@@ -327,6 +354,8 @@ struct MogModel {
         if (state) cudaFree(state);
         if (nmodes) cudaFree(nmodes);
         if (d_sum) cudaFree(d_sum);
+        if (tile_seq) cudaFree(tile_seq);
+        tile_seq = nullptr;
         state = nullptr;
         nmodes = nullptr;
         d_sum = nullptr;
@@ -372,7 +401,7 @@ static void launch_fused_px(cudaStream_t s, int K, const FusedArgs &a)
 
 static bool aligned4(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 3u) == 0; }
 
-static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true)
+static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true, bool allow_chain = false)
 {
     a.rows = m.g.rows;
     a.cols = m.g.cols;
@@ -388,6 +417,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
     // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
     // the state write-back; with a live rate every live mode changes every frame anyway.
     const bool frozen = (a.c.aT == 0.0f) && !a.reset && !getenv("OAT_B200_NO_TRACK");
+    unsigned long long pipe_uid = 0;
     if (vec && !a.reset && m.K == 5 && allow_pipe && !c->no_pipe) {
         // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
         // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
@@ -408,10 +438,24 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
         const int grid = pa.ntiles < PIPE_CTAS_PER_SM * c->num_sms ? pa.ntiles : PIPE_CTAS_PER_SM * c->num_sms;
         pa.grid_tiles = grid;
-        // launches on one context are stream-ordered: two counters ping-pong, each launch arms the next one's
-        pa.tile_counter = c->tile_counter + (c->pipe_launches & 1u);
-        pa.tile_counter_next = c->tile_counter + ((c->pipe_launches + 1u) & 1u);
+        const unsigned slot = c->pipe_launches & 3u;
+        pa.tile_counter = c->tile_counter + slot;
+        pa.counter_base = c->tile_base[slot];
+        if (linear) {
+            // draws of this launch (mog_pipe.cuh, next_tile): every CTA that starts its last static tile
+            // draws once, and every valid number drawn is followed by one more draw
+            const int S = PIPE_STAGES;
+            const long long reach = std::min<long long>(grid, std::max<long long>(0, (long long)pa.ntiles - (long long)(S - 2) * grid));
+            const long long valid = std::max<long long>(0, (long long)pa.ntiles - (long long)S * grid);
+            c->tile_base[slot] += (unsigned)(reach + valid);
+        }
         ++c->pipe_launches;
+        // chain to the previous launch tile by tile when that launch was this model's pipelined kernel,
+        // it is the last kernel on the stream, and both grids fill the machine (so at most two overlap)
+        pa.tile_seq = m.tile_seq;
+        pa.seq_expect = m.seq++;
+        pa.chain = (allow_chain && c->pdl && !c->no_chain && c->chain_uid == m.uid && grid == PIPE_CTAS_PER_SM * c->num_sms) ? 1 : 0;
+        pipe_uid = m.uid;
         // programmatic dependent launch: the next frame's CTAs become resident (and run their prologue:
         // mbarrier + queue initialisation) while this frame's last CTAs drain; the kernel orders its
         // first global access behind the previous grid with griddepcontrol.wait
@@ -440,6 +484,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
     else
         launch_fused_px<1, true>(c->stream, m.K, a);
     LAUNCH_CHECK(c);
+    c->chain_uid = pipe_uid;
     return OAT_OK;
 }
 
@@ -1201,10 +1246,134 @@ struct Slot {
     oat_hsv_params hp{};
     bool fast = false;              // the one-launch tail was used (status must be checked at collect)
     cudaEvent_t copied = nullptr, done = nullptr;
+    oat_position *d_pos = nullptr, *h_pos = nullptr;  // attached position filter: this frame's filtered position
+    cudaEvent_t pos_done = nullptr;
+    bool has_pos = false;
 };
+
+// ---- posifilt kalman + posicom mean (posfilt.cuh) ----------------------------------------------
+struct oat_posfilt {
+    oat_ctx *ctx;
+    int n = 1, combine = 0, heading_anchor = -1;
+    KalmanConsts kc{};
+    PosfiltDev *dev = nullptr;
+    oat_position *d_raw = nullptr, *d_out = nullptr;  // staging of oat_posfilt_apply
+    oat_position *h_io = nullptr;                     // pinned: [0..n) raw in, [n..2n) out
+    int attached = 0;
+};
+
+extern "C" void oat_kalman_default_params(oat_kalman_params *p)
+{
+    if (!p) return;
+    p->dt = 0.02;  // KalmanFilter2D.h:66-70
+    p->timeout = 0.0;
+    p->sigma_accel = 5.0;
+    p->sigma_noise = 0.0;
+}
+
+extern "C" int oat_posfilt_create(oat_ctx *c, int n_sources, const oat_kalman_params *kp, int combine_mean,
+                                  int heading_anchor, oat_posfilt **out)
+{
+    REQUIRE(c && out, "oat_posfilt_create: null argument");
+    REQUIRE(n_sources >= 1 && n_sources <= 8, "oat_posfilt_create: 1..8 sources");
+    REQUIRE(heading_anchor < n_sources, "heading-anchor must be a SOURCE index");  // MeanPosition.cpp:52-54
+    REQUIRE(!kp || kp->dt > 0.0, "kalman: dt must be positive");
+    CKRET(bind(c));
+    oat_posfilt *f = new (std::nothrow) oat_posfilt();
+    REQUIRE(f, "out of memory");
+    f->ctx = c;
+    f->n = n_sources;
+    f->combine = combine_mean ? 1 : 0;
+    f->heading_anchor = heading_anchor < 0 ? -1 : heading_anchor;
+    if (kp) {  // initializeStaticMatracies, KalmanFilter2D.cpp:162-200
+        const double dt = kp->dt, sa = kp->sigma_accel;
+        f->kc.enabled = 1;
+        f->kc.dt = dt;
+        f->kc.q00 = sa * sa * (dt * dt * dt * dt) / 4.0;
+        f->kc.q01 = sa * sa * (dt * dt * dt) / 2.0;
+        f->kc.q11 = sa * sa * (dt * dt);
+        f->kc.r = kp->sigma_noise * kp->sigma_noise;
+        f->kc.not_found_thr = (int)(kp->timeout / kp->dt);  // KalmanFilter2D.cpp:74-76
+    }
+    CK(cudaMalloc(&f->dev, sizeof(PosfiltDev)));
+    CK(cudaMalloc(&f->d_raw, 8 * sizeof(oat_position)));
+    CK(cudaMalloc(&f->d_out, 8 * sizeof(oat_position)));
+    CK(cudaHostAlloc(&f->h_io, 16 * sizeof(oat_position), cudaHostAllocDefault));
+    posfilt_reset_kernel<<<1, 32, 0, c->post>>>(f->dev);
+    const unsigned long long keep = c->chain_uid;
+    LAUNCH_CHECK(c);
+    c->chain_uid = keep;
+    *out = f;
+    return OAT_OK;
+}
+
+extern "C" int oat_posfilt_destroy(oat_posfilt *f)
+{
+    if (!f) return OAT_OK;
+    REQUIRE(!f->attached, "oat_posfilt_destroy: still attached to a tracker");
+    bind(f->ctx);
+    cudaStreamSynchronize(f->ctx->post);
+    if (f->dev) cudaFree(f->dev);
+    if (f->d_raw) cudaFree(f->d_raw);
+    if (f->d_out) cudaFree(f->d_out);
+    if (f->h_io) cudaFreeHost(f->h_io);
+    delete f;
+    return OAT_OK;
+}
+
+extern "C" int oat_posfilt_reset(oat_posfilt *f)
+{
+    REQUIRE(f, "null handle");
+    oat_ctx *c = f->ctx;
+    CKRET(bind(c));
+    posfilt_reset_kernel<<<1, 32, 0, c->post>>>(f->dev);
+    const unsigned long long keep = c->chain_uid;
+    LAUNCH_CHECK(c);
+    c->chain_uid = keep;
+    return OAT_OK;
+}
+
+static int posfilt_launch(oat_posfilt *f, const oat_position *raw, const oat_detection *det, const int32_t *status,
+                          int force, oat_position *out)
+{
+    oat_ctx *c = f->ctx;
+    PosfiltArgs a{};
+    a.dev = f->dev;
+    a.kc = f->kc;
+    a.n = f->n;
+    a.combine = f->combine;
+    a.heading_anchor = f->heading_anchor;
+    a.raw = raw;
+    a.det = det;
+    a.det_status = status;
+    a.force = force;
+    a.out = out;
+    posfilt_kernel<<<1, 32, 0, c->post>>>(a);
+    const unsigned long long keep = c->chain_uid;  // not on the compute stream: the fused-kernel chain is intact
+    LAUNCH_CHECK(c);
+    c->chain_uid = keep;
+    return OAT_OK;
+}
+
+extern "C" int oat_posfilt_apply(oat_posfilt *f, const oat_position *sources, oat_position *out)
+{
+    REQUIRE(f && sources && out, "oat_posfilt_apply: null argument");
+    REQUIRE(!f->attached, "oat_posfilt_apply: the filter is fed by a tracker");
+    oat_ctx *c = f->ctx;
+    CKRET(bind(c));
+    const int nout = f->combine ? 1 : f->n;
+    memcpy(f->h_io, sources, f->n * sizeof(oat_position));
+    CK(cudaMemcpyAsync(f->d_raw, f->h_io, f->n * sizeof(oat_position), cudaMemcpyHostToDevice, c->post));
+    CKRET(posfilt_launch(f, f->d_raw, nullptr, nullptr, 1, f->d_out));
+    CK(cudaMemcpyAsync(f->h_io + 8, f->d_out, nout * sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
+    CK(cudaStreamSynchronize(c->post));
+    memcpy(out, f->h_io + 8, nout * sizeof(oat_position));
+    return OAT_OK;
+}
 
 struct oat_tracker {
     oat_ctx *ctx;
+    oat_posfilt *pf = nullptr;
     MogModel m;
     Tail tail;
     std::vector<Slot> ring;
@@ -1269,6 +1438,7 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
     cudaStreamSynchronize(t->ctx->h2d);
     cudaStreamSynchronize(t->ctx->stream);
     for (int i = 0; i < oat_ctx::NTAIL; ++i) cudaStreamSynchronize(t->ctx->tail[i]);
+    cudaStreamSynchronize(t->ctx->post);
     t->m.destroy();
     t->tail.destroy();
     for (auto &s : t->ring) {
@@ -1281,7 +1451,11 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
         if (s.fused_done) cudaEventDestroy(s.fused_done);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.pos_done) cudaEventDestroy(s.pos_done);
+        if (s.d_pos) cudaFree(s.d_pos);
+        if (s.h_pos) cudaFreeHost(s.h_pos);
     }
+    if (t->pf) t->pf->attached = 0;
     for (auto &pr : t->prof_pending) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -1344,7 +1518,11 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     }
     a.slow_count = s.d_slow;
     if (t->use_generic) ++t->generic_frames;
-    CKRET(launch_fused(c, t->m, a, !t->use_generic));
+    // tile-granular chaining to the previous frame's launch: only when nothing but this stream's own
+    // kernels order the frame (device-resident input, no egress buffers that a copy still reads)
+    const bool chainable = mem_kind(bgr_in) == MEM_DEVICE && !ob.d && !ofg.d && !ohsv.d && !othr.d && !t->prof;
+    CKRET(launch_fused(c, t->m, a, !t->use_generic, chainable));
+    const unsigned long long chain_after_fused = c->chain_uid;
     if (t->prof) {
         CK(cudaEventRecord(e1, c->stream));
         t->prof_pending.emplace_back(e0, e1);
@@ -1367,9 +1545,22 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
             CKRET(t->tail.run(c, s.bits, *p, &s.d_res->det, othr.d, othr.dpitch, nullptr));
         }
     }
+    // a tail that went to another stream left the fused kernel the last kernel on the compute stream
+    if (ts != c->stream) c->chain_uid = chain_after_fused;
     CKRET(finish_out(ts, othr));
     CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(TailResult), cudaMemcpyDeviceToHost, ts));
     CK(cudaEventRecord(s.done, ts));
+    s.has_pos = false;
+    if (t->pf) {
+        // the position epilogue: one warp on the in-order `post` stream behind this frame's tail.  A frame
+        // whose one-launch tail overflowed has no final detection yet: the kernel holds the filter (and
+        // every later frame's update) until collect has replayed the frame and re-runs them in order.
+        CK(cudaStreamWaitEvent(c->post, s.done, 0));
+        CKRET(posfilt_launch(t->pf, nullptr, &s.d_res->det, s.fast ? &s.d_res->status : nullptr, 0, s.d_pos));
+        CK(cudaMemcpyAsync(s.h_pos, s.d_pos, sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
+        CK(cudaEventRecord(s.pos_done, c->post));
+        s.has_pos = true;
+    }
     ++t->head;
     return OAT_OK;
 }
@@ -1406,12 +1597,44 @@ extern "C" int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_
     a.hi[1] = p->s_max;
     a.hi[2] = p->v_max;
     a.thr_bits = s.bits;
-    return launch_fused(c, t->m, a);
+    return launch_fused(c, t->m, a, true, true);
 }
 
+static int tracker_collect(oat_tracker *t, oat_detection *out, oat_position *pos);
 extern "C" int oat_tracker_collect(oat_tracker *t, oat_detection *out)
 {
     REQUIRE(t && out, "oat_tracker_collect: null argument");
+    return tracker_collect(t, out, nullptr);
+}
+
+extern "C" int oat_tracker_collect_position(oat_tracker *t, oat_detection *det, oat_position *pos)
+{
+    REQUIRE(t && det && pos, "oat_tracker_collect_position: null argument");
+    REQUIRE(t->pf, "oat_tracker_collect_position: no position filter attached");
+    return tracker_collect(t, det, pos);
+}
+
+extern "C" int oat_tracker_attach_posfilt(oat_tracker *t, oat_posfilt *f)
+{
+    REQUIRE(t, "null handle");
+    REQUIRE(t->head == t->tailpos, "oat_tracker_attach_posfilt: frames are still outstanding");
+    REQUIRE(!f || (f->ctx == t->ctx && f->n == 1 && !f->attached), "oat_tracker_attach_posfilt: needs an unattached single-source filter of the same context");
+    CKRET(bind(t->ctx));
+    if (t->pf) t->pf->attached = 0;
+    t->pf = f;
+    if (f) {
+        f->attached = 1;
+        for (auto &s : t->ring) {
+            if (!s.d_pos) CK(cudaMalloc(&s.d_pos, sizeof(oat_position)));
+            if (!s.h_pos) CK(cudaHostAlloc(&s.h_pos, sizeof(oat_position), cudaHostAllocDefault));
+            if (!s.pos_done) CK(cudaEventCreateWithFlags(&s.pos_done, cudaEventDisableTiming));
+        }
+    }
+    return OAT_OK;
+}
+
+static int tracker_collect(oat_tracker *t, oat_detection *out, oat_position *pos)
+{
     if (t->tailpos == t->head) return fail(OAT_ERR_STATE, "oat_tracker_collect: nothing outstanding");
     CKRET(bind(t->ctx));
     Slot &s = t->ring[t->tailpos % t->ring.size()];
@@ -1432,6 +1655,28 @@ extern "C" int oat_tracker_collect(oat_tracker *t, oat_detection *out)
         else if (t->use_generic && t->slow_frac < 0.15) t->use_generic = false;
     }
     *out = s.h_res->det;
+    if (s.has_pos) {
+        oat_ctx *c = t->ctx;
+        CK(cudaEventSynchronize(s.pos_done));
+        if (s.h_pos->reserved == -1) {
+            // the filter was held at this frame (its detection was not final when the epilogue ran): the
+            // detection is final now -- run this frame, then re-run the frames submitted after it, in order
+            CKRET(posfilt_launch(t->pf, nullptr, &s.d_res->det, nullptr, 1, s.d_pos));
+            CK(cudaMemcpyAsync(s.h_pos, s.d_pos, sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
+            for (uint64_t u = t->tailpos + 1; u < t->head; ++u) {
+                Slot &n = t->ring[u % t->ring.size()];
+                if (!n.has_pos) continue;
+                CK(cudaStreamWaitEvent(c->post, n.done, 0));
+                CKRET(posfilt_launch(t->pf, nullptr, &n.d_res->det, n.fast ? &n.d_res->status : nullptr, 0, n.d_pos));
+                CK(cudaMemcpyAsync(n.h_pos, n.d_pos, sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
+                CK(cudaEventRecord(n.pos_done, c->post));
+            }
+            CK(cudaStreamSynchronize(c->post));
+        }
+        if (pos) *pos = *s.h_pos;
+    } else if (pos) {
+        return fail(OAT_ERR_STATE, "oat_tracker_collect_position: the frame was submitted before the filter was attached");
+    }
     ++t->tailpos;
     return OAT_OK;
 }

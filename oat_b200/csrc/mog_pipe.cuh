@@ -55,6 +55,17 @@ __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
 {
@@ -109,6 +120,11 @@ __device__ __forceinline__ void bulk_wait_read()
 {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all()  // writes of all but the N latest groups are COMPLETE (not just read)
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *b)
 {
@@ -130,8 +146,16 @@ struct PipeArgs {
     unsigned long long div_magic;  // ceil(2^64 / pitch_px): y = umul64hi(pidx, magic), exact for every pidx < 2^32
     int zero_in;                   // HSV (0,0,0) lies inside the inRange band
     int grid_tiles;                // tile stride between consecutive tiles of one CTA (= gridDim.x)
-    unsigned int *tile_counter;    // dynamic tile scheduler (LINEAR frames): next tile number of THIS launch (starts at 0)
-    unsigned int *tile_counter_next;  // the counter the NEXT launch on this context will use: zeroed by this launch
+    unsigned int *tile_counter;    // dynamic tile scheduler (LINEAR frames): monotonic draw counter of THIS launch's slot
+    unsigned int counter_base;     // value of *tile_counter before this launch's first draw (the host knows every launch's draw count)
+    // Tile-granular ordering between consecutive launches on one model ("chain"): tile_seq[i] holds the
+    // sequence number of the last launch that has finished (stored + made visible) tile i.  A chained
+    // launch is NOT ordered behind its predecessor grid (no griddepcontrol.wait): its producer loads
+    // tile i once tile_seq[i] == seq_expect, so its first tiles stream in while the predecessor's
+    // last tiles are still being computed.  Every launch publishes seq_expect + 1.
+    unsigned int *tile_seq;
+    unsigned int seq_expect;
+    int chain;
 };
 
 // One pixel with one or two live modes whose sample fits mode 0 (the heavier one): the m = 0
@@ -365,9 +389,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
     __syncthreads();
     // everything above touched shared memory only; global memory (GMM state, scheduler counters) is
     // ordered behind the previous grid on the stream from here on
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    // the two scheduler counters ping-pong between launches (stream-ordered): arm the other one
-    if (LINEAR && blockIdx.x == 0 && tid == 0) *pa.tile_counter_next = 0u;
+    // (a chained launch orders itself tile by tile through pa.tile_seq instead)
+    if (!pa.chain) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // Tile order.  LINEAR frames use a dynamic scheduler: the producer draws tile numbers from a
     // global counter (tiles that hit the multi-mode slow path take several times longer than the
@@ -390,11 +413,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             const size_t rem = a.plane - p0;
             npx = rem < (size_t)PIPE_TILE ? (uint32_t)rem : (uint32_t)PIPE_TILE;
         };
-        auto issue_load = [&](int s, int tile) {
+        auto issue_load = [&](int s, int tile, uint32_t seen) {
             size_t p0;
             uint32_t npx;
             tile_span(tile, p0, npx);
             uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
+            // chained launch: the predecessor must have published this tile.  `seen` is a relaxed read of
+            // the flag taken one refill earlier (hides the L2 round trip in the steady state, where the
+            // predecessor is long past this tile); state bytes reach this SM only through bulk copies and
+            // L1::no_allocate loads, i.e. from L2, where the publisher's release ordered them before the flag.
+            if (pa.chain && seen != pa.seq_expect)
+                while (ld_acquire_gpu(pa.tile_seq + tile) != pa.seq_expect) __nanosleep(20);
             mbar_expect_tx(&full[s], npx * (DYN ? 24u : 21u));
 #pragma unroll
             for (int cc = 0; cc < 5; ++cc)
@@ -409,15 +438,43 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         // of the atomic hides behind the wait for the stage.
         int seq = 0, ahead = 0;
         bool ended = false;
-        auto draw = [&]() -> int { return (int)atomicAdd(pa.tile_counter, 1u) + PIPE_STAGES * (int)gridDim.x; };
+        auto draw = [&]() -> int {
+            const uint32_t d = atomicAdd(pa.tile_counter, 1u) - pa.counter_base;
+            return d < 0x40000000u ? (int)d + PIPE_STAGES * (int)gridDim.x : 0x7fffffff;
+        };
+        // publish a finished tile (its bulk stores are complete, the compute warps' direct stores
+        // were ordered by done[s]) to the next launch on this model
+        const uint32_t seq_out = pa.seq_expect + 1u;
+        // Steady-state publishes are RELAXED stores: a release would cost a MEMBAR.GPU that also waits for
+        // the bulk loads just issued by the refill (measured: +0.6 us per tile, 4K frame 62 -> 80 us).  What
+        // orders the data before the flag instead: the tile's bulk stores are complete
+        // (cp.async.bulk.wait_group, non-.read) and the compute warps' few direct stores (modes >= 1,
+        // write-through, L1::no_allocate) were issued a whole tile time (~2 us) earlier; the consumer is a
+        // full frame behind except at the frame boundary, whose tiles go out with a release below.
+        auto publish = [&](int tile) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(pa.tile_seq + tile), "r"(seq_out) : "memory");
+        };
+        int unpublished = -1;
+        uint32_t ahead_seen = pa.seq_expect + 1u, seen = pa.seq_expect + 1u;  // "not seen yet"
+        auto peek = [&]() {  // relaxed look at the flag of the tile drawn for the NEXT refill
+            if (pa.chain && ahead < pa.ntiles) ahead_seen = *reinterpret_cast<const volatile unsigned int *>(pa.tile_seq + ahead);
+        };
         auto next_tile = [&]() -> int {
             int t;
+            seen = pa.seq_expect + 1u;
             if (DYN && seq >= PIPE_STAGES) {
                 t = ahead;
-                if (t < pa.ntiles) ahead = draw();
+                seen = ahead_seen;
+                if (t < pa.ntiles) {
+                    ahead = draw();
+                    peek();
+                }
             } else {
                 t = first + seq * stride;
-                if (DYN && seq == PIPE_STAGES - 1) ahead = draw();
+                if (DYN && seq == PIPE_STAGES - 1) {
+                    ahead = draw();
+                    peek();
+                }
             }
             ++seq;
             if (t >= pa.ntiles) {
@@ -430,7 +487,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             const int t = next_tile();
             *stage_tile(s) = t;
             if (t >= 0)
-                issue_load(s, t);
+                issue_load(s, t, seen);
             else if (DYN)
                 mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
         };
@@ -478,8 +535,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             } else if (!DYN) {
                 *stage_tile(s) = -1;
             }
+            // off the refill's critical path: the PREVIOUS tile's stores (committed one tile time ago) are
+            // complete by now -- publish it to the next launch on this model
+            if (unpublished >= 0) {
+                bulk_wait_all<1>();
+                publish(unpublished);
+            }
+            unpublished = tile;
         }
-        bulk_wait_read<0>();  // shared memory must outlive the last bulk stores
+        bulk_wait_all<0>();  // shared memory must outlive the last bulk stores; and they must be complete
+        if (unpublished >= 0) st_release_gpu(pa.tile_seq + unpublished, seq_out);
         return;
     }
 

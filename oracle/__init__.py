@@ -62,6 +62,26 @@ class Detection(C.Structure):
         return (bool(self.position_valid), self.x, self.y, self.area)
 
 
+class Position(C.Structure):
+    """The Position2D fields the position filters/combiners touch (lib/datatypes/Position2D.h:112-155)."""
+    _fields_ = [
+        ("position_valid", C.c_int32),
+        ("velocity_valid", C.c_int32),
+        ("heading_valid", C.c_int32),
+        ("reserved", C.c_int32),
+        ("x", C.c_double),
+        ("y", C.c_double),
+        ("vx", C.c_double),
+        ("vy", C.c_double),
+        ("hx", C.c_double),
+        ("hy", C.c_double),
+    ]
+
+    def as_tuple(self):
+        return (bool(self.position_valid), bool(self.velocity_valid), bool(self.heading_valid),
+                self.x, self.y, self.vx, self.vy, self.hx, self.hy)
+
+
 class ContourRec(C.Structure):
     _fields_ = [
         ("first_index", C.c_int32),
@@ -108,6 +128,11 @@ def _load():
     L.orc_bsub_create.restype = vp
     L.orc_bsub_destroy.argtypes = [vp]
     L.orc_bsub_apply.argtypes = [vp, u8p, sz, u8p, sz]
+    L.orc_kalman_create.argtypes = [dbl, dbl, dbl, dbl]
+    L.orc_kalman_create.restype = vp
+    L.orc_kalman_destroy.argtypes = [vp]
+    L.orc_kalman_filter.argtypes = [vp, C.POINTER(Position)]
+    L.orc_mean_combine.argtypes = [C.POINTER(Position), i, i, C.POINTER(Position)]
     _lib = L
     return L
 
@@ -392,3 +417,29 @@ class DifferenceDetector:
                 m = blur_nonzero(m, self.blur)
         self.last = grey.copy()
         return sift_contours(m, self.area[0], self.area[1]), m
+
+
+# ---- posifilt kalman / posicom mean -------------------------------------
+class Kalman2D:
+    """KalmanFilter2D (src/positionfilter/KalmanFilter2D.cpp:95-200); defaults KalmanFilter2D.h:66-83."""
+
+    def __init__(self, dt=0.02, timeout=0.0, sigma_accel=5.0, sigma_noise=0.0):
+        self._h = _load().orc_kalman_create(dt, timeout, sigma_accel, sigma_noise)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _load().orc_kalman_destroy(self._h)
+            self._h = None
+
+    def filter(self, valid: bool, x: float = 0.0, y: float = 0.0) -> Position:
+        p = Position(position_valid=int(valid), x=x, y=y)
+        _load().orc_kalman_filter(self._h, C.byref(p))
+        return p
+
+
+def mean_combine(sources, heading_anchor: int = -1) -> Position:
+    """MeanPosition::combine (src/positioncombiner/MeanPosition.cpp:60-118)."""
+    arr = (Position * len(sources))(*sources)
+    out = Position()
+    _load().orc_mean_combine(arr, len(sources), heading_anchor, C.byref(out))
+    return out

@@ -127,3 +127,53 @@ class Pipeline:
         cv2.copyTo(frame, self.mask, self.filt)
         cv2.cvtColor(self.filt, cv2.COLOR_BGR2HSV, dst=self.hsv)
         return self.det.detect(self.hsv)
+
+
+class KalmanFilter2D:
+    """KalmanFilter2D::filter on the real cv::KalmanFilter(4, 2, 0, CV_64F)
+    (src/positionfilter/KalmanFilter2D.cpp:95-200).  Returns (valid, x, vx, y, vy)."""
+
+    def __init__(self, dt=0.02, timeout=0.0, sigma_accel=5.0, sigma_noise=0.0):
+        self.dt, self.sa, self.sn = dt, sigma_accel, sigma_noise
+        self.thr = int(timeout / dt)
+        self.kf = cv2.KalmanFilter(4, 2, 0, cv2.CV_64F)
+        self.found, self.nf = False, 0
+        self.meas = np.full((2, 1), 6.0)
+        self.pred = np.full((4, 1), 6.0)
+
+    def _init(self):
+        dt, sa = self.dt, self.sa
+        A = np.eye(4)
+        A[0, 1] = dt
+        A[2, 3] = dt
+        self.kf.transitionMatrix = A
+        H = np.zeros((2, 4))
+        H[0, 0] = 1.0
+        H[1, 2] = 1.0
+        self.kf.measurementMatrix = H
+        Q = np.zeros((4, 4))
+        Q[0, 0] = Q[2, 2] = sa * sa * (dt * dt * dt * dt) / 4.0
+        Q[0, 1] = Q[1, 0] = Q[2, 3] = Q[3, 2] = sa * sa * (dt * dt * dt) / 2.0
+        Q[1, 1] = Q[3, 3] = sa * sa * (dt * dt)
+        self.kf.processNoiseCov = Q
+        self.kf.measurementNoiseCov = np.eye(2) * (self.sn * self.sn)
+        self.kf.errorCovPre = np.eye(4) * 1000.0
+        s0 = np.array([[self.meas[0, 0]], [0.0], [self.meas[1, 0]], [0.0]])
+        self.kf.statePre = s0.copy()
+        self.kf.statePost = s0.copy()
+
+    def filter(self, valid, x=0.0, y=0.0):
+        if valid:
+            self.meas = np.array([[x], [y]], dtype=np.float64)
+            self.nf = 0
+            if not self.found:
+                self._init()
+            self.found = True
+        else:
+            self.nf += 1
+        if self.nf >= self.thr:
+            self.found = False
+        if self.found:
+            self.pred = self.kf.predict().copy()
+            self.kf.correct(self.meas)
+        return (self.found, self.pred[0, 0], self.pred[1, 0], self.pred[2, 0], self.pred[3, 0])

@@ -832,3 +832,217 @@ ORC_API void orc_bsub_apply(orc_bsub *b, const uint8_t *in, size_t in_pitch, uin
             out[(size_t)y * out_pitch + i] = (uint8_t)(d < 0 ? 0 : d);
         }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* posifilt kalman + posicom mean.                              */
+/* KalmanFilter2D::filter / initializeFilter / initializeStaticMatracies                */
+/* (src/positionfilter/KalmanFilter2D.cpp:95-200) on cv::KalmanFilter(4, 2, 0, CV_64F): */
+/*   predict(): statePre = A*statePost; errorCovPre = A*errorCovPost*A' + Q;            */
+/*              statePost = statePre; errorCovPost = errorCovPre; returns statePre      */
+/*   correct(z): S = H*errorCovPre*H' + R; gain' = pinv_SVD(S)*(H*errorCovPre);         */
+/*              statePost = statePre + gain*(z - H*statePre);                           */
+/*              errorCovPost = errorCovPre - gain*(H*errorCovPre)                       */
+/* The reference's quirks are kept: the filter reports the PREDICTED (prior) state;     */
+/* initializeFilter sets errorCovPre (overwritten by the next predict) and leaves       */
+/* errorCovPost as it was; with the default timeout 0 the count test `0 >= 0` switches  */
+/* the filter off again in the same call, so every output is invalid; an invalid sample */
+/* inside the timeout re-uses the last valid measurement in correct().  Before the      */
+/* first prediction the reported state is whatever `cv::Mat_<double>{4, 1, CV_64F}`     */
+/* holds (KalmanFilter2D.h:63) -- the fill value 6.0 with the OpenCV 3.0-3.2 reading;   */
+/* those outputs are flagged invalid and only the flags are part of the contract.       */
+/* MeanPosition::combine (src/positioncombiner/MeanPosition.cpp:60-118).                */
+/* ------------------------------------------------------------------------------------ */
+typedef struct orc_position {
+    int32_t position_valid, velocity_valid, heading_valid, reserved;
+    double x, y, vx, vy, hx, hy;
+} orc_position;
+
+typedef struct orc_kalman {
+    double dt, sig_accel, sig_noise;
+    int found, not_found, not_found_thr;
+    double A[4][4], H[2][4], Q[4][4], R[2][2];
+    double state_pre[4], state_post[4], P_pre[4][4], P_post[4][4];
+    double predicted[4], meas[2];
+} orc_kalman;
+
+ORC_API orc_kalman *orc_kalman_create(double dt, double timeout, double sig_accel, double sig_noise)
+{
+    orc_kalman *k = (orc_kalman *)calloc(1, sizeof(orc_kalman));
+    k->dt = dt;
+    k->sig_accel = sig_accel;
+    k->sig_noise = sig_noise;
+    k->not_found_thr = (int)(timeout / dt); /* KalmanFilter2D.cpp:74-76 */
+    /* cv::KalmanFilter::init: A = I, Q = I, R = I, H = 0, everything else 0 */
+    for (int i = 0; i < 4; ++i) k->A[i][i] = k->Q[i][i] = 1.0;
+    k->R[0][0] = k->R[1][1] = 1.0;
+    for (int i = 0; i < 4; ++i) k->predicted[i] = 6.0;
+    k->meas[0] = k->meas[1] = 6.0;
+    return k;
+}
+ORC_API void orc_kalman_destroy(orc_kalman *k) { free(k); }
+
+static void kal_static(orc_kalman *k) /* initializeStaticMatracies, :162-200 */
+{
+    const double dt = k->dt, sa = k->sig_accel;
+    memset(k->A, 0, sizeof k->A);
+    for (int i = 0; i < 4; ++i) k->A[i][i] = 1.0;
+    k->A[0][1] = dt;
+    k->A[2][3] = dt;
+    memset(k->H, 0, sizeof k->H);
+    k->H[0][0] = 1.0;
+    k->H[1][2] = 1.0;
+    memset(k->Q, 0, sizeof k->Q);
+    k->Q[0][0] = sa * sa * (dt * dt * dt * dt) / 4.0;
+    k->Q[0][1] = sa * sa * (dt * dt * dt) / 2.0;
+    k->Q[1][0] = sa * sa * (dt * dt * dt) / 2.0;
+    k->Q[1][1] = sa * sa * (dt * dt);
+    k->Q[2][2] = sa * sa * (dt * dt * dt * dt) / 4.0;
+    k->Q[2][3] = sa * sa * (dt * dt * dt) / 2.0;
+    k->Q[3][2] = sa * sa * (dt * dt * dt) / 2.0;
+    k->Q[3][3] = sa * sa * (dt * dt);
+    memset(k->R, 0, sizeof k->R);
+    k->R[0][0] = k->R[1][1] = k->sig_noise * k->sig_noise;
+}
+
+/* pseudo-inverse of a symmetric 2x2 through its eigen-decomposition, singular values below
+ * 2*DBL_EPSILON*sum treated as zero -- what cv::solve(..., DECOMP_SVD) (SVD::backSubst) does */
+static void pinv_sym2(const double S[2][2], double Si[2][2])
+{
+    const double a = S[0][0], b = 0.5 * (S[0][1] + S[1][0]), d = S[1][1];
+    const double tr = a + d, df = a - d;
+    const double rad = sqrt(df * df + 4.0 * b * b);
+    double l1 = 0.5 * (tr + rad), l2 = 0.5 * (tr - rad);
+    double v1x, v1y; /* unit eigenvector of l1 */
+    if (fabs(b) > 0.0) {
+        v1x = l1 - d;
+        v1y = b;
+        const double n = sqrt(v1x * v1x + v1y * v1y);
+        v1x /= n;
+        v1y /= n;
+    } else if (a >= d) {
+        v1x = 1.0, v1y = 0.0;
+    } else {
+        v1x = 0.0, v1y = 1.0;
+    }
+    const double v2x = -v1y, v2y = v1x;
+    const double thr = 2.0 * DBL_EPSILON * (fabs(l1) + fabs(l2));
+    const double i1 = fabs(l1) > thr ? 1.0 / l1 : 0.0, i2 = fabs(l2) > thr ? 1.0 / l2 : 0.0;
+    Si[0][0] = i1 * v1x * v1x + i2 * v2x * v2x;
+    Si[0][1] = Si[1][0] = i1 * v1x * v1y + i2 * v2x * v2y;
+    Si[1][1] = i1 * v1y * v1y + i2 * v2y * v2y;
+}
+
+ORC_API void orc_kalman_filter(orc_kalman *k, orc_position *p) /* KalmanFilter2D::filter, :95-145 */
+{
+    if (p->position_valid) {
+        k->meas[0] = p->x;
+        k->meas[1] = p->y;
+        k->not_found = 0;
+        if (!k->found) { /* initializeFilter, :147-170 */
+            kal_static(k);
+            memset(k->P_pre, 0, sizeof k->P_pre);
+            for (int i = 0; i < 4; ++i) k->P_pre[i][i] = 1000.0;
+            const double s0[4] = {k->meas[0], 0.0, k->meas[1], 0.0};
+            memcpy(k->state_pre, s0, sizeof s0);
+            memcpy(k->state_post, s0, sizeof s0);
+        }
+        k->found = 1;
+    } else {
+        k->not_found++;
+    }
+    if (k->not_found >= k->not_found_thr) k->found = 0;
+    if (k->found) {
+        double T[4][4];
+        /* predict */
+        for (int i = 0; i < 4; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < 4; ++j) s += k->A[i][j] * k->state_post[j];
+            k->state_pre[i] = s;
+        }
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double s = 0.0;
+                for (int q = 0; q < 4; ++q) s += k->A[i][q] * k->P_post[q][j];
+                T[i][j] = s;
+            }
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double s = 0.0;
+                for (int q = 0; q < 4; ++q) s += T[i][q] * k->A[j][q];
+                k->P_pre[i][j] = s + k->Q[i][j];
+            }
+        memcpy(k->state_post, k->state_pre, sizeof k->state_pre);
+        memcpy(k->P_post, k->P_pre, sizeof k->P_pre);
+        memcpy(k->predicted, k->state_pre, sizeof k->state_pre);
+        /* correct */
+        double HP[2][4], S[2][2], Si[2][2], G[4][2], innov[2];
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double s = 0.0;
+                for (int q = 0; q < 4; ++q) s += k->H[i][q] * k->P_pre[q][j];
+                HP[i][j] = s;
+            }
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                double s = 0.0;
+                for (int q = 0; q < 4; ++q) s += HP[i][q] * k->H[j][q];
+                S[i][j] = s + k->R[i][j];
+            }
+        pinv_sym2(S, Si);
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 2; ++j) /* gain = (Si * HP)' */
+                G[i][j] = Si[j][0] * HP[0][i] + Si[j][1] * HP[1][i];
+        for (int i = 0; i < 2; ++i) {
+            double s = 0.0;
+            for (int q = 0; q < 4; ++q) s += k->H[i][q] * k->state_pre[q];
+            innov[i] = k->meas[i] - s;
+        }
+        for (int i = 0; i < 4; ++i) k->state_post[i] = k->state_pre[i] + (G[i][0] * innov[0] + G[i][1] * innov[1]);
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) k->P_post[i][j] = k->P_pre[i][j] - (G[i][0] * HP[0][j] + G[i][1] * HP[1][j]);
+    }
+    p->x = k->predicted[0];
+    p->vx = k->predicted[1];
+    p->y = k->predicted[2];
+    p->vy = k->predicted[3];
+    p->position_valid = p->velocity_valid = k->found ? 1 : 0;
+}
+
+/* MeanPosition::combine (MeanPosition.cpp:60-118); heading_anchor < 0: no heading generation */
+ORC_API void orc_mean_combine(const orc_position *src, int n, int heading_anchor, orc_position *out)
+{
+    const double md = 1.0 / (double)n;
+    memset(out, 0, sizeof *out);
+    out->position_valid = out->velocity_valid = out->heading_valid = 1;
+    for (int i = 0; i < n; ++i) {
+        const orc_position *p = &src[i];
+        if (p->position_valid) {
+            out->x += md * p->x;
+            out->y += md * p->y;
+        } else
+            out->position_valid = 0;
+        if (p->velocity_valid) {
+            out->vx += md * p->vx;
+            out->vy += md * p->vy;
+        } else
+            out->velocity_valid = 0;
+        if (heading_anchor >= 0) {
+            if (out->position_valid) {
+                out->hx += p->x - src[heading_anchor].x;
+                out->hy += p->y - src[heading_anchor].y;
+            } else
+                out->heading_valid = 0;
+        } else {
+            if (p->heading_valid) {
+                out->hx += p->hx;
+                out->hy += p->hy;
+            } else
+                out->heading_valid = 0;
+        }
+    }
+    if (out->heading_valid) {
+        const double mag = sqrt(pow(out->hx, 2.0) + pow(out->hy, 2.0));
+        out->hx = out->hx / mag;
+        out->hy = out->hy / mag;
+    }
+}

@@ -132,3 +132,33 @@ def contour_masks():
 def bsub_frames():
     rng = np.random.default_rng(0)
     return [rng.integers(0, 256, (40, 56, 3)).astype(np.uint8) for _ in range(6)]
+
+
+# ---- posifilt kalman / posicom mean ------------------------------------
+# name -> (dt, timeout, sigma_accel, sigma_noise, seed, samples)
+KALMAN_CASES = {
+    "default": (0.02, 0.0, 5.0, 0.0, 11, 60),          # Oat defaults: timeout 0 -> never valid
+    "t1": (0.02, 1.0, 5.0, 0.0, 12, 300),
+    "noisy": (1.0 / 30.0, 0.5, 50.0, 3.5, 13, 300),
+    "stiff": (0.01, 0.2, 1.0, 1.0, 14, 300),
+    "degenerate": (0.02, 1.0, 0.0, 0.0, 15, 120),       # singular innovation covariance
+}
+
+
+def kalman_track(seed, n):
+    """Seeded measurement stream [(valid, x, y)]: a random walk with drop-outs, incl. gaps longer than
+    any timeout above (re-initialisation) and an invalid lead-in."""
+    rng = np.random.default_rng(seed)
+    x, y = 320.0, 240.0
+    out = []
+    for t in range(n):
+        x += rng.normal() * 3.0 + 1.0
+        y += rng.normal() * 3.0 - 0.5
+        if t < 3:
+            valid = False
+        elif (t // 50) % 3 == 2:
+            valid = rng.random() > 0.93
+        else:
+            valid = rng.random() > 0.2
+        out.append((bool(valid), float(x), float(y)))
+    return out

@@ -110,3 +110,58 @@ def test_hsv_requires_hsv_source():
     serve.wait(timeout=30)
     assert det.returncode == 255 and "Maybe use oat-framefilt col?" in se
     subprocess.run([os.path.join(BIN, "oat-clean"), name, name + "_pos"], capture_output=True)
+
+
+def test_two_colour_graph_with_kalman_and_mean():
+    """examples/mouse-track/two-color-det.sh shape: two detectors on one frame SOURCE -> posifilt kalman each ->
+    posicom mean -> posisock; seven processes, positions compared with the oracle's
+    Tracker -> Kalman2D -> mean_combine on the same frames."""
+    tag = "oatb200pipe_2c_"
+    names = [tag + n for n in ("raw", "pa", "pb", "ka", "kb", "pos")]
+    raw, pa, pb, ka, kb, pos = names
+    subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+    kargs = ["--dt", "0.01", "-T", "0.05", "-a", "20", "-n", "0.5"]
+    argvs = [["oat-posicom", "mean", ka, kb, pos],
+             ["oat-posifilt", "kalman", pa, ka] + kargs,
+             ["oat-posifilt", "kalman", pb, kb] + kargs,
+             ["oat-posidet", "track", raw, pa, "-A", "0.05"] + HSV_ARGS,
+             ["oat-posidet", "track", raw, pb, "-A", "0.0"] + HSV_ARGS]
+    procs = []
+    try:
+        sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", pos], stdout=subprocess.PIPE, text=True)
+        for argv in argvs:
+            procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+            time.sleep(0.3)
+        time.sleep(0.5)
+        serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", raw, "--rows", str(ROWS), "--cols", str(COLS),
+                                  "--num-samples", str(N), "--fps", "100"])
+        out, _ = sock.communicate(timeout=120)
+        assert serve.wait(timeout=30) == 0
+        for p in procs:
+            so, se = p.communicate(timeout=30)
+            assert p.returncode == 0, (p.args, so, se)
+        got = [json.loads(line) for line in out.splitlines() if line.strip()]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+    hp = oracle.HsvParams(**BAND)
+    trk = [oracle.Tracker(ROWS, COLS), oracle.Tracker(ROWS, COLS)]
+    kal = [oracle.Kalman2D(0.01, 0.05, 20.0, 0.5), oracle.Kalman2D(0.01, 0.05, 20.0, 0.5)]
+    assert len(got) == N
+    n_valid = 0
+    for t in range(N):
+        f = oracle.synth_frame(ROWS, COLS, 1000, t)
+        filt = []
+        for k, (tr, lr) in zip(kal, zip(trk, (0.05, 0.0))):
+            o, _ = tr.track(f, lr, hp)
+            filt.append(k.filter(bool(o.position_valid), o.x, o.y))
+        w = oracle.mean_combine(filt, -1)
+        p = got[t]
+        assert p["pos_ok"] == bool(w.position_valid) and p["vel_ok"] == bool(w.velocity_valid), (t, p)
+        if w.position_valid:
+            n_valid += 1
+            assert abs(p["pos_xy"][0] - w.x) < 1e-4 and abs(p["pos_xy"][1] - w.y) < 1e-4, (t, p, w.x, w.y)
+            assert abs(p["vel_xy"][0] - w.vx) < 1e-4 and abs(p["vel_xy"][1] - w.vy) < 1e-4, (t, p, w.vx, w.vy)
+    assert n_valid >= N - 3
