@@ -269,6 +269,13 @@ int oat_posfilt_apply(oat_posfilt *f, const oat_position *sources, oat_position 
  * Pass NULL to detach. */
 int oat_tracker_attach_posfilt(oat_tracker *t, oat_posfilt *f);
 int oat_tracker_collect_position(oat_tracker *t, oat_detection *det, oat_position *pos);
+/* A whole clip: frames[0..n) through submit/collect with up to `depth` frames in flight (clamped to the
+ * tracker's ring depth), the pipelining loop running natively -- what a file-fed graph
+ * (oat frameserve file, src/frameserver/FileReader.cpp:103-131) amounts to.  out: n detections in frame
+ * order; pos: NULL, or n filtered positions when a position filter is attached. */
+int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames, size_t n, size_t in_pitch,
+                         double learning_rate, const oat_hsv_params *p, int depth, oat_detection *out,
+                         oat_position *pos);
 /* GMM state egress, as oat_mog_get_state. */
 int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, float *variance,
                           float *mean);

@@ -156,6 +156,8 @@ _SIGS = {
     "oat_tracker_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams), C.c_void_p,
                                      C.c_size_t]),
     "oat_tracker_collect": (C.c_int, [C.c_void_p, C.POINTER(Detection)]),
+    "oat_tracker_run_clip": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_double,
+                                       C.POINTER(HsvParams), C.c_int, C.POINTER(Detection), C.POINTER(Position)]),
     "oat_tracker_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "oat_kalman_default_params": (None, [C.POINTER(KalmanParams)]),
     "oat_posfilt_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(KalmanParams), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -659,6 +661,17 @@ class Tracker:
         d = Detection()
         _ck(lib().oat_tracker_collect(self._h, C.byref(d)))
         return d
+
+    def run_clip(self, frames, depth=4, learning_rate=None, positions=False):
+        """frames: device buffers / arrays of one clip -> list of Detection (and of Position with a filter attached);
+        the submit/collect pipelining loop runs natively (oat_tracker_run_clip)."""
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        n = len(frames)
+        ptrs = (C.c_void_p * n)(*[_ptr(f).value for f in frames])
+        out = (Detection * n)()
+        pos = (Position * n)() if positions else None
+        _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, self.cols * 3, lr, C.byref(self.hsv), depth, out, pos))
+        return (list(out), list(pos)) if positions else list(out)
 
     def attach_posfilt(self, f: "PositionFilter | None"):
         """Fuse a single-source position filter behind this tracker (device-side epilogue, frame order)."""

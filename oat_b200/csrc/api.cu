@@ -89,8 +89,8 @@ struct oat_ctx {
     // consecutive launches (at most two launches overlap); the host knows how many draws each launch makes
     unsigned int *tile_counter = nullptr;
     unsigned int tile_base[4] = {0, 0, 0, 0};
-    // model whose pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the next
-    // launch on the same model may chain to it tile by tile instead of waiting for the whole grid
+    // model whose full-grid pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
+    // next pipelined launch may chain to it tile by tile instead of waiting for the whole grid
     unsigned long long chain_uid = 0;
     bool no_chain = false;
     uint64_t pipe_launches = 0;
@@ -319,6 +319,7 @@ struct MogModel {
     unsigned long long *d_sum = nullptr;
     unsigned int *tile_seq = nullptr;  // per tile of the pipelined kernel: sequence number of the last launch that finished it
     unsigned int seq = 0;              // sequence number the next pipelined launch expects (and publishes + 1)
+    bool flags_current = false;        // the last kernel that touched the state was the pipelined one (tile_seq is valid)
     unsigned long long uid = 0;
 
     int create(int rows, int cols, const oat_mog_params *params)
@@ -418,6 +419,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
     // the state write-back; with a live rate every live mode changes every frame anyway.
     const bool frozen = (a.c.aT == 0.0f) && !a.reset && !getenv("OAT_B200_NO_TRACK");
     unsigned long long pipe_uid = 0;
+    bool pipe_launch = false;
     if (vec && !a.reset && m.K == 5 && allow_pipe && !c->no_pipe) {
         // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
         // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
@@ -454,8 +456,12 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         // it is the last kernel on the stream, and both grids fill the machine (so at most two overlap)
         pa.tile_seq = m.tile_seq;
         pa.seq_expect = m.seq++;
-        pa.chain = (allow_chain && c->pdl && !c->no_chain && c->chain_uid == m.uid && grid == PIPE_CTAS_PER_SM * c->num_sms) ? 1 : 0;
-        pipe_uid = m.uid;
+        // (the predecessor may belong to another model -- independent streams share nothing -- as long as
+        // THIS model's flags are current, i.e. its own last launch was the pipelined kernel)
+        const bool full = grid == PIPE_CTAS_PER_SM * c->num_sms;
+        pa.chain = (allow_chain && c->pdl && !c->no_chain && c->chain_uid != 0 && m.flags_current && full) ? 1 : 0;
+        pipe_uid = full ? m.uid : 0;
+        pipe_launch = true;
         // programmatic dependent launch: the next frame's CTAs become resident (and run their prologue:
         // mbarrier + queue initialisation) while this frame's last CTAs drain; the kernel orders its
         // first global access behind the previous grid with griddepcontrol.wait
@@ -485,6 +491,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         launch_fused_px<1, true>(c->stream, m.K, a);
     LAUNCH_CHECK(c);
     c->chain_uid = pipe_uid;
+    m.flags_current = pipe_launch;  // the generic kernels do not publish tile flags
     return OAT_OK;
 }
 
@@ -837,7 +844,8 @@ struct Tail {
     // Fast path: ONE launch (tail_fast.cuh).  Returns false (nothing enqueued) if this geometry /
     // kernel size cannot use it; res->status == TAIL_OVERFLOW after completion means "replay with run()".
     bool run_fast(oat_ctx *c, cudaStream_t stream, const FastBufs &b, const uint32_t *src, const oat_hsv_params &p,
-                  TailResult *d_res, uint8_t *thresh_dev, size_t thresh_pitch, int *err, unsigned int *slow_in = nullptr)
+                  TailResult *d_res, uint8_t *thresh_dev, size_t thresh_pitch, int *err, unsigned int *slow_in = nullptr,
+                  TailResult *h_mirror = nullptr)
     {
         *err = OAT_OK;
         const BitGeom g = tb.g;
@@ -870,6 +878,7 @@ struct Tail {
         fa.min_area = p.min_area;
         fa.max_area = p.max_area;
         fa.res = d_res;
+        fa.res_host = h_mirror;
         fa.smem_bytes = (int)smem;
         fa.max_comps = fast_comps;
         fa.slow_in = slow_in;
@@ -1409,7 +1418,7 @@ extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_
     if (r == OAT_OK) {
         t->ring.resize(ring_depth);
         for (auto &s : t->ring) {
-            if (cudaHostAlloc(&s.h_res, sizeof(TailResult), cudaHostAllocDefault) != cudaSuccess ||
+            if (cudaHostAlloc(&s.h_res, sizeof(TailResult), cudaHostAllocMapped) != cudaSuccess ||
                 cudaMalloc(&s.d_res, sizeof(TailResult)) != cudaSuccess ||
                 cudaMalloc(&s.bits, t->tail.nwords * 4) != cudaSuccess ||
                 s.fb.create(t->tail.nwords, rows) != OAT_OK || cudaMalloc(&s.d_slow, sizeof(unsigned int)) != cudaSuccess ||
@@ -1538,7 +1547,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     }
     {
         int err = OAT_OK;
-        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err, s.d_slow);
+        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err, s.d_slow, s.h_res);
         CKRET(err);
         if (!s.fast) {
             ts = c->stream;  // the unbounded path owns shared buffers: compute stream only
@@ -1548,7 +1557,8 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     // a tail that went to another stream left the fused kernel the last kernel on the compute stream
     if (ts != c->stream) c->chain_uid = chain_after_fused;
     CKRET(finish_out(ts, othr));
-    CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(TailResult), cudaMemcpyDeviceToHost, ts));
+    // the one-launch tail wrote its result into the pinned mirror itself
+    if (!s.fast) CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(TailResult), cudaMemcpyDeviceToHost, ts));
     CK(cudaEventRecord(s.done, ts));
     s.has_pos = false;
     if (t->pf) {
@@ -1697,6 +1707,27 @@ extern "C" int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t 
     OutView ob, none1, none2, none3;
     CKRET(stage_out(t->out_bgr, bgr_out, bgr_out_pitch, rows, (size_t)3 * cols, &ob));
     return tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, none1, none2, none3, true);
+}
+
+extern "C" int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames, size_t n, size_t in_pitch,
+                                    double learning_rate, const oat_hsv_params *p, int depth, oat_detection *out,
+                                    oat_position *pos)
+{
+    REQUIRE(t && frames && out, "oat_tracker_run_clip: null argument");
+    REQUIRE(t->head == t->tailpos, "oat_tracker_run_clip: frames are still outstanding (collect first)");
+    REQUIRE(!pos || t->pf, "oat_tracker_run_clip: positions requested but no position filter is attached");
+    size_t d = depth < 1 ? 1 : (size_t)depth;
+    if (d > t->ring.size()) d = t->ring.size();
+    size_t done = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (i - done == d) {
+            CKRET(tracker_collect(t, &out[done], pos ? &pos[done] : nullptr));
+            ++done;
+        }
+        CKRET(oat_tracker_submit(t, frames[i], in_pitch, learning_rate, p, nullptr, 0));
+    }
+    for (; done < n; ++done) CKRET(tracker_collect(t, &out[done], pos ? &pos[done] : nullptr));
+    return OAT_OK;
 }
 
 extern "C" int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,

@@ -422,8 +422,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             // the flag taken one refill earlier (hides the L2 round trip in the steady state, where the
             // predecessor is long past this tile); state bytes reach this SM only through bulk copies and
             // L1::no_allocate loads, i.e. from L2, where the publisher's release ordered them before the flag.
-            if (pa.chain && seen != pa.seq_expect)
-                while (ld_acquire_gpu(pa.tile_seq + tile) != pa.seq_expect) __nanosleep(20);
+            if (pa.chain && seen != pa.seq_expect) {
+                // bounded: a predecessor that died (launch error) must surface as an error, not hang the GPU
+                unsigned spins = 0;
+                while (ld_acquire_gpu(pa.tile_seq + tile) != pa.seq_expect) {
+                    __nanosleep(20);
+                    if (++spins > (1u << 23)) __trap();
+                }
+            }
             mbar_expect_tx(&full[s], npx * (DYN ? 24u : 21u));
 #pragma unroll
             for (int cc = 0; cc < 5; ++cc)

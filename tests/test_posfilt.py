@@ -214,3 +214,34 @@ def test_gpu_tracker_epilogue(ctx, pipelined):
     trk.attach_posfilt(None)
     f.close()
     trk.close()
+
+
+@pytest.mark.gpu
+def test_gpu_run_clip_matches_per_frame(ctx):
+    """oat_tracker_run_clip (native pipelining loop) == frame-by-frame track(), detections and filtered positions."""
+    rows, cols, n = 240, 320, 30
+    band = dict(h=(40, 80), s=(100, 256), v=(100, 256))
+    kp = dict(dt=1 / 30, timeout=0.3, sigma_accel=20.0, sigma_noise=0.5)
+    bufs = [ctx.alloc(rows * cols * 3) for _ in range(n)]
+    for t, b in enumerate(bufs):
+        ctx.synth_frame(rows, cols, 1000, t, out=b)
+    res = []
+    for mode in ("clip", "frames"):
+        trk = oat_b200.Tracker(ctx, rows, cols, 0.01, oat_b200.HsvParams.make(**band), ring_depth=4)
+        f = oat_b200.PositionFilter(ctx, 1, kp)
+        trk.attach_posfilt(f)
+        if mode == "clip":
+            dets, poss = trk.run_clip(bufs, depth=4, positions=True)
+        else:
+            dets, poss = [], []
+            for b in bufs:
+                trk.submit(b)
+                d, p = trk.collect_position()
+                dets.append(d)
+                poss.append(p)
+        res.append([(d.position_valid, d.x, d.y, d.area, p.position_valid, p.x, p.y, p.vx, p.vy) for d, p in zip(dets, poss)])
+        trk.attach_posfilt(None)
+        f.close()
+        trk.close()
+    assert res[0] == res[1]
+    assert any(r[4] for r in res[0])
