@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--alpha", type=float, default=0.01, help="framefilt mog --adaptation-coeff")
     ap.add_argument("--ring", type=int, default=32, help="distinct synthetic frames cycled as input")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--loop", default="native", choices=["native", "python"],
+                    help="who runs the submit/collect loop of the timed frames: the C ABI (oat_tracker_run_clip) or this script")
     ap.add_argument("--streams", type=int, default=0,
                     help="extra measurement: aggregate frames/s of this many independent streams on each GPU (BASELINE configs 3-4)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
@@ -257,7 +259,12 @@ def run_b200(args):
     trk.submit(f0)
     trk.collect()
 
-    def run_pipelined(n, start):
+    def make_clip(n, start):
+        return oat_b200.frame_pointers([dev_frames[(start + i) % R] for i in range(n)])
+
+    def run_pipelined(n, start, clip=None):
+        if clip is not None:  # the same submit/collect pipelining, looped natively (oat_tracker_run_clip)
+            return trk.run_clip(clip, depth=DEPTH)[-1]
         out = 0
         last = None
         for i in range(n):
@@ -275,12 +282,13 @@ def run_b200(args):
     modes_before = trk.live_modes() / npx
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clip = make_clip(K, W) if args.loop == "native" else None
     barrier()
     launches0 = ctx.kernel_launches
     sampler.start()
     wall0 = time.perf_counter()
     e0.record(stream)
-    last = run_pipelined(K, W)  # every collect waits for that frame's detect tail (other streams included)
+    last = run_pipelined(K, W, clip)  # every collect waits for that frame's detect tail (other streams included)
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
@@ -439,6 +447,8 @@ def run_b200(args):
                 "l2": f"no flush: the inputs ({R * npx * 3 / 1e6:.0f} MB ring) are larger than the 126 MB L2; one CUDA-event pair on the "
                       f"launching stream around the {K} pipelined frames (depth {DEPTH}); cold single-frame latency reported separately",
                 "mean_live_modes": mbar,
+                "loop": ("oat_tracker_run_clip (submit/collect pipelining looped natively in the C ABI)" if args.loop == "native"
+                         else "submit/collect called per frame from this script"),
                 "parallelism": f"{world} independent stream(s), one per GPU, no collective",
             },
             "roofline": {
@@ -454,7 +464,8 @@ def run_b200(args):
                 "kernel_launches_timed": kern_n,
                 "how": f"average over {kern_n} launches: batches of {S} back-to-back launches (one per independent stream, fused "
                        f"kernel only) between one CUDA-event pair on the launching stream; {S} states ({S * 45 * npx / 1e6:.0f} MB live) > L2, "
-                       "no flush",
+                       "no flush; consecutive launches overlap (programmatic dependent launch, tile-granular ordering): the "
+                       "figure is steady-state time per launch, as in the pipelined run",
                 "mean_live_modes": mbar_roof,
                 "single_launch_event_bracket_ms": single_ms,
                 "traffic": load_traffic(args.workload, args.alpha),

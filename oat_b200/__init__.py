@@ -236,6 +236,12 @@ def _ptr(a):
     return C.c_void_p(int(a))
 
 
+def frame_pointers(frames):
+    """A clip as the C ABI takes it: an array of frame pointers (device buffers, pinned pointers or numpy arrays --
+    the caller keeps them alive).  Lets a harness build the array outside its timed region."""
+    return (C.c_void_p * len(frames))(*[_ptr(f).value for f in frames])
+
+
 class Context:
     """One per (thread, device); owns the CUDA streams (BackgroundSubtractorMOG::configureGPU,
     src/framefilter/BackgroundSubtractorMOG.cpp:92-111)."""
@@ -666,8 +672,8 @@ class Tracker:
         """frames: device buffers / arrays of one clip -> list of Detection (and of Position with a filter attached);
         the submit/collect pipelining loop runs natively (oat_tracker_run_clip)."""
         lr = self.learning_coeff if learning_rate is None else learning_rate
-        n = len(frames)
-        ptrs = (C.c_void_p * n)(*[_ptr(f).value for f in frames])
+        ptrs = frames if isinstance(frames, C.Array) else frame_pointers(frames)
+        n = len(ptrs)
         out = (Detection * n)()
         pos = (Position * n)() if positions else None
         _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, self.cols * 3, lr, C.byref(self.hsv), depth, out, pos))

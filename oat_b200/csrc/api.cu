@@ -344,6 +344,7 @@ struct MogModel {
         const size_t ntiles = (plane + PIPE_TILE - 1) / PIPE_TILE;
         CK(cudaMalloc(&tile_seq, ntiles * sizeof(unsigned int)));
         CK(cudaMemset(tile_seq, 0, ntiles * sizeof(unsigned int)));
+        CK(cudaStreamSynchronize(cudaStreamLegacy));  // the memsets ran on the legacy stream; the context's streams do not wait for it
         static std::atomic<unsigned long long> next_uid{1};
         uid = next_uid++;
         seq = 0;

@@ -41,12 +41,13 @@ __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v)
 {
     __stcs(reinterpret_cast<unsigned int *>(p), v);  // st.global.cs
 }
-// GMM state: read-modify-write by the same thread; bypass L1 (no reuse inside a frame) but
-// keep the default L2 policy so the planes can stay L2-resident between frames.
+// GMM state: read-modify-write by the same thread; loads are served by L2, never by L1 (ld.cg) -- there
+// is no reuse inside a frame, the planes can stay L2-resident between frames, and a launch that overlaps
+// its predecessor (tile-granular chaining, mog_pipe.cuh) must not see a line an earlier launch left in L1.
 __device__ __forceinline__ float4 ld_state_f4(const float *p)
 {
     float4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
     return v;
@@ -60,7 +61,7 @@ __device__ __forceinline__ void st_state_f4(float *p, float4 v)
 __device__ __forceinline__ float ld_state_f1(const float *p)
 {
     float v;
-    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_state_f1(float *p, float v)

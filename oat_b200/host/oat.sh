@@ -3,7 +3,7 @@
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 if [ $# -lt 1 ] || [ "$1" = "help" ] || [ "$1" = "--help" ]; then
     echo "Usage: oat <component> [TYPE] [IO] [CONFIGURATION]"
-    echo "Components: framefilt posidet frameserve posisock clean"
+    echo "Components: framefilt posidet posifilt posicom frameserve posisock clean"
     exit 0
 fi
 cmd="$1"; shift

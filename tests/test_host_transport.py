@@ -55,6 +55,13 @@ def test_dispatcher_and_usage(host_bin):
     (["oat-posidet", "thresh", "a", "b", "-T", "[10,999]"], "Values of thresh should be between 0 and 256."),
     (["oat-framefilt", "thresh", "a", "b", "-I", "[-1,5]"], "Values of intensity should be between 0 and 256."),
     (["oat-framefilt", "mask", "a", "b", "-m", "/nonexistent.pgm"], "could not be read"),
+    (["oat-posifilt", "homography", "a", "b"], "invalid TYPE"),
+    (["oat-posifilt", "kalman", "a"], "a SINK name must be specified"),
+    (["oat-posifilt", "kalman", "a", "b", "--dt", "-1"], "out of bounds"),
+    (["oat-posifilt", "kalman", "a", "b", "--nonsense", "1"], "unrecognised option"),
+    (["oat-posicom", "median", "a", "b", "c"], "invalid TYPE"),
+    (["oat-posicom", "mean", "a", "b"], "At least two SOURCES and a SINK must be specified."),   # PositionCombiner.cpp:41-42
+    (["oat-posicom", "mean", "a", "b", "c", "-h", "2"], "out of bounds"),                          # MeanPosition.cpp:52-54
 ])
 def test_cli_errors_exit_minus_one(host_bin, args, msg):
     """Every exception is caught in main -> 'name: message' on stderr -> return -1 (main.cpp:278-295)."""
