@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--alpha", type=float, default=0.01, help="framefilt mog --adaptation-coeff")
     ap.add_argument("--ring", type=int, default=32, help="distinct synthetic frames cycled as input")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=8, help="frames in flight in the pipelined runs (submit/collect ring depth)")
     ap.add_argument("--loop", default="native", choices=["native", "python"],
                     help="who runs the submit/collect loop of the timed frames: the C ABI (oat_tracker_run_clip) or this script")
     ap.add_argument("--streams", type=int, default=0,
@@ -254,7 +255,7 @@ def run_b200(args):
     # ---- value: whole-frame throughput, device-resident input, frames pipelined DEPTH deep ----------
     # Inputs (ring of R distinct frames, R*6.2 MB at 1080p) are larger than L2, so no flush is needed
     # between steps; the stream's own GMM state is re-read every frame, exactly as in production.
-    DEPTH = 4
+    DEPTH = args.depth
     trk = oat_b200.Tracker(ctx, rows, cols, args.alpha, hp, ring_depth=DEPTH)
     trk.submit(f0)
     trk.collect()
@@ -475,7 +476,7 @@ def run_b200(args):
                 "unit": "frames/s",
                 "h2d_bytes_per_step": npx * 3,
                 "d2h_bytes_per_step": 88,
-                "note": "pinned host frames via oat_tracker_submit/collect, ring depth 4, wall clock",
+                "note": f"pinned host frames via oat_tracker_submit/collect, ring depth {DEPTH}, wall clock",
             },
             "cold_frame": {"latency_ms": cold_ms, "note": "median submit->collect of one frame in flight, L2 flushed before it "
                                                           "(fused kernel + detect tail + result read-back, serialised)"},

@@ -92,7 +92,7 @@ struct oat_ctx {
     // model whose full-grid pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
     // next pipelined launch may chain to it tile by tile instead of waiting for the whole grid
     unsigned long long chain_uid = 0;
-    bool no_chain = false;
+    bool no_chain = false, no_mirror = false;
     uint64_t pipe_launches = 0;
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
@@ -144,6 +144,7 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->no_overlap = getenv("OAT_B200_NO_OVERLAP") != nullptr;
     c->pdl = getenv("OAT_B200_NO_PDL") == nullptr;
     c->no_chain = getenv("OAT_B200_NO_CHAIN") != nullptr;
+    c->no_mirror = getenv("OAT_B200_NO_MIRROR") != nullptr;
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
@@ -1548,7 +1549,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     }
     {
         int err = OAT_OK;
-        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err, s.d_slow, s.h_res);
+        s.fast = t->tail.run_fast(c, ts, s.fb, s.bits, *p, s.d_res, othr.d, othr.dpitch, &err, s.d_slow, c->no_mirror ? nullptr : s.h_res);
         CKRET(err);
         if (!s.fast) {
             ts = c->stream;  // the unbounded path owns shared buffers: compute stream only
@@ -1559,7 +1560,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     if (ts != c->stream) c->chain_uid = chain_after_fused;
     CKRET(finish_out(ts, othr));
     // the one-launch tail wrote its result into the pinned mirror itself
-    if (!s.fast) CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(TailResult), cudaMemcpyDeviceToHost, ts));
+    if (!s.fast || c->no_mirror) CK(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(TailResult), cudaMemcpyDeviceToHost, ts));
     CK(cudaEventRecord(s.done, ts));
     s.has_pos = false;
     if (t->pf) {
