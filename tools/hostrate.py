@@ -31,6 +31,17 @@ for rep in range(2):
     th = time.perf_counter() - t0
     ctx.sync()
     print(f"{res} fused-only same-model chain: GPU {1e3*a.elapsed_time(b)/N:.2f} us/launch, host enqueue {1e6*th/N:.2f} us/launch")
+# (a') the same with an event record after every launch (what the tracker does for the tail's stream)
+evs = [torch.cuda.Event() for _ in range(64)]
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ctx.sync()
+a.record(st)
+for i in range(N):
+    trk.submit_fused_only(frames[1 + (50 + i) % R])
+    evs[i % 64].record(st)
+b.record(st)
+ctx.sync()
+print(f"{res} fused-only chain + event record per launch: GPU {1e3*a.elapsed_time(b)/N:.2f} us/launch")
 for depth in (4, 8):
     ts = tc = 0.0
     out = 0
