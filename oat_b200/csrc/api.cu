@@ -76,6 +76,7 @@ struct oat_ctx {
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t h2d = nullptr;      // ingest copies (overlap with compute of the previous frame)
     static const int NTAIL = 8;
+    unsigned tail_rr = 0;
     cudaStream_t tail[NTAIL] = {};  // detect tails of in-flight frames (higher priority than compute)
     int *hsv_lut = nullptr;          // sdiv[256] | hdiv[256]
     uint64_t launches = 0;
@@ -1543,7 +1544,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     CKRET(finish_out(c->stream, ohsv));
     cudaStream_t ts = c->stream;
     if (overlap && !c->no_overlap) {
-        ts = c->tail[t->head % oat_ctx::NTAIL];
+        ts = c->tail[c->tail_rr++ % oat_ctx::NTAIL];  // context-wide round robin: trackers sharing a context do not pile onto one stream
         CK(cudaEventRecord(s.fused_done, c->stream));
         CK(cudaStreamWaitEvent(ts, s.fused_done, 0));
     }

@@ -222,7 +222,8 @@ __device__ __forceinline__ uint32_t frozen_px(const float x0, const float x1, co
     float nA = A, nB = B, nC = C, vn = V;
     if (dist2 < fmul(c.Tg, V)) {
         w = fadd(w, c.aT);
-        const float k = fdiv(c.aT, w);
+        // (this function only runs with aT == 0: 0 / w is exactly +0 for every w > 0 -- no division needed)
+        const float k = (c.aT == 0.f && w > 0.f) ? 0.f : fdiv(c.aT, w);
         nA = fsub(A, fmul(k, d0));
         nB = fsub(B, fmul(k, d1));
         nC = fsub(C, fmul(k, d2));
@@ -233,7 +234,8 @@ __device__ __forceinline__ uint32_t frozen_px(const float x0, const float x1, co
     if (w < -c.prune) return 0xffffffffu;
     const float tot = fadd(0.f, w);
     float inv = 0.f;
-    if (fabsf(tot) > FLT_EPSILON) inv = fdiv(1.f, tot);
+    if (tot == 1.f) inv = 1.f;  // the frozen one-mode model's weight: 1 / 1 is exact
+    else if (fabsf(tot) > FLT_EPSILON) inv = fdiv(1.f, tot);
     const float nW = fmul(w, inv);
     upd<true>(W, nW, dirty);
     upd<true>(V, vn, dirty);
@@ -455,8 +457,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         // the bulk loads just issued by the refill (measured: +0.6 us per tile, 4K frame 62 -> 80 us).  What
         // orders the data before the flag instead: the tile's bulk stores are complete
         // (cp.async.bulk.wait_group, non-.read) and the compute warps' few direct stores (modes >= 1,
-        // write-through, L1::no_allocate) were issued a whole tile time (~2 us) earlier; the consumer is a
-        // full frame behind except at the frame boundary, whose tiles go out with a release below.
+        // write-through) were issued before those bulk stores, i.e. at least a store round trip earlier (a whole
+        // tile time, ~2 us, for all but a CTA's last tile); the consumer is a full frame behind except at
+        // the frame boundary, and reads state only from L2 (bulk copies, ld.cg).
         auto publish = [&](int tile) {
             asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(pa.tile_seq + tile), "r"(seq_out) : "memory");
         };
@@ -550,7 +553,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             unpublished = tile;
         }
         bulk_wait_all<0>();  // shared memory must outlive the last bulk stores; and they must be complete
-        if (unpublished >= 0) st_release_gpu(pa.tile_seq + unpublished, seq_out);
+        // the last tile too: its bulk stores are complete, and the compute warps' direct stores were issued before
+        // those (a release here is a MEMBAR.GPU on every CTA's exit path, ~0.7 us that the successor's CTA waits for)
+        if (unpublished >= 0) publish(unpublished);
         return;
     }
 
