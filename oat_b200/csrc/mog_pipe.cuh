@@ -446,10 +446,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         // of the atomic hides behind the wait for the stage.
         int seq = 0, ahead = 0;
         bool ended = false;
-        auto draw = [&]() -> int {
-            const uint32_t d = atomicAdd(pa.tile_counter, 1u) - pa.counter_base;
-            return d < 0x40000000u ? (int)d + PIPE_STAGES * (int)gridDim.x : 0x7fffffff;
-        };
         // publish a finished tile (its bulk stores are complete, the compute warps' direct stores
         // were ordered by done[s]) to the next launch on this model
         const uint32_t seq_out = pa.seq_expect + 1u;
@@ -468,6 +464,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         auto peek = [&]() {  // relaxed look at the flag of the tile drawn for the NEXT refill
             if (pa.chain && ahead < pa.ntiles) ahead_seen = *reinterpret_cast<const volatile unsigned int *>(pa.tile_seq + ahead);
         };
+        uint32_t raw = 0;
+        bool drew = false;
         auto next_tile = [&]() -> int {
             int t;
             seen = pa.seq_expect + 1u;
@@ -475,14 +473,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                 t = ahead;
                 seen = ahead_seen;
                 if (t < pa.ntiles) {
-                    ahead = draw();
-                    peek();
+                    raw = atomicAdd(pa.tile_counter, 1u);  // issued now, consumed after this tile's loads are on their way
+                    drew = true;
                 }
             } else {
                 t = first + seq * stride;
                 if (DYN && seq == PIPE_STAGES - 1) {
-                    ahead = draw();
-                    peek();
+                    raw = atomicAdd(pa.tile_counter, 1u);
+                    drew = true;
                 }
             }
             ++seq;
@@ -499,6 +497,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                 issue_load(s, t, seen);
             else if (DYN)
                 mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
+            if (drew) {  // the scheduler's answer (an L2 round trip) and the look at that tile's flag: off the load's path
+                const uint32_t d = raw - pa.counter_base;
+                ahead = d < 0x40000000u ? (int)d + PIPE_STAGES * (int)gridDim.x : 0x7fffffff;
+                peek();
+                drew = false;
+            }
         };
         for (int k = 0; k < PIPE_STAGES && !ended; ++k) refill(k);  // every stage starts loaded
         for (int i = 0;; ++i) {
