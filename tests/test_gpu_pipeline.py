@@ -33,7 +33,7 @@ def oracle_positions(lr):
     return out
 
 
-def run_graph(tag, nodes, serve_args=()):
+def run_graph(tag, nodes, serve_args=(), rows=ROWS, cols=COLS, n=N):
     """nodes: list of argv lists; consumers are started first, the frame server last (examples/*/*.sh)."""
     names = [f"oatb200pipe_{tag}_{n}" for n in ("raw", "filt", "hsv", "pos")]
     subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
@@ -44,8 +44,8 @@ def run_graph(tag, nodes, serve_args=()):
             procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                                           text=True))
         time.sleep(0.5)
-        serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(ROWS), "--cols", str(COLS),
-                                  "--num-samples", str(N), "--fps", "100"] + list(serve_args))
+        serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(rows), "--cols", str(cols),
+                                  "--num-samples", str(n), "--fps", "100"] + list(serve_args))
         out, _ = sock.communicate(timeout=120)
         assert serve.wait(timeout=30) == 0
         for p in procs:
@@ -96,6 +96,29 @@ def test_fused_tracker_component():
         return [["oat-posidet", "track", n[0], n[3], "-A", "0.05"] + HSV_ARGS]
 
     check(run_graph("fused", nodes), oracle_positions(0.05))
+
+
+def test_config0_bsub_chain_analytic():
+    """BASELINE config 0: 640x480, 120 frames, frameserve -> framefilt bsub ->
+    framefilt col -C HSV -> posidet hsv -H [40,80] -S [100,256] -V [90,256] through real shared memory.  The
+    first frame becomes the background (no position); afterwards the difference image is the disc alone and
+    the centroid is EXACTLY the disc centre + 0.5."""
+    from oracle import synth
+
+    rows, cols, n = 480, 640, 120
+
+    def nodes(nm):
+        return [["oat-posidet", "hsv", nm[2], nm[3], "-H", "[40,80]", "-S", "[100,256]", "-V", "[90,256]"],
+                ["oat-framefilt", "col", nm[1], nm[2], "-C", "HSV"],
+                ["oat-framefilt", "bsub", nm[0], nm[1]]]
+
+    got = run_graph("cfg0", nodes, rows=rows, cols=cols, n=n)
+    assert len(got) == n
+    assert got[0]["pos_ok"] is False
+    for t in range(1, n):
+        cx, cy = synth.disc_centre(rows, cols, t)
+        assert got[t]["tick"] == t + 1 and got[t]["pos_ok"] is True, (t, got[t])
+        assert got[t]["pos_xy"] == [cx + 0.5, cy + 0.5], (t, got[t], cx, cy)
 
 
 def test_hsv_requires_hsv_source():

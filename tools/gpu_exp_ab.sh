@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU tests on the experimental build, then bench A/B (main vs exp) for the live and the frozen model
-EXP=$PWD/oat_b200/liboatgpu_exp.so
+EXP=${EXP:-$PWD/oat_b200/liboatgpu_exp.so}
 val() { python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value']), round(d['roofline']['frac'],3), round(d['cold_frame']['latency_ms']*1e3,1), d['multi_stream'] and round(d['multi_stream']['value']))"; }
