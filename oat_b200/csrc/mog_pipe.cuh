@@ -61,11 +61,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_gpu(unsigned int *p, uint32_t v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
 {
@@ -440,7 +435,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             if (DYN) bulk_g2s_hint(st + PIPE_OFF_BGR, a.bgr + 3 * p0, npx * 3u, &full[s], pol_first);
         };
         // next tile of this CTA's sequence, or -1 when the frame is exhausted (DYN: every CTA draws
-        // exactly one number >= ntiles; the CTA that draws the last one re-arms the counter)
+        // exactly one number >= ntiles, so the host knows a launch's draw count and the counters never
+        // need re-arming: each launch is told where its numbers start, pa.counter_base)
         // DYN: the first PIPE_STAGES tiles of a CTA are fixed (no atomic on the start-up path); later
         // ones are drawn from the global counter one refill AHEAD of their use, so the L2 round trip
         // of the atomic hides behind the wait for the stage.
