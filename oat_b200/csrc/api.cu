@@ -86,10 +86,11 @@ struct oat_ctx {
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
     cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
-    // dynamic tile scheduler of the pipelined fused kernel: 4 monotonic draw counters used round-robin by
-    // consecutive launches (at most two launches overlap); the host knows how many draws each launch makes
+    // dynamic tile scheduler of the pipelined fused kernel: 8 monotonic draw counters used round-robin by
+    // consecutive launches (two launches overlap, three at most); the host knows how many draws each launch makes
     unsigned int *tile_counter = nullptr;
-    unsigned int tile_base[4] = {0, 0, 0, 0};
+    static const unsigned NCOUNTERS = 8;
+    unsigned int tile_base[NCOUNTERS] = {};
     // model whose full-grid pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
     // next pipelined launch may chain to it tile by tile instead of waiting for the whole grid
     unsigned long long chain_uid = 0;
@@ -163,8 +164,8 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     }
     CK(cudaMalloc(&c->slow_count, sizeof(unsigned int)));
     CK(cudaMemset(c->slow_count, 0, sizeof(unsigned int)));
-    CK(cudaMalloc(&c->tile_counter, 4 * sizeof(unsigned int)));
-    CK(cudaMemset(c->tile_counter, 0, 4 * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->tile_counter, oat_ctx::NCOUNTERS * sizeof(unsigned int)));
+    CK(cudaMemset(c->tile_counter, 0, oat_ctx::NCOUNTERS * sizeof(unsigned int)));
     CK(cudaMalloc(&c->hsv_lut, sizeof(lut)));
     CK(cudaMemcpy(c->hsv_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     *out = c;
@@ -443,7 +444,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
         const int grid = pa.ntiles < PIPE_CTAS_PER_SM * c->num_sms ? pa.ntiles : PIPE_CTAS_PER_SM * c->num_sms;
         pa.grid_tiles = grid;
-        const unsigned slot = c->pipe_launches & 3u;
+        const unsigned slot = c->pipe_launches % oat_ctx::NCOUNTERS;
         pa.tile_counter = c->tile_counter + slot;
         pa.counter_base = c->tile_base[slot];
         if (linear) {
