@@ -86,10 +86,12 @@ struct oat_ctx {
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
     cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
-    // dynamic tile scheduler of the pipelined fused kernel: 8 monotonic draw counters used round-robin by
-    // consecutive launches (two launches overlap, three at most); the host knows how many draws each launch makes
+    // dynamic tile scheduler of the pipelined fused kernel: monotonic draw counters used round-robin by consecutive
+    // launches; the host knows how many draws each launch makes, so a counter is never reset.  Two launches that
+    // share a slot must not have draws outstanding at the same time: launch N+64 starts only after every CTA of
+    // N+1..N+63 has started, i.e. a CTA of N would have to outlive ~63 whole launches
     unsigned int *tile_counter = nullptr;
-    static const unsigned NCOUNTERS = 8;
+    static const unsigned NCOUNTERS = 64;
     unsigned int tile_base[NCOUNTERS] = {};
     // model whose full-grid pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
     // next pipelined launch may chain to it tile by tile instead of waiting for the whole grid
