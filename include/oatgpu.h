@@ -285,6 +285,10 @@ int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, fl
 int oat_tracker_profile(oat_tracker *t, int enable);
 int oat_tracker_profile_read(oat_tracker *t, double *mean_mog_kernel_ms, uint64_t *launches);
 
+/* Diagnostic, no device needed: how many numbers one launch of the pipelined fused kernel draws from its tile
+ * scheduler for `ntiles` tiles on a grid of `grid` CTAs (the host keeps the counters monotonic with it);
+ * *stages (may be NULL) receives the kernel's pipeline depth. */
+int oat_debug_pipe_draws(int ntiles, int grid, int *stages);
 /* Diagnostic: enqueue only the fused MOG+HSV+threshold kernel for the next frame (device-resident
  * frame; the model advances exactly as in oat_tracker_submit, no detection is produced, nothing
  * to collect). For timing back-to-back launches of the dominant kernel in isolation. */

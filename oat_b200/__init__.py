@@ -169,6 +169,7 @@ _SIGS = {
     "oat_tracker_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oat_tracker_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "oat_tracker_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "oat_debug_pipe_draws": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "oat_tracker_submit_fused_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams)]),
     "oat_tracker_tail_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "oat_synth_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),

@@ -408,6 +408,23 @@ static void launch_fused_px(cudaStream_t s, int K, const FusedArgs &a)
 
 static bool aligned4(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 3u) == 0; }
 
+// Numbers one launch of the pipelined kernel draws from its scheduler counter (mog_pipe.cuh, next_tile): every
+// CTA that starts its last static tile draws once, and every valid number drawn is followed by one more draw.
+// Deterministic, so the host can tell each launch where its numbers start and no counter is ever reset.
+static unsigned pipe_draws(int ntiles, int grid)
+{
+    const int S = PIPE_STAGES;
+    const long long reach = std::min<long long>(grid, std::max<long long>(0, (long long)ntiles - (long long)(S - 2) * grid));
+    const long long valid = std::max<long long>(0, (long long)ntiles - (long long)S * grid);
+    return (unsigned)(reach + valid);
+}
+// Diagnostic (CPU-side tests pin the formula against a transcription of the kernel's scheduler loop).
+extern "C" int oat_debug_pipe_draws(int ntiles, int grid, int *stages)
+{
+    if (stages) *stages = PIPE_STAGES;
+    return (int)pipe_draws(ntiles, grid);
+}
+
 static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true, bool allow_chain = false)
 {
     a.rows = m.g.rows;
@@ -449,14 +466,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         const unsigned slot = c->pipe_launches % oat_ctx::NCOUNTERS;
         pa.tile_counter = c->tile_counter + slot;
         pa.counter_base = c->tile_base[slot];
-        if (linear) {
-            // draws of this launch (mog_pipe.cuh, next_tile): every CTA that starts its last static tile
-            // draws once, and every valid number drawn is followed by one more draw
-            const int S = PIPE_STAGES;
-            const long long reach = std::min<long long>(grid, std::max<long long>(0, (long long)pa.ntiles - (long long)(S - 2) * grid));
-            const long long valid = std::max<long long>(0, (long long)pa.ntiles - (long long)S * grid);
-            c->tile_base[slot] += (unsigned)(reach + valid);
-        }
+        if (linear) c->tile_base[slot] += pipe_draws(pa.ntiles, grid);
         ++c->pipe_launches;
         // chain to the previous launch tile by tile when that launch was this model's pipelined kernel,
         // it is the last kernel on the stream, and both grids fill the machine (so at most two overlap)

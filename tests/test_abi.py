@@ -73,3 +73,62 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dp, fn), errors="replace").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f"{fn} imports oracle"
                 assert "oat_oracle" not in src and "orc_" not in src, f"{fn} references the oracle"
+
+
+def _simulate_draws(ntiles, grid, stages):
+    """The producer lane's scheduler loop of mog_pipe_kernel (csrc/mog_pipe.cuh: next_tile/refill), transcribed:
+    every CTA walks its static tiles first + seq*grid, draws once when it starts the last static one, and then
+    once more after every valid number; numbers are handed out in arrival order (here: round-robin over the CTAs
+    that are still drawing -- the COUNT does not depend on the order).  Returns (draws, tiles processed)."""
+    counter = 0
+    tiles = []
+    state = []  # per CTA: [seq, ahead, ended]
+    for b in range(grid):
+        seq, ahead, ended = 0, None, False
+        for k in range(stages):  # the initial refills
+            if ended:
+                break
+            t = b + seq * grid
+            if seq == stages - 1:
+                ahead = counter + stages * grid
+                counter += 1
+            seq += 1
+            if t >= ntiles:
+                ended = True
+            else:
+                tiles.append(t)
+        state.append([seq, ahead, ended])
+    live = [s for s in state if not s[2]]
+    while live:
+        nxt = []
+        for s in live:
+            t = s[1]
+            if t is None:          # never reached its last static tile: no number in hand -> nothing more to do
+                s[2] = True
+                continue
+            if t < ntiles:
+                tiles.append(t)
+                s[1] = counter + stages * grid
+                counter += 1
+                nxt.append(s)
+            else:
+                s[2] = True
+        live = nxt
+    return counter, tiles
+
+
+def test_tile_scheduler_draw_count_matches_kernel_logic():
+    """The host keeps the scheduler counters monotonic by knowing how many numbers each launch draws
+    (api.cu: pipe_draws).  Pin that formula against the kernel's loop for every frame size / grid shape class,
+    and check the loop hands out every tile exactly once."""
+    L = oat_b200.lib()
+    st = C.c_int()
+    L.oat_debug_pipe_draws(1, 1, C.byref(st))
+    S = st.value
+    assert S >= 2
+    cases = [(nt, g) for g in (1, 2, 3, 7, 148, 296, 592, 740) for nt in
+             (g, g + 1, 2 * g - 1, 2 * g, 2 * g + 1, S * g - 1, S * g, S * g + 1, S * g + 37, 7 * g, 2025, 4050, 8100, 16200) if nt >= g]
+    for ntiles, grid in cases:
+        draws, tiles = _simulate_draws(ntiles, grid, S)
+        assert sorted(tiles) == list(range(ntiles)), (ntiles, grid)
+        assert L.oat_debug_pipe_draws(ntiles, grid, None) == draws, (ntiles, grid, draws)
