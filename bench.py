@@ -9,7 +9,8 @@ A "step" is ONE frame of ONE video stream through the whole path (framefilt mog 
 largest-blob centroid) -- the unit BASELINE.json's metric counts.  Three measurements per run:
 
 * value    : device-resident input frames (a ring of distinct synthetic frames in HBM, larger than
-             L2), K frames pipelined 4 deep through submit/collect, one CUDA-event pair on the
+             L2), K frames pipelined --depth (8) deep through submit/collect (looped natively by
+             oat_tracker_run_clip unless --loop python), one CUDA-event pair on the
              library's stream around the K frames;
 * e2e      : the same frames in pinned HOST memory through the public C-ABI (oat_tracker_submit /
              collect): the H2D copy of every frame and the D2H read of every detection are inside

@@ -469,7 +469,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         if (linear) c->tile_base[slot] += pipe_draws(pa.ntiles, grid);
         ++c->pipe_launches;
         // chain to the previous launch tile by tile when that launch was this model's pipelined kernel,
-        // it is the last kernel on the stream, and both grids fill the machine (so at most two overlap)
+        // it is the last kernel on the stream, and both grids fill the machine (so launches overlap pairwise)
         pa.tile_seq = m.tile_seq;
         pa.seq_expect = m.seq++;
         // (the predecessor may belong to another model -- independent streams share nothing -- as long as
