@@ -70,6 +70,11 @@ int oat_ctx_sync(oat_ctx *ctx);
 void *oat_ctx_stream(oat_ctx *ctx);
 /* Number of kernels of THIS library launched through ctx since creation. */
 uint64_t oat_ctx_kernel_launches(const oat_ctx *ctx);
+/* Device timing of the resident fused kernel (the dominant, HBM-bound kernel): while enabled, every launch is
+ * bracketed by a CUDA-event pair on the compute stream; read returns the summed duration, the number of launches
+ * and the number of frames they processed since the last read (and waits for the stream). */
+int oat_ctx_profile_resident(oat_ctx *ctx, int enable);
+int oat_ctx_profile_resident_read(oat_ctx *ctx, double *total_ms, uint64_t *launches, uint64_t *frames);
 
 /* ---- framefilt mog --------------------------------------------------------------------
  * Parameters of cv::BackgroundSubtractorMOG2; oat_mog_default_params() gives what
@@ -107,6 +112,11 @@ int oat_mog_reset(oat_mog *mog);
  * Synchronous: outputs are valid on return. */
 int oat_mog_apply(oat_mog *mog, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out,
                   size_t out_pitch, uint8_t *mask_out, size_t mask_pitch, double learning_rate);
+/* Stream variant for device-resident frames (SharedFrameHeader memory kind DEVICE on both sides): enqueues
+ * the frame on the context's stream and returns; every image pointer must be device memory; consecutive
+ * frames overlap on the device.  oat_ctx_sync() (or any synchronous entry point) waits for them. */
+int oat_mog_apply_async(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out,
+                        size_t out_pitch, uint8_t *mask_out, size_t mask_pitch, double learning_rate);
 /* Test/diagnostic egress of the GMM state in OpenCV's layout (host pointers, any may be NULL):
  * modes_used u8[rows*cols]; weight,variance f32[rows*cols*K]; mean f32[rows*cols*K*3]. */
 int oat_mog_get_state(oat_mog *mog, uint8_t *modes_used, float *weight, float *variance,
@@ -269,13 +279,29 @@ int oat_posfilt_apply(oat_posfilt *f, const oat_position *sources, oat_position 
  * Pass NULL to detach. */
 int oat_tracker_attach_posfilt(oat_tracker *t, oat_posfilt *f);
 int oat_tracker_collect_position(oat_tracker *t, oat_detection *det, oat_position *pos);
-/* A whole clip: frames[0..n) through submit/collect with up to `depth` frames in flight (clamped to the
- * tracker's ring depth), the pipelining loop running natively -- what a file-fed graph
- * (oat frameserve file, src/frameserver/FileReader.cpp:103-131) amounts to.  out: n detections in frame
- * order; pos: NULL, or n filtered positions when a position filter is attached. */
+/* A whole clip -- what a file-fed graph (oat frameserve file, src/frameserver/FileReader.cpp:103-131)
+ * amounts to.  out: n detections in frame order; pos: NULL, or n filtered positions when a position
+ * filter is attached.
+ * Device-resident frames in the steady state (every frame after the model's first, a fixed learning rate in
+ * [0,1), rows 16-byte aligned) go through the RESIDENT engine: the clip is cut into chunks of half the
+ * tracker's ring, and per chunk ONE launch of the fused kernel and ONE launch of the tail server work
+ * through a queue of frame descriptors on the device -- no host work per frame (`depth` is not used there;
+ * create the tracker with a ring of 64 for 32-frame chunks).  Anything else (host frames, the first frame,
+ * learning rate < 0 or >= 1) runs frames[0..n) through submit/collect with up to `depth` frames in flight.
+ * Results are identical either way. */
 int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames, size_t n, size_t in_pitch,
                          double learning_rate, const oat_hsv_params *p, int depth, oat_detection *out,
                          oat_position *pos);
+/* Several independent streams on one GPU (BASELINE configs 3-4: --gpu-index shards streams over GPUs,
+ * src/framefilter/BackgroundSubtractorMOG.cpp:92-111; this batches the streams of ONE GPU): frame i of
+ * tracker s is frames[i * n_trackers + s], its detection out[i * n_trackers + s].  The trackers must share
+ * context, geometry and MOG parameters and have seen the same number of frames.  Device-resident frames are
+ * interleaved in one queue of the resident engine.  flags & OAT_CLIPS_FUSED_ONLY: run only the fused
+ * MOG+HSV+threshold kernel (no detect tail, out may be NULL) -- diagnostics / roofline timing. */
+#define OAT_CLIPS_FUSED_ONLY 1
+int oat_tracker_run_clips(oat_tracker *const *trackers, int n_trackers, const uint8_t *const *frames,
+                          size_t n_frames, size_t in_pitch, double learning_rate, const oat_hsv_params *p,
+                          int flags, oat_detection *out);
 /* GMM state egress, as oat_mog_get_state. */
 int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, float *variance,
                           float *mean);
@@ -285,19 +311,16 @@ int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, fl
 int oat_tracker_profile(oat_tracker *t, int enable);
 int oat_tracker_profile_read(oat_tracker *t, double *mean_mog_kernel_ms, uint64_t *launches);
 
-/* Diagnostic, no device needed: how many numbers one launch of the pipelined fused kernel draws from its tile
- * scheduler for `ntiles` tiles on a grid of `grid` CTAs (the host keeps the counters monotonic with it);
- * *stages (may be NULL) receives the kernel's pipeline depth. */
-int oat_debug_pipe_draws(int ntiles, int grid, int *stages);
 /* Diagnostic: enqueue only the fused MOG+HSV+threshold kernel for the next frame (device-resident
  * frame; the model advances exactly as in oat_tracker_submit, no detection is produced, nothing
  * to collect). For timing back-to-back launches of the dominant kernel in isolation. */
 int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch,
                                   double learning_rate, const oat_hsv_params *p);
-/* Diagnostic: the detect tail of the most recently collected frame. out[14] = { status (0 = the
+/* Diagnostic: the detect tail of the most recently collected frame. out[15] = { status (0 = the
  * one-launch tail sufficed, 1 = replayed through the unbounded path), run-table entries needed,
  * replays so far, one-launch tail used, 8 SM-clock stamps of its labelling CTA, frames run on the generic fused
- * kernel so far (adaptive kernel choice), 4-pixel groups that left the fused kernel's fast path in that frame }. */
+ * kernel so far (adaptive kernel choice), 4-pixel groups that left the fused kernel's fast path in that frame,
+ * frames served by the resident clip engine so far }. */
 int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out);
 
 /* ---- synthetic frame source (measurement + parity) --------------------

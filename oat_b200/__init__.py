@@ -117,12 +117,17 @@ _SIGS = {
     "oat_ctx_sync": (C.c_int, [C.c_void_p]),
     "oat_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "oat_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "oat_ctx_profile_resident": (C.c_int, [C.c_void_p, C.c_int]),
+    "oat_ctx_profile_resident_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                                C.POINTER(C.c_uint64)]),
     "oat_mog_default_params": (None, [C.POINTER(MogParams)]),
     "oat_mog_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(MogParams), C.POINTER(C.c_void_p)]),
     "oat_mog_destroy": (C.c_int, [C.c_void_p]),
     "oat_mog_reset": (C.c_int, [C.c_void_p]),
     "oat_mog_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                 C.c_double]),
+    "oat_mog_apply_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                      C.c_double]),
     "oat_mog_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oat_mog_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "oat_bgr2hsv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
@@ -169,7 +174,8 @@ _SIGS = {
     "oat_tracker_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oat_tracker_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "oat_tracker_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
-    "oat_debug_pipe_draws": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "oat_tracker_run_clips": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t,
+                                        C.c_double, C.POINTER(HsvParams), C.c_int, C.POINTER(Detection)]),
     "oat_tracker_submit_fused_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams)]),
     "oat_tracker_tail_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "oat_synth_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32]),
@@ -274,6 +280,16 @@ class Context:
     def kernel_launches(self) -> int:
         return int(lib().oat_ctx_kernel_launches(self._h))
 
+    def profile_resident(self, enable: bool):
+        """Bracket every launch of the resident fused kernel with CUDA events (oat_ctx_profile_resident)."""
+        _ck(lib().oat_ctx_profile_resident(self._h, 1 if enable else 0))
+
+    def profile_resident_read(self):
+        """(total ms, launches, frames) of the resident fused kernel since the last read."""
+        ms, n, f = C.c_double(), C.c_uint64(), C.c_uint64()
+        _ck(lib().oat_ctx_profile_resident_read(self._h, C.byref(ms), C.byref(n), C.byref(f)))
+        return ms.value, n.value, f.value
+
     def flush_l2(self):
         _ck(lib().oat_flush_l2(self._h))
 
@@ -283,12 +299,13 @@ class Context:
     def memcpy(self, dst, src, nbytes: int):
         _ck(lib().oat_memcpy(self._h, _ptr(dst), _ptr(src), nbytes))
 
-    def synth_frame(self, rows: int, cols: int, seed: int, t: int, out=None):
-        """Synthetic BGR frame; out = numpy array, DeviceBuffer or None (-> numpy)."""
+    def synth_frame(self, rows: int, cols: int, seed: int, t: int, out=None, pitch: int | None = None):
+        """Synthetic BGR frame (SURVEY.md 8(d)); out = numpy array, DeviceBuffer or None (-> numpy);
+        pitch: row pitch in bytes of a device buffer (default tight)."""
         ret = None
         if out is None:
             out = ret = np.empty((rows, cols, 3), np.uint8)
-        _ck(lib().oat_synth_frame(self._h, _ptr(out), cols * 3, rows, cols, seed, t))
+        _ck(lib().oat_synth_frame(self._h, _ptr(out), pitch or cols * 3, rows, cols, seed, t))
         return ret if ret is not None else out
 
 
@@ -403,6 +420,12 @@ class BackgroundSubtractorMOG:
         _ck(lib().oat_mog_apply(self._h, _ptr(frame), self.cols * 3, _ptr(out), self.cols * 3, _ptr(mask), self.cols,
                                 lr))
         return out, mask
+
+    def apply_async(self, frame, out=None, mask=None, learning_rate=None, pitch=None):
+        """Device-resident frame in, device-resident filtered frame / mask out; returns at once (Context.sync waits)."""
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        _ck(lib().oat_mog_apply_async(self._h, _ptr(frame), pitch or self.cols * 3, _ptr(out), pitch or self.cols * 3,
+                                      _ptr(mask), self.cols, lr))
 
     def filter(self, frame: np.ndarray) -> np.ndarray:
         """In place on a host frame, like FrameFilter::filter(cv::Mat&)."""
@@ -654,30 +677,31 @@ class Tracker:
                                     _ptr(outs["thresh"]), c))
         return d, {k: v for k, v in outs.items() if v is not None}
 
-    def submit(self, bgr, bgr_out=None, learning_rate=None):
+    def submit(self, bgr, bgr_out=None, learning_rate=None, pitch=None):
         lr = self.learning_coeff if learning_rate is None else learning_rate
-        _ck(lib().oat_tracker_submit(self._h, _ptr(bgr), self.cols * 3, lr, C.byref(self.hsv), _ptr(bgr_out),
+        _ck(lib().oat_tracker_submit(self._h, _ptr(bgr), pitch or self.cols * 3, lr, C.byref(self.hsv), _ptr(bgr_out),
                                      self.cols * 3))
 
-    def submit_fused_only(self, bgr, learning_rate=None):
+    def submit_fused_only(self, bgr, learning_rate=None, pitch=None):
         """Diagnostic: only the fused kernel of the next frame (see oat_tracker_submit_fused_only)."""
         lr = self.learning_coeff if learning_rate is None else learning_rate
-        _ck(lib().oat_tracker_submit_fused_only(self._h, _ptr(bgr), self.cols * 3, lr, C.byref(self.hsv)))
+        _ck(lib().oat_tracker_submit_fused_only(self._h, _ptr(bgr), pitch or self.cols * 3, lr, C.byref(self.hsv)))
 
     def collect(self) -> Detection:
         d = Detection()
         _ck(lib().oat_tracker_collect(self._h, C.byref(d)))
         return d
 
-    def run_clip(self, frames, depth=4, learning_rate=None, positions=False):
-        """frames: device buffers / arrays of one clip -> list of Detection (and of Position with a filter attached);
-        the submit/collect pipelining loop runs natively (oat_tracker_run_clip)."""
+    def run_clip(self, frames, depth=4, learning_rate=None, positions=False, pitch=None):
+        """frames: device buffers / arrays of one clip -> list of Detection (and of Position with a filter attached).
+        Device-resident frames go through the resident engine (one launch per chunk of frames), anything else
+        through the natively looped submit/collect pipeline (oat_tracker_run_clip)."""
         lr = self.learning_coeff if learning_rate is None else learning_rate
         ptrs = frames if isinstance(frames, C.Array) else frame_pointers(frames)
         n = len(ptrs)
         out = (Detection * n)()
         pos = (Position * n)() if positions else None
-        _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, self.cols * 3, lr, C.byref(self.hsv), depth, out, pos))
+        _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, pitch or self.cols * 3, lr, C.byref(self.hsv), depth, out, pos))
         return (list(out), list(pos)) if positions else list(out)
 
     def attach_posfilt(self, f: "PositionFilter | None"):
@@ -703,11 +727,28 @@ class Tracker:
 
     def tail_stats(self):
         """Diagnostics of the detect tail of the last collected frame (see oat_tracker_tail_stats)."""
-        a = (C.c_uint32 * 14)()
+        a = (C.c_uint32 * 15)()
         _ck(lib().oat_tracker_tail_stats(self._h, a))
         v = list(a)
         return {"status": v[0], "nodes": v[1], "replays": v[2], "fast": v[3], "cyc": v[4:12], "generic_frames": v[12],
-                "slow_groups": v[13]}
+                "slow_groups": v[13], "clip_frames": v[14]}
+
+    @staticmethod
+    def run_clips(trackers, frames, learning_rate=None, fused_only=False, pitch=None):
+        """Several independent streams of one GPU through ONE queue of the resident engine (oat_tracker_run_clips).
+        frames: list over time of lists over trackers (device buffers), or a prebuilt pointer array of
+        len(trackers) * n_frames entries, frame-major.  Returns detections[i][s] (None with fused_only)."""
+        S = len(trackers)
+        t0 = trackers[0]
+        lr = t0.learning_coeff if learning_rate is None else learning_rate
+        ptrs = frames if isinstance(frames, C.Array) else frame_pointers([f for row in frames for f in row])
+        n = len(ptrs) // S
+        handles = (C.c_void_p * S)(*[t._h.value for t in trackers])
+        out = None if fused_only else (Detection * (n * S))()
+        _ck(lib().oat_tracker_run_clips(handles, S, ptrs, n, pitch or t0.cols * 3, lr, C.byref(t0.hsv), 1 if fused_only else 0, out))
+        if fused_only:
+            return None
+        return [[out[i * S + s] for s in range(S)] for i in range(n)]
 
     def profile(self, enable: bool):
         _ck(lib().oat_tracker_profile(self._h, 1 if enable else 0))

@@ -71,6 +71,55 @@ struct DevBuf {
     }
 };
 
+namespace {
+struct ProfRec {  // one bracketed launch of the resident fused kernel (oat_ctx_profile_resident)
+    cudaEvent_t e0, e1;
+    uint64_t frames;
+};
+}  // namespace
+
+// staging of one chunk of the resident clip engine (see clip_run)
+struct ClipHalf {
+    FrameDesc *h_desc = nullptr, *d_desc = nullptr;
+    TailFrame *h_tf = nullptr, *d_tf = nullptr;
+    unsigned int *d_ctr = nullptr;  // band counters of the tail server, 2 per frame
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    int ensure(size_t n)
+    {
+        if (!done) CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        if (n <= cap) return OAT_OK;
+        release_bufs();
+        CK(cudaHostAlloc(&h_desc, n * sizeof(FrameDesc), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h_tf, n * sizeof(TailFrame), cudaHostAllocDefault));
+        CK(cudaMalloc(&d_desc, n * sizeof(FrameDesc)));
+        CK(cudaMalloc(&d_tf, n * sizeof(TailFrame)));
+        CK(cudaMalloc(&d_ctr, 2 * n * sizeof(unsigned int)));
+        cap = n;
+        return OAT_OK;
+    }
+    void release_bufs()
+    {
+        if (h_desc) cudaFreeHost(h_desc);
+        if (h_tf) cudaFreeHost(h_tf);
+        if (d_desc) cudaFree(d_desc);
+        if (d_tf) cudaFree(d_tf);
+        if (d_ctr) cudaFree(d_ctr);
+        h_desc = nullptr;
+        h_tf = nullptr;
+        d_desc = nullptr;
+        d_tf = nullptr;
+        d_ctr = nullptr;
+        cap = 0;
+    }
+    void release()
+    {
+        release_bufs();
+        if (done) cudaEventDestroy(done);
+        done = nullptr;
+    }
+};
+
 struct oat_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   // compute
@@ -86,18 +135,28 @@ struct oat_ctx {
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
     cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
-    // dynamic tile scheduler of the pipelined fused kernel: monotonic draw counters used round-robin by consecutive
-    // launches; the host knows how many draws each launch makes, so a counter is never reset.  Two launches that
-    // share a slot must not have draws outstanding at the same time: launch N+64 starts only after every CTA of
-    // N+1..N+63 has started, i.e. a CTA of N would have to outlive ~63 whole launches
-    unsigned int *tile_counter = nullptr;
-    static const unsigned NCOUNTERS = 64;
-    unsigned int tile_base[NCOUNTERS] = {};
-    // model whose full-grid pipelined fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
-    // next pipelined launch may chain to it tile by tile instead of waiting for the whole grid
+    // Work scheduler of the resident fused kernel (mog_pipe.cuh): every launch draws its (frame, tile) items from
+    // one counter of this ring (slot = launch number % NSLOTS; counter and exit ticket are re-armed by the
+    // launch's last CTA, which then writes the launch number into done_host[slot], pinned host memory).  A slot
+    // is handed to a new launch only once done_host shows that its previous user has left -- so two live
+    // launches never share a slot, whatever the number of launches in flight.
+    static const unsigned NSLOTS = 64;
+    unsigned int *work_counter = nullptr;   // [NSLOTS] counters, then [NSLOTS] exit tickets
+    volatile unsigned int *done_host = nullptr;  // [NSLOTS] pinned + mapped
+    unsigned int *done_dev = nullptr;            // device view of done_host
+    unsigned int slot_user[NSLOTS] = {};         // launch number (+1) of the slot's last user, 0 = never used
+    // model whose full-grid resident fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
+    // next launch may order itself behind it tile by tile instead of waiting for the whole grid
     unsigned long long chain_uid = 0;
-    bool no_chain = false, no_mirror = false;
+    bool no_chain = false, no_mirror = false, no_track = false, no_clip = false, relaxed_publish = false;
     uint64_t pipe_launches = 0;
+    cudaStream_t aux = nullptr;  // small host-synchronous uploads (frame descriptors of a clip)
+    ClipHalf clip[2];            // two chunks of the resident clip engine in flight
+    // device timing of the resident fused kernel: a CUDA-event pair on the compute stream around every launch
+    // (consecutive launches overlap tile by tile, so the brackets partition the timeline: their sum is the time
+    // from the first launch's start to the last one's end)
+    int prof_resident = 0;
+    std::vector<ProfRec> prof_recs;
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
     DevBuf scratch_in, scratch_out, scratch_roi;  // staging for the stateless entry points
@@ -149,10 +208,14 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->pdl = getenv("OAT_B200_NO_PDL") == nullptr;
     c->no_chain = getenv("OAT_B200_NO_CHAIN") != nullptr;
     c->no_mirror = getenv("OAT_B200_NO_MIRROR") != nullptr;
+    c->no_track = getenv("OAT_B200_NO_TRACK") != nullptr;
+    c->no_clip = getenv("OAT_B200_NO_CLIP") != nullptr;
+    c->relaxed_publish = getenv("OAT_B200_RELAXED_PUBLISH") != nullptr;  // measurement only: prices the release fence
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->post, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;  // numerically lower = higher priority
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -166,8 +229,16 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     }
     CK(cudaMalloc(&c->slow_count, sizeof(unsigned int)));
     CK(cudaMemset(c->slow_count, 0, sizeof(unsigned int)));
-    CK(cudaMalloc(&c->tile_counter, oat_ctx::NCOUNTERS * sizeof(unsigned int)));
-    CK(cudaMemset(c->tile_counter, 0, oat_ctx::NCOUNTERS * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->work_counter, 2 * oat_ctx::NSLOTS * sizeof(unsigned int)));
+    CK(cudaMemset(c->work_counter, 0, 2 * oat_ctx::NSLOTS * sizeof(unsigned int)));
+    {
+        void *hp = nullptr, *dp = nullptr;
+        CK(cudaHostAlloc(&hp, oat_ctx::NSLOTS * sizeof(unsigned int), cudaHostAllocMapped));
+        memset(hp, 0, oat_ctx::NSLOTS * sizeof(unsigned int));
+        CK(cudaHostGetDevicePointer(&dp, hp, 0));
+        c->done_host = (volatile unsigned int *)hp;
+        c->done_dev = (unsigned int *)dp;
+    }
     CK(cudaMalloc(&c->hsv_lut, sizeof(lut)));
     CK(cudaMemcpy(c->hsv_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     *out = c;
@@ -194,7 +265,14 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     c->scratch_out.release();
     c->scratch_roi.release();
     if (c->hsv_lut) cudaFree(c->hsv_lut);
-    if (c->tile_counter) cudaFree(c->tile_counter);
+    c->clip[0].release();
+    c->clip[1].release();
+    if (c->work_counter) cudaFree(c->work_counter);
+    if (c->done_host) cudaFreeHost((void *)c->done_host);
+    if (c->aux) {
+        cudaStreamSynchronize(c->aux);
+        cudaStreamDestroy(c->aux);
+    }
     if (c->slow_count) cudaFree(c->slow_count);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
@@ -212,6 +290,32 @@ extern "C" int oat_ctx_sync(oat_ctx *c)
 }
 extern "C" void *oat_ctx_stream(oat_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" uint64_t oat_ctx_kernel_launches(const oat_ctx *c) { return c ? c->launches : 0; }
+extern "C" int oat_ctx_profile_resident(oat_ctx *c, int enable)
+{
+    CKRET(bind(c));
+    c->prof_resident = enable ? 1 : 0;
+    return OAT_OK;
+}
+extern "C" int oat_ctx_profile_resident_read(oat_ctx *c, double *total_ms, uint64_t *launches, uint64_t *frames)
+{
+    CKRET(bind(c));
+    CK(cudaStreamSynchronize(c->stream));
+    double ms = 0.0;
+    uint64_t nf = 0;
+    for (auto &r : c->prof_recs) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms += t;
+        nf += r.frames;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = c->prof_recs.size();
+    if (frames) *frames = nf;
+    c->prof_recs.clear();
+    return OAT_OK;
+}
 
 // ---- pointer classification + staging ------------------------------------------------------
 enum MemKind { MEM_PAGEABLE, MEM_PINNED, MEM_DEVICE };
@@ -408,21 +512,111 @@ static void launch_fused_px(cudaStream_t s, int K, const FusedArgs &a)
 
 static bool aligned4(const void *p, size_t pitch) { return (((uintptr_t)p | pitch) & 3u) == 0; }
 
-// Numbers one launch of the pipelined kernel draws from its scheduler counter (mog_pipe.cuh, next_tile): every
-// CTA that starts its last static tile draws once, and every valid number drawn is followed by one more draw.
-// Deterministic, so the host can tell each launch where its numbers start and no counter is ever reset.
-static unsigned pipe_draws(int ntiles, int grid)
+// Scheduler slot for the next launch of the resident fused kernel: the slot's previous user (NSLOTS launches
+// ago) must have left -- its last CTA says so in pinned host memory.  In practice that happened long ago; the
+// wait is bounded so that a dead context surfaces as an error.
+static int acquire_slot(oat_ctx *c, unsigned *slot_out)
 {
-    const int S = PIPE_STAGES;
-    const long long reach = std::min<long long>(grid, std::max<long long>(0, (long long)ntiles - (long long)(S - 2) * grid));
-    const long long valid = std::max<long long>(0, (long long)ntiles - (long long)S * grid);
-    return (unsigned)(reach + valid);
+    const unsigned slot = (unsigned)(c->pipe_launches % oat_ctx::NSLOTS);
+    const unsigned want = c->slot_user[slot];
+    if (want != 0u) {
+        unsigned long long spins = 0;
+        while (c->done_host[slot] != want) {
+            if ((++spins & 0xfffull) == 0) {
+                cudaError_t e = cudaStreamQuery(c->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady)
+                    return fail(OAT_ERR_CUDA, std::string("resident fused kernel: ") + cudaGetErrorString(e));
+                if (spins > (1ull << 34)) return fail(OAT_ERR_CUDA, "resident fused kernel: scheduler slot never released");
+            }
+        }
+    }
+    *slot_out = slot;
+    return OAT_OK;
 }
-// Diagnostic (CPU-side tests pin the formula against a transcription of the kernel's scheduler loop).
-extern "C" int oat_debug_pipe_draws(int ntiles, int grid, int *stages)
+
+// Geometry/aliasing class of a frame for the resident fused kernel: 2 = LINEAR (tight pitches, cols % 32 == 0:
+// one bulk copy per tile), 1 = every row starts 16-byte aligned (one bulk copy per row segment), 0 = neither
+// (generic per-thread kernel).  Egress images, when present, only need 4-byte alignment unless LINEAR.
+static int pipe_class(const MogModel &m, const FusedArgs &a)
 {
-    if (stages) *stages = PIPE_STAGES;
-    return (int)pipe_draws(ntiles, grid);
+    const size_t tight3 = (size_t)3 * m.g.cols;
+    const bool linear = (m.g.cols % 32 == 0) && a.in_pitch == tight3 && (((uintptr_t)a.bgr & 15u) == 0) &&
+                        (!a.bgr_out || a.bgr_out_pitch == tight3) && (!a.hsv_out || a.hsv_pitch == tight3) &&
+                        (!a.fg_out || a.fg_pitch == (size_t)m.g.cols);
+    if (linear) return 2;
+    if ((((uintptr_t)a.bgr | a.in_pitch) & 15u) == 0 && m.g.cols >= 64) return 1;
+    return 0;
+}
+
+// One launch of the resident fused kernel over `pa.nframes` frames (descriptors in pa.descs, or pa.one).
+// Fills in the scheduler slot; commits the host bookkeeping only once the launch call has succeeded.
+static int launch_stream(oat_ctx *c, StreamArgs &pa, bool frozen, bool linear)
+{
+    if (!c->pipe_attr_set) {
+        CK(cudaFuncSetAttribute(mog_stream_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(mog_stream_kernel<5, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(mog_stream_kernel<5, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(mog_stream_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
+        c->pipe_attr_set = true;
+    }
+    const long long total = (long long)pa.ntiles * pa.nframes;
+    REQUIRE(total > 0 && total < (1ll << 30), "resident fused kernel: bad work size");
+    const int full = PIPE_CTAS_PER_SM * c->num_sms;
+    const int grid = total < full ? (int)total : full;
+    unsigned slot = 0;
+    CKRET(acquire_slot(c, &slot));
+    pa.work_counter = c->work_counter + slot;
+    pa.exit_ticket = c->work_counter + oat_ctx::NSLOTS + slot;
+    pa.done_flag = c->done_dev + slot;
+    pa.launch_id = (unsigned)(c->pipe_launches + 1);
+    pa.relaxed_publish = c->relaxed_publish ? 1 : 0;
+    if (pa.launch_id == 0u) pa.launch_id = 1u;  // 0 means "never used"
+    // programmatic dependent launch: the next launch's CTAs become resident (and run their prologue: mbarrier
+    // + queue initialisation, first draw) while this launch's last CTAs drain
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3(PIPE_THREADS);
+    lc.dynamicSmemBytes = PIPE_SMEM_BYTES;
+    lc.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = c->pdl ? 1u : 0u;
+    if (!c->pdl) pa.wait_grid = 0;  // plain stream order: nothing to wait for inside the kernel
+    ProfRec pr{nullptr, nullptr, (uint64_t)pa.nframes};
+    if (c->prof_resident) {
+        CK(cudaEventCreate(&pr.e0));
+        CK(cudaEventCreate(&pr.e1));
+        CK(cudaEventRecord(pr.e0, c->stream));
+    }
+    if (frozen && linear)
+        CK(cudaLaunchKernelEx(&lc, mog_stream_kernel<5, true, true>, pa));
+    else if (frozen)
+        CK(cudaLaunchKernelEx(&lc, mog_stream_kernel<5, true, false>, pa));
+    else if (linear)
+        CK(cudaLaunchKernelEx(&lc, mog_stream_kernel<5, false, true>, pa));
+    else
+        CK(cudaLaunchKernelEx(&lc, mog_stream_kernel<5, false, false>, pa));
+    c->slot_user[slot] = pa.launch_id;
+    ++c->pipe_launches;
+    ++c->launches;
+    if (c->prof_resident) {
+        CK(cudaEventRecord(pr.e1, c->stream));
+        c->prof_recs.push_back(pr);
+    }
+    return OAT_OK;
+}
+
+static void stream_args_common(oat_ctx *c, const MogModel &m, const FusedArgs &a, StreamArgs &pa)
+{
+    pa.f = a;
+    pa.ntiles = (int)((m.plane + PIPE_TILE - 1) / PIPE_TILE);
+    pa.nframes = 1;
+    pa.descs = nullptr;
+    pa.div_magic = 0xffffffffffffffffull / (unsigned long long)m.g.pitch_px() + 1ull;
+    pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
+    pa.wait_grid = 1;
 }
 
 static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true, bool allow_chain = false)
@@ -440,74 +634,47 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
                      (!a.fg_out || aligned4(a.fg_out, a.fg_pitch)) && (!a.hsv_out || aligned4(a.hsv_out, a.hsv_pitch));
     // a frozen model (learning rate 0) rewrites nothing: that variant tracks changes and skips
     // the state write-back; with a live rate every live mode changes every frame anyway.
-    const bool frozen = (a.c.aT == 0.0f) && !a.reset && !getenv("OAT_B200_NO_TRACK");
-    unsigned long long pipe_uid = 0;
-    bool pipe_launch = false;
-    if (vec && !a.reset && m.K == 5 && allow_pipe && !c->no_pipe) {
-        // steady state: bulk-async staged pipeline (mog_pipe.cuh), persistent grid of 2 CTAs per SM
-        // LINEAR: no row padding and tight pitches -> byte offsets are multiples of the pixel index
-        const size_t tight3 = (size_t)3 * m.g.cols;
-        const bool linear = (m.g.cols % 32 == 0) && a.in_pitch == tight3 && (((uintptr_t)a.bgr & 15u) == 0) && (!a.bgr_out || a.bgr_out_pitch == tight3) &&
-                            (!a.hsv_out || a.hsv_pitch == tight3) && (!a.fg_out || a.fg_pitch == (size_t)m.g.cols);
-        if (!c->pipe_attr_set) {
-            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(mog_pipe_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
-            c->pipe_attr_set = true;
+    const bool frozen = (a.c.aT == 0.0f) && !a.reset && !c->no_track;
+    const int cls = pipe_class(m, a);
+    if (vec && cls > 0 && !a.reset && m.K == 5 && allow_pipe && !c->no_pipe) {
+        // steady state: the resident bulk-async staged kernel (mog_pipe.cuh), here over a queue of one frame
+        StreamArgs pa;
+        stream_args_common(c, m, a, pa);
+        const bool full = (long long)pa.ntiles >= (long long)PIPE_CTAS_PER_SM * c->num_sms;
+        // order the frame behind the previous launch tile by tile (not grid by grid) when that launch was the
+        // resident kernel too, it is the last kernel on the stream, both grids fill the machine, and this model's
+        // tile flags are current (its own last launch was the resident kernel; the predecessor on the stream may
+        // belong to another model -- independent streams share nothing)
+        const bool chain = allow_chain && c->pdl && !c->no_chain && c->chain_uid != 0 && m.flags_current && full;
+        FrameDesc &one = pa.inl[0];
+        one.bgr = a.bgr;
+        one.state = m.state;
+        one.nmodes = m.nmodes;
+        one.thr_bits = a.thr_bits;
+        one.tile_seq = m.tile_seq;
+        one.slow_count = a.slow_count;
+        one.done_count = nullptr;
+        one.seq_expect = m.seq;
+        one.flags = chain ? FD_CHAIN : 0u;
+        pa.wait_grid = chain ? 0 : 1;
+        const int r = launch_stream(c, pa, frozen, cls == 2);
+        if (r != OAT_OK) {  // nothing was enqueued: the model's sequence numbers and flags stand as they were
+            c->chain_uid = 0;
+            return r;
         }
-        PipeArgs pa;
-        pa.f = a;
-        pa.ntiles = (int)((m.plane + PIPE_TILE - 1) / PIPE_TILE);
-        pa.div_magic = 0xffffffffffffffffull / (unsigned long long)m.g.pitch_px() + 1ull;
-        pa.zero_in = a.do_hsv && a.lo[0] <= 0 && a.hi[0] >= 0 && a.lo[1] <= 0 && a.hi[1] >= 0 && a.lo[2] <= 0 && a.hi[2] >= 0;
-        const int grid = pa.ntiles < PIPE_CTAS_PER_SM * c->num_sms ? pa.ntiles : PIPE_CTAS_PER_SM * c->num_sms;
-        pa.grid_tiles = grid;
-        const unsigned slot = c->pipe_launches % oat_ctx::NCOUNTERS;
-        pa.tile_counter = c->tile_counter + slot;
-        pa.counter_base = c->tile_base[slot];
-        if (linear) c->tile_base[slot] += pipe_draws(pa.ntiles, grid);
-        ++c->pipe_launches;
-        // chain to the previous launch tile by tile when that launch was this model's pipelined kernel,
-        // it is the last kernel on the stream, and both grids fill the machine (so launches overlap pairwise)
-        pa.tile_seq = m.tile_seq;
-        pa.seq_expect = m.seq++;
-        // (the predecessor may belong to another model -- independent streams share nothing -- as long as
-        // THIS model's flags are current, i.e. its own last launch was the pipelined kernel)
-        const bool full = grid == PIPE_CTAS_PER_SM * c->num_sms;
-        pa.chain = (allow_chain && c->pdl && !c->no_chain && c->chain_uid != 0 && m.flags_current && full) ? 1 : 0;
-        pipe_uid = full ? m.uid : 0;
-        pipe_launch = true;
-        // programmatic dependent launch: the next frame's CTAs become resident (and run their prologue:
-        // mbarrier + queue initialisation) while this frame's last CTAs drain; the kernel orders its
-        // first global access behind the previous grid with griddepcontrol.wait
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3((unsigned)grid);
-        lc.blockDim = dim3(PIPE_THREADS);
-        lc.dynamicSmemBytes = PIPE_SMEM_BYTES;
-        lc.stream = c->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at;
-        lc.numAttrs = c->pdl ? 1u : 0u;
-        if (frozen && linear)
-            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, true, true>, pa));
-        else if (frozen)
-            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, true, false>, pa));
-        else if (linear)
-            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, false, true>, pa));
-        else
-            CK(cudaLaunchKernelEx(&lc, mog_pipe_kernel<5, false, false>, pa));
-    } else if (vec && frozen)
+        ++m.seq;
+        c->chain_uid = full ? m.uid : 0;
+        m.flags_current = true;
+        return OAT_OK;
+    }
+    if (vec && frozen)
         launch_fused_px<4, true>(c->stream, m.K, a);
     else if (vec)
         launch_fused_px<4, false>(c->stream, m.K, a);
     else
         launch_fused_px<1, true>(c->stream, m.K, a);
     LAUNCH_CHECK(c);
-    c->chain_uid = pipe_uid;
-    m.flags_current = pipe_launch;  // the generic kernels do not publish tile flags
+    m.flags_current = false;  // the generic kernels do not publish tile flags
     return OAT_OK;
 }
 
@@ -567,8 +734,8 @@ extern "C" int oat_mog_reset(oat_mog *h)
     return OAT_OK;
 }
 
-extern "C" int oat_mog_apply(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out, size_t out_pitch,
-                             uint8_t *mask_out, size_t mask_pitch, double learning_rate)
+static int mog_apply_common(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out, size_t out_pitch,
+                            uint8_t *mask_out, size_t mask_pitch, double learning_rate, bool async)
 {
     REQUIRE(h && bgr_in, "oat_mog_apply: null handle or input");
     oat_ctx *c = h->ctx;
@@ -577,6 +744,10 @@ extern "C" int oat_mog_apply(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch,
     REQUIRE(in_pitch >= (size_t)3 * cols, "oat_mog_apply: input pitch too small");
     REQUIRE(!bgr_out || out_pitch >= (size_t)3 * cols, "oat_mog_apply: output pitch too small");
     REQUIRE(!mask_out || mask_pitch >= (size_t)cols, "oat_mog_apply: mask pitch too small");
+    if (async)
+        REQUIRE(mem_kind(bgr_in) == MEM_DEVICE && (!bgr_out || mem_kind(bgr_out) == MEM_DEVICE) &&
+                    (!mask_out || mem_kind(mask_out) == MEM_DEVICE),
+                "oat_mog_apply_async: device-resident images only");
     FusedArgs a{};
     CKRET(stage_in(c, c->stream, h->in, bgr_in, in_pitch, rows, (size_t)3 * cols, &a.bgr, &a.in_pitch));
     OutView ob, om;
@@ -589,11 +760,26 @@ extern "C" int oat_mog_apply(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch,
     a.bgr_out_pitch = ob.dpitch;
     a.fg_out = om.d;
     a.fg_pitch = om.dpitch;
-    CKRET(launch_fused(c, h->m, a));
+    // device-resident frames in, device-resident frames out: nothing but this stream's own kernels orders the
+    // frame, so consecutive launches may overlap tile by tile
+    CKRET(launch_fused(c, h->m, a, true, async));
+    if (async) return OAT_OK;
     CKRET(finish_out(c->stream, ob));
     CKRET(finish_out(c->stream, om));
     CK(cudaStreamSynchronize(c->stream));
     return OAT_OK;
+}
+
+extern "C" int oat_mog_apply(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out, size_t out_pitch,
+                             uint8_t *mask_out, size_t mask_pitch, double learning_rate)
+{
+    return mog_apply_common(h, bgr_in, in_pitch, bgr_out, out_pitch, mask_out, mask_pitch, learning_rate, false);
+}
+
+extern "C" int oat_mog_apply_async(oat_mog *h, const uint8_t *bgr_in, size_t in_pitch, uint8_t *bgr_out, size_t out_pitch,
+                                   uint8_t *mask_out, size_t mask_pitch, double learning_rate)
+{
+    return mog_apply_common(h, bgr_in, in_pitch, bgr_out, out_pitch, mask_out, mask_pitch, learning_rate, true);
 }
 
 extern "C" int oat_mog_live_modes(oat_mog *h, uint64_t *sum)
@@ -1267,6 +1453,8 @@ struct Slot {
     uint32_t *bits = nullptr;       // this frame's threshold mask (kept until collect: overflow replay)
     FastBufs fb;                    // this frame's one-launch tail buffers
     unsigned int *d_slow = nullptr; // fused kernel's slow-path census of this frame (re-armed by the tail)
+    unsigned int *d_done = nullptr; // resident path: tiles of this slot's frames published so far (monotonic)
+    unsigned int done_total = 0;    //                host mirror: value of *d_done once every frame enqueued so far is complete
     cudaEvent_t fused_done = nullptr;
     oat_hsv_params hp{};
     bool fast = false;              // the one-launch tail was used (status must be checked at collect)
@@ -1416,6 +1604,8 @@ struct oat_tracker {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
     double prof_ms = 0.0;
     uint64_t prof_n = 0;
+    size_t last_slot = 0;            // ring slot of the most recently collected frame (oat_tracker_tail_stats)
+    uint64_t clip_frames = 0;        // frames that went through the resident clip engine
 };
 
 extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_params *mp, int ring_depth,
@@ -1434,11 +1624,12 @@ extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_
     if (r == OAT_OK) {
         t->ring.resize(ring_depth);
         for (auto &s : t->ring) {
+            s.done_total = 0;
             if (cudaHostAlloc(&s.h_res, sizeof(TailResult), cudaHostAllocMapped) != cudaSuccess ||
                 cudaMalloc(&s.d_res, sizeof(TailResult)) != cudaSuccess ||
                 cudaMalloc(&s.bits, t->tail.nwords * 4) != cudaSuccess ||
-                s.fb.create(t->tail.nwords, rows) != OAT_OK || cudaMalloc(&s.d_slow, sizeof(unsigned int)) != cudaSuccess ||
-                cudaMemset(s.d_slow, 0, sizeof(unsigned int)) != cudaSuccess ||
+                s.fb.create(t->tail.nwords, rows) != OAT_OK || cudaMalloc(&s.d_slow, 2 * sizeof(unsigned int)) != cudaSuccess ||
+                cudaMemset(s.d_slow, 0, 2 * sizeof(unsigned int)) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.fused_done, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
@@ -1447,6 +1638,11 @@ extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_
                 break;
             }
         }
+    }
+    if (r == OAT_OK) {
+        for (auto &s : t->ring) s.d_done = s.d_slow + 1;
+        if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess)  // the memsets ran on the legacy stream
+            r = fail(OAT_ERR_CUDA, "tracker ring initialisation failed");
     }
     if (r != OAT_OK) {
         oat_tracker_destroy(t);
@@ -1703,6 +1899,7 @@ static int tracker_collect(oat_tracker *t, oat_detection *out, oat_position *pos
     } else if (pos) {
         return fail(OAT_ERR_STATE, "oat_tracker_collect_position: the frame was submitted before the filter was attached");
     }
+    t->last_slot = (size_t)(t->tailpos % t->ring.size());
     ++t->tailpos;
     return OAT_OK;
 }
@@ -1725,13 +1922,277 @@ extern "C" int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t 
     return tracker_enqueue(t, bgr_in, in_pitch, learning_rate, p, ob, none1, none2, none3, true);
 }
 
-extern "C" int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames, size_t n, size_t in_pitch,
-                                    double learning_rate, const oat_hsv_params *p, int depth, oat_detection *out,
-                                    oat_position *pos)
+// ---- resident clip engine ----------------------------------------------------------------------
+// A clip of device-resident frames does not need the host per frame: the frames of a chunk (half of every
+// tracker's ring) become a queue of FrameDesc / TailFrame descriptors, ONE launch of the resident fused kernel
+// (compute stream) and ONE launch of the resident tail server (a tail stream) work through it, and the two
+// kernels hand frames over on the device (Slot::d_done).  Two chunks are kept in flight: the fused kernel of
+// chunk q+1 follows chunk q's tile by tile (FD_CHAIN), so neither a frame boundary nor a chunk boundary drains
+// the machine.  Frames of several trackers (independent streams on one GPU) can be interleaved in one queue.
+
+// Can this tracker's next frames go through the resident engine?  (Steady state only: the first frame of a
+// model, a learning rate that changes per frame or re-initialises, a stream the census moved to the generic
+// kernel, and geometries the one-launch tail cannot take stay on the per-frame path.)
+static bool clip_eligible(const oat_tracker *t, double learning_rate, const oat_hsv_params *p, bool need_tail)
 {
-    REQUIRE(t && frames && out, "oat_tracker_run_clip: null argument");
-    REQUIRE(t->head == t->tailpos, "oat_tracker_run_clip: frames are still outstanding (collect first)");
-    REQUIRE(!pos || t->pf, "oat_tracker_run_clip: positions requested but no position filter is attached");
+    const oat_ctx *c = t->ctx;
+    if (c->no_pipe || c->no_clip || t->prof || t->use_generic) return false;
+    if (t->m.K != 5 || t->m.nframes < 1 || !(learning_rate >= 0.0 && learning_rate < 1.0)) return false;
+    if (t->m.g.cols % 4 != 0 || t->ring.size() < 2) return false;
+    if (need_tail) {
+        if (c->no_fast_tail || t->tail.fast_smem == 0 || t->m.g.rows < 2) return false;
+        const int ke = p->erode_px > 0 ? p->erode_px : 0, kd = p->dilate_px > 0 ? p->dilate_px : 0;
+        const size_t nin = (size_t)8 + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
+        if (2 * nin * (size_t)t->m.g.wpr * sizeof(uint32_t) > 200 * 1024) return false;
+    }
+    return true;
+}
+static bool clip_frame_ok(const oat_tracker *t, const uint8_t *frame, size_t in_pitch, int *cls_out)
+{
+    if (!frame || mem_kind(frame) != MEM_DEVICE || !aligned4(frame, in_pitch)) return false;
+    FusedArgs a{};
+    a.bgr = frame;
+    a.in_pitch = in_pitch;
+    const int cls = pipe_class(t->m, a);
+    if (cls_out) *cls_out = cls;
+    return cls > 0;
+}
+
+// frames: [n][S] frame-major; out / pos likewise (pos only with S == 1).  *used = frames (per tracker) consumed;
+// fewer than n if a frame or a tracker stopped being eligible -- the caller continues on the per-frame path.
+static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *const *frames, size_t n, size_t in_pitch,
+                    double learning_rate, const oat_hsv_params *p, bool fused_only, oat_detection *out, oat_position *pos,
+                    size_t *used)
+{
+    *used = 0;
+    size_t chunkF = trk[0]->ring.size() / 2;
+    for (int s = 0; s < S; ++s) chunkF = std::min(chunkF, trk[s]->ring.size() / 2);
+    if (chunkF == 0 || n == 0) return OAT_OK;
+    ClipHalf *half = c->clip;
+    oat_tracker *t0 = trk[0];
+    const BitGeom g = t0->tail.tb.g;
+    const int ntiles = (int)((t0->m.plane + PIPE_TILE - 1) / PIPE_TILE);
+    const int ke = p->erode_px > 0 ? p->erode_px : 0, kd = p->dilate_px > 0 ? p->dilate_px : 0;
+    const int R = 8;
+    const size_t nin = (size_t)R + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
+    const size_t stage = 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
+    const size_t tail_smem = std::max(stage, t0->tail.fast_smem);
+    static size_t tail_stream_smem_set = 48 * 1024;
+    if (!fused_only && tail_smem + 2048 > tail_stream_smem_set) {
+        CK(cudaFuncSetAttribute(tail_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        tail_stream_smem_set = 200 * 1024;
+    }
+    struct Flight {
+        size_t first = 0, count = 0;
+        bool live = false;
+    } fl[2];
+    size_t next = 0, nchunk = 0;
+    bool stop = false;  // no new chunks: something stopped being eligible
+    int class_all = 2;
+
+    auto retire = [&](int h) -> int {
+        Flight &f = fl[h];
+        CK(cudaEventSynchronize(half[h].done));
+        if (!fused_only) {
+            bool replayed = false;
+            for (size_t i = 0; i < f.count; ++i)
+                for (int s = 0; s < S; ++s) {
+                    oat_tracker *t = trk[s];
+                    Slot &sl = t->ring[(size_t)h * chunkF + i];
+                    if (sl.h_res->status != TAIL_OK) {
+                        // the mask overflowed the one-launch tail's run table: replay this frame's mask through the
+                        // unbounded path (its bits are still in the slot)
+                        CKRET(t->tail.run(c, sl.bits, sl.hp, &sl.d_res->det, nullptr, 0, nullptr));
+                        CK(cudaMemcpyAsync(&sl.h_res->det, &sl.d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
+                        ++t->replays;
+                        replayed = true;
+                    }
+                }
+            if (replayed) CK(cudaStreamSynchronize(c->stream));
+            for (size_t i = 0; i < f.count; ++i)
+                for (int s = 0; s < S; ++s) {
+                    oat_tracker *t = trk[s];
+                    Slot &sl = t->ring[(size_t)h * chunkF + i];
+                    const double groups = (double)t->m.g.rows * t->m.g.cols / 4.0;
+                    t->slow_frac = 0.75 * t->slow_frac + 0.25 * ((double)sl.h_res->slow_groups / groups);
+                    if (!t->use_generic && t->slow_frac > 0.30) t->use_generic = true;
+                    if (out) out[(f.first + i) * S + s] = sl.h_res->det;
+                    t->last_slot = (size_t)h * chunkF + i;
+                }
+            if (pos) {  // S == 1: the position epilogue over the chunk's final detections, in frame order
+                oat_tracker *t = trk[0];
+                for (size_t i = 0; i < f.count; ++i) {
+                    Slot &sl = t->ring[(size_t)h * chunkF + i];
+                    CKRET(posfilt_launch(t->pf, nullptr, &sl.d_res->det, nullptr, 1, sl.d_pos));
+                    CK(cudaMemcpyAsync(sl.h_pos, sl.d_pos, sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
+                }
+                CK(cudaStreamSynchronize(c->post));
+                for (size_t i = 0; i < f.count; ++i) pos[f.first + i] = *t->ring[(size_t)h * chunkF + i].h_pos;
+            }
+        }
+        for (int s = 0; s < S; ++s) trk[s]->clip_frames += f.count;
+        *used = f.first + f.count;
+        f.live = false;
+        return OAT_OK;
+    };
+
+    auto launch_chunk = [&](int h) -> int {
+        if (stop) return OAT_OK;
+        for (int s = 0; s < S; ++s)
+            if (!clip_eligible(trk[s], learning_rate, p, !fused_only)) {
+                stop = true;
+                return OAT_OK;
+            }
+        // how many frames of the clip can go into this chunk
+        size_t cnt = 0;
+        for (; cnt < chunkF && next + cnt < n; ++cnt) {
+            bool ok = true;
+            for (int s = 0; s < S && ok; ++s) {
+                int cls = 0;
+                ok = clip_frame_ok(trk[s], frames[(next + cnt) * S + s], in_pitch, &cls);
+                if (ok) class_all = std::min(class_all, cls);
+            }
+            if (!ok) {
+                stop = true;  // this chunk ends before the frame; the caller takes it from there
+                break;
+            }
+        }
+        if (cnt == 0) return OAT_OK;
+        CKRET(half[h].ensure(chunkF * (size_t)S));
+        const bool full = (long long)ntiles * (long long)(cnt * S) >= (long long)PIPE_CTAS_PER_SM * c->num_sms;
+        bool chain_launch = c->pdl && !c->no_chain && c->chain_uid != 0 && full;
+        for (int s = 0; s < S; ++s) chain_launch = chain_launch && trk[s]->m.flags_current;
+        FusedArgs a{};
+        bool seen[64] = {};  // (n_trackers <= 64)
+        for (size_t i = 0; i < cnt; ++i)
+            for (int s = 0; s < S; ++s) {
+                oat_tracker *t = trk[s];
+                Slot &sl = t->ring[(size_t)h * chunkF + i];
+                MogConsts mc;
+                int reset = 0;
+                t->m.frame_consts(learning_rate, &mc, &reset);
+                if (i == 0 && s == 0) a.c = mc;
+                FrameDesc &d = half[h].h_desc[i * S + s];
+                d.bgr = frames[(next + i) * S + s];
+                d.state = t->m.state;
+                d.nmodes = t->m.nmodes;
+                d.thr_bits = sl.bits;
+                d.tile_seq = t->m.tile_seq;
+                d.slow_count = sl.d_slow;
+                d.done_count = fused_only ? nullptr : sl.d_done;
+                d.seq_expect = t->m.seq++;
+                d.flags = (seen[s] || chain_launch) ? FD_CHAIN : 0u;  // later frames of a model follow its earlier ones in this launch
+                seen[s] = true;
+                sl.hp = *p;
+                sl.fast = true;
+                sl.has_pos = false;
+                if (!fused_only) {
+                    sl.done_total += (unsigned)ntiles;
+                    TailFrame &tf = half[h].h_tf[i * S + s];
+                    FastArgs &fa = tf.a;
+                    fa.in = sl.bits;
+                    fa.out = sl.fb.di;
+                    fa.ke = ke;
+                    fa.kd = kd;
+                    fa.R = R;
+                    fa.g = g;
+                    fa.rowext = sl.fb.rowext;
+                    fa.rowcnt = sl.fb.rowcnt;
+                    fa.bbox = sl.fb.bbox;
+                    fa.ticket = sl.fb.ticket;
+                    fa.min_area = p->min_area;
+                    fa.max_area = p->max_area;
+                    fa.res = sl.d_res;
+                    fa.res_host = sl.h_res;
+                    fa.smem_bytes = (int)tail_smem;
+                    fa.max_comps = t->tail.fast_comps;
+                    fa.slow_in = sl.d_slow;
+                    tf.done_count = sl.d_done;
+                    tf.done_target = sl.done_total;
+                    tf.pad = 0;
+                }
+            }
+        const size_t nitems = cnt * (size_t)S;
+        // descriptors: a short queue travels in the kernel parameters; a long one is uploaded on a side stream and
+        // waited for by the HOST, so that nothing but the previous fused kernel precedes this launch on the compute
+        // stream (the launches overlap tile by tile)
+        const bool inline_descs = nitems <= (size_t)PIPE_INLINE_DESCS;
+        if (!inline_descs) {
+            CK(cudaMemcpyAsync(half[h].d_desc, half[h].h_desc, nitems * sizeof(FrameDesc), cudaMemcpyHostToDevice, c->aux));
+            CK(cudaStreamSynchronize(c->aux));
+        }
+        a.in_pitch = in_pitch;
+        a.rows = t0->m.g.rows;
+        a.cols = t0->m.g.cols;
+        a.wpr = t0->m.g.wpr;
+        a.plane = t0->m.plane;
+        a.hsv_lut = c->hsv_lut;
+        a.do_hsv = 1;
+        a.lo[0] = p->h_min;
+        a.lo[1] = p->s_min;
+        a.lo[2] = p->v_min;
+        a.hi[0] = p->h_max;
+        a.hi[1] = p->s_max;
+        a.hi[2] = p->v_max;
+        a.thr_bits = half[h].h_desc[0].thr_bits;  // (non-NULL: the kernel reads the per-frame pointer)
+        a.bgr = half[h].h_desc[0].bgr;
+        StreamArgs pa;
+        stream_args_common(c, t0->m, a, pa);
+        pa.nframes = (int)nitems;
+        pa.descs = inline_descs ? nullptr : half[h].d_desc;
+        if (inline_descs) memcpy(pa.inl, half[h].h_desc, nitems * sizeof(FrameDesc));
+        pa.wait_grid = chain_launch ? 0 : 1;
+        const bool frozen = (a.c.aT == 0.0f) && !c->no_track;
+        CKRET(launch_stream(c, pa, frozen, class_all == 2));
+        for (int s = 0; s < S; ++s) trk[s]->m.flags_current = true;
+        c->chain_uid = full ? t0->m.uid : 0;
+        if (!fused_only) {
+            cudaStream_t ts = c->tail[c->tail_rr++ % oat_ctx::NTAIL];
+            CK(cudaMemcpyAsync(half[h].d_tf, half[h].h_tf, nitems * sizeof(TailFrame), cudaMemcpyHostToDevice, ts));
+            CK(cudaMemsetAsync(half[h].d_ctr, 0, 2 * nitems * sizeof(unsigned int), ts));
+            const int nbands = div_up(g.rows, R);
+            const int gridT = std::max(1, std::min(nbands, c->num_sms / 2));
+            tail_stream_kernel<<<gridT, 256, tail_smem, ts>>>(half[h].d_tf, (int)nitems, half[h].d_ctr, half[h].d_ctr + nitems);
+            ++c->launches;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(half[h].done, ts));
+        } else {
+            CK(cudaEventRecord(half[h].done, c->stream));
+        }
+        fl[h].first = next;
+        fl[h].count = cnt;
+        fl[h].live = true;
+        next += cnt;
+        ++nchunk;
+        return OAT_OK;
+    };
+
+    for (;;) {
+        const int h = (int)(nchunk & 1);
+        if (next < n && !stop && !fl[h].live) {
+            const size_t before = next;
+            CKRET(launch_chunk(h));
+            if (next != before) continue;
+            stop = true;  // nothing could be launched
+        }
+        // retire the older live chunk
+        int r = -1;
+        if (fl[0].live && fl[1].live)
+            r = fl[0].first < fl[1].first ? 0 : 1;
+        else if (fl[0].live)
+            r = 0;
+        else if (fl[1].live)
+            r = 1;
+        if (r < 0) break;
+        CKRET(retire(r));
+    }
+    return OAT_OK;
+}
+
+// the per-frame submit/collect loop, `depth` frames in flight (host-fed clips, first frames, generic-kernel streams)
+static int run_clip_per_frame(oat_tracker *t, const uint8_t *const *frames, size_t n, size_t in_pitch, double learning_rate,
+                              const oat_hsv_params *p, int depth, oat_detection *out, oat_position *pos)
+{
     size_t d = depth < 1 ? 1 : (size_t)depth;
     if (d > t->ring.size()) d = t->ring.size();
     size_t done = 0;
@@ -1743,6 +2204,86 @@ extern "C" int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames
         CKRET(oat_tracker_submit(t, frames[i], in_pitch, learning_rate, p, nullptr, 0));
     }
     for (; done < n; ++done) CKRET(tracker_collect(t, &out[done], pos ? &pos[done] : nullptr));
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames, size_t n, size_t in_pitch,
+                                    double learning_rate, const oat_hsv_params *p, int depth, oat_detection *out,
+                                    oat_position *pos)
+{
+    REQUIRE(t && frames && out, "oat_tracker_run_clip: null argument");
+    REQUIRE(t->head == t->tailpos, "oat_tracker_run_clip: frames are still outstanding (collect first)");
+    REQUIRE(!pos || t->pf, "oat_tracker_run_clip: positions requested but no position filter is attached");
+    if (n == 0) return OAT_OK;
+    CKRET(tracker_check(t, frames[0], in_pitch, p));
+    CKRET(bind(t->ctx));
+    size_t done = 0;
+    while (done < n) {
+        // device-resident frames in the steady state: the resident engine (one launch per chunk)
+        if (clip_eligible(t, learning_rate, p, true) && clip_frame_ok(t, frames[done], in_pitch, nullptr)) {
+            size_t used = 0;
+            CKRET(clip_run(t->ctx, &t, 1, frames + done, n - done, in_pitch, learning_rate, p, false, out + done,
+                           pos ? pos + done : nullptr, &used));
+            done += used;
+            if (used) continue;
+        }
+        // otherwise frame by frame: the first frame of a model on its own (the engine takes over from the second),
+        // everything else (host frames, generic-kernel streams, ...) pipelined `depth` deep
+        const bool first_only = t->m.nframes == 0 && learning_rate >= 0.0 && learning_rate < 1.0;
+        const size_t cnt = first_only ? 1 : n - done;
+        CKRET(run_clip_per_frame(t, frames + done, cnt, in_pitch, learning_rate, p, depth, out + done, pos ? pos + done : nullptr));
+        done += cnt;
+    }
+    return OAT_OK;
+}
+
+// Frames of several independent streams on one GPU, interleaved in ONE queue of the resident engine:
+// frames[i * n_trackers + s] is frame i of tracker s (all device-resident, same geometry, same parameters);
+// out likewise.  flags & 1: fused kernel only (no detect tail, nothing returned; diagnostics / roofline).
+extern "C" int oat_tracker_run_clips(oat_tracker *const *trackers, int n_trackers, const uint8_t *const *frames, size_t n_frames,
+                                     size_t in_pitch, double learning_rate, const oat_hsv_params *p, int flags, oat_detection *out)
+{
+    REQUIRE(trackers && n_trackers >= 1 && n_trackers <= 64 && frames, "oat_tracker_run_clips: bad arguments");
+    const bool fused_only = (flags & 1) != 0;
+    REQUIRE(fused_only || out, "oat_tracker_run_clips: null output");
+    oat_tracker *t0 = trackers[0];
+    REQUIRE(t0, "oat_tracker_run_clips: null tracker");
+    CKRET(check_hsv_params(p));
+    for (int s = 0; s < n_trackers; ++s) {
+        oat_tracker *t = trackers[s];
+        REQUIRE(t && t->ctx == t0->ctx && t->m.g.rows == t0->m.g.rows && t->m.g.cols == t0->m.g.cols &&
+                    memcmp(&t->m.p, &t0->m.p, sizeof(oat_mog_params)) == 0,
+                "oat_tracker_run_clips: the trackers must share context, geometry and MOG parameters");
+        REQUIRE(t->head == t->tailpos, "oat_tracker_run_clips: frames are still outstanding (collect first)");
+        REQUIRE(t->m.nframes == t0->m.nframes, "oat_tracker_run_clips: the trackers must have seen the same number of frames");
+        for (int u = 0; u < s; ++u) REQUIRE(trackers[u] != t, "oat_tracker_run_clips: a tracker appears twice");
+    }
+    REQUIRE(in_pitch >= (size_t)3 * t0->m.g.cols, "tracker: input pitch too small");
+    CKRET(bind(t0->ctx));
+    size_t done = 0;
+    while (done < n_frames) {
+        bool ok = true;
+        for (int s = 0; s < n_trackers; ++s)
+            ok = ok && clip_eligible(trackers[s], learning_rate, p, !fused_only) &&
+                 clip_frame_ok(trackers[s], frames[done * n_trackers + s], in_pitch, nullptr);
+        if (ok) {
+            size_t used = 0;
+            CKRET(clip_run(t0->ctx, trackers, n_trackers, frames + done * n_trackers, n_frames - done, in_pitch, learning_rate, p,
+                           fused_only, out ? out + done * n_trackers : nullptr, nullptr, &used));
+            done += used;
+            if (used) continue;
+        }
+        // one frame of every stream on the per-frame path
+        for (int s = 0; s < n_trackers; ++s) {
+            if (fused_only)
+                CKRET(oat_tracker_submit_fused_only(trackers[s], frames[done * n_trackers + s], in_pitch, learning_rate, p));
+            else
+                CKRET(oat_tracker_submit(trackers[s], frames[done * n_trackers + s], in_pitch, learning_rate, p, nullptr, 0));
+        }
+        if (!fused_only)
+            for (int s = 0; s < n_trackers; ++s) CKRET(tracker_collect(trackers[s], &out[done * n_trackers + s], nullptr));
+        ++done;
+    }
     return OAT_OK;
 }
 
@@ -1785,15 +2326,16 @@ extern "C" int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float 
 }
 
 // Diagnostic: what the one-launch tail needed for the most recently collected frame.
-extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [14]: status, nodes, replays, fast, cyc[8], generic frames, slow groups */)
+extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [15]: status, nodes, replays, fast, cyc[8], generic frames, slow groups, clip frames */)
 {
     REQUIRE(t && out, "null argument");
-    const Slot &s = t->ring[(t->tailpos + t->ring.size() - 1) % t->ring.size()];
+    const Slot &s = t->ring[t->last_slot];
     out[0] = (uint32_t)s.h_res->status;
     out[1] = s.h_res->nodes;
     out[2] = (uint32_t)t->replays;
     out[3] = s.fast ? 1u : 0u;
     for (int i = 0; i < 8; ++i) out[4 + i] = s.h_res->cyc[i];
+    out[14] = (uint32_t)t->clip_frames;      // frames served by the resident clip engine (one launch per chunk)
     out[12] = (uint32_t)t->generic_frames;  // frames that ran the generic fused kernel (adaptive choice)
     out[13] = s.h_res->slow_groups;          // census of that frame
     return OAT_OK;

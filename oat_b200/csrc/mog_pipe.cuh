@@ -1,16 +1,22 @@
 // mog_pipe.cuh -- the steady-state form of the fused kernel (mog_fused.cuh has the semantics and
 // the generic fallback): the same per-pixel MOG2 + setTo(0) + BGR->HSV + inRange arithmetic, fed by
-// an asynchronous bulk-copy pipeline instead of per-thread global loads.
+// an asynchronous bulk-copy pipeline instead of per-thread global loads, and RESIDENT across frames:
+// one launch works through a queue of frame descriptors (a whole clip, frames of several independent
+// streams interleaved, or a single frame), so CTA start-up, pipeline fill and drain are paid once
+// per launch instead of once per frame and the host does nothing per frame.
 //
-//   * persistent grid (CTAs/SM x SM count), each CTA walks tiles of PIPE_TILE = 1024 consecutive
-//     padded pixels (4 per thread);
+//   * persistent grid (CTAs/SM x SM count); work items are (frame, tile) pairs, tile = PIPE_TILE = 1024
+//     consecutive padded pixels (4 per thread), drawn from ONE global counter in frame-major order;
 //   * the hot GMM planes -- mode 0 {weight, variance, mean b/g/r} and the mode-count bytes, i.e.
-//     everything a single-mode pixel needs -- are staged global -> shared with cp.async.bulk
-//     (TMA engine, SASS UBLKCP) into a PIPE_STAGES-deep ring tracked by mbarriers, updated IN PLACE
-//     in shared memory and written back with cp.async.bulk shared -> global; no warp ever waits on
-//     a global load of state in the common case, and the bytes in flight per SM are set by the ring
-//     depth, not by registers/occupancy;
-//   * BGR input (12 B/thread) is register-prefetched one tile ahead;
+//     everything a single-mode pixel needs -- and the tile's BGR bytes are staged global -> shared with
+//     cp.async.bulk (TMA engine, SASS UBLKCP) into a PIPE_STAGES-deep ring tracked by mbarriers,
+//     updated IN PLACE in shared memory and written back with cp.async.bulk shared -> global; no warp
+//     ever waits on a global load of state in the common case, and the bytes in flight per SM are set
+//     by the ring depth, not by registers/occupancy;
+//   * frame t+1 of a model needs frame t's state only tile by tile: every finished tile is PUBLISHED
+//     (release) in tile_seq[] and acquired by whoever loads that tile for the next frame -- inside one
+//     launch and across consecutive launches alike, so neither a frame boundary nor a launch boundary
+//     drains the machine;
 //   * modes 1..4 (pixels whose model currently has more than one live mode, ~1-2 % on the
 //     benchmark stream) are read/written with direct 128-bit global accesses in a slow path that
 //     runs the literal mog2_pixel(); a thread whose 4 pixels all have one mode that fits takes a
@@ -43,11 +49,27 @@ constexpr int PIPE_STAGES = PIPE_STAGES_CFG;
 constexpr int PIPE_CTAS_PER_SM = PIPE_CTAS_PER_SM_CFG;  // persistent grid = this x SM count
 constexpr int PIPE_OFF_NM = 5 * PIPE_TILE * 4;       // stage layout: 5 fp32 planes | mode counts | BGR | flag
 constexpr int PIPE_OFF_BGR = PIPE_OFF_NM + PIPE_TILE;
-constexpr int PIPE_OFF_FLAG = PIPE_OFF_BGR + 3 * PIPE_TILE;   // +0 dirty flag, +4 tile number, +8 queue count, +12 queue head
+constexpr int PIPE_OFF_FLAG = PIPE_OFF_BGR + 3 * PIPE_TILE;   // stage header, 128 B (u32 words, see HDR_*)
 constexpr int PIPE_OFF_BITS = PIPE_OFF_FLAG + 128;            // threshold bits of the tile (PIPE_TILE / 8 bytes)
 constexpr int PIPE_OFF_QUEUE = PIPE_OFF_BITS + PIPE_TILE / 8;  // slow-pixel queue (u16 pixel-in-tile, 0xffff = empty)
 constexpr int PIPE_STAGE_BYTES = PIPE_OFF_QUEUE + 2 * PIPE_TILE;  // 26880 B
 constexpr int PIPE_SMEM_BYTES = PIPE_STAGES * PIPE_STAGE_BYTES;
+// stage header words: what the producer lane tells the compute warps (tile, state) and its own store side
+// (everything else) about the tile a stage holds
+enum {
+    HDR_DIRTY = 0,    // TRACK: some state word of the tile changed
+    HDR_TILE = 1,     // tile number inside its frame, -1 = no more work
+    HDR_QCNT = 2,     // slow-pixel queue: entries pushed
+    HDR_QHEAD = 3,    //                   entries claimed
+    HDR_FRAME = 4,    // frame index inside the launch
+    HDR_SEQ_OUT = 5,  // value to publish in tile_seq
+    HDR_STATE = 6,    // (64-bit) GMM planes of the frame's model
+    HDR_NMODES = 8,
+    HDR_THR = 10,
+    HDR_TSEQ = 12,
+    HDR_SLOW = 14,
+    HDR_DONE = 16,
+};
 
 // ---- PTX wrappers: mbarrier + bulk async copies (sm_90+; SASS UBLKCP / SYNCS) ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,32 +147,57 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// Ampere-style 4-byte async copy (SASS LDGSTS) whose completion is counted by an mbarrier.
-__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem)
+// release side of the tile hand-off: everything this thread has observed (its own completed bulk stores, and
+// -- through the CTA-scope mbarrier it waited on -- the compute warps' direct stores) becomes visible at GPU
+// scope before the flag stores that follow
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// acquire side: the async proxy (bulk copies) must not read global memory ahead of the generic-proxy acquire
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int *p, unsigned int v)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *b)
+__device__ __forceinline__ void red_add_relaxed_gpu(unsigned int *p, unsigned int v)
 {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-struct PipeArgs {
-    FusedArgs f;
-    int ntiles;
+// One frame of work.  A launch reads its descriptors from device memory (a long queue) or, up to
+// PIPE_INLINE_DESCS frames, from the kernel parameters themselves (no copy to enqueue, nothing to wait for).  All frames of a launch share geometry, pitches, GMM
+// constants and the inRange band (StreamArgs::f); what differs per frame is below.
+struct FrameDesc {
+    const uint8_t *bgr;        // input frame
+    float *state;              // GMM planes of the frame's model
+    uint8_t *nmodes;
+    uint32_t *thr_bits;        // threshold bits out (or NULL)
+    unsigned int *tile_seq;    // per tile of the model: sequence number of the last frame that finished it
+    unsigned int *slow_count;  // or NULL: += 4-pixel groups that left the fast path in this frame
+    unsigned int *done_count;  // or NULL: += 1 per published tile (the tail server starts the frame at ntiles)
+    unsigned int seq_expect;   // tile_seq value that means "the model's previous frame has finished this tile"
+    unsigned int flags;        // FD_CHAIN
+};
+constexpr int PIPE_INLINE_DESCS = 32;
+enum { FD_CHAIN = 1u };        // order every tile behind tile_seq (else: the launch is ordered behind the stream)
+static_assert(sizeof(FrameDesc) == 64, "FrameDesc is 64 bytes");
+
+struct StreamArgs {
+    FusedArgs f;                   // geometry, pitches, constants, band, egress (bgr/state/nmodes/thr_bits: see FrameDesc)
+    int ntiles;                    // tiles per frame
+    int nframes;                   // frames in this launch
+    const FrameDesc *descs;        // [nframes] in device memory, or NULL: `inl` (short queues travel with the launch)
+    FrameDesc inl[PIPE_INLINE_DESCS];
     unsigned long long div_magic;  // ceil(2^64 / pitch_px): y = umul64hi(pidx, magic), exact for every pidx < 2^32
     int zero_in;                   // HSV (0,0,0) lies inside the inRange band
-    int grid_tiles;                // tile stride between consecutive tiles of one CTA (= gridDim.x)
-    unsigned int *tile_counter;    // dynamic tile scheduler (LINEAR frames): monotonic draw counter of THIS launch's slot
-    unsigned int counter_base;     // value of *tile_counter before this launch's first draw (the host knows every launch's draw count)
-    // Tile-granular ordering between consecutive launches on one model ("chain"): tile_seq[i] holds the
-    // sequence number of the last launch that has finished (stored + made visible) tile i.  A chained
-    // launch is NOT ordered behind its predecessor grid (no griddepcontrol.wait): its producer loads
-    // tile i once tile_seq[i] == seq_expect, so its first tiles stream in while the predecessor's
-    // last tiles are still being computed.  Every launch publishes seq_expect + 1.
-    unsigned int *tile_seq;
-    unsigned int seq_expect;
-    int chain;
+    int wait_grid;                 // 1: order the whole launch behind the previous grid on the stream (griddepcontrol.wait)
+    // Work scheduler: every (frame, tile) item is drawn from this counter (0 when the launch starts; the last CTA
+    // to leave re-arms it and the ticket, then tells the host).  The host hands the slots of a ring out to
+    // consecutive launches and re-uses a slot only after its previous user has said so (api.cu), so no two live
+    // launches ever share one.
+    unsigned int *work_counter;
+    unsigned int *exit_ticket;
+    unsigned int *done_flag;       // pinned host word of the slot: the last CTA to leave stores launch_id there
+    unsigned int launch_id;
+    int relaxed_publish;           // measurement switch ONLY (OAT_B200_RELAXED_PUBLISH): publish without the release fence, to price it
 };
 
 // One pixel with one or two live modes whose sample fits mode 0 (the heavier one): the m = 0
@@ -267,7 +314,7 @@ __device__ __forceinline__ void set4(float4 &v, int i, float x)
 // tile, not the caller's own.  Runs the rolled mog2_pixel_rolled(): cold code, small footprint.
 // Mode 0, the counts and the BGR bytes are in the shared-memory stage `st`; modes >= 1 in global memory.
 template <int K, bool TRACK>
-__device__ __forceinline__ void slow_pixel(const PipeArgs &pa, uint8_t *st, const int e, const size_t pidx)
+__device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, uint8_t *st, const int e, const size_t pidx)
 {
     const FusedArgs &a = pa.f;
     float *sm0 = reinterpret_cast<float *>(st) + e;
@@ -283,7 +330,7 @@ __device__ __forceinline__ void slow_pixel(const PipeArgs &pa, uint8_t *st, cons
     C[0] = sm0[4 * PIPE_TILE];
 #pragma unroll 1
     for (int m = 1; m < n; ++m) {
-        const float *g = a.state + (size_t)(m * 5) * a.plane + pidx;
+        const float *g = state + (size_t)(m * 5) * a.plane + pidx;
         W[m] = ld_state_f1(g);
         V[m] = ld_state_f1(g + a.plane);
         A[m] = ld_state_f1(g + 2 * a.plane);
@@ -323,7 +370,7 @@ __device__ __forceinline__ void slow_pixel(const PipeArgs &pa, uint8_t *st, cons
         *smn = (uint8_t)n;
 #pragma unroll 1
         for (int m = 1; m < nw; ++m) {
-            float *g = a.state + (size_t)(m * 5) * a.plane + pidx;
+            float *g = state + (size_t)(m * 5) * a.plane + pidx;
             st_state_f1(g, W[m]);
             st_state_f1(g + a.plane, V[m]);
             st_state_f1(g + 2 * a.plane, A[m]);
@@ -357,23 +404,49 @@ __device__ __forceinline__ void slow_pixel(const PipeArgs &pa, uint8_t *st, cons
     }
 }
 
-// LINEAR: cols % 32 == 0 and every image pitch is tight, so a pixel's byte offsets are plain
-// multiples of its padded index (no row/column split anywhere in the steady-state loop).
+
+// ---------------------------------------------------------------------------------------------------
+// The resident fused kernel.
+//
+// Roles inside a CTA: PIPE_CTHREADS compute threads + ONE producer lane that drives the bulk-copy engine in
+// both directions (loads of the next tiles, write-back + publication of the finished ones).
+//
+// Ordering of a tile between the frame that wrote it (any CTA, this launch or the previous one) and the frame
+// that reads it next -- a release/acquire pair at GPU scope, correct under the PTX memory model:
+//   writer   compute warps' direct stores (modes >= 1)  --mbarrier done[s] (release.cta / acquire.cta)-->  producer lane;
+//            the tile's bulk stores are COMPLETE (cp.async.bulk.wait_group, not .read);
+//            fence.acq_rel.gpu  (cumulative: covers what the producer lane observed through the mbarrier);
+//            st.relaxed.gpu tile_seq[tile]  (+ red.add done_count for the tail server)
+//   reader   ld.acquire.gpu tile_seq[tile] == seq_expect;  fence.proxy.async.global;  bulk loads;
+//            the compute warps' own ld.global.cg follow the mbarrier full[s] the loads complete on.
+// The fence is issued when nothing of this lane is in flight except loads it started a tile period earlier:
+// right after done[s], BEFORE the tile's stores and the refill's loads (a MEMBAR.GPU also waits for the
+// issuing lane's outstanding bulk copies; r01 measured +0.6 us per tile with the fence behind the refill).
+//
+// LINEAR: cols % 32 == 0 and every image pitch is tight, so a pixel's byte offsets are plain multiples of its
+// padded index (one bulk copy brings a tile's BGR bytes).  Otherwise the producer lane issues one bulk copy
+// per row segment of the tile (rows start 16-byte aligned: the host checks pointer and pitch), landing the
+// bytes at the same place, 3 * (pixel in tile); padding pixels are never evaluated.
+// ---------------------------------------------------------------------------------------------------
 template <int K, bool TRACK, bool LINEAR>
-__global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_kernel(const __grid_constant__ PipeArgs pa)
+__global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_kernel(const __grid_constant__ StreamArgs pa)
 {
     extern __shared__ __align__(128) uint8_t stage_mem[];
-    __shared__ __align__(8) uint64_t full[PIPE_STAGES];  // stage loaded: 1 expect_tx arrive + 256 cp.async arrives
+    __shared__ __align__(8) uint64_t full[PIPE_STAGES];  // stage loaded (expect_tx of the producer lane) or end marker
     __shared__ __align__(8) uint64_t done[PIPE_STAGES];  // stage updated in place by all compute threads
     const FusedArgs &a = pa.f;
     const int tid = threadIdx.x;
+    const bool is_producer = (tid == PIPE_CTHREADS);
     // let the next launch on this stream (programmatic dependent launch) become resident as CTAs of
-    // this one retire; it parks in griddepcontrol.wait below until this grid has completed and flushed
+    // this one retire; it either parks in griddepcontrol.wait below or orders itself tile by tile
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // the scheduler's first answer (PIPE_STAGES consecutive items) travels while the CTA initialises
+    uint32_t raw0 = 0;
+    if (is_producer) raw0 = atomicAdd(pa.work_counter, (unsigned)PIPE_STAGES);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < PIPE_STAGES; ++s) {
-            mbar_init(&full[s], LINEAR ? 1 : 1 + PIPE_CTHREADS);
+            mbar_init(&full[s], 1);
             mbar_init(&done[s], PIPE_CTHREADS);
         }
         fence_mbar_init();
@@ -384,178 +457,259 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         for (int i = tid; i < PIPE_TILE; i += PIPE_THREADS) reinterpret_cast<uint16_t *>(st + PIPE_OFF_QUEUE)[i] = 0xffffu;
     }
     __syncthreads();
-    // everything above touched shared memory only; global memory (GMM state, scheduler counters) is
-    // ordered behind the previous grid on the stream from here on
-    // (a chained launch orders itself tile by tile through pa.tile_seq instead)
-    if (!pa.chain) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // everything above touched shared memory and the scheduler counter only; frames, GMM state and flags are
+    // ordered behind the previous grid on the stream from here on (FD_CHAIN frames order themselves tile by tile)
+    if (pa.wait_grid) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // Tile order.  LINEAR frames use a dynamic scheduler: the producer draws tile numbers from a
-    // global counter (tiles that hit the multi-mode slow path take several times longer than the
-    // rest, so a static split leaves the kernel waiting for its unluckiest CTA) and also brings the
-    // BGR bytes in with one more bulk copy.  Otherwise tile i of this CTA is blockIdx.x + i*gridDim.x
-    // and every compute thread copies its own 12 input bytes with cp.async.
-    constexpr bool DYN = LINEAR;
-    const int first = blockIdx.x, stride = pa.grid_tiles;
-    const int my_n = DYN ? 0x7fffffff : (first < pa.ntiles ? (pa.ntiles - first + stride - 1) / stride : 0);
-    auto stage_tile = [&](int s) -> volatile int * {
-        return reinterpret_cast<volatile int *>(stage_mem + (size_t)s * PIPE_STAGE_BYTES + PIPE_OFF_FLAG + 4);
+    auto hdr_of = [&](int s) -> volatile uint32_t * {
+        return reinterpret_cast<volatile uint32_t *>(stage_mem + (size_t)s * PIPE_STAGE_BYTES + PIPE_OFF_FLAG);
     };
 
     if (tid >= PIPE_CTHREADS) {
         // ---- producer warp: one lane drives the bulk-copy engine -------------------------------
-        if (tid != PIPE_CTHREADS) return;
+        if (!is_producer) return;
         const uint64_t pol_first = l2_policy_evict_first();
+        const uint32_t total = (uint32_t)pa.nframes * (uint32_t)pa.ntiles;
+        const unsigned pitch_px = (unsigned)a.wpr * 32u;
+
+        // a drawn work item, resolved against its frame's descriptor
+        struct Item {
+            int tile;  // -1: the queue is exhausted
+            int frame;
+            const uint8_t *bgr;
+            float *state;
+            uint8_t *nmodes;
+            uint32_t *thr;
+            unsigned int *tseq, *slow, *donec;
+            uint32_t seq, flags, seen;
+        };
+        int dframe = -1;   // descriptor cache (draws are monotonic: the frame index never goes back)
+        FrameDesc dcur;
+        uint32_t fbase = 0;  // first work number of frame `dframe_pos`
+        int fpos = 0;
+        auto resolve = [&](uint32_t g, Item &it) {
+            if (g >= total) {
+                it.tile = -1;
+                return;
+            }
+            while (g >= fbase + (uint32_t)pa.ntiles) {
+                fbase += (uint32_t)pa.ntiles;
+                ++fpos;
+            }
+            if (fpos != dframe) {
+                const FrameDesc *dp = pa.descs ? pa.descs + fpos : &pa.inl[fpos];
+                const uint4 *q = reinterpret_cast<const uint4 *>(dp);
+                uint4 *w = reinterpret_cast<uint4 *>(&dcur);
+                w[0] = q[0];
+                w[1] = q[1];
+                w[2] = q[2];
+                w[3] = q[3];
+                dframe = fpos;
+            }
+            it.tile = (int)(g - fbase);
+            it.frame = fpos;
+            it.bgr = dcur.bgr;
+            it.state = dcur.state;
+            it.nmodes = dcur.nmodes;
+            it.thr = dcur.thr_bits;
+            it.tseq = dcur.tile_seq;
+            it.slow = dcur.slow_count;
+            it.donec = dcur.done_count;
+            it.seq = dcur.seq_expect;
+            it.flags = dcur.flags;
+            // a look at the tile's flag well before the loads are due (an acquire: if it already shows the
+            // expected value nothing more is needed when the tile is loaded)
+            it.seen = it.seq + 1u;
+            if (it.flags & FD_CHAIN) it.seen = ld_acquire_gpu(it.tseq + it.tile);
+        };
         auto tile_span = [&](int tile, size_t &p0, uint32_t &npx) {
             p0 = (size_t)tile * PIPE_TILE;
             const size_t rem = a.plane - p0;
             npx = rem < (size_t)PIPE_TILE ? (uint32_t)rem : (uint32_t)PIPE_TILE;
         };
-        auto issue_load = [&](int s, int tile, uint32_t seen) {
+
+        // the one finished tile whose publication is still owed
+        unsigned int *pend_tseq = nullptr, *pend_done = nullptr;
+        uint32_t pend_tile = 0, pend_seq = 0;
+        bool pend = false;
+        auto publish_pending = [&]() {
+            if (!pend) return;
+            bulk_wait_all<0>();   // its bulk stores are complete (they were committed a tile period ago)
+            if (!pa.relaxed_publish) fence_acq_rel_gpu();  // ... and, with the compute warps' direct stores, visible before the flag
+            st_relaxed_gpu(pend_tseq + pend_tile, pend_seq);
+            if (pend_done) red_add_relaxed_gpu(pend_done, 1u);
+            pend = false;
+        };
+
+        auto issue_load = [&](int s, const Item &it) {
+            uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
+            volatile uint32_t *h = hdr_of(s);
+            h[HDR_TILE] = (uint32_t)it.tile;
+            h[HDR_FRAME] = (uint32_t)it.frame;
+            h[HDR_SEQ_OUT] = it.seq + 1u;
+            *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE)) = it.state;
+            *reinterpret_cast<uint8_t *volatile *>(const_cast<uint32_t *>(h + HDR_NMODES)) = it.nmodes;
+            *reinterpret_cast<uint32_t *volatile *>(const_cast<uint32_t *>(h + HDR_THR)) = it.thr;
+            *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_TSEQ)) = it.tseq;
+            *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_SLOW)) = it.slow;
+            *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_DONE)) = it.donec;
+            // (the caller has seen tile_seq == seq_expect with an acquire load)
+            if (it.flags & FD_CHAIN) fence_proxy_async_global();
+            size_t p0;
+            uint32_t npx;
+            tile_span(it.tile, p0, npx);
+            if (LINEAR) {
+                mbar_expect_tx(&full[s], npx * 24u);
+                bulk_g2s_hint(st + PIPE_OFF_BGR, it.bgr + 3 * p0, npx * 3u, &full[s], pol_first);
+            } else {
+                // BGR: one bulk copy per row segment of the tile (16-byte aligned on both sides, see the header)
+                const uint32_t y0 = (uint32_t)__umul64hi((unsigned long long)p0, pa.div_magic);
+                uint32_t bytes = 0;
+                {
+                    uint32_t y = y0, xa = (uint32_t)(p0 - (size_t)y0 * pitch_px), left = npx;
+                    while (left) {
+                        const uint32_t xb = min(pitch_px, xa + left), xv = min(xb, (uint32_t)a.cols);
+                        if (xv > xa) bytes += (3u * (xv - xa) + 15u) & ~15u;
+                        left -= xb - xa;
+                        xa = 0;
+                        ++y;
+                    }
+                }
+                mbar_expect_tx(&full[s], npx * 21u + bytes);
+                uint32_t y = y0, xa = (uint32_t)(p0 - (size_t)y0 * pitch_px), left = npx, e0 = 0;
+                while (left) {
+                    const uint32_t xb = min(pitch_px, xa + left), xv = min(xb, (uint32_t)a.cols);
+                    if (xv > xa)
+                        bulk_g2s_hint(st + PIPE_OFF_BGR + 3u * e0, it.bgr + (size_t)y * a.in_pitch + 3u * xa,
+                                      (3u * (xv - xa) + 15u) & ~15u, &full[s], pol_first);
+                    left -= xb - xa;
+                    e0 += xb - xa;
+                    xa = 0;
+                    ++y;
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 5; ++cc)
+                bulk_g2s(st + cc * (PIPE_TILE * 4), it.state + (size_t)cc * a.plane + p0, npx * 4u, &full[s]);
+            bulk_g2s(st + PIPE_OFF_NM, it.nmodes + p0, npx, &full[s]);
+        };
+        auto mark_end = [&](int s) {
+            hdr_of(s)[HDR_TILE] = 0xffffffffu;
+            mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
+        };
+
+        // Two cursors over the ring: stage li % S is the next to fill, stage si % S the next to retire.
+        //   A. fill free stages in ring order while the next item's previous frame has published the tile;
+        //   C. retire the oldest stage: wait for the compute warps, publish the tile retired before, write this
+        //      one back (and go back to A, which refills the stage at once).
+        // An item whose tile is still in flight -- possibly in one of THIS CTA's own stages, when frames are
+        // smaller than the ring -- never blocks C, and with nothing left to retire the lane publishes what it owes
+        // before it waits: the protocol cannot deadlock (tests/test_abi.py pins a model of it on the CPU).
+        Item nxt, cur;
+        uint32_t batch_next = raw0 + 1u, batch_left = (uint32_t)PIPE_STAGES - 1u;  // the first PIPE_STAGES items are consecutive
+        resolve(raw0, nxt);
+        int li = 0, si = 0;
+        bool ended = false;
+        unsigned idle_spins = 0;
+        for (;;) {
+            // ---- A ----
+            while (!ended && li - si < PIPE_STAGES) {
+                const int s = li % PIPE_STAGES;
+                if (nxt.tile < 0) {
+                    mark_end(s);
+                    ended = true;
+                    break;
+                }
+                if ((nxt.flags & FD_CHAIN) && nxt.seen != nxt.seq) {
+                    nxt.seen = ld_acquire_gpu(nxt.tseq + nxt.tile);
+                    if (nxt.seen != nxt.seq) break;  // still in flight somewhere: retire own tiles meanwhile
+                }
+                cur = nxt;
+                uint32_t rawn;
+                if (batch_left) {
+                    rawn = batch_next++;
+                    --batch_left;
+                } else {
+                    rawn = atomicAdd(pa.work_counter, 1u);  // issued now, consumed after this tile's loads are on their way
+                }
+                issue_load(s, cur);
+                resolve(rawn, nxt);
+                ++li;
+                idle_spins = 0;
+            }
+            if (si == li) {
+                if (ended) break;
+                // every stage is empty and the next tile's previous frame is in flight in another CTA (or in the
+                // previous launch): pay the publication debt, then wait.  Bounded: a writer that died (launch
+                // error) must surface as an error, not hang the GPU.
+                publish_pending();
+                __nanosleep(64);
+                if (++idle_spins > (1u << 23)) __trap();
+                continue;
+            }
+            // ---- C ----
+            const int s = si % PIPE_STAGES;
+            volatile uint32_t *h = hdr_of(s);
+            const int tile = (int)h[HDR_TILE];
+            uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
+            mbar_wait(&done[s], (uint32_t)(si / PIPE_STAGES) & 1u);
+            // 1. the tile retired before has had a whole tile period for its bulk stores: publish it
+            publish_pending();
+            // 2. write this tile back
+            float *state = *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE));
+            uint8_t *nmodes = *reinterpret_cast<uint8_t *volatile *>(const_cast<uint32_t *>(h + HDR_NMODES));
+            uint32_t *thr = *reinterpret_cast<uint32_t *volatile *>(const_cast<uint32_t *>(h + HDR_THR));
+            bool store = true;
+            if (TRACK) {
+                store = (h[HDR_DIRTY] != 0u);
+                h[HDR_DIRTY] = 0u;
+            }
             size_t p0;
             uint32_t npx;
             tile_span(tile, p0, npx);
-            uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
-            // chained launch: the predecessor must have published this tile.  `seen` is a relaxed read of
-            // the flag taken one refill earlier (hides the L2 round trip in the steady state, where the
-            // predecessor is long past this tile); state bytes reach this SM only through bulk copies and
-            // L1::no_allocate loads, i.e. from L2, where the publisher's release ordered them before the flag.
-            if (pa.chain && seen != pa.seq_expect) {
-                // bounded: a predecessor that died (launch error) must surface as an error, not hang the GPU
-                unsigned spins = 0;
-                while (ld_acquire_gpu(pa.tile_seq + tile) != pa.seq_expect) {
-                    __nanosleep(20);
-                    if (++spins > (1u << 23)) __trap();
-                }
-            }
-            mbar_expect_tx(&full[s], npx * (DYN ? 24u : 21u));
-#pragma unroll
-            for (int cc = 0; cc < 5; ++cc)
-                bulk_g2s(st + cc * (PIPE_TILE * 4), a.state + (size_t)cc * a.plane + p0, npx * 4u, &full[s]);
-            bulk_g2s(st + PIPE_OFF_NM, a.nmodes + p0, npx, &full[s]);
-            if (DYN) bulk_g2s_hint(st + PIPE_OFF_BGR, a.bgr + 3 * p0, npx * 3u, &full[s], pol_first);
-        };
-        // next tile of this CTA's sequence, or -1 when the frame is exhausted (DYN: every CTA draws
-        // exactly one number >= ntiles, so the host knows a launch's draw count and the counters never
-        // need re-arming: each launch is told where its numbers start, pa.counter_base)
-        // DYN: the first PIPE_STAGES tiles of a CTA are fixed (no atomic on the start-up path); later
-        // ones are drawn from the global counter one refill AHEAD of their use, so the L2 round trip
-        // of the atomic hides behind the wait for the stage.
-        int seq = 0, ahead = 0;
-        bool ended = false;
-        // publish a finished tile (its bulk stores are complete, the compute warps' direct stores
-        // were ordered by done[s]) to the next launch on this model
-        const uint32_t seq_out = pa.seq_expect + 1u;
-        // Steady-state publishes are RELAXED stores: a release would cost a MEMBAR.GPU that also waits for
-        // the bulk loads just issued by the refill (measured: +0.6 us per tile, 4K frame 62 -> 80 us).  What
-        // orders the data before the flag instead: the tile's bulk stores are complete
-        // (cp.async.bulk.wait_group, non-.read) and the compute warps' few direct stores (modes >= 1,
-        // write-through) were issued before those bulk stores, i.e. at least a store round trip earlier (a whole
-        // tile time, ~2 us, for all but a CTA's last tile); the consumer is a full frame behind except at
-        // the frame boundary, and reads state only from L2 (bulk copies, ld.cg).
-        auto publish = [&](int tile) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(pa.tile_seq + tile), "r"(seq_out) : "memory");
-        };
-        int unpublished = -1;
-        uint32_t ahead_seen = pa.seq_expect + 1u, seen = pa.seq_expect + 1u;  // "not seen yet"
-        auto peek = [&]() {  // relaxed look at the flag of the tile drawn for the NEXT refill
-            if (pa.chain && ahead < pa.ntiles) ahead_seen = *reinterpret_cast<const volatile unsigned int *>(pa.tile_seq + ahead);
-        };
-        uint32_t raw = 0;
-        bool drew = false;
-        auto next_tile = [&]() -> int {
-            int t;
-            seen = pa.seq_expect + 1u;
-            if (DYN && seq >= PIPE_STAGES) {
-                t = ahead;
-                seen = ahead_seen;
-                if (t < pa.ntiles) {
-                    raw = atomicAdd(pa.tile_counter, 1u);  // issued now, consumed after this tile's loads are on their way
-                    drew = true;
-                }
-            } else {
-                t = first + seq * stride;
-                if (DYN && seq == PIPE_STAGES - 1) {
-                    raw = atomicAdd(pa.tile_counter, 1u);
-                    drew = true;
-                }
-            }
-            ++seq;
-            if (t >= pa.ntiles) {
-                ended = true;
-                return -1;
-            }
-            return t;
-        };
-        auto refill = [&](int s) {  // give stage s its next tile, or the end marker
-            const int t = next_tile();
-            *stage_tile(s) = t;
-            if (t >= 0)
-                issue_load(s, t, seen);
-            else if (DYN)
-                mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
-            if (drew) {  // the scheduler's answer (an L2 round trip) and the look at that tile's flag: off the load's path
-                const uint32_t d = raw - pa.counter_base;
-                ahead = d < 0x40000000u ? (int)d + PIPE_STAGES * (int)gridDim.x : 0x7fffffff;
-                peek();
-                drew = false;
-            }
-        };
-        for (int k = 0; k < PIPE_STAGES && !ended; ++k) refill(k);  // every stage starts loaded
-        for (int i = 0;; ++i) {
-            const int s = i % PIPE_STAGES;
-            const int tile = *stage_tile(s);
-            if (tile < 0) break;
-            uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
-            mbar_wait(&done[s], (uint32_t)(i / PIPE_STAGES) & 1u);
-            bool store = true;
-            if (TRACK) {
-                volatile uint32_t *flag = reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG);
-                store = (*flag != 0u);
-                *flag = 0u;
-            }
             if (store) {
-                size_t p0;
-                uint32_t npx;
-                tile_span(tile, p0, npx);
 #pragma unroll
                 for (int cc = 0; cc < 5; ++cc)
-                    bulk_s2g(a.state + (size_t)cc * a.plane + p0, st + cc * (PIPE_TILE * 4), npx * 4u);
-                bulk_s2g(a.nmodes + p0, st + PIPE_OFF_NM, npx);
+                    bulk_s2g(state + (size_t)cc * a.plane + p0, st + cc * (PIPE_TILE * 4), npx * 4u);
+                bulk_s2g(nmodes + p0, st + PIPE_OFF_NM, npx);
             }
-            if (a.thr_bits) {  // the tile's threshold bits: 128 B, one bulk store (word loop for a ragged last tile)
-                size_t p0;
-                uint32_t npx;
-                tile_span(tile, p0, npx);
+            if (thr) {  // the tile's threshold bits: 128 B, one bulk store (word loop for a ragged last tile)
                 if (npx == (uint32_t)PIPE_TILE) {
-                    bulk_s2g(a.thr_bits + (p0 >> 5), st + PIPE_OFF_BITS, PIPE_TILE / 8);
+                    bulk_s2g(thr + (p0 >> 5), st + PIPE_OFF_BITS, PIPE_TILE / 8);
                 } else {
                     const volatile uint32_t *bw = reinterpret_cast<const volatile uint32_t *>(st + PIPE_OFF_BITS);
-                    for (uint32_t w = 0; w < npx / 32u; ++w) a.thr_bits[(p0 >> 5) + w] = bw[w];
+                    for (uint32_t w = 0; w < npx / 32u; ++w) thr[(p0 >> 5) + w] = bw[w];
                 }
             }
-            reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG)[2] = 0u;  // re-arm the slow-pixel queue
-            reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG)[3] = 0u;
             bulk_commit();
-            // refill THIS stage as soon as its stores have read it (not one tile later): its next tile is
-            // then in flight for PIPE_STAGES-1 tile times instead of one
-            if (!ended) {
-                bulk_wait_read<0>();
-                refill(s);
-            } else if (!DYN) {
-                *stage_tile(s) = -1;
+            // slow-path census of the tile (the queue count is 4 x the number of 4-pixel groups that left the fast path)
+            {
+                const uint32_t q = h[HDR_QCNT];
+                unsigned int *slow = *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_SLOW));
+                if (q && slow) red_add_relaxed_gpu(slow, q >> 2);
             }
-            // off the refill's critical path: the PREVIOUS tile's stores (committed one tile time ago) are
-            // complete by now -- publish it to the next launch on this model
-            if (unpublished >= 0) {
-                bulk_wait_all<1>();
-                publish(unpublished);
-            }
-            unpublished = tile;
+            h[HDR_QCNT] = 0u;  // re-arm the slow-pixel queue
+            h[HDR_QHEAD] = 0u;
+            pend_tseq = *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_TSEQ));
+            pend_done = *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_DONE));
+            pend_tile = (uint32_t)tile;
+            pend_seq = h[HDR_SEQ_OUT];
+            pend = true;
+            // 3. the stage can be refilled as soon as its stores have READ it (A does so at once: its next tile is
+            // then in flight for PIPE_STAGES-1 tile periods instead of one)
+            bulk_wait_read<0>();
+            ++si;
         }
-        bulk_wait_all<0>();  // shared memory must outlive the last bulk stores; and they must be complete
-        // the last tile too: its bulk stores are complete, and the compute warps' direct stores were issued before
-        // those (a release here is a MEMBAR.GPU on every CTA's exit path, ~0.7 us that the successor's CTA waits for)
-        if (unpublished >= 0) publish(unpublished);
+        publish_pending();
+        bulk_wait_all<0>();  // shared memory must outlive the last bulk stores
+        // the last CTA to leave re-arms the scheduler slot for its next user (a launch the host starts only
+        // after this one's completion event)
+        if (atomicAdd(pa.exit_ticket, 1u) == gridDim.x - 1u) {
+            *pa.work_counter = 0u;
+            *pa.exit_ticket = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int *>(pa.done_flag) = pa.launch_id;
+        }
         return;
     }
 
@@ -572,36 +726,18 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         x = (int)(pidx - (size_t)y * pitch_px);
         return (pidx < a.plane) && (x < a.cols);
     };
-    auto bgr_issue = [&](int i) {  // (static order only) this thread's 12 input bytes of its i-th tile
-        const int s = i % PIPE_STAGES;
-        size_t pidx;
-        int y, x;
-        if (locate(first + i * stride, pidx, y, x)) {
-            const uint8_t *src = a.bgr + (size_t)y * a.in_pitch + 3 * x;
-            uint8_t *dst = stage_mem + (size_t)s * PIPE_STAGE_BYTES + PIPE_OFF_BGR + tid * 12;
-            cp_async4(dst, src);
-            cp_async4(dst + 4, src + 4);
-            cp_async4(dst + 8, src + 8);
-        }
-        cp_async_arrive_noinc(&full[s]);
-    };
-    if (!DYN) {
-        const int pre = my_n < PIPE_STAGES - 1 ? my_n : PIPE_STAGES - 1;
-        for (int i = 0; i < pre; ++i) bgr_issue(i);
-    }
     const uint32_t zero_nib = pa.zero_in ? 0xFu : 0u;
-    unsigned nslow = 0;
 
-    for (int i = 0; i < my_n; ++i) {
+    for (int i = 0;; ++i) {
         const int s = i % PIPE_STAGES;
-        if (!DYN && i + PIPE_STAGES - 1 < my_n) bgr_issue(i + PIPE_STAGES - 1);
         uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
         float *sm0 = reinterpret_cast<float *>(st) + tid * 4;
+        volatile uint32_t *h = hdr_of(s);
 
         mbar_wait(&full[s], (uint32_t)(i / PIPE_STAGES) & 1u);
 
-        const int tile = DYN ? *stage_tile(s) : first + i * stride;
-        if (DYN && tile < 0) break;
+        const int tile = (int)h[HDR_TILE];
+        if (tile < 0) break;
         size_t pidx;
         int y, x;
         const bool active = locate(tile, pidx, y, x);
@@ -643,9 +779,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
                     if ((m0 | m1 | m2 | m3) != 0u && a.do_hsv) {  // some pixel keeps its colour: threshold it
                         auto bit = [&](uint32_t mk, uint32_t b, uint32_t g, uint32_t r) -> uint32_t {
                             if (!mk) return zero_nib & 1u;
-                            int h, sa, v;
-                            bgr2hsv_px_div((int)b, (int)g, (int)r, h, sa, v);
-                            return ((a.lo[0] <= h) & (h <= a.hi[0]) & (a.lo[1] <= sa) & (sa <= a.hi[1]) & (a.lo[2] <= v) & (v <= a.hi[2])) ? 1u : 0u;
+                            int hh, sa, v;
+                            bgr2hsv_px_div((int)b, (int)g, (int)r, hh, sa, v);
+                            return ((a.lo[0] <= hh) & (hh <= a.hi[0]) & (a.lo[1] <= sa) & (sa <= a.hi[1]) & (a.lo[2] <= v) & (v <= a.hi[2])) ? 1u : 0u;
                         };
                         nib = bit(m0, b0, g0, r0) | (bit(m1, b1, g1, r1) << 1) | (bit(m2, b2, g2, r2) << 2) | (bit(m3, b3, g3, r3) << 3);
                     }
@@ -653,8 +789,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             } else if ((two & ~0x01010101u) == 0u && (K >= 2 || two == 0u)) {
                 // mode 1's weights first: the only global read of this path, in flight during the mode-0 maths
                 float4 W1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                float *w1p = a.state + (size_t)5 * a.plane + pidx;
-                if (two != 0u) W1 = ld_state_f4(w1p);
+                float *w1p = nullptr;
+                if (two != 0u) {
+                    float *state = *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE));
+                    w1p = state + (size_t)5 * a.plane + pidx;
+                    W1 = ld_state_f4(w1p);
+                }
                 const uint32_t *smb = reinterpret_cast<const uint32_t *>(st + PIPE_OFF_BGR) + tid * 3;
                 const uint32_t w0 = smb[0], w1 = smb[1], w2 = smb[2];
                 float4 W = *reinterpret_cast<const float4 *>(sm0);
@@ -718,25 +858,24 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
         }
         __syncwarp();  // the words are in place before any of this warp's pixels can be claimed
         // queue the pixels that left the fast path, then help drain the tile's queue
-        volatile uint32_t *qcnt = reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG) + 2;
-        volatile uint32_t *qhead = qcnt + 1;
+        volatile uint32_t *qcnt = h + HDR_QCNT;
+        volatile uint32_t *qhead = h + HDR_QHEAD;
         volatile uint16_t *queue = reinterpret_cast<volatile uint16_t *>(st + PIPE_OFF_QUEUE);
         if (slow) {
-            ++nslow;
             const uint32_t base = atomicAdd(const_cast<uint32_t *>(qcnt), 4u);
             __threadfence_block();  // release: this warp's threshold words are visible before its pixels can be claimed
 #pragma unroll
-            for (int i = 0; i < 4; ++i) queue[base + i] = (uint16_t)(tid * 4 + i);  // relaxed (volatile) flag-style publish
+            for (int q = 0; q < 4; ++q) queue[base + q] = (uint16_t)(tid * 4 + q);  // relaxed (volatile) flag-style publish
         }
         __syncwarp();  // this warp's entries are published before any of its lanes starts claiming
         for (;;) {     // warp-level claiming: lane 0 takes up to 32 queue slots, one pixel per lane
             uint32_t h0 = 0, take = 0;
             if ((tid & 31) == 0) {
-                const uint32_t h = *qhead, c = *qcnt;
-                if (h < c) {
-                    take = min(32u, c - h);
-                    if (atomicCAS(const_cast<uint32_t *>(qhead), h, h + take) == h)
-                        h0 = h;
+                const uint32_t hd = *qhead, c = *qcnt;
+                if (hd < c) {
+                    take = min(32u, c - hd);
+                    if (atomicCAS(const_cast<uint32_t *>(qhead), hd, hd + take) == hd)
+                        h0 = hd;
                     else
                         take = 0xffffffffu;  // lost the race: look again
                 }
@@ -746,23 +885,21 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_pipe_ker
             if (take == 0u) break;
             if (take == 0xffffffffu) continue;
             if ((uint32_t)(tid & 31) < take) {
-                const uint32_t h = h0 + (uint32_t)(tid & 31);
+                const uint32_t hq = h0 + (uint32_t)(tid & 31);
                 uint32_t e;
-                while ((e = queue[h]) == 0xffffu) {}  // reserved by a pusher of another warp that is about to fill it
-                __threadfence_block();                // acquire: pairs with the pusher's fence
-                queue[h] = 0xffffu;
-                slow_pixel<K, TRACK>(pa, st, (int)e, (size_t)tile * PIPE_TILE + e);
+                while ((e = queue[hq]) == 0xffffu) {}  // reserved by a pusher of another warp that is about to fill it
+                __threadfence_block();                 // acquire: pairs with the pusher's fence
+                queue[hq] = 0xffffu;
+                float *state = *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE));
+                slow_pixel<K, TRACK>(pa, state, st, (int)e, (size_t)tile * PIPE_TILE + e);
             }
             __syncwarp();
         }
-        if (TRACK && dirty) *reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG) = 1u;
+        if (TRACK && dirty) h[HDR_DIRTY] = 1u;
         // hand the stage to the producer: generic-proxy writes -> async proxy, then arrive
         fence_proxy_async();
         mbar_arrive(&done[s]);
     }
-    // slow-path census (drives the host's choice between this kernel and the generic one)
-    nslow = __reduce_add_sync(0xffffffffu, nslow);
-    if ((tid & 31) == 0 && nslow && a.slow_count) atomicAdd(a.slow_count, nslow);
 }
 
 }  // namespace oat

@@ -512,15 +512,13 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     }
 }
 
-// One launch: [erode] -> [dilate] -> row extents on bands of R rows (all CTAs), then the last CTA
-// labels.  Dynamic shared memory: max(morphology staging, a.smem_bytes).
-__global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
+// One band of R rows: [erode] -> [dilate] -> publish the rows (mask, extents, run counts, vertical bounding range).
+// Dynamic shared memory: 2 x (R + ke - 1 + kd - 1) rows of the mask.
+__device__ __forceinline__ void tail_band(const FastArgs &a, const int band, uint32_t *sm)
 {
-    extern __shared__ __align__(16) uint32_t sm[];
-    const uint32_t t_start = (uint32_t)clock64();
     const BitGeom g = a.g;
     const int wpr = g.wpr, rows = g.rows;
-    const int y0 = blockIdx.x * a.R, y1 = min(y0 + a.R, rows) - 1;
+    const int y0 = band * a.R, y1 = min(y0 + a.R, rows) - 1;
     const int ae = a.ke / 2, ad = a.kd / 2;
     const int e0 = max(a.kd > 0 ? y0 - ad : y0, 0), e1 = min(a.kd > 0 ? y1 - ad + a.kd - 1 : y1, rows - 1);
     const int i0 = max(a.ke > 0 ? e0 - ae : e0, 0), i1 = min(a.ke > 0 ? e1 - ae + a.ke - 1 : e1, rows - 1);
@@ -529,7 +527,7 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
     uint32_t any = 0;
     for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) {
         const int r = t / wpr, j = t % wpr;
-        const uint32_t w = a.in[(size_t)(i0 + r) * wpr + j] & g.valid_mask(j);
+        const uint32_t w = __ldcg(a.in + (size_t)(i0 + r) * wpr + j) & g.valid_mask(j);
         A[t] = w;
         any |= w;
     }
@@ -542,7 +540,8 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
             a.rowext[y] = make_int2(INT_MAX, -1);
             a.rowcnt[y] = make_int2(0, 0);
         }
-    } else {
+        return;
+    }
     if (a.ke > 0) {
         for (int t = threadIdx.x; t < nin * wpr; t += blockDim.x) B[t] = hpass_word<false>(A + (t / wpr) * wpr, t % wpr, g, a.ke);
         __syncthreads();
@@ -619,7 +618,15 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
         atomicMin(a.bbox, bymin);
         atomicMax(a.bbox + 1, bymax);
     }
-    }  // !band_empty
+}
+
+// One launch: [erode] -> [dilate] -> row extents on bands of R rows (all CTAs), then the last CTA
+// labels.  Dynamic shared memory: max(morphology staging, a.smem_bytes).
+__global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
+{
+    extern __shared__ __align__(16) uint32_t sm[];
+    const uint32_t t_start = (uint32_t)clock64();
+    tail_band(a, (int)blockIdx.x, sm);
     __shared__ bool s_last;
     __shared__ int s_ymin, s_ymax;
     __threadfence();
@@ -636,6 +643,77 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
     __syncthreads();
     if (!s_last) return;
     tail_label_phase(a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The resident tail server: ONE launch serves the detect tails of a whole queue of frames (the clip the
+// resident fused kernel, mog_pipe.cuh, is working through).  Per frame: wait until the fused kernel has
+// published every tile of the frame's threshold mask (done_count, release/acquire at GPU scope), then the
+// CTAs claim the frame's bands dynamically; the CTA that finishes the frame's last band labels it (~15 us)
+// while the others are already on the next frame.  Nothing is re-armed inside the launch -- a CTA that
+// comes back late from labelling finds a frame's band counter exhausted and moves on -- the per-launch
+// counters are zeroed by a memset the host puts in front of the launch.
+// ---------------------------------------------------------------------------------------------------
+struct TailFrame {
+    FastArgs a;                       // a.ticket is not used here
+    const unsigned int *done_count;   // or NULL: the frame's mask is ready when the launch starts
+    unsigned int done_target;         // the frame is complete when (int)(*done_count - done_target) >= 0
+    unsigned int pad;
+};
+
+__global__ void __launch_bounds__(256, 6) tail_stream_kernel(const TailFrame *frames, const int nframes,
+                                                             unsigned int *band_ctr /* [nframes], zeroed */,
+                                                             unsigned int *band_done /* [nframes], zeroed */)
+{
+    extern __shared__ __align__(16) uint32_t sm[];
+    __shared__ TailFrame s_tf;
+    __shared__ int s_band;
+    __shared__ bool s_last;
+    __shared__ int s_ymin, s_ymax;
+    for (int f = 0; f < nframes; ++f) {
+        __syncthreads();  // the previous frame's use of s_tf / s_band is over
+        for (int i = threadIdx.x; i < (int)(sizeof(TailFrame) / 4); i += blockDim.x)
+            reinterpret_cast<uint32_t *>(&s_tf)[i] = reinterpret_cast<const uint32_t *>(frames + f)[i];
+        __syncthreads();
+        const int nbands = (s_tf.a.g.rows + s_tf.a.R - 1) / s_tf.a.R;
+        if (threadIdx.x == 0) {
+            int b = (int)atomicAdd(band_ctr + f, 1u);
+            if (b < nbands && s_tf.done_count) {
+                // bounded: a fused kernel that died must surface as an error, not hang the GPU
+                unsigned spins = 0;
+                unsigned int v;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(s_tf.done_count) : "memory");
+                    if ((int)(v - s_tf.done_target) >= 0) break;
+                    __nanosleep(256);
+                    if (++spins > (1u << 24)) __trap();
+                }
+            }
+            s_band = b;
+        }
+        __syncthreads();
+        while (s_band < nbands) {
+            const uint32_t t_start = (uint32_t)clock64();
+            tail_band(s_tf.a, s_band, sm);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_last = (atomicAdd(band_done + f, 1u) == (unsigned)nbands - 1u);
+                if (s_last) {
+                    __threadfence();
+                    s_ymin = atomicExch(s_tf.a.bbox, INT_MAX);  // read + reset for the slot's next frame
+                    s_ymax = atomicExch(s_tf.a.bbox + 1, -1);
+                }
+                s_band = s_last ? nbands : (int)atomicAdd(band_ctr + f, 1u);
+            }
+            __syncthreads();
+            if (s_last) {
+                tail_label_phase(s_tf.a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start);
+                __syncthreads();
+                if (threadIdx.x == 0) s_last = false;
+            }
+        }
+    }
 }
 
 }  // namespace oat

@@ -75,60 +75,159 @@ def test_product_never_imports_the_oracle():
                 assert "oat_oracle" not in src and "orc_" not in src, f"{fn} references the oracle"
 
 
-def _simulate_draws(ntiles, grid, stages):
-    """The producer lane's scheduler loop of mog_pipe_kernel (csrc/mog_pipe.cuh: next_tile/refill), transcribed:
-    every CTA walks its static tiles first + seq*grid, draws once when it starts the last static one, and then
-    once more after every valid number; numbers are handed out in arrival order (here: round-robin over the CTAs
-    that are still drawing -- the COUNT does not depend on the order).  Returns (draws, tiles processed)."""
-    counter = 0
-    tiles = []
-    state = []  # per CTA: [seq, ahead, ended]
-    for b in range(grid):
-        seq, ahead, ended = 0, None, False
-        for k in range(stages):  # the initial refills
-            if ended:
-                break
-            t = b + seq * grid
-            if seq == stages - 1:
-                ahead = counter + stages * grid
-                counter += 1
-            seq += 1
-            if t >= ntiles:
-                ended = True
-            else:
-                tiles.append(t)
-        state.append([seq, ahead, ended])
-    live = [s for s in state if not s[2]]
-    while live:
-        nxt = []
-        for s in live:
-            t = s[1]
-            if t is None:          # never reached its last static tile: no number in hand -> nothing more to do
-                s[2] = True
-                continue
-            if t < ntiles:
-                tiles.append(t)
-                s[1] = counter + stages * grid
-                counter += 1
-                nxt.append(s)
-            else:
-                s[2] = True
-        live = nxt
-    return counter, tiles
+class _ResidentModel:
+    """A transcription of the resident fused kernel's scheduling protocol (oat_b200/csrc/mog_pipe.cuh,
+    mog_stream_kernel): every CTA has a producer lane and compute warps around a ring of `stages` stages;
+    work items (frame, tile) are drawn from one counter (the first `stages` of a CTA in one draw, then one at
+    a time); a tile of frame f+1 of a model may only be loaded once the same tile of the model's previous
+    frame has been PUBLISHED.  The producer lane alternates between (A) filling free stages in ring order
+    while the next item's predecessor is published and (C) retiring its oldest stage (wait for the compute
+    warps, publish the tile retired before, write this one back); with nothing to retire and the next item
+    blocked it publishes what it owes and waits.  The model is stepped by an adversarial (random) scheduler;
+    it checks that every item is processed exactly once, that no load ever precedes the publication it
+    depends on, and that the protocol cannot deadlock -- including frames smaller than one CTA's ring, where
+    a CTA's next item depends on a tile still sitting in its own stages."""
+
+    def __init__(self, nframes, ntiles, grid, stages, models, rng):
+        self.nf, self.nt, self.grid, self.S, self.rng = nframes, ntiles, grid, stages, rng
+        self.total = nframes * ntiles
+        self.model_of = [f % models for f in range(nframes)]      # frames of `models` streams interleaved
+        self.prev = {}                                            # frame -> previous frame of the same model
+        last = {}
+        for f in range(nframes):
+            self.prev[f] = last.get(self.model_of[f])
+            last[self.model_of[f]] = f
+        self.counter = 0
+        self.published = set()
+        self.loaded = []
+        self.exited = 0
+        self.ctas = [self._new_cta() for _ in range(grid)]
+
+    def _new_cta(self):
+        return {"pc": "start", "stage": [None] * self.S, "computed": [False] * self.S, "li": 0, "si": 0, "ci": 0,
+                "pend": None, "nxt": None, "batch": [], "ended": False, "cdone": False}
+
+    def _item(self, g):
+        return "END" if g >= self.total else (g // self.nt, g % self.nt)
+
+    def _ready(self, it):
+        p = self.prev[it[0]]
+        return p is None or (p, it[1]) in self.published
+
+    def _publish(self, c):
+        if c["pend"] is not None:
+            self.published.add(c["pend"])
+            c["pend"] = None
+
+    def _draw(self, c):
+        if c["batch"]:
+            return c["batch"].pop(0)
+        g = self.counter
+        self.counter += 1
+        return g
+
+    def step_producer(self, c):
+        """One atomic action of the producer lane; returns False if it is blocked."""
+        S = self.S
+        pc = c["pc"]
+        if pc == "start":
+            c["batch"] = [self.counter + k for k in range(1, S)]
+            c["nxt"] = self._item(self.counter)
+            self.counter += S
+            c["pc"] = "fill"
+            return True
+        if pc == "fill":  # A: fill free stages in ring order
+            if c["ended"] or c["li"] - c["si"] >= S:
+                c["pc"] = "retire"
+                return True
+            s = c["li"] % S
+            if c["nxt"] == "END":
+                c["stage"][s] = "END"
+                c["ended"] = True
+                c["pc"] = "retire"
+                return True
+            if not self._ready(c["nxt"]):
+                c["pc"] = "retire"
+                return True
+            it = c["nxt"]
+            assert self._ready(it)
+            self.loaded.append(it)
+            c["stage"][s] = it
+            c["computed"][s] = False
+            c["nxt"] = self._item(self._draw(c))
+            c["li"] += 1
+            return True
+        if pc == "retire":
+            if c["si"] == c["li"]:
+                if c["ended"]:
+                    c["pc"] = "drain"
+                    return True
+                self._publish(c)  # pay the debt before waiting for somebody else
+                if self._ready(c["nxt"]):
+                    c["pc"] = "fill"
+                    return True
+                return False
+            s = c["si"] % S
+            if not c["computed"][s]:
+                return False  # mbar_wait(done[s]): only this CTA's own compute warps are waited for
+            self._publish(c)            # the tile retired before
+            c["pend"] = c["stage"][s]   # this tile's stores are committed; its publication is owed
+            c["stage"][s] = None
+            c["si"] += 1
+            c["pc"] = "fill"
+            return True
+        if pc == "drain":
+            self._publish(c)
+            self.exited += 1
+            c["pc"] = "gone"
+            return True
+        return False
+
+    def step_compute(self, c):
+        s = c["ci"] % self.S
+        it = c["stage"][s]
+        if c["cdone"] or it is None or c["computed"][s] or c["ci"] >= c["li"] + (1 if c["ended"] else 0):
+            return False
+        if it == "END":
+            c["cdone"] = True
+            return True
+        c["computed"][s] = True
+        c["ci"] += 1
+        return True
+
+    def run(self, max_steps=10_000_000):
+        steps = 0
+        while self.exited < self.grid:
+            order = list(range(self.grid))
+            self.rng.shuffle(order)
+            progressed = False
+            for b in order:
+                c = self.ctas[b]
+                acts = [self.step_producer, self.step_compute]
+                self.rng.shuffle(acts)
+                for act in acts:
+                    if self.rng.random() < 0.7:  # an adversarial scheduler: some actors simply do not run this round
+                        progressed |= act(c)
+            if not progressed:
+                # nobody moved in a randomised round: give everybody a deterministic chance before calling it a deadlock
+                for c in self.ctas:
+                    progressed |= self.step_producer(c) | self.step_compute(c)
+                assert progressed, "deadlock: no CTA can make progress"
+            steps += 1
+            assert steps < max_steps
+        return self
 
 
-def test_tile_scheduler_draw_count_matches_kernel_logic():
-    """The host keeps the scheduler counters monotonic by knowing how many numbers each launch draws
-    (api.cu: pipe_draws).  Pin that formula against the kernel's loop for every frame size / grid shape class,
-    and check the loop hands out every tile exactly once."""
-    L = oat_b200.lib()
-    st = C.c_int()
-    L.oat_debug_pipe_draws(1, 1, C.byref(st))
-    S = st.value
-    assert S >= 2
-    cases = [(nt, g) for g in (1, 2, 3, 7, 148, 296, 592, 740) for nt in
-             (g, g + 1, 2 * g - 1, 2 * g, 2 * g + 1, S * g - 1, S * g, S * g + 1, S * g + 37, 7 * g, 2025, 4050, 8100, 16200) if nt >= g]
-    for ntiles, grid in cases:
-        draws, tiles = _simulate_draws(ntiles, grid, S)
-        assert sorted(tiles) == list(range(ntiles)), (ntiles, grid)
-        assert L.oat_debug_pipe_draws(ntiles, grid, None) == draws, (ntiles, grid, draws)
+def test_resident_scheduler_protocol_model():
+    """Pins the resident kernel's work distribution + publication protocol on the CPU (see _ResidentModel)."""
+    import random
+
+    rng = random.Random(1234)
+    S = 3
+    cases = [(1, 1, 1, 1), (1, 7, 3, 1), (4, 5, 8, 1), (6, 2, 8, 2), (8, 13, 5, 1), (16, 3, 7, 4), (5, 40, 6, 1),
+             (12, 9, 4, 3), (3, 1, 5, 1), (20, 2, 3, 2), (9, 1, 1, 1), (30, 2, 1, 1), (10, 4, 2, 2), (64, 75, 16, 1)]
+    for nframes, ntiles, grid, models in cases:
+        for rep in range(3):
+            m = _ResidentModel(nframes, ntiles, grid, S, models, rng).run()
+            assert sorted(m.loaded) == [(f, t) for f in range(nframes) for t in range(ntiles)], (nframes, ntiles, grid)
+            assert len(m.published) == nframes * ntiles

@@ -1,0 +1,282 @@
+"""The resident clip engine (oat_tracker_run_clip / oat_tracker_run_clips on device-resident frames): ONE launch of
+the fused kernel + ONE launch of the tail server per chunk of frames, frame-to-frame ordering tile by tile on
+the device.  Everything it produces -- detections, filtered positions, the whole GMM state -- must be bit-identical
+to the frame-by-frame synchronous path (which tests/test_gpu_tracker.py pins to the oracle), for every geometry
+class, for frames smaller than one CTA's pipeline, across chunk and launch boundaries, and over long runs."""
+import numpy as np
+import pytest
+
+import oat_b200
+import oracle
+
+pytestmark = pytest.mark.gpu
+HSV_BAND = dict(h=(40, 80), s=(100, 256), v=(100, 256))
+TOL = 1e-6
+
+
+def _det(d):
+    return (d.position_valid, d.n_components, d.x, d.y, d.area)
+
+
+def _frames(ctx, rows, cols, seed, n, pitch=None):
+    """n synthetic frames of one stream in device memory (t = 0..n-1); pitch: row pitch in bytes (default tight)."""
+    bufs = []
+    for t in range(n):
+        if pitch is None:
+            b = ctx.alloc(rows * cols * 3)
+            ctx.synth_frame(rows, cols, seed, t, out=b)
+        else:
+            f = oracle.synth_frame(rows, cols, seed, t)
+            padded = np.zeros((rows, pitch), np.uint8)
+            padded[:, :cols * 3] = f.reshape(rows, cols * 3)
+            b = ctx.alloc(rows * pitch)
+            b.upload(padded)
+        bufs.append(b)
+    return bufs
+
+
+def _state_equal(a, b):
+    for x, y in zip(a.state(), b.state()):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+
+
+@pytest.mark.parametrize("shape", [(120, 160), (240, 320), (64, 64), (20, 32), (480, 640)])
+@pytest.mark.parametrize("lr", [0.0, 0.02])
+@pytest.mark.parametrize("ring", [2, 8, 64])
+def test_clip_engine_equals_frame_by_frame(ctx, shape, lr, ring):
+    """Small frames: fewer tiles than CTAs, frames smaller than one CTA's ring of stages (a CTA's next tile depends on a
+    tile in its own pipeline), chunks of 1 / 4 / 32 frames."""
+    rows, cols = shape
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    n = 41
+    bufs = _frames(ctx, rows, cols, 1000, n)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=ring)
+    got = [_det(d) for d in a.run_clip(bufs, depth=4)]
+    assert a.tail_stats()["clip_frames"] == n - 1, "the resident engine did not take the clip"
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    want = [_det(b.track(f)[0]) for f in bufs]
+    assert got == want
+    _state_equal(a, b)
+    # and against the oracle directly
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t in range(n):
+        o, _ = orc.track(oracle.synth_frame(rows, cols, 1000, t), lr, op)
+        d = got[t]
+        assert bool(d[0]) == bool(o.position_valid) and d[1] == o.n_components
+        assert abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
+    assert a.live_modes() == int(orc.mog.state()[0].sum())
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("cols", [80, 144, 1008])
+def test_clip_engine_ragged_widths(ctx, cols):
+    """cols % 32 != 0 with 16-byte aligned rows: the producer lane stages the BGR bytes with one bulk copy per row
+    segment (no per-thread loads), dynamic scheduler and all."""
+    rows, lr, n = 90, 0.03, 19
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    assert (3 * cols) % 16 == 0 and cols % 32 != 0
+    bufs = _frames(ctx, rows, cols, 1003, n)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=8)
+    got = [_det(d) for d in a.run_clip(bufs, depth=4)]
+    assert a.tail_stats()["clip_frames"] == n - 1
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t in range(n):
+        o, _ = orc.track(oracle.synth_frame(rows, cols, 1003, t), lr, op)
+        d = got[t]
+        assert bool(d[0]) == bool(o.position_valid) and d[1] == o.n_components
+        assert abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
+    om, ow, ov, omu = orc.mog.state()
+    gm, gw, gv, gmu = a.state()
+    assert np.array_equal(gm, om)
+    live = np.arange(gw.shape[2])[None, None, :] < om[:, :, None]
+    assert np.array_equal(gw.view(np.uint32)[live], ow.view(np.uint32)[live])
+    assert np.array_equal(gv.view(np.uint32)[live], ov.view(np.uint32)[live])
+    a.close()
+
+
+@pytest.mark.parametrize("cols,pitch", [(100, 304), (1000, 3008), (68, 208)])
+def test_pitched_frames_take_the_staged_kernel(ctx, cols, pitch):
+    """Row pitch > 3*cols (what host frames become in the staging buffer, and what a 1000-column frame needs to have
+    16-byte aligned rows): egress, masks and state against the oracle, frame by frame."""
+    rows, lr = 75, 0.02
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    trk = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t in range(12):
+        f = oracle.synth_frame(rows, cols, 1000, t)
+        d, eg = trk.track(f, egress=("bgr", "fgmask", "hsv", "thresh"))  # host frame: staged with a 16-byte aligned pitch
+        o, oeg = orc.track(f, lr, op)
+        for k in ("fgmask", "bgr", "hsv", "thresh"):
+            assert np.array_equal(eg[k], oeg[k]), f"{k} differs at t={t}"
+        assert _det(d)[:2] == (o.position_valid, o.n_components)
+        assert abs(d.x - o.x) <= TOL and abs(d.y - o.y) <= TOL and abs(d.area - o.area) <= TOL
+    trk.close()
+    # the same stream as a pitched device-resident clip through the resident engine
+    bufs = _frames(ctx, rows, cols, 1000, 12, pitch=pitch)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=8)
+    ptrs = oat_b200.frame_pointers(bufs)
+    import ctypes as C
+    out = (oat_b200.Detection * 12)()
+    oat_b200._ck(oat_b200.lib().oat_tracker_run_clip(a._h, ptrs, 12, pitch, lr, C.byref(a.hsv), 4, out, None))
+    orc = oracle.Tracker(rows, cols)
+    for t in range(12):
+        o, _ = orc.track(oracle.synth_frame(rows, cols, 1000, t), lr, op)
+        assert bool(out[t].position_valid) == bool(o.position_valid)
+        assert abs(out[t].x - o.x) <= TOL and abs(out[t].y - o.y) <= TOL and abs(out[t].area - o.area) <= TOL
+    assert a.tail_stats()["clip_frames"] == 11
+    a.close()
+
+
+def test_clip_engine_soak_1080p(ctx):
+    """The benchmark's own configuration, long: 2000 frames 1080p, -a 0.01, chunks of 32 frames (62 chunk boundaries,
+    every one of them overlapped tile by tile with its predecessor) against the synchronous frame-by-frame path:
+    every detection and the whole GMM state bit-identical."""
+    rows, cols, lr, n = 1080, 1920, 0.01, 2000
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    R = 24
+    bufs = _frames(ctx, rows, cols, 1000, R + 1)
+    seq = [bufs[0]] + [bufs[1 + i % R] for i in range(n - 1)]
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=64)
+    got = [_det(d) for d in a.run_clip(seq)]
+    assert a.tail_stats()["clip_frames"] == n - 1
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    want = [_det(b.track(f)[0]) for f in seq]
+    assert got == want
+    assert a.live_modes() == b.live_modes()
+    _state_equal(a, b)
+    a.close()
+    b.close()
+
+
+def test_clip_engine_interleaved_streams(ctx):
+    """Three independent 1080p streams interleaved in ONE queue (oat_tracker_run_clips), 400 frames each: per-stream
+    detections and state equal each stream's own synchronous run; then the same again continuing on the per-frame
+    path (a resident launch followed by chained single-frame launches)."""
+    rows, cols, lr, n, S = 1080, 1920, 0.02, 400, 3
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    R = 10
+    bufs = [_frames(ctx, rows, cols, 1000 + s, R + 1) for s in range(S)]
+    seqs = [[bufs[s][0]] + [bufs[s][1 + i % R] for i in range(n - 1)] for s in range(S)]
+    trks = [oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=16) for _ in range(S)]
+    for s in range(S):  # the first frame of every model goes frame by frame
+        trks[s].submit(seqs[s][0])
+        trks[s].collect()
+    got = oat_b200.Tracker.run_clips(trks, [[seqs[s][i] for s in range(S)] for i in range(1, n)])
+    assert all(t.tail_stats()["clip_frames"] == n - 1 for t in trks)
+    tails = [[] for _ in range(S)]
+    for i in range(5):  # ... and a few more frames through submit/collect, chained to the resident launch
+        for s in range(S):
+            trks[s].submit(seqs[s][1 + i])
+        for s in range(S):
+            tails[s].append(_det(trks[s].collect()))
+    for s in range(S):
+        ref = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+        want = [_det(ref.track(f)[0]) for f in seqs[s]]
+        assert [_det(got[i][s]) for i in range(n - 1)] == want[1:], s
+        want_tail = [_det(ref.track(seqs[s][1 + i])[0]) for i in range(5)]
+        assert tails[s] == want_tail, s
+        _state_equal(trks[s], ref)
+        ref.close()
+        trks[s].close()
+
+
+def test_clip_engine_fused_only_advances_the_model_identically(ctx):
+    rows, cols, lr, n, S = 480, 640, 0.05, 30, 2
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    bufs = [_frames(ctx, rows, cols, 1000 + s, n) for s in range(S)]
+    trks = [oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=8) for _ in range(S)]
+    for s in range(S):
+        trks[s].submit(bufs[s][0])
+        trks[s].collect()
+    assert oat_b200.Tracker.run_clips(trks, [[bufs[s][i] for s in range(S)] for i in range(1, n)], fused_only=True) is None
+    for s in range(S):
+        ref = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+        for f in bufs[s]:
+            ref.track(f)
+        _state_equal(trks[s], ref)
+        # the tracker is usable afterwards
+        assert _det(trks[s].track(bufs[s][3])[0]) == _det(ref.track(bufs[s][3])[0])
+        ref.close()
+        trks[s].close()
+
+
+def test_clip_engine_with_position_filter(ctx):
+    rows, cols, lr, n = 240, 320, 0.01, 40
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    kal = dict(dt=1 / 30, timeout=0.3, sigma_accel=20.0, sigma_noise=0.5)
+    bufs = _frames(ctx, rows, cols, 1000, n)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=16)
+    pa = oat_b200.PositionFilter(ctx, 1, kal)
+    a.attach_posfilt(pa)
+    dets, poss = a.run_clip(bufs, positions=True)
+    assert a.tail_stats()["clip_frames"] == n - 1
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=2)
+    pb = oat_b200.PositionFilter(ctx, 1, kal)
+    b.attach_posfilt(pb)
+    for t in range(n):
+        b.submit(bufs[t])
+        d, p = b.collect_position()
+        assert _det(d) == _det(dets[t])
+        q = poss[t]
+        assert (p.position_valid, p.x, p.y, p.vx, p.vy) == (q.position_valid, q.x, q.y, q.vx, q.vy), t
+    for trk, f in ((a, pa), (b, pb)):
+        trk.attach_posfilt(None)
+        f.close()
+        trk.close()
+
+
+def test_clip_engine_overflowing_masks_are_replayed(ctx):
+    """A band that passes everything on a noisy stream: the threshold mask is the (speckled) foreground mask, far more
+    runs than the one-launch tail's table holds.  Those frames are replayed through the unbounded path after their
+    chunk; detections must still equal the synchronous path."""
+    from test_gpu_mog import noisy_stream
+
+    rows, cols, lr, n = 480, 640, 0.05, 20
+    hp = oat_b200.HsvParams.make(h=(0, 256), s=(0, 256), v=(1, 256), dilate=0)
+    host = list(noisy_stream(rows, cols, n, 15.0, seed=3))
+    bufs = []
+    for f in host:
+        b = ctx.alloc(rows * cols * 3)
+        b.upload(f)
+        bufs.append(b)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=8)
+    got = [_det(d) for d in a.run_clip(bufs)]
+    st = a.tail_stats()
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    want = [_det(b.track(f)[0]) for f in bufs]
+    assert got == want
+    assert st["clip_frames"] > 0 and st["replays"] > 0, st
+    _state_equal(a, b)
+    a.close()
+    b.close()
+
+
+def test_clip_engine_hands_over_to_generic_kernel_on_busy_stream(ctx):
+    """The census still drives the kernel choice: a stream that leaves the fast path on most pixels leaves the resident
+    engine after the chunk that noticed, and the rest of the clip runs frame by frame on the generic kernel."""
+    from test_gpu_mog import noisy_stream
+
+    rows, cols, lr, n = 96, 128, 0.3, 60
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    host = list(noisy_stream(rows, cols, n, 20.0, seed=7))
+    bufs = []
+    for f in host:
+        b = ctx.alloc(rows * cols * 3)
+        b.upload(f)
+        bufs.append(b)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=8)
+    got = [_det(d) for d in a.run_clip(bufs)]
+    st = a.tail_stats()
+    assert st["generic_frames"] > 0 and 0 < st["clip_frames"] < n - 1, st
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t in range(n):
+        o, _ = orc.track(host[t], lr, op)
+        d = got[t]
+        assert bool(d[0]) == bool(o.position_valid) and abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
+    assert a.live_modes() == int(orc.mog.state()[0].sum())
+    a.close()
