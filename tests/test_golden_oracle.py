@@ -70,3 +70,30 @@ def test_bsub():
     b = oracle.Bsub(40, 56, 3, 0.0)
     for t, f in enumerate(inputs.bsub_frames()):
         assert np.array_equal(b.apply(f), G["bsub_a0"][t])
+
+
+# ---- full size: the C restatement against the cv2 pins of the headline configurations -------------------
+FULLSIZE = {"1080p_a001": (1080, 1920, 24, 0.01), "1080p_a0": (1080, 1920, 12, 0.0), "4k_a001": (2160, 3840, 5, 0.01)}
+
+
+@pytest.mark.parametrize("name", list(FULLSIZE))
+def test_oracle_matches_cv2_pins_at_full_size(name):
+    """tests/golden/golden_fullsize.npz (cv2, the reference's call sequence, 1080p / 4K): the oracle reproduces the first
+    frames' foreground mask, HSV frame, threshold mask (CRC32) and detection -- so the GPU-vs-oracle parity tests at
+    full size stand on a pinned oracle."""
+    import os
+    import zlib
+
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_fullsize.npz"))
+    rows, cols, n, lr = FULLSIZE[name]
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**inputs.HSV_BAND)
+    for t in range(n):
+        d, eg = orc.track(inputs.synth_frame(rows, cols, inputs.SEED, t), lr, op)
+        want = G2[f"{name}_crc"][t]
+        assert zlib.crc32(np.ascontiguousarray(eg["fgmask"]).tobytes()) == want[0], t
+        assert zlib.crc32(np.ascontiguousarray(eg["hsv"]).tobytes()) == want[1], t
+        assert zlib.crc32(np.ascontiguousarray(eg["thresh"]).tobytes()) == want[2], t
+        valid, x, y, area = G2[f"{name}_det"][t]
+        assert bool(d.position_valid) == bool(valid)
+        assert abs(d.x - x) <= 1e-6 and abs(d.y - y) <= 1e-6 and abs(d.area - area) <= 1e-6
