@@ -148,7 +148,7 @@ struct oat_ctx {
     // model whose full-grid resident fused kernel was the LAST kernel enqueued on `stream` (0 = none): the
     // next launch may order itself behind it tile by tile instead of waiting for the whole grid
     unsigned long long chain_uid = 0;
-    bool no_chain = false, no_mirror = false, no_track = false, no_clip = false, relaxed_publish = false;
+    bool no_chain = false, no_mirror = false, no_track = false, no_clip = false, relaxed_publish = false, fence_always = false;
     uint64_t pipe_launches = 0;
     cudaStream_t aux = nullptr;  // small host-synchronous uploads (frame descriptors of a clip)
     ClipHalf clip[2];            // two chunks of the resident clip engine in flight
@@ -210,7 +210,8 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->no_mirror = getenv("OAT_B200_NO_MIRROR") != nullptr;
     c->no_track = getenv("OAT_B200_NO_TRACK") != nullptr;
     c->no_clip = getenv("OAT_B200_NO_CLIP") != nullptr;
-    c->relaxed_publish = getenv("OAT_B200_RELAXED_PUBLISH") != nullptr;  // measurement only: prices the release fence
+    c->relaxed_publish = getenv("OAT_B200_RELAXED_PUBLISH") != nullptr;  // measurement only: prices the release fences
+    c->fence_always = getenv("OAT_B200_FENCE_ALWAYS") != nullptr;        // measurement only: a fence for every tile
     CK(cudaSetDevice(device_index));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
@@ -550,7 +551,13 @@ static int pipe_class(const MogModel &m, const FusedArgs &a)
 
 // One launch of the resident fused kernel over `pa.nframes` frames (descriptors in pa.descs, or pa.one).
 // Fills in the scheduler slot; commits the host bookkeeping only once the launch call has succeeded.
-static int launch_stream(oat_ctx *c, StreamArgs &pa, bool frozen, bool linear)
+static int pipe_grid_full(const oat_ctx *c, bool beside_tail)
+{
+    const int g = PIPE_CTAS_PER_SM * c->num_sms - (beside_tail ? PIPE_RESERVED_CTAS_CFG : 0);
+    return g > 0 ? g : 1;
+}
+
+static int launch_stream(oat_ctx *c, StreamArgs &pa, bool frozen, bool linear, bool beside_tail)
 {
     if (!c->pipe_attr_set) {
         CK(cudaFuncSetAttribute(mog_stream_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
@@ -561,7 +568,7 @@ static int launch_stream(oat_ctx *c, StreamArgs &pa, bool frozen, bool linear)
     }
     const long long total = (long long)pa.ntiles * pa.nframes;
     REQUIRE(total > 0 && total < (1ll << 30), "resident fused kernel: bad work size");
-    const int full = PIPE_CTAS_PER_SM * c->num_sms;
+    const int full = pipe_grid_full(c, beside_tail);
     const int grid = total < full ? (int)total : full;
     unsigned slot = 0;
     CKRET(acquire_slot(c, &slot));
@@ -570,6 +577,7 @@ static int launch_stream(oat_ctx *c, StreamArgs &pa, bool frozen, bool linear)
     pa.done_flag = c->done_dev + slot;
     pa.launch_id = (unsigned)(c->pipe_launches + 1);
     pa.relaxed_publish = c->relaxed_publish ? 1 : 0;
+    pa.fence_always = c->fence_always ? 1 : 0;
     if (pa.launch_id == 0u) pa.launch_id = 1u;  // 0 means "never used"
     // programmatic dependent launch: the next launch's CTAs become resident (and run their prologue: mbarrier
     // + queue initialisation, first draw) while this launch's last CTAs drain
@@ -619,7 +627,8 @@ static void stream_args_common(oat_ctx *c, const MogModel &m, const FusedArgs &a
     pa.wait_grid = 1;
 }
 
-static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true, bool allow_chain = false)
+static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe = true, bool allow_chain = false,
+                        bool beside_tail = false)
 {
     a.rows = m.g.rows;
     a.cols = m.g.cols;
@@ -640,7 +649,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         // steady state: the resident bulk-async staged kernel (mog_pipe.cuh), here over a queue of one frame
         StreamArgs pa;
         stream_args_common(c, m, a, pa);
-        const bool full = (long long)pa.ntiles >= (long long)PIPE_CTAS_PER_SM * c->num_sms;
+        const bool full = (long long)pa.ntiles >= (long long)pipe_grid_full(c, beside_tail);
         // order the frame behind the previous launch tile by tile (not grid by grid) when that launch was the
         // resident kernel too, it is the last kernel on the stream, both grids fill the machine, and this model's
         // tile flags are current (its own last launch was the resident kernel; the predecessor on the stream may
@@ -657,7 +666,7 @@ static int launch_fused(oat_ctx *c, MogModel &m, FusedArgs &a, bool allow_pipe =
         one.seq_expect = m.seq;
         one.flags = chain ? FD_CHAIN : 0u;
         pa.wait_grid = chain ? 0 : 1;
-        const int r = launch_stream(c, pa, frozen, cls == 2);
+        const int r = launch_stream(c, pa, frozen, cls == 2, beside_tail);
         if (r != OAT_OK) {  // nothing was enqueued: the model's sequence numbers and flags stand as they were
             c->chain_uid = 0;
             return r;
@@ -1742,7 +1751,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     // tile-granular chaining to the previous frame's launch: only when nothing but this stream's own
     // kernels order the frame (device-resident input, no egress buffers that a copy still reads)
     const bool chainable = mem_kind(bgr_in) == MEM_DEVICE && !ob.d && !ofg.d && !ohsv.d && !othr.d && !t->prof;
-    CKRET(launch_fused(c, t->m, a, !t->use_generic, chainable));
+    CKRET(launch_fused(c, t->m, a, !t->use_generic, chainable, true));
     const unsigned long long chain_after_fused = c->chain_uid;
     if (t->prof) {
         CK(cudaEventRecord(e1, c->stream));
@@ -2059,7 +2068,7 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
         }
         if (cnt == 0) return OAT_OK;
         CKRET(half[h].ensure(chunkF * (size_t)S));
-        const bool full = (long long)ntiles * (long long)(cnt * S) >= (long long)PIPE_CTAS_PER_SM * c->num_sms;
+        const bool full = (long long)ntiles * (long long)(cnt * S) >= (long long)pipe_grid_full(c, !fused_only);
         bool chain_launch = c->pdl && !c->no_chain && c->chain_uid != 0 && full;
         for (int s = 0; s < S; ++s) chain_launch = chain_launch && trk[s]->m.flags_current;
         FusedArgs a{};
@@ -2143,7 +2152,7 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
         if (inline_descs) memcpy(pa.inl, half[h].h_desc, nitems * sizeof(FrameDesc));
         pa.wait_grid = chain_launch ? 0 : 1;
         const bool frozen = (a.c.aT == 0.0f) && !c->no_track;
-        CKRET(launch_stream(c, pa, frozen, class_all == 2));
+        CKRET(launch_stream(c, pa, frozen, class_all == 2, !fused_only));
         for (int s = 0; s < S; ++s) trk[s]->m.flags_current = true;
         c->chain_uid = full ? t0->m.uid : 0;
         if (!fused_only) {
@@ -2151,7 +2160,7 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
             CK(cudaMemcpyAsync(half[h].d_tf, half[h].h_tf, nitems * sizeof(TailFrame), cudaMemcpyHostToDevice, ts));
             CK(cudaMemsetAsync(half[h].d_ctr, 0, 2 * nitems * sizeof(unsigned int), ts));
             const int nbands = div_up(g.rows, R);
-            const int gridT = std::max(1, std::min(nbands, c->num_sms / 2));
+            const int gridT = std::max(1, std::min(nbands, (int)PIPE_TAIL_GRID_CFG));
             tail_stream_kernel<<<gridT, 256, tail_smem, ts>>>(half[h].d_tf, (int)nitems, half[h].d_ctr, half[h].d_ctr + nitems);
             ++c->launches;
             CK(cudaGetLastError());

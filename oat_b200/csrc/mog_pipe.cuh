@@ -34,13 +34,22 @@ namespace oat {
 #define PIPE_CTHREADS_CFG 256
 #endif
 #ifndef PIPE_STAGES_CFG
-#define PIPE_STAGES_CFG 3
+#define PIPE_STAGES_CFG 4
+#endif
+// Launches that run next to a detect tail (the resident tail server, or per-frame tail kernels) leave this many CTA
+// slots of the persistent grid unused: the SMs that then hold one fused CTA instead of two are where the tail's
+// CTAs find room (two fused CTAs fill an SM's shared memory and registers).
+#ifndef PIPE_RESERVED_CTAS_CFG
+#define PIPE_RESERVED_CTAS_CFG 24
+#endif
+#ifndef PIPE_TAIL_GRID_CFG
+#define PIPE_TAIL_GRID_CFG 48   // CTAs of the resident tail server (two fit beside one fused CTA)
 #endif
 #ifndef PIPE_MINBLOCKS_CFG
 #define PIPE_MINBLOCKS_CFG 2
 #endif
 constexpr int PIPE_CTHREADS = PIPE_CTHREADS_CFG;    // compute threads (8 warps), 4 pixels each
-constexpr int PIPE_THREADS = PIPE_CTHREADS + 32;     // + one producer warp (bulk loads / stores)
+constexpr int PIPE_THREADS = PIPE_CTHREADS + 64;     // + a loader warp (bulk loads) and a storer warp (write-back + publication)
 constexpr int PIPE_TILE = PIPE_CTHREADS * 4;        // pixels per tile
 constexpr int PIPE_STAGES = PIPE_STAGES_CFG;
 #ifndef PIPE_CTAS_PER_SM_CFG
@@ -69,6 +78,7 @@ enum {
     HDR_TSEQ = 12,
     HDR_SLOW = 14,
     HDR_DONE = 16,
+    HDR_DIRECT = 18,  // some compute thread wrote GMM state of this tile with direct global stores (modes >= 1)
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (sm_90+; SASS UBLKCP / SYNCS) ----------------
@@ -101,6 +111,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
         "}\n" ::"r"(smem_u32(b)),
         "r"(parity)
         : "memory");
+}
+// one bounded attempt: true once the phase has completed, false after roughly `ns` nanoseconds without it
+__device__ __forceinline__ bool mbar_try_wait_ns(uint64_t *b, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0u;
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
@@ -197,7 +222,8 @@ struct StreamArgs {
     unsigned int *exit_ticket;
     unsigned int *done_flag;       // pinned host word of the slot: the last CTA to leave stores launch_id there
     unsigned int launch_id;
-    int relaxed_publish;           // measurement switch ONLY (OAT_B200_RELAXED_PUBLISH): publish without the release fence, to price it
+    int relaxed_publish;           // measurement switch ONLY (OAT_B200_RELAXED_PUBLISH): never fence, to price the fences
+    int fence_always;              // measurement switch ONLY (OAT_B200_FENCE_ALWAYS): fence every tile
 };
 
 // One pixel with one or two live modes whose sample fits mode 0 (the heavier one): the m = 0
@@ -368,6 +394,7 @@ __device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, u
         sm0[3 * PIPE_TILE] = B[0];
         sm0[4 * PIPE_TILE] = C[0];
         *smn = (uint8_t)n;
+        if (nw > 1) *reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG + 4 * HDR_DIRECT) = 1u;
 #pragma unroll 1
         for (int m = 1; m < nw; ++m) {
             float *g = state + (size_t)(m * 5) * a.plane + pidx;
@@ -408,52 +435,68 @@ __device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, u
 // ---------------------------------------------------------------------------------------------------
 // The resident fused kernel.
 //
-// Roles inside a CTA: PIPE_CTHREADS compute threads + ONE producer lane that drives the bulk-copy engine in
-// both directions (loads of the next tiles, write-back + publication of the finished ones).
+// Roles inside a CTA: PIPE_CTHREADS compute threads, a LOADER lane (draws work, waits for the tile's previous
+// frame, issues the bulk loads) and a STORER lane (writes finished tiles back with bulk stores and publishes
+// them), each in a warp of its own, around a ring of PIPE_STAGES stages:
+//
+//     loader --full[s]--> compute warps --done[s]--> storer --freed[s]--> loader
 //
 // Ordering of a tile between the frame that wrote it (any CTA, this launch or the previous one) and the frame
 // that reads it next -- a release/acquire pair at GPU scope, correct under the PTX memory model:
-//   writer   compute warps' direct stores (modes >= 1)  --mbarrier done[s] (release.cta / acquire.cta)-->  producer lane;
+//   writer   compute warps' direct stores (modes >= 1)  --mbarrier done[s] (release.cta / acquire.cta)-->  storer lane;
 //            the tile's bulk stores are COMPLETE (cp.async.bulk.wait_group, not .read);
-//            fence.acq_rel.gpu  (cumulative: covers what the producer lane observed through the mbarrier);
+//            if the tile had direct stores (HDR_DIRECT, a few % of the tiles): fence.acq_rel.gpu  (cumulative:
+//            covers what the storer lane observed through the mbarrier);
 //            st.relaxed.gpu tile_seq[tile]  (+ red.add done_count for the tail server)
-//   reader   ld.acquire.gpu tile_seq[tile] == seq_expect;  fence.proxy.async.global;  bulk loads;
+//   reader   loader lane: ld.acquire.gpu tile_seq[tile] == seq_expect;  fence.proxy.async.global;  bulk loads;
 //            the compute warps' own ld.global.cg follow the mbarrier full[s] the loads complete on.
-// The fence is issued when nothing of this lane is in flight except loads it started a tile period earlier:
-// right after done[s], BEFORE the tile's stores and the refill's loads (a MEMBAR.GPU also waits for the
-// issuing lane's outstanding bulk copies; r01 measured +0.6 us per tile with the fence behind the refill).
+// The release fence is a MEMBAR.GPU: a round trip through a memory system that this kernel keeps saturated.  It
+// lives in the storer lane, where it delays nothing but the next write-back, and is issued only for tiles whose
+// state was (also) written by the compute warps' direct stores; tiles written by bulk stores alone -- 95 % and
+// more -- are published behind the COMPLETION of those stores.  (Fence on every tile: 0.71 of the HBM peak with one
+// lane doing loads and stores, 0.83 with it in the storer lane; as built: see profiles/.)
+// The storer publishes a tile when it comes back for the next one (its stores have had a tile period to
+// complete), or after a bounded wait if nothing comes -- so a tile is never withheld from a CTA that waits for it.
 //
 // LINEAR: cols % 32 == 0 and every image pitch is tight, so a pixel's byte offsets are plain multiples of its
-// padded index (one bulk copy brings a tile's BGR bytes).  Otherwise the producer lane issues one bulk copy
+// padded index (one bulk copy brings a tile's BGR bytes).  Otherwise the loader lane issues one bulk copy
 // per row segment of the tile (rows start 16-byte aligned: the host checks pointer and pitch), landing the
 // bytes at the same place, 3 * (pixel in tile); padding pixels are never evaluated.
 // ---------------------------------------------------------------------------------------------------
+#ifdef PIPE_MAXNREG_CFG
+#define PIPE_KERNEL_BOUNDS __maxnreg__(PIPE_MAXNREG_CFG)
+#else
+#define PIPE_KERNEL_BOUNDS __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG)
+#endif
 template <int K, bool TRACK, bool LINEAR>
-__global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_kernel(const __grid_constant__ StreamArgs pa)
+__global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ StreamArgs pa)
 {
     extern __shared__ __align__(128) uint8_t stage_mem[];
-    __shared__ __align__(8) uint64_t full[PIPE_STAGES];  // stage loaded (expect_tx of the producer lane) or end marker
-    __shared__ __align__(8) uint64_t done[PIPE_STAGES];  // stage updated in place by all compute threads
+    __shared__ __align__(8) uint64_t full[PIPE_STAGES];   // stage loaded (expect_tx of the loader lane) or end marker
+    __shared__ __align__(8) uint64_t done[PIPE_STAGES];   // stage updated in place by all compute threads
+    __shared__ __align__(8) uint64_t freed[PIPE_STAGES];  // stage written back (its bulk stores have read it)
     const FusedArgs &a = pa.f;
     const int tid = threadIdx.x;
-    const bool is_producer = (tid == PIPE_CTHREADS);
+    const bool is_loader = (tid == PIPE_CTHREADS), is_storer = (tid == PIPE_CTHREADS + 32);
     // let the next launch on this stream (programmatic dependent launch) become resident as CTAs of
     // this one retire; it either parks in griddepcontrol.wait below or orders itself tile by tile
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // the scheduler's first answer (PIPE_STAGES consecutive items) travels while the CTA initialises
     uint32_t raw0 = 0;
-    if (is_producer) raw0 = atomicAdd(pa.work_counter, (unsigned)PIPE_STAGES);
+    if (is_loader) raw0 = atomicAdd(pa.work_counter, (unsigned)PIPE_STAGES);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < PIPE_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&done[s], PIPE_CTHREADS);
+            mbar_init(&freed[s], 1);
         }
         fence_mbar_init();
     }
     for (int s = 0; s < PIPE_STAGES; ++s) {
         uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
         if (tid < 4) reinterpret_cast<uint32_t *>(st + PIPE_OFF_FLAG)[tid] = 0u;  // dirty, tile, queue count, queue head
+        if (tid == 4) reinterpret_cast<uint32_t *>(st + PIPE_OFF_FLAG)[HDR_DIRECT] = 0u;
         for (int i = tid; i < PIPE_TILE; i += PIPE_THREADS) reinterpret_cast<uint16_t *>(st + PIPE_OFF_QUEUE)[i] = 0xffffu;
     }
     __syncthreads();
@@ -464,165 +507,144 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
     auto hdr_of = [&](int s) -> volatile uint32_t * {
         return reinterpret_cast<volatile uint32_t *>(stage_mem + (size_t)s * PIPE_STAGE_BYTES + PIPE_OFF_FLAG);
     };
+    auto hdr_ptr = [&](volatile uint32_t *h, int word) -> void *volatile * {
+        return reinterpret_cast<void *volatile *>(const_cast<uint32_t *>(h + word));
+    };
+    auto tile_span = [&](int tile, size_t &p0, uint32_t &npx) {
+        p0 = (size_t)tile * PIPE_TILE;
+        const size_t rem = a.plane - p0;
+        npx = rem < (size_t)PIPE_TILE ? (uint32_t)rem : (uint32_t)PIPE_TILE;
+    };
 
     if (tid >= PIPE_CTHREADS) {
-        // ---- producer warp: one lane drives the bulk-copy engine -------------------------------
-        if (!is_producer) return;
-        const uint64_t pol_first = l2_policy_evict_first();
-        const uint32_t total = (uint32_t)pa.nframes * (uint32_t)pa.ntiles;
-        const unsigned pitch_px = (unsigned)a.wpr * 32u;
-
-        // a drawn work item, resolved against its frame's descriptor
-        struct Item {
-            int tile;  // -1: the queue is exhausted
-            int frame;
-            const uint8_t *bgr;
-            float *state;
-            uint8_t *nmodes;
-            uint32_t *thr;
-            unsigned int *tseq, *slow, *donec;
-            uint32_t seq, flags, seen;
-        };
-        int dframe = -1;   // descriptor cache (draws are monotonic: the frame index never goes back)
-        FrameDesc dcur;
-        uint32_t fbase = 0;  // first work number of frame `dframe_pos`
-        int fpos = 0;
-        auto resolve = [&](uint32_t g, Item &it) {
-            if (g >= total) {
-                it.tile = -1;
-                return;
-            }
-            while (g >= fbase + (uint32_t)pa.ntiles) {
-                fbase += (uint32_t)pa.ntiles;
-                ++fpos;
-            }
-            if (fpos != dframe) {
-                const FrameDesc *dp = pa.descs ? pa.descs + fpos : &pa.inl[fpos];
-                const uint4 *q = reinterpret_cast<const uint4 *>(dp);
-                uint4 *w = reinterpret_cast<uint4 *>(&dcur);
-                w[0] = q[0];
-                w[1] = q[1];
-                w[2] = q[2];
-                w[3] = q[3];
-                dframe = fpos;
-            }
-            it.tile = (int)(g - fbase);
-            it.frame = fpos;
-            it.bgr = dcur.bgr;
-            it.state = dcur.state;
-            it.nmodes = dcur.nmodes;
-            it.thr = dcur.thr_bits;
-            it.tseq = dcur.tile_seq;
-            it.slow = dcur.slow_count;
-            it.donec = dcur.done_count;
-            it.seq = dcur.seq_expect;
-            it.flags = dcur.flags;
-            // a look at the tile's flag well before the loads are due (an acquire: if it already shows the
-            // expected value nothing more is needed when the tile is loaded)
-            it.seen = it.seq + 1u;
-            if (it.flags & FD_CHAIN) it.seen = ld_acquire_gpu(it.tseq + it.tile);
-        };
-        auto tile_span = [&](int tile, size_t &p0, uint32_t &npx) {
-            p0 = (size_t)tile * PIPE_TILE;
-            const size_t rem = a.plane - p0;
-            npx = rem < (size_t)PIPE_TILE ? (uint32_t)rem : (uint32_t)PIPE_TILE;
-        };
-
-        // the one finished tile whose publication is still owed
-        unsigned int *pend_tseq = nullptr, *pend_done = nullptr;
-        uint32_t pend_tile = 0, pend_seq = 0;
-        bool pend = false;
-        auto publish_pending = [&]() {
-            if (!pend) return;
-            bulk_wait_all<0>();   // its bulk stores are complete (they were committed a tile period ago)
-            if (!pa.relaxed_publish) fence_acq_rel_gpu();  // ... and, with the compute warps' direct stores, visible before the flag
-            st_relaxed_gpu(pend_tseq + pend_tile, pend_seq);
-            if (pend_done) red_add_relaxed_gpu(pend_done, 1u);
-            pend = false;
-        };
-
-        auto issue_load = [&](int s, const Item &it) {
-            uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
-            volatile uint32_t *h = hdr_of(s);
-            h[HDR_TILE] = (uint32_t)it.tile;
-            h[HDR_FRAME] = (uint32_t)it.frame;
-            h[HDR_SEQ_OUT] = it.seq + 1u;
-            *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE)) = it.state;
-            *reinterpret_cast<uint8_t *volatile *>(const_cast<uint32_t *>(h + HDR_NMODES)) = it.nmodes;
-            *reinterpret_cast<uint32_t *volatile *>(const_cast<uint32_t *>(h + HDR_THR)) = it.thr;
-            *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_TSEQ)) = it.tseq;
-            *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_SLOW)) = it.slow;
-            *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_DONE)) = it.donec;
-            // (the caller has seen tile_seq == seq_expect with an acquire load)
-            if (it.flags & FD_CHAIN) fence_proxy_async_global();
-            size_t p0;
-            uint32_t npx;
-            tile_span(it.tile, p0, npx);
-            if (LINEAR) {
-                mbar_expect_tx(&full[s], npx * 24u);
-                bulk_g2s_hint(st + PIPE_OFF_BGR, it.bgr + 3 * p0, npx * 3u, &full[s], pol_first);
-            } else {
-                // BGR: one bulk copy per row segment of the tile (16-byte aligned on both sides, see the header)
-                const uint32_t y0 = (uint32_t)__umul64hi((unsigned long long)p0, pa.div_magic);
-                uint32_t bytes = 0;
-                {
-                    uint32_t y = y0, xa = (uint32_t)(p0 - (size_t)y0 * pitch_px), left = npx;
+        if (is_loader) {
+            // ---- loader lane -----------------------------------------------------------------------
+            const uint64_t pol_first = l2_policy_evict_first();
+            const uint32_t total = (uint32_t)pa.nframes * (uint32_t)pa.ntiles;
+            const unsigned pitch_px = (unsigned)a.wpr * 32u;
+            // a drawn work item, resolved against its frame's descriptor
+            struct Item {
+                int tile;  // -1: the queue is exhausted
+                int frame;
+                const uint8_t *bgr;
+                float *state;
+                uint8_t *nmodes;
+                uint32_t *thr;
+                unsigned int *tseq, *slow, *donec;
+                uint32_t seq, flags, seen;
+            };
+            int dframe = -1;  // descriptor cache (draws are monotonic: the frame index never goes back)
+            FrameDesc dcur;
+            uint32_t fbase = 0;  // first work number of frame fpos
+            int fpos = 0;
+            auto resolve = [&](uint32_t g, Item &it) {
+                if (g >= total) {
+                    it.tile = -1;
+                    return;
+                }
+                while (g >= fbase + (uint32_t)pa.ntiles) {
+                    fbase += (uint32_t)pa.ntiles;
+                    ++fpos;
+                }
+                if (fpos != dframe) {
+                    const FrameDesc *dp = pa.descs ? pa.descs + fpos : &pa.inl[fpos];
+                    const uint4 *q = reinterpret_cast<const uint4 *>(dp);
+                    uint4 *w = reinterpret_cast<uint4 *>(&dcur);
+                    w[0] = q[0];
+                    w[1] = q[1];
+                    w[2] = q[2];
+                    w[3] = q[3];
+                    dframe = fpos;
+                }
+                it.tile = (int)(g - fbase);
+                it.frame = fpos;
+                it.bgr = dcur.bgr;
+                it.state = dcur.state;
+                it.nmodes = dcur.nmodes;
+                it.thr = dcur.thr_bits;
+                it.tseq = dcur.tile_seq;
+                it.slow = dcur.slow_count;
+                it.donec = dcur.done_count;
+                it.seq = dcur.seq_expect;
+                it.flags = dcur.flags;
+                // a look at the tile's flag well before the loads are due (an acquire: if it already shows the
+                // expected value nothing more is needed when the tile is loaded)
+                it.seen = it.seq + 1u;
+                if (it.flags & FD_CHAIN) it.seen = ld_acquire_gpu(it.tseq + it.tile);
+            };
+            auto issue_load = [&](int s, const Item &it) {
+                uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
+                volatile uint32_t *h = hdr_of(s);
+                h[HDR_TILE] = (uint32_t)it.tile;
+                h[HDR_FRAME] = (uint32_t)it.frame;
+                h[HDR_SEQ_OUT] = it.seq + 1u;
+                *hdr_ptr(h, HDR_STATE) = it.state;
+                *hdr_ptr(h, HDR_NMODES) = it.nmodes;
+                *hdr_ptr(h, HDR_THR) = it.thr;
+                *hdr_ptr(h, HDR_TSEQ) = it.tseq;
+                *hdr_ptr(h, HDR_SLOW) = it.slow;
+                *hdr_ptr(h, HDR_DONE) = it.donec;
+                // (the caller has seen tile_seq == seq_expect with an acquire load)
+                if (it.flags & FD_CHAIN) fence_proxy_async_global();
+                size_t p0;
+                uint32_t npx;
+                tile_span(it.tile, p0, npx);
+                if (LINEAR) {
+                    mbar_expect_tx(&full[s], npx * 24u);
+                    bulk_g2s_hint(st + PIPE_OFF_BGR, it.bgr + 3 * p0, npx * 3u, &full[s], pol_first);
+                } else {
+                    // BGR: one bulk copy per row segment of the tile (16-byte aligned on both sides, see the header)
+                    const uint32_t y0 = (uint32_t)__umul64hi((unsigned long long)p0, pa.div_magic);
+                    uint32_t bytes = 0;
+                    {
+                        uint32_t xa = (uint32_t)(p0 - (size_t)y0 * pitch_px), left = npx;
+                        while (left) {
+                            const uint32_t xb = min(pitch_px, xa + left), xv = min(xb, (uint32_t)a.cols);
+                            if (xv > xa) bytes += (3u * (xv - xa) + 15u) & ~15u;
+                            left -= xb - xa;
+                            xa = 0;
+                        }
+                    }
+                    mbar_expect_tx(&full[s], npx * 21u + bytes);
+                    uint32_t y = y0, xa = (uint32_t)(p0 - (size_t)y0 * pitch_px), left = npx, e0 = 0;
                     while (left) {
                         const uint32_t xb = min(pitch_px, xa + left), xv = min(xb, (uint32_t)a.cols);
-                        if (xv > xa) bytes += (3u * (xv - xa) + 15u) & ~15u;
+                        if (xv > xa)
+                            bulk_g2s_hint(st + PIPE_OFF_BGR + 3u * e0, it.bgr + (size_t)y * a.in_pitch + 3u * xa,
+                                          (3u * (xv - xa) + 15u) & ~15u, &full[s], pol_first);
                         left -= xb - xa;
+                        e0 += xb - xa;
                         xa = 0;
                         ++y;
                     }
                 }
-                mbar_expect_tx(&full[s], npx * 21u + bytes);
-                uint32_t y = y0, xa = (uint32_t)(p0 - (size_t)y0 * pitch_px), left = npx, e0 = 0;
-                while (left) {
-                    const uint32_t xb = min(pitch_px, xa + left), xv = min(xb, (uint32_t)a.cols);
-                    if (xv > xa)
-                        bulk_g2s_hint(st + PIPE_OFF_BGR + 3u * e0, it.bgr + (size_t)y * a.in_pitch + 3u * xa,
-                                      (3u * (xv - xa) + 15u) & ~15u, &full[s], pol_first);
-                    left -= xb - xa;
-                    e0 += xb - xa;
-                    xa = 0;
-                    ++y;
-                }
-            }
 #pragma unroll
-            for (int cc = 0; cc < 5; ++cc)
-                bulk_g2s(st + cc * (PIPE_TILE * 4), it.state + (size_t)cc * a.plane + p0, npx * 4u, &full[s]);
-            bulk_g2s(st + PIPE_OFF_NM, it.nmodes + p0, npx, &full[s]);
-        };
-        auto mark_end = [&](int s) {
-            hdr_of(s)[HDR_TILE] = 0xffffffffu;
-            mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker and stop
-        };
+                for (int cc = 0; cc < 5; ++cc)
+                    bulk_g2s(st + cc * (PIPE_TILE * 4), it.state + (size_t)cc * a.plane + p0, npx * 4u, &full[s]);
+                bulk_g2s(st + PIPE_OFF_NM, it.nmodes + p0, npx, &full[s]);
+            };
 
-        // Two cursors over the ring: stage li % S is the next to fill, stage si % S the next to retire.
-        //   A. fill free stages in ring order while the next item's previous frame has published the tile;
-        //   C. retire the oldest stage: wait for the compute warps, publish the tile retired before, write this
-        //      one back (and go back to A, which refills the stage at once).
-        // An item whose tile is still in flight -- possibly in one of THIS CTA's own stages, when frames are
-        // smaller than the ring -- never blocks C, and with nothing left to retire the lane publishes what it owes
-        // before it waits: the protocol cannot deadlock (tests/test_abi.py pins a model of it on the CPU).
-        Item nxt, cur;
-        uint32_t batch_next = raw0 + 1u, batch_left = (uint32_t)PIPE_STAGES - 1u;  // the first PIPE_STAGES items are consecutive
-        resolve(raw0, nxt);
-        int li = 0, si = 0;
-        bool ended = false;
-        unsigned idle_spins = 0;
-        for (;;) {
-            // ---- A ----
-            while (!ended && li - si < PIPE_STAGES) {
+            Item nxt, cur;
+            uint32_t batch_next = raw0 + 1u, batch_left = (uint32_t)PIPE_STAGES - 1u;  // the first PIPE_STAGES items are consecutive
+            resolve(raw0, nxt);
+            for (int li = 0;; ++li) {
                 const int s = li % PIPE_STAGES;
+                // the stage's previous tile has been written back
+                if (li >= PIPE_STAGES) mbar_wait(&freed[s], (uint32_t)(li / PIPE_STAGES - 1) & 1u);
                 if (nxt.tile < 0) {
-                    mark_end(s);
-                    ended = true;
+                    hdr_of(s)[HDR_TILE] = 0xffffffffu;
+                    mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker, pass it on and stop
                     break;
                 }
                 if ((nxt.flags & FD_CHAIN) && nxt.seen != nxt.seq) {
-                    nxt.seen = ld_acquire_gpu(nxt.tseq + nxt.tile);
-                    if (nxt.seen != nxt.seq) break;  // still in flight somewhere: retire own tiles meanwhile
+                    // The tile's previous frame is still in flight (in another CTA, in the previous launch, or -- frames
+                    // smaller than the ring -- in this CTA's own stages: the storer lane retires and publishes those on
+                    // its own).  Bounded: a writer that died (launch error) must surface as an error, not hang the GPU.
+                    unsigned spins = 0;
+                    while ((nxt.seen = ld_acquire_gpu(nxt.tseq + nxt.tile)) != nxt.seq) {
+                        __nanosleep(32);
+                        if (++spins > (1u << 23)) __trap();
+                    }
                 }
                 cur = nxt;
                 uint32_t rawn;
@@ -634,31 +656,46 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
                 }
                 issue_load(s, cur);
                 resolve(rawn, nxt);
-                ++li;
-                idle_spins = 0;
             }
-            if (si == li) {
-                if (ended) break;
-                // every stage is empty and the next tile's previous frame is in flight in another CTA (or in the
-                // previous launch): pay the publication debt, then wait.  Bounded: a writer that died (launch
-                // error) must surface as an error, not hang the GPU.
-                publish_pending();
-                __nanosleep(64);
-                if (++idle_spins > (1u << 23)) __trap();
-                continue;
-            }
-            // ---- C ----
+            return;
+        }
+        if (!is_storer) return;
+        // ---- storer lane ---------------------------------------------------------------------------
+        unsigned int *pend_tseq = nullptr, *pend_done = nullptr;  // the one finished tile whose publication is still owed
+        uint32_t pend_tile = 0, pend_seq = 0;
+        bool pend = false, pend_direct = false;
+        auto publish_pending = [&]() {
+            if (!pend) return;
+            bulk_wait_all<0>();  // its bulk stores are complete: performed, not merely read out of shared memory
+            // ... and the compute warps' direct stores of the tile, if it had any, are made visible at GPU scope before
+            // the flag (cumulative over what this lane observed through done[s]).  A MEMBAR.GPU costs a loaded
+            // memory round trip (2-3 us at the HBM roofline, more than a tile period -- r02c measured 0.83 instead of
+            // 0.97 of the peak with a fence on every tile, even in this lane), so it is paid only by the few tiles
+            // that need it; a tile written by bulk stores alone is published behind their completion.
+            if (pend_direct && !pa.relaxed_publish) fence_acq_rel_gpu();
+            st_relaxed_gpu(pend_tseq + pend_tile, pend_seq);
+            if (pend_done) red_add_relaxed_gpu(pend_done, 1u);
+            pend = false;
+        };
+        for (int si = 0;; ++si) {
             const int s = si % PIPE_STAGES;
+            const uint32_t par = (uint32_t)(si / PIPE_STAGES) & 1u;
             volatile uint32_t *h = hdr_of(s);
-            const int tile = (int)h[HDR_TILE];
             uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
-            mbar_wait(&done[s], (uint32_t)(si / PIPE_STAGES) & 1u);
+            // the next tile normally arrives within a tile period; if it does not, somebody may be waiting for the
+            // tile this lane still owes: publish it, then wait for as long as it takes
+            if (!mbar_try_wait_ns(&done[s], par, 4000u)) {
+                publish_pending();
+                mbar_wait(&done[s], par);
+            }
+            const int tile = (int)h[HDR_TILE];
+            if (tile < 0) break;
             // 1. the tile retired before has had a whole tile period for its bulk stores: publish it
             publish_pending();
             // 2. write this tile back
-            float *state = *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE));
-            uint8_t *nmodes = *reinterpret_cast<uint8_t *volatile *>(const_cast<uint32_t *>(h + HDR_NMODES));
-            uint32_t *thr = *reinterpret_cast<uint32_t *volatile *>(const_cast<uint32_t *>(h + HDR_THR));
+            float *state = reinterpret_cast<float *>(*hdr_ptr(h, HDR_STATE));
+            uint8_t *nmodes = reinterpret_cast<uint8_t *>(*hdr_ptr(h, HDR_NMODES));
+            uint32_t *thr = reinterpret_cast<uint32_t *>(*hdr_ptr(h, HDR_THR));
             bool store = true;
             if (TRACK) {
                 store = (h[HDR_DIRTY] != 0u);
@@ -685,25 +722,27 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
             // slow-path census of the tile (the queue count is 4 x the number of 4-pixel groups that left the fast path)
             {
                 const uint32_t q = h[HDR_QCNT];
-                unsigned int *slow = *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_SLOW));
+                unsigned int *slow = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_SLOW));
                 if (q && slow) red_add_relaxed_gpu(slow, q >> 2);
             }
             h[HDR_QCNT] = 0u;  // re-arm the slow-pixel queue
             h[HDR_QHEAD] = 0u;
-            pend_tseq = *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_TSEQ));
-            pend_done = *reinterpret_cast<unsigned int *volatile *>(const_cast<uint32_t *>(h + HDR_DONE));
+            pend_tseq = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_TSEQ));
+            pend_done = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_DONE));
             pend_tile = (uint32_t)tile;
             pend_seq = h[HDR_SEQ_OUT];
+            pend_direct = (h[HDR_DIRECT] != 0u) || pa.fence_always;
+            h[HDR_DIRECT] = 0u;
             pend = true;
-            // 3. the stage can be refilled as soon as its stores have READ it (A does so at once: its next tile is
-            // then in flight for PIPE_STAGES-1 tile periods instead of one)
+            // 3. hand the stage back as soon as its stores have READ it
             bulk_wait_read<0>();
-            ++si;
+            mbar_arrive(&freed[s]);
         }
         publish_pending();
         bulk_wait_all<0>();  // shared memory must outlive the last bulk stores
+        // (the loader lane has drawn its last number before it passed the end marker on)
         // the last CTA to leave re-arms the scheduler slot for its next user (a launch the host starts only
-        // after this one's completion event)
+        // after this one has said so) and tells the host
         if (atomicAdd(pa.exit_ticket, 1u) == gridDim.x - 1u) {
             *pa.work_counter = 0u;
             *pa.exit_ticket = 0u;
@@ -737,7 +776,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
         mbar_wait(&full[s], (uint32_t)(i / PIPE_STAGES) & 1u);
 
         const int tile = (int)h[HDR_TILE];
-        if (tile < 0) break;
+        if (tile < 0) {
+            mbar_arrive(&done[s]);  // the storer lane reads the marker too
+            break;
+        }
         size_t pidx;
         int y, x;
         const bool active = locate(tile, pidx, y, x);
@@ -791,7 +833,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
                 float4 W1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float *w1p = nullptr;
                 if (two != 0u) {
-                    float *state = *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE));
+                    float *state = reinterpret_cast<float *>(*hdr_ptr(h, HDR_STATE));
                     w1p = state + (size_t)5 * a.plane + pidx;
                     W1 = ld_state_f4(w1p);
                 }
@@ -821,6 +863,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
                         *reinterpret_cast<float4 *>(sm0 + 3 * PIPE_TILE) = B;
                         *reinterpret_cast<float4 *>(sm0 + 4 * PIPE_TILE) = C;
                         if (two != 0u) {
+                            h[HDR_DIRECT] = 1u;
                             st_state_f4(w1p, W1);
                             const uint32_t nnew = n0 | (n1 << 8) | (n2 << 16) | (n3 << 24);
                             if (nnew != nm) *(reinterpret_cast<uint32_t *>(st + PIPE_OFF_NM) + tid) = nnew;
@@ -890,7 +933,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_MINBLOCKS_CFG) mog_stream_k
                 while ((e = queue[hq]) == 0xffffu) {}  // reserved by a pusher of another warp that is about to fill it
                 __threadfence_block();                 // acquire: pairs with the pusher's fence
                 queue[hq] = 0xffffu;
-                float *state = *reinterpret_cast<float *volatile *>(const_cast<uint32_t *>(h + HDR_STATE));
+                float *state = reinterpret_cast<float *>(*hdr_ptr(h, HDR_STATE));
                 slow_pixel<K, TRACK>(pa, state, st, (int)e, (size_t)tile * PIPE_TILE + e);
             }
             __syncwarp();

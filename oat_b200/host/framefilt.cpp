@@ -36,7 +36,7 @@ protected:
         in_ = frame_source_.parameters();
         const PixelColor out_color = outputColor(in_.color);
         const size_t out_bytes = in_.rows * in_.cols * (size_t)color_bytes(out_color);
-        frame_sink_.bind(frame_sink_address_, out_bytes);
+        frame_sink_.bind(frame_sink_address_, out_bytes, false);  // announced below, once the memory kind is final
         shared_frame_ = frame_sink_.retrieve(in_.rows, in_.cols, color_bytes(out_color), out_color);
         ctx_.reset(new gpu::Context(gpu_index_));
         d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
@@ -58,12 +58,16 @@ protected:
             frame_sink_.set_memory(FrameMemory::HOST_PINNED, gpu_index_);
         }
         setup();
+        src_memory_ = frame_source_.header()->memory;
+        frame_sink_.announce();  // frame parameters, memory kind and IPC handle are in place: let SOURCEs connect
         return true;
     }
     // FrameFilter::process (FrameFilter.cpp:59-98), with the heap copies replaced by DMA
     int process() override
     {
         if (frame_source_.wait() == NodeState::END) return 1;
+        if (frame_source_.header()->memory != src_memory_)
+            throw std::runtime_error("SOURCE frame memory kind changed after connect()");
         gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? src_dev_->p : frame_source_.pixels(), in_.bytes));
         const Sample sample = frame_source_.retrieve()->sample();
         frame_source_.post();
@@ -94,6 +98,7 @@ protected:
     FrameParams in_;
     size_t out_bytes_{0};
     int gpu_index_{0};
+    FrameMemory src_memory_{FrameMemory::HOST_SHM};  // what the SOURCE said when this component connected
     bool device_sink_{false};  // --device-sink: publish frames in device memory (SharedFrameHeader memory kind DEVICE)
     std::unique_ptr<gpu::Context> ctx_;
     std::unique_ptr<gpu::HostRegistration> src_pin_, dst_pin_;

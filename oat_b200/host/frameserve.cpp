@@ -1,74 +1,163 @@
-// oat-frameserve -- stand-in pure SINK for the reference's `oat frameserve test` (src/frameserver/
-// TestFrame.cpp:81-128): serves N frames of the synthetic stream into a frame SINK,
-// advancing the Sample clock the way frame servers do.  TYPE `synth` only; camera / codec sources are
-// out of scope.
+// oat-frameserve -- the pure frame SINKs the hot path is measured with:
+//
+//   test   `oat frameserve test SINK -f IMAGE [-n N] [-r FPS] [-C COLOR]` -- the reference's TestFrame
+//          (src/frameserver/TestFrame.cpp:37-128): ONE static image, published N times with zero copies (only the
+//          Sample clock advances).  It is the driver of the reference's own performance protocol
+//          (test/perf/framefilt-mog.sh:1-3, test/perf/results.md:12-18: 1000 x 1 MP frames, free-running).
+//          The image is a binary PPM/PGM or a NumPy .npy (image_io.h; cv::imread is not available here).
+//   synth  the synthetic tracking stream of SURVEY.md 8(d) (deterministic, the same arithmetic as the oracle and
+//          the CUDA generator), N frames.
+//
+// Both take the GPU Frame variant: --device publishes the frames in device memory (SharedFrameHeader memory kind
+// DEVICE, CUDA IPC handle in the header) on --gpu-index; a test image is uploaded once, synthetic frames are
+// generated on the device.  Cameras, video files and codecs are out of scope.
 #include <iostream>
+#include <limits>
+#include <memory>
 #include <thread>
 
-#include <memory>
-
 #include "gpu.h"
+#include "image_io.h"
 #include "oat_cli.h"
 #include "oat_host.h"
 #include "synth.h"
 
+static void printUsage(std::ostream &out)
+{
+    out << "Usage: frameserve [INFO]\n"
+           "   or: frameserve TYPE SINK [CONFIGURATION]\n"
+           "Serve frames to SINK.\n\n"
+           "TYPE\n"
+           "  test: Serve a static test image (binary PPM/PGM or uint8 .npy).\n"
+           "  synth: Serve the synthetic single-blob tracking stream.\n\n"
+           "SINK:\n  User-supplied name of the memory segment to publish frames to (e.g. raw).\n\n"
+           "INFO:\n  --help                 Produce help message.\n  -v [ --version ]       Print version information.\n\n"
+           "CONFIGURATION:\n  -c [ --config ] FILE KEY   Configuration file/key pair.\n";
+}
+
 int main(int argc, char *argv[])
 {
     using namespace oat;
-    const std::string comp_name = "frameserve";
+    std::string comp_name = "frameserve";
     try {
-        if (argc < 3 || std::string(argv[1]) != "synth") {
-            std::cout << "Usage: frameserve synth SINK [--rows R --cols C --num-samples N --fps F --seed S --device --gpu-index I]\n";
-            return argc < 2 ? 0 : -1;
+        for (int i = 1; i < argc; ++i) {
+            const std::string a = argv[i];
+            if (a == "--help" && argc == 2) { printUsage(std::cout); return 0; }
+            if (a == "-v" || a == "--version") { std::cout << "Oat Frame Server (B200) version 0.1\n"; return 0; }
+        }
+        if (argc < 2) { printUsage(std::cout); return 0; }
+        const std::string type = argv[1];
+        if (type != "test" && type != "synth") {
+            printUsage(std::cout);
+            std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
+            return -1;
+        }
+        if (argc < 3 || argv[2][0] == '-') {
+            printUsage(std::cout);
+            std::cerr << whoError(comp_name, "Error: a SINK must be specified.\n");
+            return -1;
         }
         struct Server : Component {
-            std::string name() const override { return "synthserve"; }
+            std::string name() const override { return "frameserve"; }
             bool connectToNode() override { return true; }
             int process() override { return 1; }
         } sig_owner;  // installs the SIGINT handler
         const std::string sink_addr = argv[2];
-        const std::vector<config::OptionSpec> opts = {{"rows", 0, true, ""}, {"cols", 0, true, ""}, {"num-samples", 'n', true, ""},
-                                                      {"fps", 'r', true, ""}, {"seed", 0, true, ""}, {"device", 0, false, ""},
-                                                      {"gpu-index", 0, true, ""}};
-        const config::VariableMap vm = config::parse(argc, argv, 3, opts);
-        config::OptionTable none;
-        int rows = 480, cols = 640, seed = 1000;
-        uint64_t n = 100;
-        double fps = 0.0;
-        config::getNumericValue<int>(vm, none, "rows", rows, 20, 32768);
-        config::getNumericValue<int>(vm, none, "cols", cols, 4, 32768);
-        config::getNumericValue<uint64_t>(vm, none, "num-samples", n, 0, (uint64_t)1 << 62);
-        config::getNumericValue<double>(vm, none, "fps", fps, 0.0, 1e6);
-        config::getNumericValue<int>(vm, none, "seed", seed, 0, 1 << 30);
+        comp_name = (type == "test" ? "testframe[*->" : "synthserve[*->") + sink_addr + "]";
 
+        std::vector<config::OptionSpec> opts;
+        if (type == "test")  // TestFrame::options (TestFrame.cpp:37-55)
+            opts = {{"test-image", 'f', true, "Path to test image used as frame source."},
+                    {"color", 'C', true, "Pixel color format. Defaults to BGR. Values: GREY, BGR."},
+                    {"fps", 'r', true, "Frames to serve per second."},
+                    {"num-frames", 'n', true, "Number of frames to serve before exiting."}};
+        else
+            opts = {{"rows", 0, true, "Frame height."}, {"cols", 0, true, "Frame width."},
+                    {"num-samples", 'n', true, "Number of frames to serve before exiting."},
+                    {"fps", 'r', true, "Frames to serve per second."}, {"seed", 0, true, "Stream seed."}};
+        opts.push_back({"device", 0, false, "Publish frames in device memory (CUDA IPC)."});
+        opts.push_back({"gpu-index", 0, true, "Index of the GPU to use."});
+        const std::vector<config::OptionSpec> own = opts;
+        opts.push_back({"config", 'c', true, "Configuration file/key pair."});
+        opts.push_back({"help", 0, false, ""});
+        const config::VariableMap vm = config::parse(argc, argv, 3, opts);
+        if (vm.count("help")) {
+            printUsage(std::cout);
+            for (const auto &o : own) std::cout << "  --" << o.long_name << "  " << o.help << "\n";
+            return 0;
+        }
+        config::OptionTable table;
+        if (vm.count("config")) {
+            table = config::getConfigTable(vm.values.at("config"), vm.values.at("config-key"));
+            config::checkKeys(own, table);
+        }
+
+        int rows = 480, cols = 640, seed = 1000, channels = 3;
+        uint64_t n = type == "test" ? std::numeric_limits<uint64_t>::max() : 100;  // TestFrame.h: serves until interrupted by default
+        double fps = 0.0;
+        PixelColor color = PIX_BGR;
+        Image image;
+        if (type == "test") {
+            std::string file, col;
+            if (!config::getString(vm, table, "test-image", file))
+                throw std::runtime_error("Required configuration key 'test-image' was not specified.");  // getValue(..., required = true)
+            if (config::getString(vm, table, "color", col)) {
+                if (col == "GREY") color = PIX_GREY;
+                else if (col == "BGR") color = PIX_BGR;
+                else throw std::runtime_error("Invalid color format: " + col);
+            }
+            config::getNumericValue<uint64_t>(vm, table, "num-frames", n, 1, std::numeric_limits<uint64_t>::max());
+            image = to_channels(read_image(file), color == PIX_GREY ? 1 : 3);
+            rows = image.rows;
+            cols = image.cols;
+            channels = image.channels;
+        } else {
+            config::getNumericValue<int>(vm, table, "rows", rows, 20, 32768);
+            config::getNumericValue<int>(vm, table, "cols", cols, 4, 32768);
+            config::getNumericValue<uint64_t>(vm, table, "num-samples", n, 0, (uint64_t)1 << 62);
+            config::getNumericValue<int>(vm, table, "seed", seed, 0, 1 << 30);
+        }
+        config::getNumericValue<double>(vm, table, "fps", fps, 0.0, 1e6);
         int gpu_index = 0;
-        config::getNumericValue<int>(vm, none, "gpu-index", gpu_index, 0, 1 << 20);
-        const bool device = vm.count("device");  // frames are generated on the GPU and published in device memory
+        config::getNumericValue<int>(vm, table, "gpu-index", gpu_index, 0, 1 << 20);
+        const bool device = vm.count("device");  // frames live in device memory and are published through a CUDA IPC handle
+        const size_t bytes = (size_t)rows * cols * channels;
+
         Sink<Frame> frame_sink;
-        frame_sink.bind(sink_addr, (size_t)rows * cols * 3);
-        Frame shared_frame = frame_sink.retrieve(rows, cols, 3, PIX_BGR);
+        frame_sink.bind(sink_addr, bytes, false);  // announced once parameters and memory kind are final
+        Frame shared_frame = frame_sink.retrieve(rows, cols, channels, color);
         if (fps > 0.0) shared_frame.set_rate_hz(fps);
         std::unique_ptr<gpu::Context> ctx;
         std::unique_ptr<gpu::DeviceBuffer> d_frame;
         if (device) {
             ctx.reset(new gpu::Context(gpu_index));
-            d_frame.reset(new gpu::DeviceBuffer(*ctx, (size_t)rows * cols * 3));
+            d_frame.reset(new gpu::DeviceBuffer(*ctx, bytes));
             unsigned char handle[64];
             gpu::ck(oat_ipc_export(ctx->h, d_frame->p, handle));
             frame_sink.publish_device(handle, gpu_index);
         }
-        std::vector<uint8_t> next((size_t)rows * cols * 3);
+        if (type == "test") {  // static image, never changes (TestFrame.cpp:93-94)
+            if (device)
+                gpu::ck(oat_memcpy(ctx->h, d_frame->p, image.data.data(), bytes));
+            else
+                std::memcpy(shared_frame.data(), image.data.data(), bytes);
+        }
+        frame_sink.announce();
+
+        std::vector<uint8_t> next(type == "synth" && !device ? bytes : 0);
         auto tick = std::chrono::steady_clock::now();
         for (uint64_t t = 0; t < n && !quit; ++t) {
-            if (!device) synth::frame(next.data(), rows, cols, (uint32_t)seed, (uint32_t)t);  // outside the critical section
+            if (type == "synth" && !device) synth::frame(next.data(), rows, cols, (uint32_t)seed, (uint32_t)t);  // outside the critical section
             frame_sink.wait();
-            if (device)
-                gpu::ck(oat_synth_frame(ctx->h, d_frame->u8(), (size_t)cols * 3, rows, cols, (uint32_t)seed, (uint32_t)t));
-            else
-                std::memcpy(shared_frame.data(), next.data(), next.size());
+            if (type == "synth") {
+                if (device)
+                    gpu::ck(oat_synth_frame(ctx->h, d_frame->u8(), (size_t)cols * 3, rows, cols, (uint32_t)seed, (uint32_t)t));
+                else
+                    std::memcpy(shared_frame.data(), next.data(), next.size());
+            }
             shared_frame.incrementSampleCount();  // only pure SINKs advance time (TestFrame.cpp:114)
             frame_sink.post();
-            if (fps > 0.0) {
+            if (fps > 0.0) {  // without --fps the server free-runs (TestFrame.cpp:122; the perf protocol relies on it)
                 tick += std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(1.0 / fps));
                 std::this_thread::sleep_until(tick);
             }

@@ -548,15 +548,24 @@ public:
 template <>
 class Sink<Frame> : public SinkBase<SharedFrameHeader> {
 public:
-    void bind(const std::string &address, size_t bytes)  // Sink.h:232-272
+    // announce_now = false: the node stays un-announced (SOURCEs keep waiting in connect()) until announce() -- for
+    // components that must first fill in what a SOURCE reads ONCE when it connects: the frame parameters
+    // (retrieve()) and, new with the GPU Frame variants, the memory kind / CUDA IPC handle / device index, which
+    // only exist after the CUDA context and the device buffers do (hundreds of ms).
+    void bind(const std::string &address, size_t bytes, bool announce_now = true)  // Sink.h:232-272
     {
         bind_segments(address, sizeof(SharedFrameHeader) + bytes + sizeof(Sample) + 64, type_hash_of(typeid(SharedFrameHeader).name()));
         sh_object_ = new (obj_shmem_.base() + OBJ_OFFSET) SharedFrameHeader();
         sh_object_->memory = FrameMemory::HOST_SHM;
         sh_object_->device_index = -1;
         pixel_bytes_ = bytes;
-        node_->set_sink_state(NodeState::SINK_BOUND);
         bound_ = true;
+        if (announce_now) announce();
+    }
+    void announce()
+    {
+        if (!bound_) throw std::runtime_error("SINK must be bound before it is announced.");
+        node_->set_sink_state(NodeState::SINK_BOUND);
     }
     Frame retrieve(size_t rows, size_t cols, int channels, PixelColor color)  // Sink.h:274-298
     {

@@ -38,6 +38,7 @@ protected:
         else
             src_pin_.reset(new gpu::HostRegistration(frame_source_.pixels(), in_.bytes));
         d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
+        src_memory_ = frame_source_.header()->memory;
         setup();
         return true;
     }
@@ -46,6 +47,8 @@ protected:
     {
         Position2D internal_pos("");
         if (frame_source_.wait() == NodeState::END) return 1;
+        if (frame_source_.header()->memory != src_memory_)
+            throw std::runtime_error("SOURCE frame memory kind changed after connect()");
         gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? src_dev_->p : frame_source_.pixels(), in_.bytes));
         internal_pos.set_sample(frame_source_.retrieve()->sample());  // propagate tick / usec (:80)
         frame_source_.post();
@@ -68,6 +71,7 @@ protected:
     Sink<Position2D> position_sink_;
     Position2D *shared_position_{nullptr};
     FrameParams in_;
+    FrameMemory src_memory_{FrameMemory::HOST_SHM};  // what the SOURCE said when this component connected
     int gpu_index_{0};
     std::unique_ptr<gpu::Context> ctx_;
     std::unique_ptr<gpu::HostRegistration> src_pin_;

@@ -327,9 +327,31 @@ static int emit_positions(const std::string &addr, int n)
     return 0;
 }
 
+// helper mode for the frame-server tests: read frames from ADDR until the SINK leaves; per frame one line
+// "tick usec rows cols channels color fnv1a(pixels)" on stdout (a plain Source<Frame>, like any reference component)
+static int dump_frames(const std::string &addr)
+{
+    Source<Frame> src;
+    src.touch(addr);
+    if (src.connect() != SourceState::CONNECTED) return 2;
+    Frame internal;
+    for (;;) {
+        if (src.wait() == NodeState::END) break;
+        src.copyTo(internal);
+        src.post();
+        uint64_t hsh = 1469598103934665603ull;
+        const uint8_t *p = internal.data();
+        for (size_t i = 0; i < internal.bytes(); ++i) hsh = (hsh ^ p[i]) * 1099511628211ull;
+        std::cout << internal.sample().count() << " " << internal.sample().microseconds() << " " << internal.rows() << " "
+                  << internal.cols() << " " << internal.channels() << " " << (int)internal.color() << " " << hsh << std::endl;
+    }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 3 && std::string(argv[1]) == "emit-positions") return emit_positions(argv[2], std::atoi(argv[3]));
+    if (argc > 2 && std::string(argv[1]) == "dump-frames") return dump_frames(argv[2]);
     test_node();
     test_sink();
     test_source();

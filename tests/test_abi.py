@@ -77,16 +77,15 @@ def test_product_never_imports_the_oracle():
 
 class _ResidentModel:
     """A transcription of the resident fused kernel's scheduling protocol (oat_b200/csrc/mog_pipe.cuh,
-    mog_stream_kernel): every CTA has a producer lane and compute warps around a ring of `stages` stages;
-    work items (frame, tile) are drawn from one counter (the first `stages` of a CTA in one draw, then one at
-    a time); a tile of frame f+1 of a model may only be loaded once the same tile of the model's previous
-    frame has been PUBLISHED.  The producer lane alternates between (A) filling free stages in ring order
-    while the next item's predecessor is published and (C) retiring its oldest stage (wait for the compute
-    warps, publish the tile retired before, write this one back); with nothing to retire and the next item
-    blocked it publishes what it owes and waits.  The model is stepped by an adversarial (random) scheduler;
-    it checks that every item is processed exactly once, that no load ever precedes the publication it
-    depends on, and that the protocol cannot deadlock -- including frames smaller than one CTA's ring, where
-    a CTA's next item depends on a tile still sitting in its own stages."""
+    mog_stream_kernel): every CTA has a LOADER lane, compute warps and a STORER lane around a ring of `stages`
+    stages (loader --full--> compute --done--> storer --freed--> loader); work items (frame, tile) are drawn from
+    one counter (the first `stages` of a CTA in one draw, then one at a time); a tile of frame f+1 of a model may
+    only be loaded once the same tile of the model's previous frame has been PUBLISHED.  The storer publishes a
+    tile when it comes back for the next one, or -- if the next one does not arrive in time -- while it waits.
+    The model is stepped by an adversarial (random) scheduler; it checks that every item is processed exactly
+    once, that no load ever precedes the publication it depends on, and that the protocol cannot deadlock --
+    including frames smaller than one CTA's ring, where the loader waits for a tile that still sits in its own
+    CTA's stages."""
 
     def __init__(self, nframes, ntiles, grid, stages, models, rng):
         self.nf, self.nt, self.grid, self.S, self.rng = nframes, ntiles, grid, stages, rng
@@ -104,8 +103,9 @@ class _ResidentModel:
         self.ctas = [self._new_cta() for _ in range(grid)]
 
     def _new_cta(self):
-        return {"pc": "start", "stage": [None] * self.S, "computed": [False] * self.S, "li": 0, "si": 0, "ci": 0,
-                "pend": None, "nxt": None, "batch": [], "ended": False, "cdone": False}
+        # stage state: None (free) -> item (loaded) -> computed flag -> stored (free again)
+        return {"stage": [None] * self.S, "computed": [False] * self.S, "li": 0, "si": 0, "ci": 0, "pend": None,
+                "nxt": None, "batch": None, "ldone": False, "cdone": False, "sdone": False}
 
     def _item(self, g):
         return "END" if g >= self.total else (g // self.nt, g % self.nt)
@@ -114,11 +114,6 @@ class _ResidentModel:
         p = self.prev[it[0]]
         return p is None or (p, it[1]) in self.published
 
-    def _publish(self, c):
-        if c["pend"] is not None:
-            self.published.add(c["pend"])
-            c["pend"] = None
-
     def _draw(self, c):
         if c["batch"]:
             return c["batch"].pop(0)
@@ -126,73 +121,68 @@ class _ResidentModel:
         self.counter += 1
         return g
 
-    def step_producer(self, c):
-        """One atomic action of the producer lane; returns False if it is blocked."""
+    def step_loader(self, c):
         S = self.S
-        pc = c["pc"]
-        if pc == "start":
+        if c["ldone"]:
+            return False
+        if c["batch"] is None:  # the first draw: `stages` consecutive items
             c["batch"] = [self.counter + k for k in range(1, S)]
             c["nxt"] = self._item(self.counter)
             self.counter += S
-            c["pc"] = "fill"
             return True
-        if pc == "fill":  # A: fill free stages in ring order
-            if c["ended"] or c["li"] - c["si"] >= S:
-                c["pc"] = "retire"
-                return True
-            s = c["li"] % S
-            if c["nxt"] == "END":
-                c["stage"][s] = "END"
-                c["ended"] = True
-                c["pc"] = "retire"
-                return True
-            if not self._ready(c["nxt"]):
-                c["pc"] = "retire"
-                return True
-            it = c["nxt"]
-            assert self._ready(it)
-            self.loaded.append(it)
-            c["stage"][s] = it
-            c["computed"][s] = False
-            c["nxt"] = self._item(self._draw(c))
+        s = c["li"] % S
+        if c["li"] - c["si"] >= S:
+            return False  # mbar_wait(freed[s]): only this CTA's own storer lane is waited for
+        if c["nxt"] == "END":
+            c["stage"][s] = "END"
             c["li"] += 1
+            c["ldone"] = True
             return True
-        if pc == "retire":
-            if c["si"] == c["li"]:
-                if c["ended"]:
-                    c["pc"] = "drain"
-                    return True
-                self._publish(c)  # pay the debt before waiting for somebody else
-                if self._ready(c["nxt"]):
-                    c["pc"] = "fill"
-                    return True
-                return False
-            s = c["si"] % S
-            if not c["computed"][s]:
-                return False  # mbar_wait(done[s]): only this CTA's own compute warps are waited for
-            self._publish(c)            # the tile retired before
-            c["pend"] = c["stage"][s]   # this tile's stores are committed; its publication is owed
-            c["stage"][s] = None
-            c["si"] += 1
-            c["pc"] = "fill"
-            return True
-        if pc == "drain":
-            self._publish(c)
-            self.exited += 1
-            c["pc"] = "gone"
-            return True
-        return False
+        if not self._ready(c["nxt"]):
+            return False  # spins on the tile's flag
+        it = c["nxt"]
+        self.loaded.append(it)
+        c["stage"][s] = it
+        c["computed"][s] = False
+        c["nxt"] = self._item(self._draw(c))
+        c["li"] += 1
+        return True
 
     def step_compute(self, c):
-        s = c["ci"] % self.S
-        it = c["stage"][s]
-        if c["cdone"] or it is None or c["computed"][s] or c["ci"] >= c["li"] + (1 if c["ended"] else 0):
+        if c["cdone"] or c["ci"] >= c["li"]:
             return False
-        if it == "END":
+        s = c["ci"] % self.S
+        if c["stage"][s] == "END":
             c["cdone"] = True
+            c["computed"][s] = True  # passes the marker on to the storer
+            c["ci"] += 1
             return True
         c["computed"][s] = True
         c["ci"] += 1
+        return True
+
+    def step_storer(self, c):
+        if c["sdone"]:
+            return False
+        s = c["si"] % self.S
+        if c["si"] >= c["ci"]:  # done[s] has not completed: after the bounded wait, publish what is owed
+            if c["pend"] is not None:
+                self.published.add(c["pend"])
+                c["pend"] = None
+                return True
+            return False
+        if c["stage"][s] == "END":
+            if c["pend"] is not None:
+                self.published.add(c["pend"])
+                c["pend"] = None
+            c["sdone"] = True
+            self.exited += 1
+            return True
+        if c["pend"] is not None:
+            self.published.add(c["pend"])
+        c["pend"] = c["stage"][s]
+        c["stage"][s] = None
+        c["si"] += 1
         return True
 
     def run(self, max_steps=10_000_000):
@@ -203,7 +193,7 @@ class _ResidentModel:
             progressed = False
             for b in order:
                 c = self.ctas[b]
-                acts = [self.step_producer, self.step_compute]
+                acts = [self.step_loader, self.step_compute, self.step_storer]
                 self.rng.shuffle(acts)
                 for act in acts:
                     if self.rng.random() < 0.7:  # an adversarial scheduler: some actors simply do not run this round
@@ -211,7 +201,7 @@ class _ResidentModel:
             if not progressed:
                 # nobody moved in a randomised round: give everybody a deterministic chance before calling it a deadlock
                 for c in self.ctas:
-                    progressed |= self.step_producer(c) | self.step_compute(c)
+                    progressed |= self.step_loader(c) | self.step_compute(c) | self.step_storer(c)
                 assert progressed, "deadlock: no CTA can make progress"
             steps += 1
             assert steps < max_steps
@@ -223,11 +213,10 @@ def test_resident_scheduler_protocol_model():
     import random
 
     rng = random.Random(1234)
-    S = 3
     cases = [(1, 1, 1, 1), (1, 7, 3, 1), (4, 5, 8, 1), (6, 2, 8, 2), (8, 13, 5, 1), (16, 3, 7, 4), (5, 40, 6, 1),
              (12, 9, 4, 3), (3, 1, 5, 1), (20, 2, 3, 2), (9, 1, 1, 1), (30, 2, 1, 1), (10, 4, 2, 2), (64, 75, 16, 1)]
     for nframes, ntiles, grid, models in cases:
-        for rep in range(3):
+        for S in (3, 4, 2):
             m = _ResidentModel(nframes, ntiles, grid, S, models, rng).run()
             assert sorted(m.loaded) == [(f, t) for f in range(nframes) for t in range(ntiles)], (nframes, ntiles, grid)
             assert len(m.published) == nframes * ntiles

@@ -127,3 +127,69 @@ def test_position_egress_formats(host_bin, tmp_path):
             assert a["pos_ok"].tolist() == [0, 1, 1, 0, 1, 1, 0]
             assert np.allclose(a["pos_xy"][:, 0], 10.5 + np.arange(7)) and np.allclose(a["pos_xy"][:, 1], 0.125 * np.arange(7))
         subprocess.run([os.path.join(host_bin, "oat-clean"), addr], capture_output=True)
+
+
+def _fnv1a(buf: bytes) -> int:
+    h = 1469598103934665603
+    for b in buf:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("fmt", ["npy", "ppm", "pgm-as-bgr", "npy-as-grey"])
+def test_frameserve_test_serves_a_static_image(host_bin, tmp_path, fmt):
+    """`oat frameserve test SINK -f IMAGE -n N` (src/frameserver/TestFrame.cpp:37-128): the static image N times, tick
+    1..N, frame period from --fps, BGR unless -C GREY; read back by a plain Source<Frame>."""
+    import numpy as np
+
+    rng = np.random.default_rng(11)
+    rows, cols, n = 37, 52, 6
+    bgr = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    grey = rng.integers(0, 256, (rows, cols), dtype=np.uint8)
+    args, want, ch, color = [], None, 3, 2
+    if fmt == "npy":
+        path = tmp_path / "img.npy"
+        np.save(path, bgr)
+        want = bgr
+    elif fmt == "ppm":  # PPM is RGB on disk
+        path = tmp_path / "img.ppm"
+        path.write_bytes(b"P6\n# a comment\n%d %d\n255\n" % (cols, rows) + bgr[:, :, ::-1].tobytes())
+        want = bgr
+    elif fmt == "pgm-as-bgr":  # a grey file served as BGR: the three channels carry the grey value
+        path = tmp_path / "img.pgm"
+        path.write_bytes(b"P5 %d %d 255\n" % (cols, rows) + grey.tobytes())
+        want = np.repeat(grey[:, :, None], 3, axis=2)
+    else:  # a colour file served as GREY (-C GREY): OpenCV's BGR -> grey weights
+        path = tmp_path / "img.npy"
+        np.save(path, bgr)
+        args = ["-C", "GREY"]
+        b, g, r = (bgr[:, :, i].astype(np.int64) for i in range(3))
+        want = ((b * 1868 + g * 9617 + r * 4899 + (1 << 13)) >> 14).astype(np.uint8)
+        ch, color = 1, 1
+    addr = f"oatb200test_tf_{fmt.replace('-', '_')}"
+    subprocess.run([os.path.join(host_bin, "oat-clean"), addr], capture_output=True)
+    reader = subprocess.Popen([os.path.join(host_bin, "shmemdf_test"), "dump-frames", addr], stdout=subprocess.PIPE, text=True)
+    serve = run([os.path.join(host_bin, "oat-frameserve"), "test", addr, "-f", str(path), "-n", str(n), "-r", "500"] + args)
+    out, _ = reader.communicate(timeout=60)
+    assert serve.returncode == 0, serve.stderr
+    lines = [ln.split() for ln in out.splitlines() if ln.strip()]
+    assert [int(l[0]) for l in lines] == list(range(1, n + 1))
+    assert [int(l[1]) for l in lines] == [2000 * k for k in range(1, n + 1)]
+    for l in lines:
+        assert (int(l[2]), int(l[3]), int(l[4]), int(l[5])) == (rows, cols, ch, color)
+        assert int(l[6]) == _fnv1a(np.ascontiguousarray(want).tobytes())
+    subprocess.run([os.path.join(host_bin, "oat-clean"), addr], capture_output=True)
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["oat-frameserve", "bogus", "a"], "invalid TYPE"),
+    (["oat-frameserve", "test"], "a SINK must be specified"),
+    (["oat-frameserve", "test", "oatb200test_tf_err"], "Required configuration key 'test-image'"),
+    (["oat-frameserve", "test", "oatb200test_tf_err", "-f", "/nonexistent.ppm"], "could not be read"),
+    (["oat-frameserve", "test", "oatb200test_tf_err", "-f", "/dev/null", "-C", "HSV"], "Invalid color format"),
+    (["oat-frameserve", "test", "oatb200test_tf_err", "-f", "x", "-n", "0"], "out of bounds"),
+])
+def test_frameserve_cli_errors(host_bin, args, msg):
+    r = run([os.path.join(host_bin, args[0])] + args[1:])
+    assert r.returncode == 255, (r.returncode, r.stdout, r.stderr)
+    assert msg in r.stderr, r.stderr
