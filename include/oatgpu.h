@@ -242,6 +242,11 @@ int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, do
 int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
                        const oat_hsv_params *p, uint8_t *bgr_out, size_t bgr_out_pitch);
 int oat_tracker_collect(oat_tracker *t, oat_detection *out);
+/* Blocks until the most recently submitted frame's INPUT has been consumed (host frame: its H2D copy is
+ * complete; device frame: the fused kernel that reads it in place has finished) -- the moment a component may
+ * hand the frame back to its SOURCE (Source::post(), lib/shmemdf/Source.h:217-232) while the frame's detection is
+ * still in flight.  What lets a component keep several frames in flight behind a lock-step SOURCE. */
+int oat_tracker_wait_ingest(oat_tracker *t);
 int oat_tracker_live_modes(oat_tracker *t, uint64_t *sum_modes);
 
 /* ---- posifilt kalman + posicom mean: the O(1) epilogue behind the detectors ----

@@ -161,6 +161,7 @@ _SIGS = {
     "oat_tracker_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams), C.c_void_p,
                                      C.c_size_t]),
     "oat_tracker_collect": (C.c_int, [C.c_void_p, C.POINTER(Detection)]),
+    "oat_tracker_wait_ingest": (C.c_int, [C.c_void_p]),
     "oat_tracker_run_clip": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_double,
                                        C.POINTER(HsvParams), C.c_int, C.POINTER(Detection), C.POINTER(Position)]),
     "oat_tracker_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -686,6 +687,10 @@ class Tracker:
         """Diagnostic: only the fused kernel of the next frame (see oat_tracker_submit_fused_only)."""
         lr = self.learning_coeff if learning_rate is None else learning_rate
         _ck(lib().oat_tracker_submit_fused_only(self._h, _ptr(bgr), pitch or self.cols * 3, lr, C.byref(self.hsv)))
+
+    def wait_ingest(self):
+        """Blocks until the last submitted frame's input buffer may be reused (oat_tracker_wait_ingest)."""
+        _ck(lib().oat_tracker_wait_ingest(self._h))
 
     def collect(self) -> Detection:
         d = Detection()

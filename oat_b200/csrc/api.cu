@@ -1467,6 +1467,7 @@ struct Slot {
     cudaEvent_t fused_done = nullptr;
     oat_hsv_params hp{};
     bool fast = false;              // the one-launch tail was used (status must be checked at collect)
+    int ingest = 0;                 // how the frame's input is consumed: 1 = H2D copy (event `copied`), 2 = read in place by the fused kernel (event `fused_done`)
     cudaEvent_t copied = nullptr, done = nullptr;
     oat_position *d_pos = nullptr, *h_pos = nullptr;  // attached position filter: this frame's filtered position
     cudaEvent_t pos_done = nullptr;
@@ -1718,11 +1719,13 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     if (mem_kind(bgr_in) == MEM_DEVICE) {
         a.bgr = bgr_in;
         a.in_pitch = in_pitch;
+        s.ingest = 2;
     } else {
         // ingest on the copy stream so the DMA of frame t+1 overlaps the kernels of frame t
         CKRET(stage_in(c, c->h2d, s.in, bgr_in, in_pitch, rows, (size_t)3 * cols, &a.bgr, &a.in_pitch));
         CK(cudaEventRecord(s.copied, c->h2d));
         CK(cudaStreamWaitEvent(c->stream, s.copied, 0));
+        s.ingest = 1;
     }
     t->m.frame_consts(learning_rate, &a.c, &a.reset);
     a.do_hsv = 1;
@@ -1761,9 +1764,9 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
     CKRET(finish_out(c->stream, ofg));
     CKRET(finish_out(c->stream, ohsv));
     cudaStream_t ts = c->stream;
+    CK(cudaEventRecord(s.fused_done, c->stream));  // (also what oat_tracker_wait_ingest waits for when the frame is read in place)
     if (overlap && !c->no_overlap) {
         ts = c->tail[c->tail_rr++ % oat_ctx::NTAIL];  // context-wide round robin: trackers sharing a context do not pile onto one stream
-        CK(cudaEventRecord(s.fused_done, c->stream));
         CK(cudaStreamWaitEvent(ts, s.fused_done, 0));
     }
     {
@@ -2213,6 +2216,19 @@ static int run_clip_per_frame(oat_tracker *t, const uint8_t *const *frames, size
         CKRET(oat_tracker_submit(t, frames[i], in_pitch, learning_rate, p, nullptr, 0));
     }
     for (; done < n; ++done) CKRET(tracker_collect(t, &out[done], pos ? &pos[done] : nullptr));
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_wait_ingest(oat_tracker *t)
+{
+    REQUIRE(t, "null handle");
+    REQUIRE(t->head != t->tailpos, "oat_tracker_wait_ingest: nothing outstanding");
+    CKRET(bind(t->ctx));
+    Slot &s = t->ring[(t->head - 1) % t->ring.size()];
+    if (s.ingest == 1)
+        CK(cudaEventSynchronize(s.copied));
+    else
+        CK(cudaEventSynchronize(s.fused_done));
     return OAT_OK;
 }
 

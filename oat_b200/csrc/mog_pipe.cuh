@@ -42,6 +42,9 @@ namespace oat {
 #ifndef PIPE_RESERVED_CTAS_CFG
 #define PIPE_RESERVED_CTAS_CFG 24
 #endif
+#ifndef PIPE_PUBLISH_BATCH_CFG
+#define PIPE_PUBLISH_BATCH_CFG 2   // finished tiles published per release fence (storer lane)
+#endif
 #ifndef PIPE_TAIL_GRID_CFG
 #define PIPE_TAIL_GRID_CFG 48   // CTAs of the resident tail server (two fit beside one fused CTA)
 #endif
@@ -52,6 +55,7 @@ constexpr int PIPE_CTHREADS = PIPE_CTHREADS_CFG;    // compute threads (8 warps)
 constexpr int PIPE_THREADS = PIPE_CTHREADS + 64;     // + a loader warp (bulk loads) and a storer warp (write-back + publication)
 constexpr int PIPE_TILE = PIPE_CTHREADS * 4;        // pixels per tile
 constexpr int PIPE_STAGES = PIPE_STAGES_CFG;
+constexpr int PIPE_PUBLISH_BATCH = PIPE_PUBLISH_BATCH_CFG;
 #ifndef PIPE_CTAS_PER_SM_CFG
 #define PIPE_CTAS_PER_SM_CFG PIPE_MINBLOCKS_CFG
 #endif
@@ -78,7 +82,6 @@ enum {
     HDR_TSEQ = 12,
     HDR_SLOW = 14,
     HDR_DONE = 16,
-    HDR_DIRECT = 18,  // some compute thread wrote GMM state of this tile with direct global stores (modes >= 1)
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (sm_90+; SASS UBLKCP / SYNCS) ----------------
@@ -223,7 +226,7 @@ struct StreamArgs {
     unsigned int *done_flag;       // pinned host word of the slot: the last CTA to leave stores launch_id there
     unsigned int launch_id;
     int relaxed_publish;           // measurement switch ONLY (OAT_B200_RELAXED_PUBLISH): never fence, to price the fences
-    int fence_always;              // measurement switch ONLY (OAT_B200_FENCE_ALWAYS): fence every tile
+    int fence_always;              // measurement switch ONLY (OAT_B200_FENCE_ALWAYS): one fence per tile instead of per batch
 };
 
 // One pixel with one or two live modes whose sample fits mode 0 (the heavier one): the m = 0
@@ -394,7 +397,6 @@ __device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, u
         sm0[3 * PIPE_TILE] = B[0];
         sm0[4 * PIPE_TILE] = C[0];
         *smn = (uint8_t)n;
-        if (nw > 1) *reinterpret_cast<volatile uint32_t *>(st + PIPE_OFF_FLAG + 4 * HDR_DIRECT) = 1u;
 #pragma unroll 1
         for (int m = 1; m < nw; ++m) {
             float *g = state + (size_t)(m * 5) * a.plane + pidx;
@@ -445,18 +447,18 @@ __device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, u
 // that reads it next -- a release/acquire pair at GPU scope, correct under the PTX memory model:
 //   writer   compute warps' direct stores (modes >= 1)  --mbarrier done[s] (release.cta / acquire.cta)-->  storer lane;
 //            the tile's bulk stores are COMPLETE (cp.async.bulk.wait_group, not .read);
-//            if the tile had direct stores (HDR_DIRECT, a few % of the tiles): fence.acq_rel.gpu  (cumulative:
-//            covers what the storer lane observed through the mbarrier);
-//            st.relaxed.gpu tile_seq[tile]  (+ red.add done_count for the tail server)
+//            fence.acq_rel.gpu  (cumulative: covers what the storer lane observed through the mbarrier) -- ONE fence
+//            for a batch of PIPE_PUBLISH_BATCH retired tiles;
+//            st.relaxed.gpu tile_seq[tile]  (+ red.add done_count for the tail server) for every tile of the batch
 //   reader   loader lane: ld.acquire.gpu tile_seq[tile] == seq_expect;  fence.proxy.async.global;  bulk loads;
 //            the compute warps' own ld.global.cg follow the mbarrier full[s] the loads complete on.
 // The release fence is a MEMBAR.GPU: a round trip through a memory system that this kernel keeps saturated.  It
-// lives in the storer lane, where it delays nothing but the next write-back, and is issued only for tiles whose
-// state was (also) written by the compute warps' direct stores; tiles written by bulk stores alone -- 95 % and
-// more -- are published behind the COMPLETION of those stores.  (Fence on every tile: 0.71 of the HBM peak with one
-// lane doing loads and stores, 0.83 with it in the storer lane; as built: see profiles/.)
-// The storer publishes a tile when it comes back for the next one (its stores have had a tile period to
-// complete), or after a bounded wait if nothing comes -- so a tile is never withheld from a CTA that waits for it.
+// lives in the storer lane, where it delays nothing but the next write-back, and one fence publishes a batch of
+// tiles.  (Fence per tile: 0.71 of the HBM peak with one lane doing loads and stores, 0.83 with it in the storer
+// lane; NO fence -- flags behind the mere completion of the bulk stores -- reaches 0.95-0.99 but is wrong: see the
+// storer lane.  As built: profiles/.)
+// The storer publishes a batch when it is full, or after a bounded wait if no further tile arrives -- so a tile is
+// never withheld from a CTA that waits for it.
 //
 // LINEAR: cols % 32 == 0 and every image pitch is tight, so a pixel's byte offsets are plain multiples of its
 // padded index (one bulk copy brings a tile's BGR bytes).  Otherwise the loader lane issues one bulk copy
@@ -496,7 +498,6 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
     for (int s = 0; s < PIPE_STAGES; ++s) {
         uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
         if (tid < 4) reinterpret_cast<uint32_t *>(st + PIPE_OFF_FLAG)[tid] = 0u;  // dirty, tile, queue count, queue head
-        if (tid == 4) reinterpret_cast<uint32_t *>(st + PIPE_OFF_FLAG)[HDR_DIRECT] = 0u;
         for (int i = tid; i < PIPE_TILE; i += PIPE_THREADS) reinterpret_cast<uint16_t *>(st + PIPE_OFF_QUEUE)[i] = 0xffffu;
     }
     __syncthreads();
@@ -661,21 +662,28 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
         }
         if (!is_storer) return;
         // ---- storer lane ---------------------------------------------------------------------------
-        unsigned int *pend_tseq = nullptr, *pend_done = nullptr;  // the one finished tile whose publication is still owed
-        uint32_t pend_tile = 0, pend_seq = 0;
-        bool pend = false, pend_direct = false;
+        // Finished tiles whose publication is still owed (at most PIPE_PUBLISH_BATCH): ONE release fence publishes the
+        // whole batch.  A MEMBAR.GPU is a round trip through a memory system this kernel keeps saturated (~1.5 us, most
+        // of a tile period): paid per tile it makes this lane the bottleneck (0.83 instead of 0.95 of the HBM peak at
+        // 1080p), and it cannot be dropped -- without it a reader that has seen the flag can still see a stale plane of
+        // the tile (observed on 640x480 frames, where consecutive frames of a stream are in flight together).
+        constexpr int NB = PIPE_PUBLISH_BATCH;
+        unsigned int *pend_tseq[NB], *pend_done[NB];
+        uint32_t pend_tile[NB], pend_seq[NB];
+        int npend = 0;
         auto publish_pending = [&]() {
-            if (!pend) return;
-            bulk_wait_all<0>();  // its bulk stores are complete: performed, not merely read out of shared memory
-            // ... and the compute warps' direct stores of the tile, if it had any, are made visible at GPU scope before
-            // the flag (cumulative over what this lane observed through done[s]).  A MEMBAR.GPU costs a loaded
-            // memory round trip (2-3 us at the HBM roofline, more than a tile period -- r02c measured 0.83 instead of
-            // 0.97 of the peak with a fence on every tile, even in this lane), so it is paid only by the few tiles
-            // that need it; a tile written by bulk stores alone is published behind their completion.
-            if (pend_direct && !pa.relaxed_publish) fence_acq_rel_gpu();
-            st_relaxed_gpu(pend_tseq + pend_tile, pend_seq);
-            if (pend_done) red_add_relaxed_gpu(pend_done, 1u);
-            pend = false;
+            if (npend == 0) return;
+            bulk_wait_all<0>();  // their bulk stores are complete: performed, not merely read out of shared memory
+            // ... and, with the compute warps' direct stores of those tiles (observed by this lane through done[s]),
+            // visible at GPU scope before the flags
+            if (!pa.relaxed_publish) fence_acq_rel_gpu();
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (k < npend) {
+                    st_relaxed_gpu(pend_tseq[k] + pend_tile[k], pend_seq[k]);
+                    if (pend_done[k]) red_add_relaxed_gpu(pend_done[k], 1u);
+                }
+            npend = 0;
         };
         for (int si = 0;; ++si) {
             const int s = si % PIPE_STAGES;
@@ -690,8 +698,8 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
             }
             const int tile = (int)h[HDR_TILE];
             if (tile < 0) break;
-            // 1. the tile retired before has had a whole tile period for its bulk stores: publish it
-            publish_pending();
+            // 1. a full batch of retired tiles (the youngest has had a whole tile period for its bulk stores): publish it
+            if (npend == NB || pa.fence_always) publish_pending();
             // 2. write this tile back
             float *state = reinterpret_cast<float *>(*hdr_ptr(h, HDR_STATE));
             uint8_t *nmodes = reinterpret_cast<uint8_t *>(*hdr_ptr(h, HDR_NMODES));
@@ -727,13 +735,15 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
             }
             h[HDR_QCNT] = 0u;  // re-arm the slow-pixel queue
             h[HDR_QHEAD] = 0u;
-            pend_tseq = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_TSEQ));
-            pend_done = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_DONE));
-            pend_tile = (uint32_t)tile;
-            pend_seq = h[HDR_SEQ_OUT];
-            pend_direct = (h[HDR_DIRECT] != 0u) || pa.fence_always;
-            h[HDR_DIRECT] = 0u;
-            pend = true;
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (k == npend) {
+                    pend_tseq[k] = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_TSEQ));
+                    pend_done[k] = reinterpret_cast<unsigned int *>(*hdr_ptr(h, HDR_DONE));
+                    pend_tile[k] = (uint32_t)tile;
+                    pend_seq[k] = h[HDR_SEQ_OUT];
+                }
+            ++npend;
             // 3. hand the stage back as soon as its stores have READ it
             bulk_wait_read<0>();
             mbar_arrive(&freed[s]);
@@ -863,7 +873,6 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
                         *reinterpret_cast<float4 *>(sm0 + 3 * PIPE_TILE) = B;
                         *reinterpret_cast<float4 *>(sm0 + 4 * PIPE_TILE) = C;
                         if (two != 0u) {
-                            h[HDR_DIRECT] = 1u;
                             st_state_f4(w1p, W1);
                             const uint32_t nnew = n0 | (n1 << 8) | (n2 << 16) | (n3 << 24);
                             if (nnew != nm) *(reinterpret_cast<uint32_t *>(st + PIPE_OFF_NM) + tid) = nnew;

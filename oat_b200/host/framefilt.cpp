@@ -31,6 +31,9 @@ protected:
     // FrameFilter::connectToNode (FrameFilter.cpp:37-57); sink_color lets `col` re-tag its output
     bool connectToNode() override
     {
+        // the CUDA context first: creating it takes a good part of a second, and connect() below returns the moment the
+        // SOURCE's SINK appears -- a frame server must not find its first frames waiting for that
+        ctx_.reset(new gpu::Context(gpu_index_));
         frame_source_.touch(frame_source_address_);
         if (frame_source_.connect() != SourceState::CONNECTED) return false;
         in_ = frame_source_.parameters();
@@ -38,7 +41,6 @@ protected:
         const size_t out_bytes = in_.rows * in_.cols * (size_t)color_bytes(out_color);
         frame_sink_.bind(frame_sink_address_, out_bytes, false);  // announced below, once the memory kind is final
         shared_frame_ = frame_sink_.retrieve(in_.rows, in_.cols, color_bytes(out_color), out_color);
-        ctx_.reset(new gpu::Context(gpu_index_));
         d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
         d_out_.reset(new gpu::DeviceBuffer(*ctx_, out_bytes));
         out_bytes_ = out_bytes;

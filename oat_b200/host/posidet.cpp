@@ -6,6 +6,7 @@
 //   track   (extension) the fused device path: takes the RAW BGR SOURCE and does framefilt mog ->
 //           framefilt col -C HSV -> posidet hsv in one pass, no shared-memory hops in between
 #include <cfloat>
+#include <deque>
 #include <iostream>
 #include <memory>
 
@@ -26,13 +27,13 @@ protected:
     // PositionDetector::connectToNode (PositionDetector.cpp:40-56)
     bool connectToNode() override
     {
+        ctx_.reset(new gpu::Context(gpu_index_));  // before connect(): see FrameFilter::connectToNode
         frame_source_.touch(frame_source_address_);
         const SourceState rc = required_color_ == PIX_ANY ? frame_source_.connect() : frame_source_.connect(required_color_);
         if (rc != SourceState::CONNECTED) return false;
         in_ = frame_source_.parameters();
         position_sink_.bind(position_sink_address_, position_sink_address_);
         shared_position_ = position_sink_.retrieve();
-        ctx_.reset(new gpu::Context(gpu_index_));
         if (frame_source_.header()->memory == FrameMemory::DEVICE)  // device -> device hand-off
             src_dev_.reset(new gpu::IpcImport(*ctx_, frame_source_.header()->ipc_handle));
         else
@@ -247,6 +248,12 @@ private:
 };
 
 // ---- posidet track: mog -> col HSV -> hsv fused on the device ----------------------------------------------
+// With --pipeline D (default 1) the component keeps up to D frames in flight on the GPU behind its SOURCE: a frame is
+// handed back to the SOURCE as soon as its pixels have been consumed (H2D copy done / read in place by the fused
+// kernel: oat_tracker_wait_ingest), its position is published -- in order, one token at a time, every Sample intact --
+// D-1 frames later.  The SOURCE and the SINK both see the reference's lock-step protocol (one token in flight per
+// edge); what changes is that the copy of frame t+1 and the kernels of frame t overlap.  This is the GPU-aware
+// counterpart of putting an `oat buffer` (src/buffer/FrameBuffer.cpp:56-116) in front of a slow component.
 class FusedTracker : public PositionDetector {
 public:
     FusedTracker(const std::string &source, const std::string &sink) : PositionDetector(source, sink)
@@ -259,6 +266,7 @@ public:
     {
         auto o = HSVOptions::options();
         o.push_back({"adaptation-coeff", 'A', true, "framefilt mog's adaptation coefficient, 0 to 1.0. Default 0."});
+        o.push_back({"pipeline", 'p', true, "Frames kept in flight on the GPU (1 = synchronous; positions lag by pipeline-1 frames)."});
         return o;
     }
     void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
@@ -266,21 +274,47 @@ public:
         o_.apply(vm, t);
         config::getNumericValue<double>(vm, t, "adaptation-coeff", learning_coeff_, 0.0, 1.0);
         config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
+        config::getNumericValue<int>(vm, t, "pipeline", depth_, 1, 32);
     }
 
 protected:
-    void setup() override { gpu::ck(oat_tracker_create(ctx_->h, (int)in_.rows, (int)in_.cols, nullptr, 0, &trk_)); }
-    void detectPosition(const uint8_t *d_frame, Position2D &position) override
+    void setup() override { gpu::ck(oat_tracker_create(ctx_->h, (int)in_.rows, (int)in_.cols, nullptr, depth_, &trk_)); }
+    void detectPosition(const uint8_t *, Position2D &) override {}  // (process() below drives the tracker itself)
+    void publish_oldest()
     {
         oat_detection d;
-        gpu::ck(oat_tracker_track(trk_, d_frame, in_.cols * 3, learning_coeff_, &o_.p, &d, nullptr, 0, nullptr, 0, nullptr, 0,
-                                  nullptr, 0));
-        fill(position, d);
+        gpu::ck(oat_tracker_collect(trk_, &d));
+        Position2D internal_pos("");
+        internal_pos.set_sample(samples_.front());  // propagate tick / usec (PositionDetector.cpp:80)
+        samples_.pop_front();
+        fill(internal_pos, d);
+        position_sink_.wait();
+        *shared_position_ = internal_pos;  // everything but the label (Position2D.h:84-105)
+        position_sink_.post();
+    }
+    int process() override
+    {
+        if (frame_source_.wait() == NodeState::END) {
+            while (!samples_.empty() && !quit) publish_oldest();  // drain: every frame that went in comes out
+            return 1;
+        }
+        if (frame_source_.header()->memory != src_memory_)
+            throw std::runtime_error("SOURCE frame memory kind changed after connect()");
+        // the frame goes to the GPU straight from where the SOURCE keeps it (page-locked shm or device memory)
+        const uint8_t *pixels = src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) : static_cast<const uint8_t *>(frame_source_.pixels());
+        gpu::ck(oat_tracker_submit(trk_, pixels, in_.cols * 3, learning_coeff_, &o_.p, nullptr, 0));
+        samples_.push_back(frame_source_.retrieve()->sample());
+        gpu::ck(oat_tracker_wait_ingest(trk_));
+        frame_source_.post();
+        if ((int)samples_.size() >= depth_) publish_oldest();
+        return 0;
     }
 
 private:
     HSVOptions o_;
     double learning_coeff_{0.0};
+    int depth_{1};
+    std::deque<Sample> samples_;  // Samples of the frames in flight, oldest first
     oat_tracker *trk_{nullptr};
 };
 

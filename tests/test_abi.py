@@ -80,15 +80,16 @@ class _ResidentModel:
     mog_stream_kernel): every CTA has a LOADER lane, compute warps and a STORER lane around a ring of `stages`
     stages (loader --full--> compute --done--> storer --freed--> loader); work items (frame, tile) are drawn from
     one counter (the first `stages` of a CTA in one draw, then one at a time); a tile of frame f+1 of a model may
-    only be loaded once the same tile of the model's previous frame has been PUBLISHED.  The storer publishes a
-    tile when it comes back for the next one, or -- if the next one does not arrive in time -- while it waits.
+    only be loaded once the same tile of the model's previous frame has been PUBLISHED.  The storer publishes
+    retired tiles in batches (one release fence per batch): when a batch is full, or -- if the next tile does not
+    arrive in time -- while it waits.
     The model is stepped by an adversarial (random) scheduler; it checks that every item is processed exactly
     once, that no load ever precedes the publication it depends on, and that the protocol cannot deadlock --
     including frames smaller than one CTA's ring, where the loader waits for a tile that still sits in its own
     CTA's stages."""
 
-    def __init__(self, nframes, ntiles, grid, stages, models, rng):
-        self.nf, self.nt, self.grid, self.S, self.rng = nframes, ntiles, grid, stages, rng
+    def __init__(self, nframes, ntiles, grid, stages, models, rng, batch=2):
+        self.nf, self.nt, self.grid, self.S, self.rng, self.P = nframes, ntiles, grid, stages, rng, batch
         self.total = nframes * ntiles
         self.model_of = [f % models for f in range(nframes)]      # frames of `models` streams interleaved
         self.prev = {}                                            # frame -> previous frame of the same model
@@ -104,7 +105,7 @@ class _ResidentModel:
 
     def _new_cta(self):
         # stage state: None (free) -> item (loaded) -> computed flag -> stored (free again)
-        return {"stage": [None] * self.S, "computed": [False] * self.S, "li": 0, "si": 0, "ci": 0, "pend": None,
+        return {"stage": [None] * self.S, "computed": [False] * self.S, "li": 0, "si": 0, "ci": 0, "pend": [],
                 "nxt": None, "batch": None, "ldone": False, "cdone": False, "sdone": False}
 
     def _item(self, g):
@@ -166,21 +167,21 @@ class _ResidentModel:
             return False
         s = c["si"] % self.S
         if c["si"] >= c["ci"]:  # done[s] has not completed: after the bounded wait, publish what is owed
-            if c["pend"] is not None:
-                self.published.add(c["pend"])
-                c["pend"] = None
+            if c["pend"]:
+                self.published.update(c["pend"])
+                c["pend"] = []
                 return True
             return False
         if c["stage"][s] == "END":
-            if c["pend"] is not None:
-                self.published.add(c["pend"])
-                c["pend"] = None
+            self.published.update(c["pend"])
+            c["pend"] = []
             c["sdone"] = True
             self.exited += 1
             return True
-        if c["pend"] is not None:
-            self.published.add(c["pend"])
-        c["pend"] = c["stage"][s]
+        if len(c["pend"]) == self.P:  # a full batch: one fence publishes it
+            self.published.update(c["pend"])
+            c["pend"] = []
+        c["pend"].append(c["stage"][s])
         c["stage"][s] = None
         c["si"] += 1
         return True
@@ -216,7 +217,7 @@ def test_resident_scheduler_protocol_model():
     cases = [(1, 1, 1, 1), (1, 7, 3, 1), (4, 5, 8, 1), (6, 2, 8, 2), (8, 13, 5, 1), (16, 3, 7, 4), (5, 40, 6, 1),
              (12, 9, 4, 3), (3, 1, 5, 1), (20, 2, 3, 2), (9, 1, 1, 1), (30, 2, 1, 1), (10, 4, 2, 2), (64, 75, 16, 1)]
     for nframes, ntiles, grid, models in cases:
-        for S in (3, 4, 2):
-            m = _ResidentModel(nframes, ntiles, grid, S, models, rng).run()
+        for S, P in ((3, 1), (4, 2), (2, 3), (4, 4)):
+            m = _ResidentModel(nframes, ntiles, grid, S, models, rng, batch=P).run()
             assert sorted(m.loaded) == [(f, t) for f in range(nframes) for t in range(ntiles)], (nframes, ntiles, grid)
             assert len(m.published) == nframes * ntiles

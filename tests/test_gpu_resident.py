@@ -287,3 +287,27 @@ def test_clip_engine_hands_over_to_generic_kernel_on_busy_stream(ctx):
         assert bool(d[0]) == bool(o.position_valid) and abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
     assert a.live_modes() == int(orc.mog.state()[0].sum())
     a.close()
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (360, 480), (720, 1280)])
+def test_clip_engine_close_dependencies_stress(ctx, shape):
+    """Frames of about one grid's worth of tiles: consecutive frames of the stream are in flight TOGETHER, so nearly
+    every tile load really waits for the previous frame's publication of that tile (at 1080p and above the previous
+    frame's tile was published long before).  This is the regime that exposes a publication that is not a proper
+    release (an unfenced flag store behind completed bulk stores fails here about once in 30 clips).  Repeated
+    clips, whole-state comparison against the synchronous path."""
+    rows, cols = shape
+    lr, n, reps = 0.05, 160, 12
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    R = 16
+    bufs = _frames(ctx, rows, cols, 1000, R + 1)
+    seq = [bufs[0]] + [bufs[1 + i % R] for i in range(n - 1)]
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    want = [_det(b.track(f)[0]) for f in seq]
+    for rep in range(reps):
+        a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=(64, 16, 8)[rep % 3])
+        got = [_det(d) for d in a.run_clip(seq)]
+        assert got == want, rep
+        _state_equal(a, b)
+        a.close()
+    b.close()
