@@ -152,6 +152,7 @@ struct oat_ctx {
     uint64_t pipe_launches = 0;
     cudaStream_t aux = nullptr;  // small host-synchronous uploads (frame descriptors of a clip)
     ClipHalf clip[2];            // two chunks of the resident clip engine in flight
+    DevBuf tail_scratch[2];      // per chunk in flight: one global-memory labelling area per CTA of the tail server
     // device timing of the resident fused kernel: a CUDA-event pair on the compute stream around every launch
     // (consecutive launches overlap tile by tile, so the brackets partition the timeline: their sum is the time
     // from the first launch's start to the last one's end)
@@ -268,6 +269,8 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     if (c->hsv_lut) cudaFree(c->hsv_lut);
     c->clip[0].release();
     c->clip[1].release();
+    c->tail_scratch[0].release();
+    c->tail_scratch[1].release();
     if (c->work_counter) cudaFree(c->work_counter);
     if (c->done_host) cudaFreeHost((void *)c->done_host);
     if (c->aux) {
@@ -1985,10 +1988,19 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
     const BitGeom g = t0->tail.tb.g;
     const int ntiles = (int)((t0->m.plane + PIPE_TILE - 1) / PIPE_TILE);
     const int ke = p->erode_px > 0 ? p->erode_px : 0, kd = p->dilate_px > 0 ? p->dilate_px : 0;
-    const int R = 8;
-    const size_t nin = (size_t)R + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
-    const size_t stage = 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
-    const size_t tail_smem = std::max(stage, t0->tail.fast_smem);
+    // bands of 32 rows (a band costs ~3 dependent L2 round trips whatever its size; most bands of a tracking mask are
+    // empty) unless the morphology staging of such a band would not fit
+    auto stage_for = [&](int rr) {
+        const size_t nin = (size_t)rr + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
+        return 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
+    };
+    const int R = stage_for(32) <= (size_t)64 * 1024 ? 32 : 8;
+    const size_t stage = stage_for(R);
+    const size_t tail_smem = std::max(std::max(stage, t0->tail.fast_smem), (size_t)PIPE_TAIL_SMEM_KB_CFG * 1024);
+    // second labelling attempt in global memory for masks whose tables do not fit the CTA's shared memory: room for
+    // ~200 k runs and 4096 contours per CTA, plus the mask itself
+    const int scratch_comps = 4096;
+    const size_t scratch_bytes = (((size_t)g.rows * g.wpr * 4 + (size_t)g.rows * 16 + (size_t)3 * scratch_comps * 8 + ((size_t)200 << 10) * 12 + 4096) + 255) & ~(size_t)255;
     static size_t tail_stream_smem_set = 48 * 1024;
     if (!fused_only && tail_smem + 2048 > tail_stream_smem_set) {
         CK(cudaFuncSetAttribute(tail_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
@@ -2164,7 +2176,13 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
             CK(cudaMemsetAsync(half[h].d_ctr, 0, 2 * nitems * sizeof(unsigned int), ts));
             const int nbands = div_up(g.rows, R);
             const int gridT = std::max(1, std::min(nbands, (int)PIPE_TAIL_GRID_CFG));
-            tail_stream_kernel<<<gridT, 256, tail_smem, ts>>>(half[h].d_tf, (int)nitems, half[h].d_ctr, half[h].d_ctr + nitems);
+            uint8_t *scratch = nullptr;
+            if (scratch_bytes < ((size_t)1 << 31) && c->tail_scratch[h].ensure(scratch_bytes * gridT) == OAT_OK)
+                scratch = (uint8_t *)c->tail_scratch[h].p;
+            else
+                cudaGetLastError();  // no scratch: overflowing masks are replayed by the host
+            tail_stream_kernel<<<gridT, 256, tail_smem, ts>>>(half[h].d_tf, (int)nitems, half[h].d_ctr, half[h].d_ctr + nitems, scratch,
+                                                              (int)scratch_bytes, scratch_comps);
             ++c->launches;
             CK(cudaGetLastError());
             CK(cudaEventRecord(half[h].done, ts));

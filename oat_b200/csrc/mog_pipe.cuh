@@ -46,7 +46,10 @@ namespace oat {
 #define PIPE_PUBLISH_BATCH_CFG 2   // finished tiles published per release fence (storer lane)
 #endif
 #ifndef PIPE_TAIL_GRID_CFG
-#define PIPE_TAIL_GRID_CFG 48   // CTAs of the resident tail server (two fit beside one fused CTA)
+#define PIPE_TAIL_GRID_CFG 24   // CTAs of the resident tail server: one beside the single fused CTA of a reserved SM
+#endif
+#ifndef PIPE_TAIL_SMEM_KB_CFG
+#define PIPE_TAIL_SMEM_KB_CFG 110  // ... with the rest of that SM's shared memory for its labelling tables
 #endif
 #ifndef PIPE_MINBLOCKS_CFG
 #define PIPE_MINBLOCKS_CFG 2

@@ -99,9 +99,12 @@ __device__ __forceinline__ void suf_union(volatile uint32_t *P, uint32_t a, uint
 struct RegionView {
     const uint32_t *w;
     int y0, y1, j0, j1, wd;
+    bool vol;  // the words live in global memory and are updated with atomics (holes): never read them through L1
     __device__ __forceinline__ uint32_t at(int y, int j) const
     {
-        return (y < y0 || y > y1 || j < j0 || j > j1) ? 0u : w[(y - y0) * wd + (j - j0)];
+        if (y < y0 || y > y1 || j < j0 || j > j1) return 0u;
+        const uint32_t *p = w + (y - y0) * wd + (j - j0);
+        return vol ? *reinterpret_cast<const volatile uint32_t *>(p) : *p;
     }
 };
 // candidate background of an inner row: background between the row's first and last foreground pixel
@@ -123,7 +126,12 @@ __device__ __forceinline__ bool fast_any_bg(const RegionView &m, const BitGeom &
 // touches repeatedly -- the mask's bounding region, row extents, run table, parents, accumulators
 // -- is staged in shared memory first (one coalesced pass over L2), so no step chases pointers
 // through global memory.
-__device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymin, const int ymax, const uint32_t a_t0)
+// `work` is the phase's working memory (a.smem_bytes of it): the CTA's shared memory, or -- second attempt of the
+// resident tail server for a mask whose tables do not fit there -- a per-CTA scratch area in global memory (same
+// code, every hop an L2 round trip instead of ~30 cycles).  Returns false WITHOUT publishing a result if the tables
+// do not fit and this is not the final attempt; with `final` it publishes TAIL_OVERFLOW and the host replays the frame.
+__device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymin, const int ymax, const uint32_t a_t0,
+                                 const uint32_t slow_groups, const bool final)
 {
     const BitGeom g = a.g;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
@@ -136,14 +144,14 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     r.det.x = r.det.y = r.det.area = 0.0;
     r.status = TAIL_OK;
     r.nodes = 0;
-    r.slow_groups = (tid == 0 && a.slow_in) ? atomicExch(a.slow_in, 0u) : 0u;
+    r.slow_groups = slow_groups;
     r.pad = 0;
     for (int i = 0; i < 8; ++i) r.cyc[i] = 0;
     r.cyc[0] = a_t0;
     r.cyc[1] = (uint32_t)clock64();
     if (ymax < ymin) {  // empty mask
         if (tid == 0) store_result(a, r);
-        return;
+        return true;
     }
     const int H = ymax - ymin + 1;
     const int C = a.max_comps;
@@ -159,11 +167,11 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(smem + used);
     used += (size_t)3 * C * 8;
     if (used + 1024 > (size_t)a.smem_bytes) {
-        if (tid == 0) {
+        if (final && tid == 0) {
             r.status = TAIL_OVERFLOW;
             store_result(a, r);
         }
-        return;
+        return false;
     }
     if (tid == 0) {
         s_ncomp = 0;
@@ -202,11 +210,11 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     const long long avail = (long long)a.smem_bytes - (long long)used;
     const int N = avail > 0 ? (int)(avail / 12) : 0;  // start,end,row,comp: u16 x4 + parent u32 = 12 B
     if (N < 16) {
-        if (tid == 0) {
+        if (final && tid == 0) {
             r.status = TAIL_OVERFLOW;
             store_result(a, r);
         }
-        return;
+        return false;
     }
     uint32_t *parent = reinterpret_cast<uint32_t *>(smem + used);
     uint16_t *nstart = reinterpret_cast<uint16_t *>(parent + N);
@@ -221,8 +229,9 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     for (int c = tid; c < 3 * C; c += NT) acc[c] = 0ull;
     __syncthreads();
     r.cyc[2] = (uint32_t)clock64();
-    RegionView M{Ms, ymin, ymax, jmin, jmax, Wd};
-    RegionView G{Gs, ymin, ymax, jmin, jmax, Wd};
+    const bool vol = __isGlobal(smem) != 0;
+    RegionView M{Ms, ymin, ymax, jmin, jmax, Wd, vol};
+    RegionView G{Gs, ymin, ymax, jmin, jmax, Wd, vol};
 
     r.cyc[3] = (uint32_t)clock64();
     // ---- 2. exclusive scan over rows (one warp, chunked) ---------------------------------------
@@ -258,11 +267,11 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     const uint32_t nF = s_nF, nB = s_nB;
     r.nodes = nF + nB + 1;
     if (nF + nB + 1 > (uint32_t)N) {
-        if (tid == 0) {
+        if (final && tid == 0) {
             r.status = TAIL_OVERFLOW;
             store_result(a, r);
         }
-        return;
+        return false;
     }
     // node ids: 0 = EXT, 1..nF foreground runs (raster order), nF+1..nF+nB candidate background runs
     // ---- 3. fill the run table: G lanes per row (G = region width in words rounded up to a power of two,
@@ -414,11 +423,11 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     }
     __syncthreads();
     if (s_fail) {
-        if (tid == 0) {
+        if (final && tid == 0) {
             r.status = TAIL_OVERFLOW;
             store_result(a, r);
         }
-        return;
+        return false;
     }
     // ---- 7. exact 2x2-cell moments (cells are owned by their top row).  Four lanes share a run, each
     //         taking every fourth word of it; a warp whose lanes all feed the same contour (the usual
@@ -510,6 +519,7 @@ __device__ void tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
         }
         store_result(a, r);
     }
+    return true;
 }
 
 // One band of R rows: [erode] -> [dilate] -> publish the rows (mask, extents, run counts, vertical bounding range).
@@ -642,7 +652,10 @@ __global__ void __launch_bounds__(256, 6) tail_fast_kernel(const FastArgs a)
     }
     __syncthreads();
     if (!s_last) return;
-    tail_label_phase(a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start);
+    __shared__ uint32_t s_slow;
+    if (threadIdx.x == 0) s_slow = a.slow_in ? atomicExch(a.slow_in, 0u) : 0u;  // the fused kernel's census of this frame, re-armed
+    __syncthreads();
+    tail_label_phase(a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start, s_slow, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -661,9 +674,14 @@ struct TailFrame {
     unsigned int pad;
 };
 
-__global__ void __launch_bounds__(256, 6) tail_stream_kernel(const TailFrame *frames, const int nframes,
+#ifndef TAIL_STREAM_MINBLOCKS_CFG
+#define TAIL_STREAM_MINBLOCKS_CFG 2  // its CTAs sit beside ONE fused CTA on a reserved SM: registers are not what limits them
+#endif
+__global__ void __launch_bounds__(256, TAIL_STREAM_MINBLOCKS_CFG) tail_stream_kernel(const TailFrame *frames, const int nframes,
                                                              unsigned int *band_ctr /* [nframes], zeroed */,
-                                                             unsigned int *band_done /* [nframes], zeroed */)
+                                                             unsigned int *band_done /* [nframes], zeroed */,
+                                                             uint8_t *scratch /* or NULL: gridDim.x areas of scratch_bytes */,
+                                                             const int scratch_bytes, const int scratch_comps)
 {
     extern __shared__ __align__(16) uint32_t sm[];
     __shared__ TailFrame s_tf;
@@ -708,7 +726,19 @@ __global__ void __launch_bounds__(256, 6) tail_stream_kernel(const TailFrame *fr
             }
             __syncthreads();
             if (s_last) {
-                tail_label_phase(s_tf.a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start);
+                __shared__ uint32_t s_slow;
+                if (threadIdx.x == 0) s_slow = s_tf.a.slow_in ? atomicExch(s_tf.a.slow_in, 0u) : 0u;  // the frame's census, re-armed
+                __syncthreads();
+                // label in shared memory; a mask whose tables do not fit (many blobs, noise) is labelled again by this
+                // CTA in its global-memory scratch area -- slower, but on the device and beside the other CTAs' frames,
+                // instead of a round trip through the host
+                if (!tail_label_phase(s_tf.a, reinterpret_cast<uint8_t *>(sm), s_ymin, s_ymax, t_start, s_slow, scratch == nullptr)) {
+                    __syncthreads();
+                    FastArgs big = s_tf.a;
+                    big.smem_bytes = scratch_bytes;
+                    big.max_comps = scratch_comps;
+                    tail_label_phase(big, scratch + (size_t)blockIdx.x * (size_t)scratch_bytes, s_ymin, s_ymax, t_start, s_slow, true);
+                }
                 __syncthreads();
                 if (threadIdx.x == 0) s_last = false;
             }

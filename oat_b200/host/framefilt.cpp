@@ -70,7 +70,7 @@ protected:
         if (frame_source_.wait() == NodeState::END) return 1;
         if (frame_source_.header()->memory != src_memory_)
             throw std::runtime_error("SOURCE frame memory kind changed after connect()");
-        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? src_dev_->p : frame_source_.pixels(), in_.bytes));
+        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) + frame_source_.header()->device_offset : static_cast<const uint8_t *>(frame_source_.pixels()), in_.bytes));
         const Sample sample = frame_source_.retrieve()->sample();
         frame_source_.post();
 

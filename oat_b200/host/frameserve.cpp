@@ -5,6 +5,11 @@
 //          Sample clock advances).  It is the driver of the reference's own performance protocol
 //          (test/perf/framefilt-mog.sh:1-3, test/perf/results.md:12-18: 1000 x 1 MP frames, free-running).
 //          The image is a binary PPM/PGM or a NumPy .npy (image_io.h; cv::imread is not available here).
+//   file   `oat frameserve file SINK -f CLIP [-r FPS] [--roi "[x0,y0,w,h]"]` -- the reference's FileReader
+//          (src/frameserver/FileReader.cpp:36-131): the frames of a clip in order, then end of stream.  The clip is a
+//          lossless NumPy .npy (frames x rows x cols [x 3], image_io.h; cv::VideoCapture is not available here).  With
+//          --device the whole clip is uploaded to HBM once and every frame is published IN PLACE (the shared frame
+//          header's device_offset moves; no per-frame copy at all).
 //   synth  the synthetic tracking stream of SURVEY.md 8(d) (deterministic, the same arithmetic as the oracle and
 //          the CUDA generator), N frames.
 //
@@ -29,6 +34,7 @@ static void printUsage(std::ostream &out)
            "Serve frames to SINK.\n\n"
            "TYPE\n"
            "  test: Serve a static test image (binary PPM/PGM or uint8 .npy).\n"
+           "  file: Serve the frames of a clip (uint8 .npy, frames x rows x cols [x 3]).\n"
            "  synth: Serve the synthetic single-blob tracking stream.\n\n"
            "SINK:\n  User-supplied name of the memory segment to publish frames to (e.g. raw).\n\n"
            "INFO:\n  --help                 Produce help message.\n  -v [ --version ]       Print version information.\n\n"
@@ -47,7 +53,7 @@ int main(int argc, char *argv[])
         }
         if (argc < 2) { printUsage(std::cout); return 0; }
         const std::string type = argv[1];
-        if (type != "test" && type != "synth") {
+        if (type != "test" && type != "synth" && type != "file") {
             printUsage(std::cout);
             std::cerr << whoError(comp_name, "Error: invalid TYPE specified.\n");
             return -1;
@@ -63,7 +69,7 @@ int main(int argc, char *argv[])
             int process() override { return 1; }
         } sig_owner;  // installs the SIGINT handler
         const std::string sink_addr = argv[2];
-        comp_name = (type == "test" ? "testframe[*->" : "synthserve[*->") + sink_addr + "]";
+        comp_name = (type == "test" ? "testframe[*->" : type == "file" ? "filereader[*->" : "synthserve[*->") + sink_addr + "]";
 
         std::vector<config::OptionSpec> opts;
         if (type == "test")  // TestFrame::options (TestFrame.cpp:37-55)
@@ -71,6 +77,10 @@ int main(int argc, char *argv[])
                     {"color", 'C', true, "Pixel color format. Defaults to BGR. Values: GREY, BGR."},
                     {"fps", 'r', true, "Frames to serve per second."},
                     {"num-frames", 'n', true, "Number of frames to serve before exiting."}};
+        else if (type == "file")  // FileReader::options (FileReader.cpp:36-54)
+            opts = {{"video-file", 'f', true, "Path to the clip to serve frames from (uint8 .npy)."},
+                    {"fps", 'r', true, "Frames to serve per second."},
+                    {"roi", 0, true, "Four element array of unsigned ints, [x0,y0,width,height], defining a rectangular region of interest."}};
         else
             opts = {{"rows", 0, true, "Frame height."}, {"cols", 0, true, "Frame width."},
                     {"num-samples", 'n', true, "Number of frames to serve before exiting."},
@@ -97,7 +107,25 @@ int main(int argc, char *argv[])
         double fps = 0.0;
         PixelColor color = PIX_BGR;
         Image image;
-        if (type == "test") {
+        Clip clip;
+        std::vector<size_t> roi;
+        if (type == "file") {
+            std::string file;
+            if (!config::getString(vm, table, "video-file", file))
+                throw std::runtime_error("Required configuration key 'video-file' was not specified.");
+            clip.open(file);
+            rows = clip.rows;
+            cols = clip.cols;
+            channels = clip.channels;
+            color = channels == 3 ? PIX_BGR : PIX_GREY;
+            n = clip.frames;
+            if (config::getArray<size_t>(vm, table, "roi", roi, 4)) {
+                if (roi[2] == 0 || roi[3] == 0 || roi[0] + roi[2] > (size_t)cols || roi[1] + roi[3] > (size_t)rows)
+                    throw std::runtime_error("ROI must fit within the frame size.");
+                rows = (int)roi[3];
+                cols = (int)roi[2];
+            }
+        } else if (type == "test") {
             std::string file, col;
             if (!config::getString(vm, table, "test-image", file))
                 throw std::runtime_error("Required configuration key 'test-image' was not specified.");  // getValue(..., required = true)
@@ -129,9 +157,12 @@ int main(int argc, char *argv[])
         if (fps > 0.0) shared_frame.set_rate_hz(fps);
         std::unique_ptr<gpu::Context> ctx;
         std::unique_ptr<gpu::DeviceBuffer> d_frame;
+        // file --device: the whole clip lives in HBM and frames are published in place (device_offset)
+        const bool clip_in_hbm = device && type == "file" && roi.empty();
         if (device) {
             ctx.reset(new gpu::Context(gpu_index));
-            d_frame.reset(new gpu::DeviceBuffer(*ctx, bytes));
+            d_frame.reset(new gpu::DeviceBuffer(*ctx, clip_in_hbm ? clip.frames * bytes : bytes));
+            if (clip_in_hbm) gpu::ck(oat_memcpy(ctx->h, d_frame->p, clip.data, clip.frames * bytes));
             unsigned char handle[64];
             gpu::ck(oat_ipc_export(ctx->h, d_frame->p, handle));
             frame_sink.publish_device(handle, gpu_index);
@@ -144,12 +175,29 @@ int main(int argc, char *argv[])
         }
         frame_sink.announce();
 
-        std::vector<uint8_t> next(type == "synth" && !device ? bytes : 0);
+        std::vector<uint8_t> next((type == "synth" && !device) || !roi.empty() ? bytes : 0);
         auto tick = std::chrono::steady_clock::now();
         for (uint64_t t = 0; t < n && !quit; ++t) {
             if (type == "synth" && !device) synth::frame(next.data(), rows, cols, (uint32_t)seed, (uint32_t)t);  // outside the critical section
+            const uint8_t *src = nullptr;
+            if (type == "file") {
+                src = clip.data + t * clip.frame_bytes();
+                if (!roi.empty()) {  // frame(region_of_interest_) (FileReader.cpp:110-111), packed
+                    const size_t rb = (size_t)cols * channels;
+                    for (int y = 0; y < rows; ++y)
+                        std::memcpy(next.data() + (size_t)y * rb, src + ((roi[1] + y) * (size_t)clip.cols + roi[0]) * channels, rb);
+                    src = next.data();
+                }
+            }
             frame_sink.wait();
-            if (type == "synth") {
+            if (type == "file") {
+                if (clip_in_hbm)
+                    frame_sink.set_device_offset(t * bytes);
+                else if (device)
+                    gpu::ck(oat_memcpy(ctx->h, d_frame->p, src, bytes));
+                else
+                    std::memcpy(shared_frame.data(), src, bytes);
+            } else if (type == "synth") {
                 if (device)
                     gpu::ck(oat_synth_frame(ctx->h, d_frame->u8(), (size_t)cols * 3, rows, cols, (uint32_t)seed, (uint32_t)t));
                 else

@@ -4,6 +4,11 @@
 // assumed: PPM is RGB and is swapped to Oat's BGR), binary PGM (P5) and NumPy .npy (uint8, C order, shape
 // (rows, cols, 3) taken as BGR -- what cv2.imread returns -- or (rows, cols)).
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -105,6 +110,24 @@ inline Image read_image(const std::string &path)
     throw std::runtime_error("File \"" + path + "\" could not be read.");
 }
 
+// A clip for `oat-frameserve file` (the reference decodes a video file with cv::VideoCapture,
+// src/frameserver/FileReader.cpp:59, :103-131; no codec is available to this build): a NumPy .npy of uint8 frames,
+// C order, shape (frames, rows, cols, 3) taken as BGR or (frames, rows, cols) taken as GREY -- lossless, and mapped,
+// not read, so that a long clip costs no host memory.
+struct Clip {
+    size_t frames = 0;
+    int rows = 0, cols = 0, channels = 0;
+    const uint8_t *data = nullptr;  // frames * rows * cols * channels
+    void *map = nullptr;
+    size_t map_bytes = 0;
+    size_t frame_bytes() const { return (size_t)rows * cols * channels; }
+    Clip() = default;
+    Clip(const Clip &) = delete;
+    Clip &operator=(const Clip &) = delete;
+    ~Clip();
+    void open(const std::string &path);
+};
+
 // cv::imread(file, IMREAD_GRAYSCALE) for a colour file / IMREAD_COLOR for a grey one (lib/datatypes/Color.h imread_code)
 inline Image to_channels(const Image &in, int channels)
 {
@@ -124,6 +147,63 @@ inline Image to_channels(const Image &in, int channels)
         }
     }
     return out;
+}
+
+inline Clip::~Clip()
+{
+    if (map) munmap(map, map_bytes);
+}
+inline void Clip::open(const std::string &path)
+{
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("File \"" + path + "\" could not be read.");
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 16) {
+        ::close(fd);
+        throw std::runtime_error("File \"" + path + "\" could not be read.");
+    }
+    map_bytes = (size_t)st.st_size;
+    map = mmap(nullptr, map_bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (map == MAP_FAILED) {
+        map = nullptr;
+        throw std::runtime_error("File \"" + path + "\" could not be mapped.");
+    }
+    const unsigned char *b = static_cast<const unsigned char *>(map);
+    if (std::memcmp(b, "\x93NUMPY", 6) != 0) throw std::runtime_error("File \"" + path + "\": clips must be NumPy .npy files (uint8, frames x rows x cols [x 3]).");
+    size_t hoff, hlen;
+    if (b[6] == 1) {
+        hlen = b[8] | (b[9] << 8);
+        hoff = 10;
+    } else {
+        hlen = b[8] | (b[9] << 8) | (b[10] << 16) | ((size_t)b[11] << 24);
+        hoff = 12;
+    }
+    if (hoff + hlen > map_bytes) throw std::runtime_error("File \"" + path + "\" is truncated.");
+    const std::string hdr(reinterpret_cast<const char *>(b + hoff), hlen);
+    if (hdr.find("u1'") == std::string::npos) throw std::runtime_error("File \"" + path + "\": .npy clips must be uint8.");
+    if (hdr.find("'fortran_order': False") == std::string::npos) throw std::runtime_error("File \"" + path + "\": .npy clips must be C-ordered.");
+    const size_t a = hdr.find("'shape': ("), e = hdr.find(')', a);
+    if (a == std::string::npos || e == std::string::npos) throw std::runtime_error("File \"" + path + "\": malformed .npy header.");
+    std::vector<long> dims;
+    std::string num;
+    for (size_t i = a + 10; i <= e; ++i) {
+        const char c = hdr[i];
+        if (c >= '0' && c <= '9') {
+            num += c;
+        } else if (!num.empty()) {
+            dims.push_back(std::stol(num));
+            num.clear();
+        }
+    }
+    if (!(dims.size() == 3 || (dims.size() == 4 && dims[3] == 3)))
+        throw std::runtime_error("File \"" + path + "\": .npy clips must have shape (frames, rows, cols) or (frames, rows, cols, 3).");
+    frames = (size_t)dims[0];
+    rows = (int)dims[1];
+    cols = (int)dims[2];
+    channels = dims.size() == 4 ? 3 : 1;
+    if (hoff + hlen + frames * frame_bytes() > map_bytes) throw std::runtime_error("File \"" + path + "\" is truncated.");
+    data = b + hoff + hlen;
 }
 
 }  // namespace oat

@@ -465,6 +465,9 @@ struct SharedFrameHeader {
     FrameMemory memory;
     int device_index;
     unsigned char ipc_handle[64];  // cudaIpcMemHandle_t of the pixels when memory == DEVICE
+    uint64_t device_offset{0};     // memory == DEVICE: where THIS frame's pixels start inside the exported allocation
+                                   // (a SINK that keeps many frames in HBM -- a preloaded clip, a device FIFO -- exports ONE
+                                   // allocation and moves this offset between post()s; 0 for single-buffer SINKs)
 };
 
 // ---- lib/shmemdf/Sink.h -------------------------------------------------------------------------------
@@ -595,6 +598,8 @@ public:
         sh_object_->device_index = device;
         sh_object_->memory = FrameMemory::DEVICE;
     }
+    // the frame published by the NEXT post() lives at this offset of the exported allocation (call between wait() and post())
+    void set_device_offset(uint64_t off) { sh_object_->device_offset = off; }
     SharedFrameHeader *header() { return sh_object_; }
 
 private:

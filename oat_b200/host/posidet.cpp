@@ -50,7 +50,7 @@ protected:
         if (frame_source_.wait() == NodeState::END) return 1;
         if (frame_source_.header()->memory != src_memory_)
             throw std::runtime_error("SOURCE frame memory kind changed after connect()");
-        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? src_dev_->p : frame_source_.pixels(), in_.bytes));
+        gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) + frame_source_.header()->device_offset : static_cast<const uint8_t *>(frame_source_.pixels()), in_.bytes));
         internal_pos.set_sample(frame_source_.retrieve()->sample());  // propagate tick / usec (:80)
         frame_source_.post();
 
@@ -301,7 +301,8 @@ protected:
         if (frame_source_.header()->memory != src_memory_)
             throw std::runtime_error("SOURCE frame memory kind changed after connect()");
         // the frame goes to the GPU straight from where the SOURCE keeps it (page-locked shm or device memory)
-        const uint8_t *pixels = src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) : static_cast<const uint8_t *>(frame_source_.pixels());
+        const uint8_t *pixels = src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) + frame_source_.header()->device_offset
+                                         : static_cast<const uint8_t *>(frame_source_.pixels());
         gpu::ck(oat_tracker_submit(trk_, pixels, in_.cols * 3, learning_coeff_, &o_.p, nullptr, 0));
         samples_.push_back(frame_source_.retrieve()->sample());
         gpu::ck(oat_tracker_wait_ingest(trk_));

@@ -33,8 +33,9 @@ def oracle_positions(lr):
     return out
 
 
-def run_graph(tag, nodes, serve_args=(), rows=ROWS, cols=COLS, n=N):
-    """nodes: list of argv lists; consumers are started first, the frame server last (examples/*/*.sh)."""
+def run_graph(tag, nodes, serve_args=(), rows=ROWS, cols=COLS, n=N, server=None):
+    """nodes: list of argv lists; consumers are started first, the frame server last (examples/*/*.sh).
+    server: None = `frameserve synth`, else a function (raw address) -> argv of the frame server."""
     names = [f"oatb200pipe_{tag}_{n}" for n in ("raw", "filt", "hsv", "pos")]
     subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
     procs = []
@@ -44,8 +45,11 @@ def run_graph(tag, nodes, serve_args=(), rows=ROWS, cols=COLS, n=N):
             procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                                           text=True))
         time.sleep(0.5)
-        serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(rows), "--cols", str(cols),
-                                  "--num-samples", str(n), "--fps", "100"] + list(serve_args))
+        if server is None:
+            serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(rows), "--cols", str(cols),
+                                      "--num-samples", str(n), "--fps", "100"] + list(serve_args))
+        else:
+            serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve")] + server(names[0]) + list(serve_args))
         out, _ = sock.communicate(timeout=120)
         assert serve.wait(timeout=30) == 0
         for p in procs:
@@ -113,6 +117,12 @@ def test_config0_bsub_chain_analytic():
                 ["oat-framefilt", "bsub", nm[0], nm[1]]]
 
     got = run_graph("cfg0", nodes, rows=rows, cols=cols, n=n)
+    _check_config0(got, rows, cols, n)
+
+
+def _check_config0(got, rows, cols, n):
+    from oracle import synth
+
     assert len(got) == n
     assert got[0]["pos_ok"] is False
     for t in range(1, n):
@@ -188,3 +198,106 @@ def test_two_colour_graph_with_kalman_and_mean():
             assert abs(p["pos_xy"][0] - w.x) < 1e-4 and abs(p["pos_xy"][1] - w.y) < 1e-4, (t, p, w.x, w.y)
             assert abs(p["vel_xy"][0] - w.vx) < 1e-4 and abs(p["vel_xy"][1] - w.vy) < 1e-4, (t, p, w.vx, w.vy)
     assert n_valid >= N - 3
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_fused_tracker_component_pipelined(device):
+    """--pipeline 4: up to four frames in flight on the GPU behind the SOURCE; the SINK still sees one position per frame,
+    in order, each carrying its own frame's Sample -- identical to the synchronous component."""
+    def nodes(n):
+        return [["oat-posidet", "track", n[0], n[3], "-A", "0.05", "--pipeline", "4"] + HSV_ARGS]
+
+    check(run_graph("fusedp" + ("d" if device else "h"), nodes, serve_args=(("--device",) if device else ())), oracle_positions(0.05))
+
+
+def test_frameserve_test_through_mog_component(tmp_path):
+    """The reference's perf-protocol graph (test/perf/framefilt-mog.sh): `frameserve test` -> `framefilt mog`, here with a
+    reader behind it: a static image gives an all-shadow first frame (kept) and all-background frames afterwards (zeroed)."""
+    import numpy as np
+
+    img = oracle.synth_frame(ROWS, COLS, 1000, 2)
+    path = tmp_path / "img.npy"
+    np.save(path, img)
+    names = ["oatb200pipe_tf_raw", "oatb200pipe_tf_filt"]
+    subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+    reader = subprocess.Popen([os.path.join(BIN, "shmemdf_test"), "dump-frames", names[1]], stdout=subprocess.PIPE, text=True)
+    mog = subprocess.Popen([os.path.join(BIN, "oat-framefilt"), "mog", names[0], names[1], "-a", "0.0"], stdout=subprocess.DEVNULL,
+                           stderr=subprocess.PIPE, text=True)
+    time.sleep(1.0)
+    serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", names[0], "-f", str(path), "-n", "5"], capture_output=True, text=True,
+                           timeout=120)
+    assert serve.returncode == 0, serve.stderr
+    out, _ = reader.communicate(timeout=60)
+    assert mog.wait(timeout=30) == 0
+    lines = [ln.split() for ln in out.splitlines() if ln.strip()]
+    assert [int(l[0]) for l in lines] == [1, 2, 3, 4, 5]
+
+    def fnv(buf):
+        h = 1469598103934665603
+        for b in buf:
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    assert int(lines[0][6]) == fnv(img.tobytes())                       # first frame: mask all 127 -> the frame is kept
+    assert all(int(l[6]) == fnv(bytes(img.size)) for l in lines[1:])    # frozen model, static image: background -> zeros
+    subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+
+
+def _write_clip(path, rows, cols, n, seed=1000):
+    import numpy as np
+
+    clip = np.stack([oracle.synth_frame(rows, cols, seed, t) for t in range(n)])
+    np.save(path, clip)
+    return clip
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_config0_from_a_clip_file(tmp_path, device):
+    """BASELINE config 0 as worded: a 640x480 test CLIP served by `frameserve file` (FileReader.cpp:103-131; the clip is a
+    lossless .npy) -> framefilt bsub -> framefilt col -C HSV -> posidet hsv, analytic answer as above.  With --device
+    the clip is uploaded to HBM once and published in place (device_offset), and bsub / col hand device frames on."""
+    rows, cols, n = 480, 640, 60
+    path = tmp_path / "clip.npy"
+    _write_clip(path, rows, cols, n)
+    ds = ["--device-sink"] if device else []
+
+    def nodes(nm):
+        return [["oat-posidet", "hsv", nm[2], nm[3], "-H", "[40,80]", "-S", "[100,256]", "-V", "[90,256]"],
+                ["oat-framefilt", "col", nm[1], nm[2], "-C", "HSV"] + ds,
+                ["oat-framefilt", "bsub", nm[0], nm[1]] + ds]
+
+    got = run_graph("cfg0f" + ("d" if device else "h"), nodes, serve_args=(("--device",) if device else ()),
+                    server=lambda raw: ["file", raw, "-f", str(path), "-r", "100"])
+    _check_config0(got, rows, cols, n)
+
+
+@pytest.mark.parametrize("device_sink", [False, True])
+def test_buffer_component_in_front_of_the_tracker(tmp_path, device_sink):
+    """frameserve file -> `oat buffer frame` (FIFO in HBM, src/buffer/FrameBuffer.cpp:56-116) -> posidet track --pipeline 4:
+    every frame comes out once, in order, with its own Sample; positions equal the oracle's."""
+    path = tmp_path / "clip.npy"
+    _write_clip(path, ROWS, COLS, N)
+    names = ["oatb200pipe_buf_" + k + ("d" if device_sink else "h") for k in ("raw", "fifo", "pos")]
+    subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+    procs = []
+    try:
+        sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names[2]], stdout=subprocess.PIPE, text=True)
+        procs.append(subprocess.Popen([os.path.join(BIN, "oat-posidet"), "track", names[1], names[2], "-A", "0.05", "--pipeline", "4"] + HSV_ARGS,
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+        procs.append(subprocess.Popen([os.path.join(BIN, "oat-buffer"), "frame", names[0], names[1], "--capacity", "8"] +
+                                      (["--device-sink"] if device_sink else []), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+        time.sleep(1.0)
+        serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "file", names[0], "-f", str(path), "-r", "100"], capture_output=True,
+                               text=True, timeout=120)
+        assert serve.returncode == 0, serve.stderr
+        out, _ = sock.communicate(timeout=120)
+        for p in procs:
+            _, se = p.communicate(timeout=60)
+            assert p.returncode == 0, (p.args, se)
+            assert "Buffer overrun" not in se
+        check([json.loads(line) for line in out.splitlines() if line.strip()], oracle_positions(0.05))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)

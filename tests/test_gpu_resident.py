@@ -311,3 +311,32 @@ def test_clip_engine_close_dependencies_stress(ctx, shape):
         _state_equal(a, b)
         a.close()
     b.close()
+
+
+def test_clip_engine_many_blobs_are_labelled_on_the_device(ctx):
+    """~60 blobs spread over the frame: the mask's bounding region is the whole frame and its run table outgrows the
+    labelling CTA's shared memory.  The tail server labels such frames a second time in its global-memory scratch area
+    -- on the device, no host replay -- with the same result as the synchronous path (which replays through the
+    unbounded multi-kernel tail)."""
+    import bench
+
+    rows, cols, lr = 1080, 1920, 0.01
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    host = bench.multi_blob_frames(rows, cols, 60, 5)
+    bufs = []
+    for f in host:
+        b = ctx.alloc(rows * cols * 3)
+        b.upload(f)
+        bufs.append(b)
+    seq = [bufs[0]] + [bufs[1 + i % 5] for i in range(40)]
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=16)
+    got = [_det(d) for d in a.run_clip(seq)]
+    st = a.tail_stats()
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    want = [_det(b.track(f)[0]) for f in seq]
+    assert got == want
+    assert want[-1][1] >= 50, want[-1]          # the scene really has that many contours
+    assert st["clip_frames"] == 40
+    assert st["replays"] <= 1, st               # (the first frame's whole-image blob goes frame by frame and is replayed)
+    a.close()
+    b.close()

@@ -1,0 +1,108 @@
+"""The reference's own performance protocol (test/perf/framefilt-mog.sh:1-3, test/perf/results.md:12-18) through the
+drop-in components and REAL shared memory: `oat frameserve test` pushes N copies of one static image, free-running,
+through the listening component(s); the figure is N / wall time of the frame server, exactly as `time oat frameserve
+test raw -f IMAGE -c test.toml test` measured it (573 fps for cv::cuda MOG on a GTX 970, 75.7 fps for CPU MOG2 on an
+i7-5600U, 1000 x 1 MP frames).
+
+    python tools/graph_bench.py [--frames 1000] [--out FILE.json]
+
+Graphs: framefilt mog alone (the published number's graph); frameserve -> mog -> col HSV -> posidet hsv (the
+reference-shaped chain); frameserve -> posidet track (the fused component), synchronous and with --pipeline 8; each
+with host frames (page-locked shm, H2D/D2H per component) and with device-resident frames (--device /
+--device-sink: CUDA IPC, pixels never leave the GPU)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+BIN = os.path.join(ROOT, "oat_b200", "bin")
+HSV = ["-H", "[40,80]", "-S", "[100,256]", "-V", "[100,256]"]
+
+
+def make_image(path, rows, cols):
+    import oracle
+
+    np.save(path, oracle.synth_frame(rows, cols, 1000, 3))  # one frame of the tracking stream (with its blob)
+
+
+def run(tag, image, n, consumers, device, last_is_position):
+    names = {k: f"oatb200gb_{tag}_{k}" for k in ("raw", "filt", "hsv", "pos")}
+    subprocess.run([os.path.join(BIN, "oat-clean")] + list(names.values()), capture_output=True)
+    procs = []
+    try:
+        sock = None
+        if last_is_position:
+            sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names["pos"]], stdout=subprocess.PIPE, text=True)
+        for argv in consumers(names):
+            procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+        time.sleep(3.0)  # the reference's scripts sleep too: every consumer has its CUDA context and waits in connect()
+        t0 = time.perf_counter()
+        serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", names["raw"], "-f", image, "-n", str(n)] +
+                               (["--device"] if device else []), capture_output=True, text=True, timeout=600)
+        wall = time.perf_counter() - t0
+        assert serve.returncode == 0, serve.stderr
+        npos = None
+        if sock is not None:
+            out, _ = sock.communicate(timeout=120)
+            npos = len([ln for ln in out.splitlines() if ln.strip()])
+        for p in procs:
+            _, se = p.communicate(timeout=120)
+            assert p.returncode == 0, (p.args, se)
+        return {"frames": n, "wall_s": wall, "fps": n / wall, "positions": npos}
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        subprocess.run([os.path.join(BIN, "oat-clean")] + list(names.values()), capture_output=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    res = {"protocol": "N static frames from `oat-frameserve test`, free-running, through real shm; fps = N / wall time of the frame server "
+                       "(test/perf/results.md:12-18); consumers started 3 s earlier",
+           "reference_published": {"framefilt mog, cv::cuda MOG, GTX 970 (results.md:34-37)": 573.0,
+                                   "framefilt mog, CPU MOG2, i7-5600U (results.md:91-95)": 75.7,
+                                   "posidet hsv, GTX 970 box CPU path (results.md:55-58)": 214.0}}
+    tmp = "/tmp/oatb200_graph_bench"
+    os.makedirs(tmp, exist_ok=True)
+    for wl, (rows, cols) in {"1mp": (1000, 1000), "1080p": (1080, 1920)}.items():
+        img = os.path.join(tmp, f"{wl}.npy")
+        make_image(img, rows, cols)
+        r = {}
+        for dev in (False, True):
+            k = "device" if dev else "host"
+            ds = ["--device-sink"] if dev else []
+            r[f"mog_{k}"] = run(f"{wl}m{k}", img, args.frames, lambda n: [["oat-framefilt", "mog", n["raw"], n["filt"], "-a", "0.01"] + ds], dev, False)
+            r[f"chain_{k}"] = run(f"{wl}c{k}", img, args.frames, lambda n: [
+                ["oat-posidet", "hsv", n["hsv"], n["pos"]] + HSV,
+                ["oat-framefilt", "col", n["filt"], n["hsv"], "-C", "HSV"] + ds,
+                ["oat-framefilt", "mog", n["raw"], n["filt"], "-a", "0.01"] + ds], dev, True)
+            r[f"track_{k}"] = run(f"{wl}t{k}", img, args.frames, lambda n: [["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01"] + HSV], dev, True)
+            r[f"track_pipeline8_{k}"] = run(f"{wl}p{k}", img, args.frames, lambda n: [
+                ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "8"] + HSV], dev, True)
+        res[wl] = r
+        for k, v in r.items():
+            print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps  ({v['frames']} frames in {v['wall_s']:.3f} s, positions {v['positions']})", flush=True)
+    # frameserve alone (no listener), the protocol's own overhead
+    img = os.path.join(tmp, "1mp.npy")
+    subprocess.run([os.path.join(BIN, "oat-clean"), "oatb200gb_alone"], capture_output=True)
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", "oatb200gb_alone", "-f", img, "-n", str(args.frames)], check=True)
+    res["frameserve_alone_s"] = time.perf_counter() - t0
+    print("frameserve alone:", res["frameserve_alone_s"], "s")
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
