@@ -74,6 +74,11 @@ uint64_t oat_ctx_kernel_launches(const oat_ctx *ctx);
  * bracketed by a CUDA-event pair on the compute stream; read returns the summed duration, the number of launches
  * and the number of frames they processed since the last read (and waits for the stream). */
 int oat_ctx_profile_resident(oat_ctx *ctx, int enable);
+/* Host side of the resident clip engine since the last call: microseconds the calling thread spent WORKING inside
+ * oat_tracker_run_clip(s) (descriptors, launches, reading results), microseconds it spent waiting for chunks to
+ * complete, and the frames served.  (The reference's component loop is one thread, lib/base/Component.cpp:56-76:
+ * this is what that thread has left.) */
+int oat_ctx_clip_host_stats(oat_ctx *ctx, double *busy_us, double *wait_us, uint64_t *frames);
 int oat_ctx_profile_resident_read(oat_ctx *ctx, double *total_ms, uint64_t *launches, uint64_t *frames);
 
 /* ---- framefilt mog --------------------------------------------------------------------

@@ -117,6 +117,7 @@ _SIGS = {
     "oat_ctx_sync": (C.c_int, [C.c_void_p]),
     "oat_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "oat_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "oat_ctx_clip_host_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "oat_ctx_profile_resident": (C.c_int, [C.c_void_p, C.c_int]),
     "oat_ctx_profile_resident_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                                 C.POINTER(C.c_uint64)]),
@@ -280,6 +281,12 @@ class Context:
     @property
     def kernel_launches(self) -> int:
         return int(lib().oat_ctx_kernel_launches(self._h))
+
+    def clip_host_stats(self):
+        """(busy us, waiting us, frames) of the calling thread inside the resident clip engine since the last call."""
+        b, w, f = C.c_double(), C.c_double(), C.c_uint64()
+        _ck(lib().oat_ctx_clip_host_stats(self._h, C.byref(b), C.byref(w), C.byref(f)))
+        return b.value, w.value, f.value
 
     def profile_resident(self, enable: bool):
         """Bracket every launch of the resident fused kernel with CUDA events (oat_ctx_profile_resident)."""

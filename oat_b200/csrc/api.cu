@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <new>
 #include <string>
@@ -158,6 +159,10 @@ struct oat_ctx {
     // from the first launch's start to the last one's end)
     int prof_resident = 0;
     std::vector<ProfRec> prof_recs;
+    // host side of the resident clip engine: time inside clip_run() spent working (descriptors, launches, reading
+    // results) and spent waiting for a chunk's completion event, and the frames served
+    double clip_busy_ns = 0.0, clip_wait_ns = 0.0;
+    uint64_t clip_frames_total = 0;
     unsigned int *slow_count = nullptr;    // census: 4-pixel groups that left the fused kernel's fast path (cumulative)
     DevBuf flush;
     DevBuf scratch_in, scratch_out, scratch_roi;  // staging for the stateless entry points
@@ -294,6 +299,16 @@ extern "C" int oat_ctx_sync(oat_ctx *c)
 }
 extern "C" void *oat_ctx_stream(oat_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" uint64_t oat_ctx_kernel_launches(const oat_ctx *c) { return c ? c->launches : 0; }
+extern "C" int oat_ctx_clip_host_stats(oat_ctx *c, double *busy_us, double *wait_us, uint64_t *frames)
+{
+    REQUIRE(c, "null context");
+    if (busy_us) *busy_us = c->clip_busy_ns * 1e-3;
+    if (wait_us) *wait_us = c->clip_wait_ns * 1e-3;
+    if (frames) *frames = c->clip_frames_total;
+    c->clip_busy_ns = c->clip_wait_ns = 0.0;
+    c->clip_frames_total = 0;
+    return OAT_OK;
+}
 extern "C" int oat_ctx_profile_resident(oat_ctx *c, int enable)
 {
     CKRET(bind(c));
@@ -2014,9 +2029,15 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
     bool stop = false;  // no new chunks: something stopped being eligible
     int class_all = 2;
 
+    const auto t_enter = std::chrono::steady_clock::now();
+    double wait_ns = 0.0;
     auto retire = [&](int h) -> int {
         Flight &f = fl[h];
-        CK(cudaEventSynchronize(half[h].done));
+        {
+            const auto w0 = std::chrono::steady_clock::now();
+            CK(cudaEventSynchronize(half[h].done));
+            wait_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - w0).count();
+        }
         if (!fused_only) {
             bool replayed = false;
             for (size_t i = 0; i < f.count; ++i)
@@ -2216,6 +2237,9 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
         if (r < 0) break;
         CKRET(retire(r));
     }
+    c->clip_wait_ns += wait_ns;
+    c->clip_busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_enter).count() - wait_ns;
+    c->clip_frames_total += *used * (uint64_t)S;
     return OAT_OK;
 }
 

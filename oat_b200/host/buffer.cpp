@@ -52,9 +52,9 @@ public:
 protected:
     bool connectToNode() override  // FrameBuffer.cpp:33-55
     {
+        source_.touch(source_address_);
         push_ctx_.reset(new gpu::Context(gpu_index_));  // one context (stream set) per thread
         pop_ctx_.reset(new gpu::Context(gpu_index_));
-        source_.touch(source_address_);
         if (source_.connect() != SourceState::CONNECTED) return false;
         in_ = source_.parameters();
         src_memory_ = source_.header()->memory;

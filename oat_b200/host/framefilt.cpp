@@ -31,10 +31,10 @@ protected:
     // FrameFilter::connectToNode (FrameFilter.cpp:37-57); sink_color lets `col` re-tag its output
     bool connectToNode() override
     {
-        // the CUDA context first: creating it takes a good part of a second, and connect() below returns the moment the
-        // SOURCE's SINK appears -- a frame server must not find its first frames waiting for that
-        ctx_.reset(new gpu::Context(gpu_index_));
+        // touch() first (from now on the SOURCE's SINK waits for this component), then the CUDA context -- creating it
+        // takes a good part of a second and must not happen after connect(), which returns with the first frame waiting
         frame_source_.touch(frame_source_address_);
+        ctx_.reset(new gpu::Context(gpu_index_));
         if (frame_source_.connect() != SourceState::CONNECTED) return false;
         in_ = frame_source_.parameters();
         const PixelColor out_color = outputColor(in_.color);

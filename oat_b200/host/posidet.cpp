@@ -27,8 +27,8 @@ protected:
     // PositionDetector::connectToNode (PositionDetector.cpp:40-56)
     bool connectToNode() override
     {
-        ctx_.reset(new gpu::Context(gpu_index_));  // before connect(): see FrameFilter::connectToNode
         frame_source_.touch(frame_source_address_);
+        ctx_.reset(new gpu::Context(gpu_index_));  // after touch(), before connect(): see FrameFilter::connectToNode
         const SourceState rc = required_color_ == PIX_ANY ? frame_source_.connect() : frame_source_.connect(required_color_);
         if (rc != SourceState::CONNECTED) return false;
         in_ = frame_source_.parameters();

@@ -43,8 +43,21 @@ def run(tag, image, n, consumers, device, last_is_position):
             procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
         time.sleep(3.0)  # the reference's scripts sleep too: every consumer has its CUDA context and waits in connect()
         t0 = time.perf_counter()
-        serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", names["raw"], "-f", image, "-n", str(n)] +
-                               (["--device"] if device else []), capture_output=True, text=True, timeout=600)
+        try:
+            serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", names["raw"], "-f", image, "-n", str(n)] +
+                                   (["--device"] if device else []), capture_output=True, text=True, timeout=90)
+        except subprocess.TimeoutExpired:
+            # say who is still there and what they wrote before giving up on this graph
+            state = []
+            for p in procs:
+                alive = p.poll() is None
+                if alive:
+                    p.kill()
+                _, se = p.communicate(timeout=10)
+                state.append((p.args[0].split("/")[-1], p.args[1], "alive" if alive else f"rc={p.returncode}", se[-300:]))
+            if sock is not None:
+                sock.kill()
+            return {"frames": n, "error": "frame server timed out", "components": state}
         wall = time.perf_counter() - t0
         assert serve.returncode == 0, serve.stderr
         npos = None
@@ -91,7 +104,10 @@ def main():
                 ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "8"] + HSV], dev, True)
         res[wl] = r
         for k, v in r.items():
-            print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps  ({v['frames']} frames in {v['wall_s']:.3f} s, positions {v['positions']})", flush=True)
+            if "error" in v:
+                print(f"{wl:6s} {k:24s} FAILED: {v}", flush=True)
+            else:
+                print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps  ({v['frames']} frames in {v['wall_s']:.3f} s, positions {v['positions']})", flush=True)
     # frameserve alone (no listener), the protocol's own overhead
     img = os.path.join(tmp, "1mp.npy")
     subprocess.run([os.path.join(BIN, "oat-clean"), "oatb200gb_alone"], capture_output=True)
