@@ -10,6 +10,7 @@
 // per-frame copies are asynchronous DMA straight from / into shared memory (HOST_PINNED variant);
 // the SOURCE is released as soon as its pixels are on the device, as in FrameFilter::process().
 #include <cstdio>
+#include <chrono>
 #include <iostream>
 #include <memory>
 #include <vector>
@@ -65,26 +66,59 @@ protected:
         return true;
     }
     // FrameFilter::process (FrameFilter.cpp:59-98), with the heap copies replaced by DMA
+    // OAT_B200_TIMING=1: where a frame's time goes in this component (printed at end of stream)
+    struct StageClock {
+        bool on = getenv("OAT_B200_TIMING") != nullptr;
+        double t[5] = {0, 0, 0, 0, 0};
+        uint64_t n = 0;
+        std::chrono::steady_clock::time_point last;
+        void start() { if (on) last = std::chrono::steady_clock::now(); }
+        void lap(int i)
+        {
+            if (!on) return;
+            const auto now = std::chrono::steady_clock::now();
+            t[i] += std::chrono::duration<double, std::micro>(now - last).count();
+            last = now;
+        }
+        void report(const std::string &who) const
+        {
+            if (on && n)
+                std::cerr << who << ": per frame (us): wait source " << t[0] / n << ", ingest " << t[1] / n << ", filter " << t[2] / n
+                          << ", wait sink " << t[3] / n << ", egress " << t[4] / n << " over " << n << " frames\n";
+        }
+    } clk_;
     int process() override
     {
-        if (frame_source_.wait() == NodeState::END) return 1;
+        clk_.start();
+        if (frame_source_.wait() == NodeState::END) {
+            clk_.report(name_);
+            return 1;
+        }
+        clk_.lap(0);
         if (frame_source_.header()->memory != src_memory_)
             throw std::runtime_error("SOURCE frame memory kind changed after connect()");
         gpu::ck(oat_memcpy(ctx_->h, d_in_->p, src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) + frame_source_.header()->device_offset : static_cast<const uint8_t *>(frame_source_.pixels()), in_.bytes));
         const Sample sample = frame_source_.retrieve()->sample();
         frame_source_.post();
+        clk_.lap(1);
 
         if (device_sink_) {
             // the published buffer IS d_out_: it may only change while no SOURCE is reading it
             frame_sink_.wait();
+            clk_.lap(3);
             filter(d_in_->u8(), d_out_->u8());
+            clk_.lap(2);
         } else {
             filter(d_in_->u8(), d_out_->u8());
+            clk_.lap(2);
             frame_sink_.wait();
+            clk_.lap(3);
             gpu::ck(oat_memcpy(ctx_->h, frame_sink_.pixels(), d_out_->p, out_bytes_));
         }
         shared_frame_.sample() = sample;  // filters never advance time
         frame_sink_.post();
+        clk_.lap(4);
+        ++clk_.n;
         return 0;
     }
     virtual PixelColor outputColor(PixelColor in) const { return in; }

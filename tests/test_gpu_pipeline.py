@@ -274,7 +274,8 @@ def test_config0_from_a_clip_file(tmp_path, device):
 @pytest.mark.parametrize("device_sink", [False, True])
 def test_buffer_component_in_front_of_the_tracker(tmp_path, device_sink):
     """frameserve file -> `oat buffer frame` (FIFO in HBM, src/buffer/FrameBuffer.cpp:56-116) -> posidet track --pipeline 4:
-    every frame comes out once, in order, with its own Sample; positions equal the oracle's."""
+    every frame comes out once, in order, with its own Sample; positions equal the oracle's.  (The FIFO holds the whole
+    clip: the tracker spends its first half second creating its model while the server already runs.)"""
     path = tmp_path / "clip.npy"
     _write_clip(path, ROWS, COLS, N)
     names = ["oatb200pipe_buf_" + k + ("d" if device_sink else "h") for k in ("raw", "fifo", "pos")]
@@ -284,7 +285,7 @@ def test_buffer_component_in_front_of_the_tracker(tmp_path, device_sink):
         sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names[2]], stdout=subprocess.PIPE, text=True)
         procs.append(subprocess.Popen([os.path.join(BIN, "oat-posidet"), "track", names[1], names[2], "-A", "0.05", "--pipeline", "4"] + HSV_ARGS,
                                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
-        procs.append(subprocess.Popen([os.path.join(BIN, "oat-buffer"), "frame", names[0], names[1], "--capacity", "8"] +
+        procs.append(subprocess.Popen([os.path.join(BIN, "oat-buffer"), "frame", names[0], names[1], "--capacity", "32"] +
                                       (["--device-sink"] if device_sink else []), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
         time.sleep(1.0)
         serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "file", names[0], "-f", str(path), "-r", "100"], capture_output=True,

@@ -37,10 +37,12 @@ def run(tag, image, n, consumers, device, last_is_position):
     procs = []
     try:
         sock = None
+        sock_out = open(f"/tmp/oatb200_graph_bench/{tag}.positions", "w+")  # (a pipe would fill up and stall the graph)
         if last_is_position:
-            sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names["pos"]], stdout=subprocess.PIPE, text=True)
+            sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names["pos"]], stdout=sock_out, text=True)
+        env = dict(os.environ, OAT_B200_TIMING="1")
         for argv in consumers(names):
-            procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+            procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env))
         time.sleep(3.0)  # the reference's scripts sleep too: every consumer has its CUDA context and waits in connect()
         t0 = time.perf_counter()
         try:
@@ -62,12 +64,15 @@ def run(tag, image, n, consumers, device, last_is_position):
         assert serve.returncode == 0, serve.stderr
         npos = None
         if sock is not None:
-            out, _ = sock.communicate(timeout=120)
-            npos = len([ln for ln in out.splitlines() if ln.strip()])
+            sock.wait(timeout=120)
+            sock_out.seek(0)
+            npos = len([ln for ln in sock_out.read().splitlines() if ln.strip()])
+        stages = []
         for p in procs:
             _, se = p.communicate(timeout=120)
             assert p.returncode == 0, (p.args, se)
-        return {"frames": n, "wall_s": wall, "fps": n / wall, "positions": npos}
+            stages += [ln for ln in se.splitlines() if "per frame (us)" in ln]
+        return {"frames": n, "wall_s": wall, "fps": n / wall, "positions": npos, "stages": stages}
     finally:
         for p in procs:
             if p.poll() is None:
@@ -108,6 +113,8 @@ def main():
                 print(f"{wl:6s} {k:24s} FAILED: {v}", flush=True)
             else:
                 print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps  ({v['frames']} frames in {v['wall_s']:.3f} s, positions {v['positions']})", flush=True)
+                for ln in v["stages"]:
+                    print("         " + ln, flush=True)
     # frameserve alone (no listener), the protocol's own overhead
     img = os.path.join(tmp, "1mp.npy")
     subprocess.run([os.path.join(BIN, "oat-clean"), "oatb200gb_alone"], capture_output=True)
