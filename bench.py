@@ -622,7 +622,8 @@ def run_b200(args):
         peak, peak_src = load_peak()
         fps = world * K / (total_ms * 1e-3)
         # detect-only fused mode (no frame egress) moves 5 + 40*m bytes per pixel
-        b_alg = 5.0 + 40.0 * mbar_roof
+        # (a frozen model, -a 0, is compared but never written back: 4 + 20*m read, nothing but the threshold bits written)
+        b_alg = 5.0 + 40.0 * mbar_roof if args.alpha != 0 else 4.0 + 20.0 * mbar_roof
         achieved = b_alg * npx / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0
         traffic = load_traffic(args.workload, args.alpha)
         line = {
@@ -661,6 +662,7 @@ def run_b200(args):
                 "frac": achieved / peak,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_px": b_alg,
+                "algorithmic_bytes_formula": "5 + 40*m (BGR 3 + count 1+1 + state 20*m read and written)" if args.alpha != 0 else "4 + 20*m (frozen model: read only)",
                 "algorithmic_bytes_per_launch": b_alg * npx * frames_per_launch,
                 "kernel_ms": kern_ms,
                 "frames_per_launch": frames_per_launch,

@@ -1988,119 +1988,90 @@ static bool clip_frame_ok(const oat_tracker *t, const uint8_t *frame, size_t in_
     return cls > 0;
 }
 
-// frames: [n][S] frame-major; out / pos likewise (pos only with S == 1).  *used = frames (per tracker) consumed;
-// fewer than n if a frame or a tracker stopped being eligible -- the caller continues on the per-frame path.
-static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *const *frames, size_t n, size_t in_pitch,
-                    double learning_rate, const oat_hsv_params *p, bool fused_only, oat_detection *out, oat_position *pos,
-                    size_t *used)
-{
-    *used = 0;
-    size_t chunkF = trk[0]->ring.size() / 2;
-    for (int s = 0; s < S; ++s) chunkF = std::min(chunkF, trk[s]->ring.size() / 2);
-    if (chunkF == 0 || n == 0) return OAT_OK;
-    ClipHalf *half = c->clip;
-    oat_tracker *t0 = trk[0];
-    const BitGeom g = t0->tail.tb.g;
-    const int ntiles = (int)((t0->m.plane + PIPE_TILE - 1) / PIPE_TILE);
-    const int ke = p->erode_px > 0 ? p->erode_px : 0, kd = p->dilate_px > 0 ? p->dilate_px : 0;
-    // bands of 32 rows (a band costs ~3 dependent L2 round trips whatever its size; most bands of a tracking mask are
-    // empty) unless the morphology staging of such a band would not fit
-    auto stage_for = [&](int rr) {
-        const size_t nin = (size_t)rr + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
-        return 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
-    };
-    const int R = stage_for(32) <= (size_t)64 * 1024 ? 32 : 8;
-    const size_t stage = stage_for(R);
-    const size_t tail_smem = std::max(std::max(stage, t0->tail.fast_smem), (size_t)PIPE_TAIL_SMEM_KB_CFG * 1024);
-    // second labelling attempt in global memory for masks whose tables do not fit the CTA's shared memory: room for
-    // ~200 k runs and 4096 contours per CTA, plus the mask itself
-    const int scratch_comps = 4096;
-    const size_t scratch_bytes = (((size_t)g.rows * g.wpr * 4 + (size_t)g.rows * 16 + (size_t)3 * scratch_comps * 8 + ((size_t)200 << 10) * 12 + 4096) + 255) & ~(size_t)255;
-    static size_t tail_stream_smem_set = 48 * 1024;
-    if (!fused_only && tail_smem + 2048 > tail_stream_smem_set) {
-        CK(cudaFuncSetAttribute(tail_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        tail_stream_smem_set = 200 * 1024;
-    }
+// Host side of the resident engine for a fixed set of trackers: geometry of a chunk and the two chunks in flight
+// (ctx->clip[0..1]).  clip_run() drives it over a whole clip; the streaming entry points (oat_tracker_stream_*) keep
+// one alive between calls.
+struct ClipEngine {
+    oat_ctx *c = nullptr;
+    oat_tracker *trk[64] = {};
+    int S = 0;
+    bool fused_only = false;
+    size_t chunkF = 0;  // frames (per tracker) per chunk: half of the smallest ring
+    BitGeom g{};
+    int ntiles = 0;
+    size_t scratch_bytes = 0;
+    static const int scratch_comps = 4096;
     struct Flight {
-        size_t first = 0, count = 0;
+        size_t count = 0;
         bool live = false;
+        uint64_t order = 0;
     } fl[2];
-    size_t next = 0, nchunk = 0;
-    bool stop = false;  // no new chunks: something stopped being eligible
+    uint64_t nchunk = 0;  // chunks launched; the next one uses half nchunk & 1
     int class_all = 2;
-
-    const auto t_enter = std::chrono::steady_clock::now();
     double wait_ns = 0.0;
-    auto retire = [&](int h) -> int {
-        Flight &f = fl[h];
-        {
-            const auto w0 = std::chrono::steady_clock::now();
-            CK(cudaEventSynchronize(half[h].done));
-            wait_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - w0).count();
-        }
-        if (!fused_only) {
-            bool replayed = false;
-            for (size_t i = 0; i < f.count; ++i)
-                for (int s = 0; s < S; ++s) {
-                    oat_tracker *t = trk[s];
-                    Slot &sl = t->ring[(size_t)h * chunkF + i];
-                    if (sl.h_res->status != TAIL_OK) {
-                        // the mask overflowed the one-launch tail's run table: replay this frame's mask through the
-                        // unbounded path (its bits are still in the slot)
-                        CKRET(t->tail.run(c, sl.bits, sl.hp, &sl.d_res->det, nullptr, 0, nullptr));
-                        CK(cudaMemcpyAsync(&sl.h_res->det, &sl.d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
-                        ++t->replays;
-                        replayed = true;
-                    }
-                }
-            if (replayed) CK(cudaStreamSynchronize(c->stream));
-            for (size_t i = 0; i < f.count; ++i)
-                for (int s = 0; s < S; ++s) {
-                    oat_tracker *t = trk[s];
-                    Slot &sl = t->ring[(size_t)h * chunkF + i];
-                    const double groups = (double)t->m.g.rows * t->m.g.cols / 4.0;
-                    t->slow_frac = 0.75 * t->slow_frac + 0.25 * ((double)sl.h_res->slow_groups / groups);
-                    if (!t->use_generic && t->slow_frac > 0.30) t->use_generic = true;
-                    if (out) out[(f.first + i) * S + s] = sl.h_res->det;
-                    t->last_slot = (size_t)h * chunkF + i;
-                }
-            if (pos) {  // S == 1: the position epilogue over the chunk's final detections, in frame order
-                oat_tracker *t = trk[0];
-                for (size_t i = 0; i < f.count; ++i) {
-                    Slot &sl = t->ring[(size_t)h * chunkF + i];
-                    CKRET(posfilt_launch(t->pf, nullptr, &sl.d_res->det, nullptr, 1, sl.d_pos));
-                    CK(cudaMemcpyAsync(sl.h_pos, sl.d_pos, sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
-                }
-                CK(cudaStreamSynchronize(c->post));
-                for (size_t i = 0; i < f.count; ++i) pos[f.first + i] = *t->ring[(size_t)h * chunkF + i].h_pos;
-            }
-        }
-        for (int s = 0; s < S; ++s) trk[s]->clip_frames += f.count;
-        *used = f.first + f.count;
-        f.live = false;
-        return OAT_OK;
-    };
 
-    auto launch_chunk = [&](int h) -> int {
-        if (stop) return OAT_OK;
+    void init(oat_ctx *ctx, oat_tracker *const *trackers, int n_trackers, bool fused)
+    {
+        c = ctx;
+        S = n_trackers;
+        fused_only = fused;
+        chunkF = trackers[0]->ring.size() / 2;
+        for (int s = 0; s < S; ++s) {
+            trk[s] = trackers[s];
+            chunkF = std::min(chunkF, trackers[s]->ring.size() / 2);
+        }
+        g = trk[0]->tail.tb.g;
+        ntiles = (int)((trk[0]->m.plane + PIPE_TILE - 1) / PIPE_TILE);
+        // second labelling attempt in global memory for masks whose tables do not fit the CTA's shared memory: room for
+        // ~200 k runs and 4096 contours per CTA, plus the mask itself
+        scratch_bytes = (((size_t)g.rows * g.wpr * 4 + (size_t)g.rows * 16 + (size_t)3 * scratch_comps * 8 + ((size_t)200 << 10) * 12 + 4096) + 255) & ~(size_t)255;
+    }
+    int next_half() const { return (int)(nchunk & 1); }
+    bool half_free() const { return !fl[nchunk & 1].live; }
+    int oldest_live() const
+    {
+        if (fl[0].live && fl[1].live) return fl[0].order < fl[1].order ? 0 : 1;
+        return fl[0].live ? 0 : fl[1].live ? 1 : -1;
+    }
+    size_t frames_in_flight() const { return (fl[0].live ? fl[0].count : 0) + (fl[1].live ? fl[1].count : 0); }
+    bool finished(int h) const { return fl[h].live && cudaEventQuery(c->clip[h].done) == cudaSuccess; }
+
+    // One chunk: up to chunkF frames of `frames` ([n][S] frame-major) into the free half next_half().  *taken = frames
+    // (per tracker) that went in -- fewer than min(n, chunkF) when a frame or a tracker is not eligible for the engine
+    // (the caller takes it from there on the per-frame path).
+    int launch(const uint8_t *const *frames, size_t n, size_t in_pitch, double learning_rate, const oat_hsv_params *p, size_t *taken)
+    {
+        *taken = 0;
+        const int h = next_half();
+        if (fl[h].live) return fail(OAT_ERR_STATE, "resident engine: both chunks are in flight");
+        ClipHalf *half = c->clip;
+        oat_tracker *t0 = trk[0];
         for (int s = 0; s < S; ++s)
-            if (!clip_eligible(trk[s], learning_rate, p, !fused_only)) {
-                stop = true;
-                return OAT_OK;
-            }
-        // how many frames of the clip can go into this chunk
+            if (!clip_eligible(trk[s], learning_rate, p, !fused_only)) return OAT_OK;
+        const int ke = p->erode_px > 0 ? p->erode_px : 0, kd = p->dilate_px > 0 ? p->dilate_px : 0;
+        // bands of 32 rows (a band costs ~3 dependent L2 round trips whatever its size; most bands of a tracking mask are
+        // empty) unless the morphology staging of such a band would not fit
+        auto stage_for = [&](int rr) {
+            const size_t nin = (size_t)rr + (ke > 0 ? ke - 1 : 0) + (kd > 0 ? kd - 1 : 0);
+            return 2 * nin * (size_t)g.wpr * sizeof(uint32_t);
+        };
+        const int R = stage_for(32) <= (size_t)64 * 1024 ? 32 : 8;
+        const size_t tail_smem = std::max(std::max(stage_for(R), t0->tail.fast_smem), (size_t)PIPE_TAIL_SMEM_KB_CFG * 1024);
+        static size_t tail_stream_smem_set = 48 * 1024;
+        if (!fused_only && tail_smem + 2048 > tail_stream_smem_set) {
+            CK(cudaFuncSetAttribute(tail_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+            tail_stream_smem_set = 200 * 1024;
+        }
+        // how many frames can go into this chunk
         size_t cnt = 0;
-        for (; cnt < chunkF && next + cnt < n; ++cnt) {
+        for (; cnt < chunkF && cnt < n; ++cnt) {
             bool ok = true;
             for (int s = 0; s < S && ok; ++s) {
                 int cls = 0;
-                ok = clip_frame_ok(trk[s], frames[(next + cnt) * S + s], in_pitch, &cls);
+                ok = clip_frame_ok(trk[s], frames[cnt * S + s], in_pitch, &cls);
                 if (ok) class_all = std::min(class_all, cls);
             }
-            if (!ok) {
-                stop = true;  // this chunk ends before the frame; the caller takes it from there
-                break;
-            }
+            if (!ok) break;  // this chunk ends before the frame
         }
         if (cnt == 0) return OAT_OK;
         CKRET(half[h].ensure(chunkF * (size_t)S));
@@ -2118,7 +2089,7 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
                 t->m.frame_consts(learning_rate, &mc, &reset);
                 if (i == 0 && s == 0) a.c = mc;
                 FrameDesc &d = half[h].h_desc[i * S + s];
-                d.bgr = frames[(next + i) * S + s];
+                d.bgr = frames[i * S + s];
                 d.state = t->m.state;
                 d.nmodes = t->m.nmodes;
                 d.thr_bits = sl.bits;
@@ -2210,35 +2181,101 @@ static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *c
         } else {
             CK(cudaEventRecord(half[h].done, c->stream));
         }
-        fl[h].first = next;
         fl[h].count = cnt;
         fl[h].live = true;
-        next += cnt;
+        fl[h].order = nchunk;
         ++nchunk;
+        *taken = cnt;
         return OAT_OK;
-    };
-
-    for (;;) {
-        const int h = (int)(nchunk & 1);
-        if (next < n && !stop && !fl[h].live) {
-            const size_t before = next;
-            CKRET(launch_chunk(h));
-            if (next != before) continue;
-            stop = true;  // nothing could be launched
-        }
-        // retire the older live chunk
-        int r = -1;
-        if (fl[0].live && fl[1].live)
-            r = fl[0].first < fl[1].first ? 0 : 1;
-        else if (fl[0].live)
-            r = 0;
-        else if (fl[1].live)
-            r = 1;
-        if (r < 0) break;
-        CKRET(retire(r));
     }
-    c->clip_wait_ns += wait_ns;
-    c->clip_busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_enter).count() - wait_ns;
+
+    // Waits for chunk h and hands out its detections ([count][S]; pos: [count], S == 1 with a position filter).
+    int retire(int h, oat_detection *out, oat_position *pos, size_t *count)
+    {
+        Flight &f = fl[h];
+        ClipHalf *half = c->clip;
+        {
+            const auto w0 = std::chrono::steady_clock::now();
+            CK(cudaEventSynchronize(half[h].done));
+            wait_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - w0).count();
+        }
+        if (!fused_only) {
+            bool replayed = false;
+            for (size_t i = 0; i < f.count; ++i)
+                for (int s = 0; s < S; ++s) {
+                    oat_tracker *t = trk[s];
+                    Slot &sl = t->ring[(size_t)h * chunkF + i];
+                    if (sl.h_res->status != TAIL_OK) {
+                        // the mask outgrew even the tail server's global-memory tables: replay this frame's mask through
+                        // the unbounded path (its bits are still in the slot)
+                        CKRET(t->tail.run(c, sl.bits, sl.hp, &sl.d_res->det, nullptr, 0, nullptr));
+                        CK(cudaMemcpyAsync(&sl.h_res->det, &sl.d_res->det, sizeof(oat_detection), cudaMemcpyDeviceToHost, c->stream));
+                        ++t->replays;
+                        replayed = true;
+                    }
+                }
+            if (replayed) CK(cudaStreamSynchronize(c->stream));
+            for (size_t i = 0; i < f.count; ++i)
+                for (int s = 0; s < S; ++s) {
+                    oat_tracker *t = trk[s];
+                    Slot &sl = t->ring[(size_t)h * chunkF + i];
+                    const double groups = (double)t->m.g.rows * t->m.g.cols / 4.0;
+                    t->slow_frac = 0.75 * t->slow_frac + 0.25 * ((double)sl.h_res->slow_groups / groups);
+                    if (!t->use_generic && t->slow_frac > 0.30) t->use_generic = true;
+                    if (out) out[i * S + s] = sl.h_res->det;
+                    t->last_slot = (size_t)h * chunkF + i;
+                }
+            if (pos) {  // S == 1: the position epilogue over the chunk's final detections, in frame order
+                oat_tracker *t = trk[0];
+                for (size_t i = 0; i < f.count; ++i) {
+                    Slot &sl = t->ring[(size_t)h * chunkF + i];
+                    CKRET(posfilt_launch(t->pf, nullptr, &sl.d_res->det, nullptr, 1, sl.d_pos));
+                    CK(cudaMemcpyAsync(sl.h_pos, sl.d_pos, sizeof(oat_position), cudaMemcpyDeviceToHost, c->post));
+                }
+                CK(cudaStreamSynchronize(c->post));
+                for (size_t i = 0; i < f.count; ++i) pos[i] = *t->ring[(size_t)h * chunkF + i].h_pos;
+            }
+        }
+        for (int s = 0; s < S; ++s) trk[s]->clip_frames += f.count;
+        *count = f.count;
+        f.live = false;
+        return OAT_OK;
+    }
+};
+
+// frames: [n][S] frame-major; out / pos likewise (pos only with S == 1).  *used = frames (per tracker) consumed;
+// fewer than n if a frame or a tracker stopped being eligible -- the caller continues on the per-frame path.
+static int clip_run(oat_ctx *c, oat_tracker *const *trk, int S, const uint8_t *const *frames, size_t n, size_t in_pitch,
+                    double learning_rate, const oat_hsv_params *p, bool fused_only, oat_detection *out, oat_position *pos,
+                    size_t *used)
+{
+    *used = 0;
+    ClipEngine e;
+    e.init(c, trk, S, fused_only);
+    if (e.chunkF == 0 || n == 0) return OAT_OK;
+    const auto t_enter = std::chrono::steady_clock::now();
+    size_t next = 0, first[2] = {0, 0};
+    bool stop = false;  // no new chunks: something stopped being eligible
+    for (;;) {
+        const int h = e.next_half();
+        if (next < n && !stop && e.half_free()) {
+            size_t taken = 0;
+            CKRET(e.launch(frames + next * S, n - next, in_pitch, learning_rate, p, &taken));
+            if (taken < std::min(e.chunkF, n - next)) stop = true;
+            if (taken) {
+                first[h] = next;
+                next += taken;
+                continue;
+            }
+        }
+        const int r = e.oldest_live();
+        if (r < 0) break;
+        size_t cnt = 0;
+        CKRET(e.retire(r, out ? out + first[r] * S : nullptr, pos ? pos + first[r] : nullptr, &cnt));
+        *used = first[r] + cnt;
+    }
+    c->clip_wait_ns += e.wait_ns;
+    c->clip_busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_enter).count() - e.wait_ns;
     c->clip_frames_total += *used * (uint64_t)S;
     return OAT_OK;
 }
