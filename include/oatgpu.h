@@ -62,6 +62,9 @@ int oat_device_count(void);
  * device, owns the CUDA streams the handles below run on. */
 typedef struct oat_ctx oat_ctx;
 int oat_ctx_create(int device_index, oat_ctx **out);
+/* Objects created from a context keep it alive: if any still exist, the context's resources are released when the
+ * last of them is destroyed (so the order in which a garbage collector or an error path destroys handles does not
+ * matter); the handle itself must not be used after this call. */
 int oat_ctx_destroy(oat_ctx *ctx);
 /* Block until everything queued through this context has finished. */
 int oat_ctx_sync(oat_ctx *ctx);
@@ -312,6 +315,35 @@ int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames, size_t n,
 int oat_tracker_run_clips(oat_tracker *const *trackers, int n_trackers, const uint8_t *const *frames,
                           size_t n_frames, size_t in_pitch, double learning_rate, const oat_hsv_params *p,
                           int flags, oat_detection *out);
+/* STREAMING use of the resident engine -- what lets a component in a shared-memory graph (a lock-step
+ * SOURCE in front, a lock-step SINK behind: lib/shmemdf/Source.h:187-232, Sink.h:93-138) run at the engine's
+ * rate instead of one launch pair per frame; the GPU-aware counterpart of putting `oat buffer`
+ * (src/buffer/FrameBuffer.cpp:56-116) in front of a slow component.
+ *   push        hands ONE frame to the tracker and returns without waiting for its detection.  Frames are
+ *               gathered into a chunk (half the tracker's ring); a full chunk is launched at once (one fused
+ *               launch + one tail-server launch), a partial one by flush.  Two chunks are in flight; a push
+ *               that needs a third waits for the oldest and keeps its detections for poll.
+ *               flags & OAT_STREAM_COPY: the caller takes the frame's memory back after wait_ingest, so the frame
+ *               is staged into the tracker's own HBM first (H2D from host memory -- always staged --, D2D from
+ *               device memory).  Without it a device frame is read IN PLACE and must stay valid and unchanged
+ *               until its detection has been polled.
+ *               A frame the engine cannot take (the model's first frame, learning rate < 0 or >= 1, ...) goes
+ *               through the per-frame path in order, synchronously.
+ *   wait_ingest blocks until the pixels of every pushed OAT_STREAM_COPY frame have left the caller's memory.
+ *   flush       launches the gathered frames as a (short) chunk if a chunk slot is free; block != 0: waits for one.
+ *   poll        detections (and filtered positions, pos may be NULL) of finished frames, in push order; block != 0:
+ *               waits until at least one is there (flushing if need be) unless nothing is outstanding.
+ *   pending     frames gathered / in flight on the GPU / finished and waiting for poll.
+ * Results are identical to submit/collect and run_clip.  One tracker per context streams at a time; the other
+ * tracker entry points return OAT_ERR_STATE while frames are gathered or in flight. */
+#define OAT_STREAM_COPY 1u
+int oat_tracker_stream_push(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                            const oat_hsv_params *p, unsigned flags);
+int oat_tracker_stream_wait_ingest(oat_tracker *t);
+int oat_tracker_stream_flush(oat_tracker *t, int block);
+int oat_tracker_stream_poll(oat_tracker *t, oat_detection *out, oat_position *pos, size_t cap, int block,
+                            size_t *got);
+int oat_tracker_stream_pending(oat_tracker *t, size_t *gathered, size_t *in_flight, size_t *ready);
 /* GMM state egress, as oat_mog_get_state. */
 int oat_tracker_get_state(oat_tracker *t, uint8_t *modes_used, float *weight, float *variance,
                           float *mean);

@@ -166,6 +166,12 @@ _SIGS = {
     "oat_tracker_run_clip": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_double,
                                        C.POINTER(HsvParams), C.c_int, C.POINTER(Detection), C.POINTER(Position)]),
     "oat_tracker_live_modes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "oat_tracker_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(HsvParams), C.c_uint]),
+    "oat_tracker_stream_wait_ingest": (C.c_int, [C.c_void_p]),
+    "oat_tracker_stream_flush": (C.c_int, [C.c_void_p, C.c_int]),
+    "oat_tracker_stream_poll": (C.c_int, [C.c_void_p, C.POINTER(Detection), C.POINTER(Position), C.c_size_t, C.c_int,
+                                          C.POINTER(C.c_size_t)]),
+    "oat_tracker_stream_pending": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "oat_kalman_default_params": (None, [C.POINTER(KalmanParams)]),
     "oat_posfilt_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(KalmanParams), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "oat_posfilt_destroy": (C.c_int, [C.c_void_p]),
@@ -715,6 +721,32 @@ class Tracker:
         pos = (Position * n)() if positions else None
         _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, pitch or self.cols * 3, lr, C.byref(self.hsv), depth, out, pos))
         return (list(out), list(pos)) if positions else list(out)
+
+    # ---- streaming use of the resident engine (oat_tracker_stream_*) ----
+    def stream_push(self, bgr, copy=False, learning_rate=None, pitch=None):
+        """One frame into the stream; copy=True: the frame's memory is the caller's again after stream_wait_ingest()."""
+        lr = self.learning_coeff if learning_rate is None else learning_rate
+        _ck(lib().oat_tracker_stream_push(self._h, _ptr(bgr), pitch or self.cols * 3, lr, C.byref(self.hsv), 1 if copy else 0))
+
+    def stream_wait_ingest(self):
+        _ck(lib().oat_tracker_stream_wait_ingest(self._h))
+
+    def stream_flush(self, block=False):
+        _ck(lib().oat_tracker_stream_flush(self._h, 1 if block else 0))
+
+    def stream_poll(self, cap=64, block=False, positions=False):
+        """Finished detections in push order (at most cap) -> list of Detection (, list of Position)."""
+        out = (Detection * cap)()
+        pos = (Position * cap)() if positions else None
+        got = C.c_size_t()
+        _ck(lib().oat_tracker_stream_poll(self._h, out, pos, cap, 1 if block else 0, C.byref(got)))
+        return (list(out[:got.value]), list(pos[:got.value])) if positions else list(out[:got.value])
+
+    def stream_pending(self):
+        """(frames gathered, frames in flight on the GPU, detections waiting for stream_poll)."""
+        a, b, c_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _ck(lib().oat_tracker_stream_pending(self._h, C.byref(a), C.byref(b), C.byref(c_)))
+        return a.value, b.value, c_.value
 
     def attach_posfilt(self, f: "PositionFilter | None"):
         """Fuse a single-source position filter behind this tracker (device-side epilogue, frame order)."""

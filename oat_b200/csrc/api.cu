@@ -14,6 +14,7 @@
 #include <atomic>
 #include <new>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "common.cuh"
@@ -122,6 +123,7 @@ struct ClipHalf {
 };
 
 struct oat_ctx {
+    int refs = 1;  // the caller's handle + one per live object created from it: the context is released by whoever leaves last
     int device = 0;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t h2d = nullptr;      // ingest copies (overlap with compute of the previous frame)
@@ -153,6 +155,7 @@ struct oat_ctx {
     uint64_t pipe_launches = 0;
     cudaStream_t aux = nullptr;  // small host-synchronous uploads (frame descriptors of a clip)
     ClipHalf clip[2];            // two chunks of the resident clip engine in flight
+    const void *clip_owner = nullptr;  // the tracker whose stream (oat_tracker_stream_*) holds chunks in flight, if any
     DevBuf tail_scratch[2];      // per chunk in flight: one global-memory labelling area per CTA of the tail server
     // device timing of the resident fused kernel: a CUDA-event pair on the compute stream around every launch
     // (consecutive launches overlap tile by tile, so the brackets partition the timeline: their sum is the time
@@ -252,9 +255,22 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     return OAT_OK;
 }
 
+static void ctx_ref(oat_ctx *c) { ++c->refs; }
+static void ctx_free(oat_ctx *c);
+static void ctx_unref(oat_ctx *c)
+{
+    if (--c->refs == 0) ctx_free(c);
+}
+// Objects created from a context keep it alive: destroying the context first (a garbage collector's order, an
+// exception path) defers its release to the last object's destroy instead of leaving them with a dangling pointer.
 extern "C" int oat_ctx_destroy(oat_ctx *c)
 {
     if (!c) return OAT_OK;
+    ctx_unref(c);
+    return OAT_OK;
+}
+static void ctx_free(oat_ctx *c)
+{
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->h2d);
@@ -286,7 +302,6 @@ extern "C" int oat_ctx_destroy(oat_ctx *c)
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
     delete c;
-    return OAT_OK;
 }
 
 extern "C" int oat_ctx_sync(oat_ctx *c)
@@ -350,9 +365,49 @@ static MemKind mem_kind(const void *p)
     return MEM_PAGEABLE;
 }
 
+// A frame into `stage` at a 16-byte aligned pitch (`tight`).  A contiguous frame whose rows are not a multiple of 16
+// bytes (a 1000-column BGR frame: 3000 B) would need a strided 2-D DMA -- measured at about half the PCIe rate of a
+// linear one -- so, given a second buffer, a HOST frame goes up linearly into `raw` and is re-pitched on the device.
+static int repitch(cudaStream_t s, void *dst, size_t dpitch, const void *src, size_t spitch, size_t rowbytes, int rows)
+{
+    if ((((uintptr_t)dst | (uintptr_t)src | dpitch | spitch | rowbytes) & 3u) != 0) {
+        CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, rowbytes, rows, cudaMemcpyDeviceToDevice, s));
+        return OAT_OK;
+    }
+    const bool v16 = (((uintptr_t)dst | (uintptr_t)src | dpitch | spitch | rowbytes) & 15u) == 0;
+    const unsigned units = (unsigned)(rowbytes / (v16 ? 16 : 4));
+    const unsigned long long total = (unsigned long long)units * rows;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((total + 255) / 256, 148ull * 4);
+    if (v16)
+        repitch_kernel<uint4><<<grid, 256, 0, s>>>((uint8_t *)dst, dpitch, (const uint8_t *)src, spitch, units, (unsigned)rows);
+    else
+        repitch_kernel<uint32_t><<<grid, 256, 0, s>>>((uint8_t *)dst, dpitch, (const uint8_t *)src, spitch, units, (unsigned)rows);
+    CK(cudaGetLastError());
+    return OAT_OK;
+}
+static int copy_frame_in(cudaStream_t s, DevBuf &stage, DevBuf *raw, const void *src, size_t pitch, int rows, size_t rowbytes,
+                         size_t tight, bool src_is_device)
+{
+    CKRET(stage.ensure(tight * rows));
+    if (src_is_device) {
+        if (pitch == rowbytes && tight == rowbytes)
+            CKRET(repitch(s, stage.p, rowbytes * rows, src, rowbytes * rows, rowbytes * rows, 1));  // one long row
+        else
+            CKRET(repitch(s, stage.p, tight, src, pitch, rowbytes, rows));
+    } else if (pitch == rowbytes && tight == rowbytes) {  // contiguous frame: one linear DMA
+        CK(cudaMemcpyAsync(stage.p, src, rowbytes * rows, cudaMemcpyHostToDevice, s));
+    } else if (raw && pitch == rowbytes) {
+        CKRET(raw->ensure(rowbytes * rows));
+        CK(cudaMemcpyAsync(raw->p, src, rowbytes * rows, cudaMemcpyHostToDevice, s));
+        CKRET(repitch(s, stage.p, tight, raw->p, rowbytes, rowbytes, rows));
+    } else {
+        CK(cudaMemcpy2DAsync(stage.p, tight, src, pitch, rowbytes, rows, cudaMemcpyHostToDevice, s));
+    }
+    return OAT_OK;
+}
 // Input image: returns a device view (ptr,pitch); host images are copied into `stage`.
 static int stage_in(oat_ctx *c, cudaStream_t s, DevBuf &stage, const void *src, size_t pitch, int rows,
-                    size_t rowbytes, const uint8_t **dptr, size_t *dpitch)
+                    size_t rowbytes, const uint8_t **dptr, size_t *dpitch, DevBuf *raw = nullptr)
 {
     if (mem_kind(src) == MEM_DEVICE) {
         *dptr = (const uint8_t *)src;
@@ -360,11 +415,7 @@ static int stage_in(oat_ctx *c, cudaStream_t s, DevBuf &stage, const void *src, 
         return OAT_OK;
     }
     const size_t tight = (rowbytes + 15) & ~(size_t)15;
-    CKRET(stage.ensure(tight * rows));
-    if (pitch == rowbytes && tight == rowbytes)  // contiguous frame: one linear DMA
-        CK(cudaMemcpyAsync(stage.p, src, rowbytes * rows, cudaMemcpyHostToDevice, s));
-    else
-        CK(cudaMemcpy2DAsync(stage.p, tight, src, pitch, rowbytes, rows, cudaMemcpyHostToDevice, s));
+    CKRET(copy_frame_in(s, stage, raw, src, pitch, rows, rowbytes, tight, false));
     *dptr = (const uint8_t *)stage.p;
     *dpitch = tight;
     return OAT_OK;
@@ -733,10 +784,15 @@ extern "C" int oat_mog_create(oat_ctx *c, int rows, int cols, const oat_mog_para
     oat_mog *h = new (std::nothrow) oat_mog();
     if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
     h->ctx = c;
+    ctx_ref(c);
     int r = h->m.create(rows, cols, params);
     if (r != OAT_OK) {
         h->m.destroy();
-        delete h;
+        {
+            oat_ctx *owner_ = h->ctx;
+            delete h;
+            ctx_unref(owner_);
+        }
         return r;
     }
     *out = h;
@@ -751,7 +807,11 @@ extern "C" int oat_mog_destroy(oat_mog *h)
     h->in.release();
     h->out_bgr.release();
     h->out_mask.release();
-    delete h;
+    {
+        oat_ctx *owner_ = h->ctx;
+        delete h;
+        ctx_unref(owner_);
+    }
     return OAT_OK;
 }
 extern "C" int oat_mog_reset(oat_mog *h)
@@ -890,6 +950,7 @@ extern "C" int oat_bsub_create(oat_ctx *c, int rows, int cols, int channels, dou
     oat_bsub *b = new (std::nothrow) oat_bsub();
     if (!b) return fail(OAT_ERR_NOMEM, "out of host memory");
     b->ctx = c;
+    ctx_ref(c);
     b->rows = rows;
     b->cols = cols;
     b->ch = channels;
@@ -900,7 +961,11 @@ extern "C" int oat_bsub_create(oat_ctx *c, int rows, int cols, int channels, dou
     const size_t n = (size_t)rows * cols * channels;
     if (cudaMalloc(&b->bg, n) != cudaSuccess || cudaMalloc(&b->bgf, n * sizeof(float)) != cudaSuccess) {
         if (b->bg) cudaFree(b->bg);
-        delete b;
+        {
+            oat_ctx *owner_ = b->ctx;
+            delete b;
+            ctx_unref(owner_);
+        }
         cudaGetLastError();
         return fail(OAT_ERR_NOMEM, "oat_bsub_create: device allocation failed");
     }
@@ -916,7 +981,11 @@ extern "C" int oat_bsub_destroy(oat_bsub *b)
     cudaFree(b->bgf);
     b->in.release();
     b->out.release();
-    delete b;
+    {
+        oat_ctx *owner_ = b->ctx;
+        delete b;
+        ctx_unref(owner_);
+    }
     return OAT_OK;
 }
 extern "C" int oat_bsub_set_background(oat_bsub *b, const uint8_t *img, size_t pitch)
@@ -1219,13 +1288,18 @@ extern "C" int oat_hsvdet_create(oat_ctx *c, int rows, int cols, oat_hsvdet **ou
     oat_hsvdet *h = new (std::nothrow) oat_hsvdet();
     if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
     h->ctx = c;
+    ctx_ref(c);
     h->d_res = nullptr;
     int r = h->tail.create(rows, cols, 160);
     if (r == OAT_OK && cudaMalloc(&h->d_res, sizeof(TailResult)) != cudaSuccess)
         r = fail(OAT_ERR_NOMEM, "device allocation failed");
     if (r != OAT_OK) {
         h->tail.destroy();
-        delete h;
+        {
+            oat_ctx *owner_ = h->ctx;
+            delete h;
+            ctx_unref(owner_);
+        }
         return r;
     }
     *out = h;
@@ -1241,7 +1315,11 @@ extern "C" int oat_hsvdet_destroy(oat_hsvdet *h)
     h->in.release();
     h->out_thr.release();
     h->out_lab.release();
-    delete h;
+    {
+        oat_ctx *owner_ = h->ctx;
+        delete h;
+        ctx_unref(owner_);
+    }
     return OAT_OK;
 }
 
@@ -1345,6 +1423,7 @@ extern "C" int oat_diffdet_create(oat_ctx *c, int rows, int cols, oat_diffdet **
     oat_diffdet *h = new (std::nothrow) oat_diffdet();
     if (!h) return fail(OAT_ERR_NOMEM, "out of host memory");
     h->ctx = c;
+    ctx_ref(c);
     h->d_res = nullptr;
     h->last = nullptr;
     h->have_last = false;
@@ -1355,7 +1434,11 @@ extern "C" int oat_diffdet_create(oat_ctx *c, int rows, int cols, oat_diffdet **
         h->tail.destroy();
         cudaFree(h->d_res);
         cudaFree(h->last);
-        delete h;
+        {
+            oat_ctx *owner_ = h->ctx;
+            delete h;
+            ctx_unref(owner_);
+        }
         return r;
     }
     *out = h;
@@ -1371,7 +1454,11 @@ extern "C" int oat_diffdet_destroy(oat_diffdet *h)
     cudaFree(h->last);
     h->in.release();
     h->out_thr.release();
-    delete h;
+    {
+        oat_ctx *owner_ = h->ctx;
+        delete h;
+        ctx_unref(owner_);
+    }
     return OAT_OK;
 }
 extern "C" int oat_diffdet_reset(oat_diffdet *h)
@@ -1475,6 +1562,7 @@ extern "C" int oat_keep_where(oat_ctx *c, const uint8_t *in, size_t in_pitch, ui
 // ---- fused tracker -------------------------------------------------------------------------
 struct Slot {
     DevBuf in;                      // staged input frame (host-fed streams)
+    DevBuf in_raw;                  // ... its linear landing area when the rows have to be re-pitched on the device
     TailResult *h_res = nullptr;    // pinned
     TailResult *d_res = nullptr;
     uint32_t *bits = nullptr;       // this frame's threshold mask (kept until collect: overflow replay)
@@ -1523,6 +1611,7 @@ extern "C" int oat_posfilt_create(oat_ctx *c, int n_sources, const oat_kalman_pa
     oat_posfilt *f = new (std::nothrow) oat_posfilt();
     REQUIRE(f, "out of memory");
     f->ctx = c;
+    ctx_ref(c);
     f->n = n_sources;
     f->combine = combine_mean ? 1 : 0;
     f->heading_anchor = heading_anchor < 0 ? -1 : heading_anchor;
@@ -1558,7 +1647,11 @@ extern "C" int oat_posfilt_destroy(oat_posfilt *f)
     if (f->d_raw) cudaFree(f->d_raw);
     if (f->d_out) cudaFree(f->d_out);
     if (f->h_io) cudaFreeHost(f->h_io);
-    delete f;
+    {
+        oat_ctx *owner_ = f->ctx;
+        delete f;
+        ctx_unref(owner_);
+    }
     return OAT_OK;
 }
 
@@ -1634,7 +1727,11 @@ struct oat_tracker {
     uint64_t prof_n = 0;
     size_t last_slot = 0;            // ring slot of the most recently collected frame (oat_tracker_tail_stats)
     uint64_t clip_frames = 0;        // frames that went through the resident clip engine
+    struct StreamState *stream = nullptr;  // oat_tracker_stream_*: the resident engine kept alive between calls
 };
+static bool stream_busy(const oat_tracker *t);
+static void stream_destroy(oat_tracker *t);
+#define REQUIRE_NOT_STREAMING(t, who) REQUIRE(!stream_busy(t), who ": frames are gathered or in flight in the tracker's stream (poll them first)")
 
 extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_params *mp, int ring_depth,
                                   oat_tracker **out)
@@ -1647,6 +1744,7 @@ extern "C" int oat_tracker_create(oat_ctx *c, int rows, int cols, const oat_mog_
     oat_tracker *t = new (std::nothrow) oat_tracker();
     if (!t) return fail(OAT_ERR_NOMEM, "out of host memory");
     t->ctx = c;
+    ctx_ref(c);
     int r = t->m.create(rows, cols, mp);
     if (r == OAT_OK) r = t->tail.create(rows, cols);
     if (r == OAT_OK) {
@@ -1684,6 +1782,7 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
 {
     if (!t) return OAT_OK;
     cudaSetDevice(t->ctx->device);
+    stream_destroy(t);
     cudaStreamSynchronize(t->ctx->h2d);
     cudaStreamSynchronize(t->ctx->stream);
     for (int i = 0; i < oat_ctx::NTAIL; ++i) cudaStreamSynchronize(t->ctx->tail[i]);
@@ -1692,6 +1791,7 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
     t->tail.destroy();
     for (auto &s : t->ring) {
         s.in.release();
+        s.in_raw.release();
         if (s.h_res) cudaFreeHost(s.h_res);
         if (s.d_res) cudaFree(s.d_res);
         if (s.bits) cudaFree(s.bits);
@@ -1713,7 +1813,11 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
     t->out_fg.release();
     t->out_hsv.release();
     t->out_thr.release();
-    delete t;
+    {
+        oat_ctx *owner_ = t->ctx;
+        delete t;
+        ctx_unref(owner_);
+    }
     return OAT_OK;
 }
 
@@ -1721,6 +1825,7 @@ extern "C" int oat_tracker_reset(oat_tracker *t)
 {
     REQUIRE(t, "null handle");
     REQUIRE(t->head == t->tailpos, "oat_tracker_reset: frames are still outstanding");
+    REQUIRE_NOT_STREAMING(t, "oat_tracker_reset");
     t->m.nframes = 0;
     return OAT_OK;
 }
@@ -1740,7 +1845,7 @@ static int tracker_enqueue(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitc
         s.ingest = 2;
     } else {
         // ingest on the copy stream so the DMA of frame t+1 overlaps the kernels of frame t
-        CKRET(stage_in(c, c->h2d, s.in, bgr_in, in_pitch, rows, (size_t)3 * cols, &a.bgr, &a.in_pitch));
+        CKRET(stage_in(c, c->h2d, s.in, bgr_in, in_pitch, rows, (size_t)3 * cols, &a.bgr, &a.in_pitch, &s.in_raw));
         CK(cudaEventRecord(s.copied, c->h2d));
         CK(cudaStreamWaitEvent(c->stream, s.copied, 0));
         s.ingest = 1;
@@ -1834,6 +1939,7 @@ extern "C" int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_
     CKRET(tracker_check(t, bgr_in, in_pitch, p));
     CKRET(bind(t->ctx));
     REQUIRE(t->head == t->tailpos, "oat_tracker_submit_fused_only: frames are still outstanding (collect first)");
+    REQUIRE_NOT_STREAMING(t, "oat_tracker_submit_fused_only");
     REQUIRE(mem_kind(bgr_in) == MEM_DEVICE, "oat_tracker_submit_fused_only: device-resident frames only");
     oat_ctx *c = t->ctx;
     Slot &s = t->ring[t->head % t->ring.size()];
@@ -1870,6 +1976,7 @@ extern "C" int oat_tracker_attach_posfilt(oat_tracker *t, oat_posfilt *f)
 {
     REQUIRE(t, "null handle");
     REQUIRE(t->head == t->tailpos, "oat_tracker_attach_posfilt: frames are still outstanding");
+    REQUIRE_NOT_STREAMING(t, "oat_tracker_attach_posfilt");
     REQUIRE(!f || (f->ctx == t->ctx && f->n == 1 && !f->attached), "oat_tracker_attach_posfilt: needs an unattached single-source filter of the same context");
     CKRET(bind(t->ctx));
     if (t->pf) t->pf->attached = 0;
@@ -1939,6 +2046,7 @@ extern "C" int oat_tracker_submit(oat_tracker *t, const uint8_t *bgr_in, size_t 
 {
     CKRET(tracker_check(t, bgr_in, in_pitch, p));
     CKRET(bind(t->ctx));
+    REQUIRE_NOT_STREAMING(t, "oat_tracker_submit");
     if (t->head - t->tailpos >= t->ring.size())
         return fail(OAT_ERR_STATE, "oat_tracker_submit: ring full (collect first)");
     const int rows = t->m.g.rows, cols = t->m.g.cols;
@@ -1977,9 +2085,10 @@ static bool clip_eligible(const oat_tracker *t, double learning_rate, const oat_
     }
     return true;
 }
-static bool clip_frame_ok(const oat_tracker *t, const uint8_t *frame, size_t in_pitch, int *cls_out)
+// known_device: the caller has already established that the frame is device memory (cudaPointerGetAttributes is ~1 us)
+static bool clip_frame_ok(const oat_tracker *t, const uint8_t *frame, size_t in_pitch, int *cls_out, bool known_device = false)
 {
-    if (!frame || mem_kind(frame) != MEM_DEVICE || !aligned4(frame, in_pitch)) return false;
+    if (!frame || (!known_device && mem_kind(frame) != MEM_DEVICE) || !aligned4(frame, in_pitch)) return false;
     FusedArgs a{};
     a.bgr = frame;
     a.in_pitch = in_pitch;
@@ -2009,6 +2118,7 @@ struct ClipEngine {
     uint64_t nchunk = 0;  // chunks launched; the next one uses half nchunk & 1
     int class_all = 2;
     double wait_ns = 0.0;
+    bool frames_known_device = false;  // the stream checks every frame when it is pushed
 
     void init(oat_ctx *ctx, oat_tracker *const *trackers, int n_trackers, bool fused)
     {
@@ -2068,7 +2178,7 @@ struct ClipEngine {
             bool ok = true;
             for (int s = 0; s < S && ok; ++s) {
                 int cls = 0;
-                ok = clip_frame_ok(trk[s], frames[cnt * S + s], in_pitch, &cls);
+                ok = clip_frame_ok(trk[s], frames[cnt * S + s], in_pitch, &cls, frames_known_device);
                 if (ok) class_all = std::min(class_all, cls);
             }
             if (!ok) break;  // this chunk ends before the frame
@@ -2317,6 +2427,8 @@ extern "C" int oat_tracker_run_clip(oat_tracker *t, const uint8_t *const *frames
 {
     REQUIRE(t && frames && out, "oat_tracker_run_clip: null argument");
     REQUIRE(t->head == t->tailpos, "oat_tracker_run_clip: frames are still outstanding (collect first)");
+    REQUIRE_NOT_STREAMING(t, "oat_tracker_run_clip");
+    REQUIRE(!t->ctx->clip_owner, "oat_tracker_run_clip: another tracker of this context is streaming");
     REQUIRE(!pos || t->pf, "oat_tracker_run_clip: positions requested but no position filter is attached");
     if (n == 0) return OAT_OK;
     CKRET(tracker_check(t, frames[0], in_pitch, p));
@@ -2359,6 +2471,8 @@ extern "C" int oat_tracker_run_clips(oat_tracker *const *trackers, int n_tracker
                     memcmp(&t->m.p, &t0->m.p, sizeof(oat_mog_params)) == 0,
                 "oat_tracker_run_clips: the trackers must share context, geometry and MOG parameters");
         REQUIRE(t->head == t->tailpos, "oat_tracker_run_clips: frames are still outstanding (collect first)");
+        REQUIRE_NOT_STREAMING(t, "oat_tracker_run_clips");
+        REQUIRE(!t->ctx->clip_owner, "oat_tracker_run_clips: another tracker of this context is streaming");
         REQUIRE(t->m.nframes == t0->m.nframes, "oat_tracker_run_clips: the trackers must have seen the same number of frames");
         for (int u = 0; u < s; ++u) REQUIRE(trackers[u] != t, "oat_tracker_run_clips: a tracker appears twice");
     }
@@ -2391,6 +2505,202 @@ extern "C" int oat_tracker_run_clips(oat_tracker *const *trackers, int n_tracker
     return OAT_OK;
 }
 
+// ---- streaming use of the resident engine (oat_tracker_stream_*) -------------------------------------------
+struct StreamState {
+    ClipEngine eng;
+    std::vector<const uint8_t *> gathered;  // device views of the frames of the chunk being gathered
+    size_t pitch = 0;                       // ... their pitch, learning rate and detector parameters
+    double lr = 0.0;
+    oat_hsv_params p{};
+    bool staged_any = false;                // a gathered frame sits in a staging buffer: its copy precedes the launch
+    cudaEvent_t copied = nullptr;           // last staging copy on the ingest stream
+    bool copy_pending = false;
+    std::deque<std::pair<oat_detection, oat_position>> ready;
+    std::vector<oat_detection> tmp_det;
+    std::vector<oat_position> tmp_pos;
+};
+static bool stream_busy(const oat_tracker *t) { return t->stream && (!t->stream->gathered.empty() || t->stream->eng.frames_in_flight() > 0); }
+static void stream_release_owner(oat_tracker *t)
+{
+    if (t->ctx->clip_owner == t && !stream_busy(t)) t->ctx->clip_owner = nullptr;
+}
+// the oldest chunk in flight -> ready
+static int stream_retire_oldest(oat_tracker *t)
+{
+    StreamState *st = t->stream;
+    const int h = st->eng.oldest_live();
+    if (h < 0) return OAT_OK;
+    st->tmp_det.resize(st->eng.chunkF);
+    st->tmp_pos.resize(st->eng.chunkF);
+    size_t cnt = 0;
+    CKRET(st->eng.retire(h, st->tmp_det.data(), t->pf ? st->tmp_pos.data() : nullptr, &cnt));
+    for (size_t i = 0; i < cnt; ++i) st->ready.emplace_back(st->tmp_det[i], t->pf ? st->tmp_pos[i] : oat_position{});
+    t->ctx->clip_frames_total += cnt;
+    return OAT_OK;
+}
+// one frame through the per-frame path, synchronously and in order (everything before it is retired first)
+static int stream_fallback(oat_tracker *t, const uint8_t *frame, size_t pitch, double lr, const oat_hsv_params *p);
+static int stream_launch_gathered(oat_tracker *t, bool block)
+{
+    StreamState *st = t->stream;
+    if (st->gathered.empty()) return OAT_OK;
+    if (!st->eng.half_free()) {
+        if (!block) return OAT_OK;
+        CKRET(stream_retire_oldest(t));
+    }
+    if (st->staged_any && st->copy_pending) {
+        // (on the host, so that nothing but the previous fused kernel precedes this launch on the compute stream)
+        CK(cudaEventSynchronize(st->copied));
+        st->copy_pending = false;
+    }
+    size_t taken = 0;
+    CKRET(st->eng.launch(st->gathered.data(), st->gathered.size(), st->pitch, st->lr, &st->p, &taken));
+    std::vector<const uint8_t *> rest(st->gathered.begin() + taken, st->gathered.end());
+    st->gathered.clear();
+    st->staged_any = false;
+    // (the tracker stopped being eligible between push and launch, e.g. the census moved it to the generic kernel)
+    for (const uint8_t *f : rest) CKRET(stream_fallback(t, f, st->pitch, st->lr, &st->p));
+    return OAT_OK;
+}
+static int stream_fallback(oat_tracker *t, const uint8_t *frame, size_t pitch, double lr, const oat_hsv_params *p)
+{
+    StreamState *st = t->stream;
+    CKRET(stream_launch_gathered(t, true));
+    while (st->eng.oldest_live() >= 0) CKRET(stream_retire_oldest(t));
+    OutView n0, n1, n2, n3;
+    CKRET(tracker_enqueue(t, frame, pitch, lr, p, n0, n1, n2, n3, true));
+    oat_detection d;
+    oat_position pos{};
+    CKRET(tracker_collect(t, &d, t->pf ? &pos : nullptr));
+    st->ready.emplace_back(d, pos);
+    return OAT_OK;
+}
+static void stream_destroy(oat_tracker *t)
+{
+    StreamState *st = t->stream;
+    if (!st) return;
+    while (st->eng.oldest_live() >= 0)
+        if (stream_retire_oldest(t) != OAT_OK) break;
+    if (st->copied) {
+        cudaEventSynchronize(st->copied);
+        cudaEventDestroy(st->copied);
+    }
+    st->gathered.clear();
+    if (t->ctx->clip_owner == t) t->ctx->clip_owner = nullptr;
+    delete st;
+    t->stream = nullptr;
+}
+
+extern "C" int oat_tracker_stream_push(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
+                                       const oat_hsv_params *p, unsigned flags)
+{
+    CKRET(tracker_check(t, bgr_in, in_pitch, p));
+    REQUIRE(t->head == t->tailpos, "oat_tracker_stream_push: frames are still outstanding on the per-frame path (collect first)");
+    REQUIRE(t->ring.size() >= 2, "oat_tracker_stream_push: the tracker needs a ring of at least 2");
+    oat_ctx *c = t->ctx;
+    REQUIRE(!c->clip_owner || c->clip_owner == t, "oat_tracker_stream_push: another tracker of this context is streaming");
+    CKRET(bind(c));
+    if (!t->stream) {
+        t->stream = new (std::nothrow) StreamState();
+        if (!t->stream) return fail(OAT_ERR_NOMEM, "out of host memory");
+        t->stream->eng.init(c, &t, 1, false);
+        t->stream->eng.frames_known_device = true;
+        CK(cudaEventCreateWithFlags(&t->stream->copied, cudaEventDisableTiming));
+    }
+    StreamState *st = t->stream;
+    c->clip_owner = t;
+    const bool is_dev = mem_kind(bgr_in) == MEM_DEVICE;
+    // staged: on request, host memory, or a device frame the engine cannot read where it is (rows not 16-byte aligned:
+    // a tight 1000-column frame) -- a D2D copy into an aligned pitch costs microseconds, the per-frame path a launch pair
+    const bool need_stage = (flags & OAT_STREAM_COPY) || !is_dev || !clip_frame_ok(t, bgr_in, in_pitch, nullptr, true);
+    int r = OAT_OK;
+    if (!clip_eligible(t, learning_rate, p, true)) {
+        r = stream_fallback(t, bgr_in, in_pitch, learning_rate, p);  // (consumed when it returns)
+        stream_release_owner(t);
+        return r;
+    }
+    const int rows = t->m.g.rows;
+    const size_t rowbytes = (size_t)3 * t->m.g.cols, tight = (rowbytes + 15) & ~(size_t)15;
+    const size_t view_pitch = need_stage ? tight : in_pitch;
+    if (!st->gathered.empty() && (st->pitch != view_pitch || st->lr != learning_rate || memcmp(&st->p, p, sizeof(*p)) != 0))
+        CKRET(stream_launch_gathered(t, true));  // a chunk shares pitch, learning rate and detector parameters
+    const uint8_t *view = bgr_in;
+    if (need_stage) {
+        // the staging buffer of the slot this frame will occupy: the half must have been retired
+        if (!st->eng.half_free()) CKRET(stream_retire_oldest(t));
+        Slot &sl = t->ring[(size_t)st->eng.next_half() * st->eng.chunkF + st->gathered.size()];
+        CKRET(copy_frame_in(c->h2d, sl.in, &sl.in_raw, bgr_in, in_pitch, rows, rowbytes, tight, is_dev));
+        CK(cudaEventRecord(st->copied, c->h2d));
+        st->copy_pending = true;
+        st->staged_any = true;
+        view = (const uint8_t *)sl.in.p;
+    }
+    if (need_stage && !clip_frame_ok(t, view, view_pitch, nullptr, true)) {
+        r = stream_fallback(t, view, view_pitch, learning_rate, p);
+        stream_release_owner(t);
+        return r;
+    }
+    if (st->gathered.empty()) {
+        st->pitch = view_pitch;
+        st->lr = learning_rate;
+        st->p = *p;
+    }
+    st->gathered.push_back(view);
+    if (st->gathered.size() >= st->eng.chunkF) CKRET(stream_launch_gathered(t, true));
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_stream_wait_ingest(oat_tracker *t)
+{
+    REQUIRE(t, "null handle");
+    if (!t->stream || !t->stream->copy_pending) return OAT_OK;
+    CKRET(bind(t->ctx));
+    CK(cudaEventSynchronize(t->stream->copied));
+    t->stream->copy_pending = false;
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_stream_flush(oat_tracker *t, int block)
+{
+    REQUIRE(t, "null handle");
+    if (!t->stream) return OAT_OK;
+    CKRET(bind(t->ctx));
+    return stream_launch_gathered(t, block != 0);
+}
+
+extern "C" int oat_tracker_stream_poll(oat_tracker *t, oat_detection *out, oat_position *pos, size_t cap, int block, size_t *got)
+{
+    REQUIRE(t && got && (out || cap == 0), "oat_tracker_stream_poll: null argument");
+    REQUIRE(!pos || t->pf, "oat_tracker_stream_poll: positions requested but no position filter is attached");
+    *got = 0;
+    StreamState *st = t->stream;
+    if (!st) return OAT_OK;
+    CKRET(bind(t->ctx));
+    for (int h = st->eng.oldest_live(); h >= 0 && st->eng.finished(h); h = st->eng.oldest_live()) CKRET(stream_retire_oldest(t));
+    if (block && st->ready.empty()) {
+        if (st->eng.oldest_live() < 0) CKRET(stream_launch_gathered(t, true));
+        CKRET(stream_retire_oldest(t));
+    }
+    while (*got < cap && !st->ready.empty()) {
+        out[*got] = st->ready.front().first;
+        if (pos) pos[*got] = st->ready.front().second;
+        st->ready.pop_front();
+        ++*got;
+    }
+    stream_release_owner(t);
+    return OAT_OK;
+}
+
+extern "C" int oat_tracker_stream_pending(oat_tracker *t, size_t *gathered, size_t *in_flight, size_t *ready)
+{
+    REQUIRE(t, "null handle");
+    const StreamState *st = t->stream;
+    if (gathered) *gathered = st ? st->gathered.size() : 0;
+    if (in_flight) *in_flight = st ? st->eng.frames_in_flight() : 0;
+    if (ready) *ready = st ? st->ready.size() : 0;
+    return OAT_OK;
+}
+
 extern "C" int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t in_pitch, double learning_rate,
                                  const oat_hsv_params *p, oat_detection *out, uint8_t *bgr_out, size_t bgr_out_pitch,
                                  uint8_t *fgmask_out, size_t fgmask_pitch, uint8_t *hsv_out, size_t hsv_pitch,
@@ -2399,6 +2709,7 @@ extern "C" int oat_tracker_track(oat_tracker *t, const uint8_t *bgr_in, size_t i
     CKRET(tracker_check(t, bgr_in, in_pitch, p));
     REQUIRE(out, "oat_tracker_track: null output");
     REQUIRE(t->head == t->tailpos, "oat_tracker_track: frames are still outstanding (collect first)");
+    REQUIRE_NOT_STREAMING(t, "oat_tracker_track");
     CKRET(bind(t->ctx));
     const int rows = t->m.g.rows, cols = t->m.g.cols;
     REQUIRE(!bgr_out || bgr_out_pitch >= (size_t)3 * cols, "tracker: bgr_out pitch too small");

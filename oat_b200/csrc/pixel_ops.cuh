@@ -254,6 +254,24 @@ __global__ void state_export_kernel(const float *__restrict__ state, size_t plan
 }
 
 // L2 flush: overwrite a buffer larger than L2
+// Device-to-device staging of a frame into another pitch (the stream's OAT_STREAM_COPY of a device frame, the
+// re-pitch of a linearly uploaded host frame): the copy engine needs ~6-10 us per such copy on this part -- host time
+// as well as device time (tools/copy_rate.py) -- which is most of a 13 us frame period.  Rows and pitches are multiples
+// of 4 bytes; 16-byte accesses when everything is 16-byte aligned, 4-byte ones otherwise.  Grid-stride, no shared
+// memory, 32 registers: co-resides with the resident fused kernel's CTAs.
+template <typename V>
+__global__ void __launch_bounds__(256) repitch_kernel(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *__restrict__ src, size_t spitch,
+                                                      unsigned row_units, unsigned rows)
+{
+    const unsigned long long total = (unsigned long long)row_units * rows;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned y = (unsigned)(i / row_units), u = (unsigned)(i - (unsigned long long)y * row_units);
+        const V v = __ldcs(reinterpret_cast<const V *>(src + (size_t)y * spitch) + u);
+        reinterpret_cast<V *>(dst + (size_t)y * dpitch)[u] = v;
+    }
+}
+
 __global__ void flush_kernel(uint4 *buf, size_t n, uint32_t v)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;

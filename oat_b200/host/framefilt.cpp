@@ -67,26 +67,7 @@ protected:
     }
     // FrameFilter::process (FrameFilter.cpp:59-98), with the heap copies replaced by DMA
     // OAT_B200_TIMING=1: where a frame's time goes in this component (printed at end of stream)
-    struct StageClock {
-        bool on = getenv("OAT_B200_TIMING") != nullptr;
-        double t[5] = {0, 0, 0, 0, 0};
-        uint64_t n = 0;
-        std::chrono::steady_clock::time_point last;
-        void start() { if (on) last = std::chrono::steady_clock::now(); }
-        void lap(int i)
-        {
-            if (!on) return;
-            const auto now = std::chrono::steady_clock::now();
-            t[i] += std::chrono::duration<double, std::micro>(now - last).count();
-            last = now;
-        }
-        void report(const std::string &who) const
-        {
-            if (on && n)
-                std::cerr << who << ": per frame (us): wait source " << t[0] / n << ", ingest " << t[1] / n << ", filter " << t[2] / n
-                          << ", wait sink " << t[3] / n << ", egress " << t[4] / n << " over " << n << " frames\n";
-        }
-    } clk_;
+    StageClock<5> clk_{"wait source", "ingest", "filter", "wait sink", "egress"};
     int process() override
     {
         clk_.start();

@@ -16,6 +16,8 @@
 // Both take the GPU Frame variant: --device publishes the frames in device memory (SharedFrameHeader memory kind
 // DEVICE, CUDA IPC handle in the header) on --gpu-index; a test image is uploaded once, synthetic frames are
 // generated on the device.  Cameras, video files and codecs are out of scope.
+#include <chrono>
+#include <cstdlib>
 #include <iostream>
 #include <limits>
 #include <memory>
@@ -166,6 +168,9 @@ int main(int argc, char *argv[])
             unsigned char handle[64];
             gpu::ck(oat_ipc_export(ctx->h, d_frame->p, handle));
             frame_sink.publish_device(handle, gpu_index);
+            // a static image / a clip held in HBM: every published frame stays where it is, a SOURCE may read it in place
+            // after it has posted (SharedFrameHeader::persistent)
+            frame_sink.set_persistent(type == "test" || clip_in_hbm);
         }
         if (type == "test") {  // static image, never changes (TestFrame.cpp:93-94)
             if (device)
@@ -177,7 +182,9 @@ int main(int argc, char *argv[])
 
         std::vector<uint8_t> next((type == "synth" && !device) || !roi.empty() ? bytes : 0);
         auto tick = std::chrono::steady_clock::now();
-        for (uint64_t t = 0; t < n && !quit; ++t) {
+        const auto serve_t0 = tick;
+        uint64_t served = 0;
+        for (uint64_t t = 0; t < n && !quit; ++t, ++served) {
             if (type == "synth" && !device) synth::frame(next.data(), rows, cols, (uint32_t)seed, (uint32_t)t);  // outside the critical section
             const uint8_t *src = nullptr;
             if (type == "file") {
@@ -212,6 +219,16 @@ int main(int argc, char *argv[])
         }
         // let downstream read the last frame before the sink leaves (its destructor flags END)
         frame_sink.wait();
+        if (getenv("OAT_B200_TIMING")) {
+            // the serving loop alone (process start-up -- for --device the CUDA context, ~0.5 s -- is not in it)
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - serve_t0).count();
+            const double t0_epoch = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count() - sec;
+            char line[256];
+            snprintf(line, sizeof line, "%s: served %llu frames in %.6f s, serving started at %.6f\n", comp_name.c_str(), (unsigned long long)served, sec, t0_epoch);
+            std::cerr << line;
+        }
+        // persistent device frames may still be read in place: the allocation outlives its readers
+        if (device && (type == "test" || clip_in_hbm)) frame_sink.end_and_linger(20000);
         return 0;
     } catch (const std::exception &ex) {
         std::cerr << whoError(comp_name, ex.what()) << std::endl;

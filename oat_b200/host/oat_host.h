@@ -30,6 +30,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <typeinfo>
@@ -268,8 +269,43 @@ inline void packPosition(const Position2D &p, char out[Position2D::NPY_DTYPE_BYT
 enum class NodeState : int { END = -1, UNDEFINED = 0, SINK_BOUND = 1, ERROR = 2 };
 
 namespace detail {
+// A token hand-off between two running components takes a few hundred nanoseconds when the waiter is still looking
+// and 5-10 us of futex wake-up when it has gone to sleep -- at the tens of thousands of tokens per second a GPU
+// component sustains that is the whole budget.  So every barrier wait spins first (OAT_B200_SPIN_US, default
+// 200 us; 0 = sleep at once, as the reference's interprocess semaphores effectively do) and only then blocks.
+inline int spin_budget_us()
+{
+    static const int v = [] {
+        const char *e = getenv("OAT_B200_SPIN_US");
+        return e ? atoi(e) : 200;
+    }();
+    return v;
+}
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    __asm__ __volatile__("" ::: "memory");
+#endif
+}
+inline bool sem_spin(sem_t *s)
+{
+    if (sem_trywait(s) == 0) return true;
+    const int budget = spin_budget_us();
+    if (budget <= 0) return false;
+    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(budget);
+    do {
+        for (int i = 0; i < 32; ++i) {
+            if (sem_trywait(s) == 0) return true;
+            cpu_relax();
+        }
+    } while (std::chrono::steady_clock::now() < until);
+    return false;
+}
 inline bool sem_timedwait_ms(sem_t *s, int ms)
 {
+    if (sem_spin(s)) return true;
     timespec ts;
     clock_gettime(CLOCK_REALTIME, &ts);
     ts.tv_nsec += (long)ms * 1000000L;
@@ -468,6 +504,9 @@ struct SharedFrameHeader {
     uint64_t device_offset{0};     // memory == DEVICE: where THIS frame's pixels start inside the exported allocation
                                    // (a SINK that keeps many frames in HBM -- a preloaded clip, a device FIFO -- exports ONE
                                    // allocation and moves this offset between post()s; 0 for single-buffer SINKs)
+    uint32_t persistent{0};        // memory == DEVICE: the pixels of EVERY published frame stay valid and unchanged until the
+                                   // SINK leaves (a static test image, a clip preloaded into HBM): a SOURCE may post() as soon
+                                   // as it has read offset and Sample, and read the pixels in place later
 };
 
 // ---- lib/shmemdf/Sink.h -------------------------------------------------------------------------------
@@ -502,6 +541,14 @@ public:
         if (!did_wait_need_post_) throw std::runtime_error("post() called when wait() was required.");
         node_->notifySinkWriteComplete();
         did_wait_need_post_ = false;
+    }
+    // Flag END now and stay until every SOURCE has detached (or `ms` have passed): for SINKs whose published frames
+    // are read in place after post() (SharedFrameHeader::persistent) -- the memory must outlive the readers.
+    void end_and_linger(int ms)
+    {
+        if (!bound_) return;
+        node_->set_sink_state(NodeState::END);
+        for (int i = 0; i < ms && node_->source_ref_count() > 0; ++i) usleep(1000);
     }
 
 protected:
@@ -600,6 +647,8 @@ public:
     }
     // the frame published by the NEXT post() lives at this offset of the exported allocation (call between wait() and post())
     void set_device_offset(uint64_t off) { sh_object_->device_offset = off; }
+    // every frame this SINK publishes stays where it is, unchanged, until the SINK leaves (call before announce())
+    void set_persistent(bool v) { sh_object_->persistent = v ? 1u : 0u; }
     SharedFrameHeader *header() { return sh_object_; }
 
 private:
@@ -646,6 +695,18 @@ public:
         }
         did_wait_need_post_ = true;
         return node_->sink_state();
+    }
+    // wait() that does not block: true = a new token was taken (post() is required), false = none is there yet.
+    // *sink_state is what wait() would have returned (END once the SINK has left and nothing is left to read).
+    // For components that keep work in flight behind the SOURCE and have other things to do meanwhile.
+    bool try_wait(NodeState *sink_state)
+    {
+        if (state_ < SourceState::CONNECTED) throw std::runtime_error("Source must be connected before calling try_wait()");
+        if (did_wait_need_post_) throw std::runtime_error("wait() called when post() was required.");
+        const bool got = sem_trywait(&node_->read_barrier(slot_index_)) == 0;
+        *sink_state = node_->sink_state();
+        if (got) did_wait_need_post_ = true;
+        return got;
     }
     void post()  // Source.h:217-232
     {
@@ -736,6 +797,38 @@ private:
     FrameParams parameters_;
 };
 
+// OAT_B200_TIMING=1: where a token's time goes inside a component -- named laps, averaged per token, printed by the
+// component at end of stream (tools/graph_bench.py reads them).  Costs two clock reads per lap when on, a branch when off.
+template <int N>
+struct StageClock {
+    const char *names[N] = {};
+    bool on = getenv("OAT_B200_TIMING") != nullptr;
+    double t[N] = {};
+    uint64_t n = 0;
+    std::chrono::steady_clock::time_point last{};
+    explicit StageClock(std::initializer_list<const char *> l) { int i = 0; for (const char *x : l) if (i < N) names[i++] = x; }
+    void start() { if (on) last = std::chrono::steady_clock::now(); }
+    void lap(int i)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        t[i] += std::chrono::duration<double, std::micro>(now - last).count();
+        last = now;
+    }
+    void report(const std::string &who) const
+    {
+        if (!on || !n) return;
+        std::string line = who + ": per frame (us):";
+        char buf[96];
+        for (int i = 0; i < N; ++i) {
+            snprintf(buf, sizeof buf, "%s %s %.3f", i ? "," : "", names[i], t[i] / (double)n);
+            line += buf;
+        }
+        snprintf(buf, sizeof buf, " over %llu frames\n", (unsigned long long)n);
+        fputs((line + buf).c_str(), stderr);
+    }
+};
+
 // ---- lib/base/Component.{h,cpp} ---------------------------------------------------------------------------
 class Component {
 public:
@@ -747,6 +840,10 @@ public:
         if (!connectToNode()) return;
         bool end_of_stream = false;
         while (!end_of_stream && !quit) end_of_stream = process() != 0;
+        if (getenv("OAT_B200_TIMING")) {  // (measurement harness: when did the last token leave this component)
+            const double now = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
+            fprintf(stderr, "%s: end of stream at %.6f\n", name().c_str(), now);
+        }
     }
     virtual std::string name() const = 0;
 

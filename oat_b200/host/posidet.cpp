@@ -248,11 +248,14 @@ private:
 };
 
 // ---- posidet track: mog -> col HSV -> hsv fused on the device ----------------------------------------------
-// With --pipeline D (default 1) the component keeps up to D frames in flight on the GPU behind its SOURCE: a frame is
-// handed back to the SOURCE as soon as its pixels have been consumed (H2D copy done / read in place by the fused
-// kernel: oat_tracker_wait_ingest), its position is published -- in order, one token at a time, every Sample intact --
-// D-1 frames later.  The SOURCE and the SINK both see the reference's lock-step protocol (one token in flight per
-// edge); what changes is that the copy of frame t+1 and the kernels of frame t overlap.  This is the GPU-aware
+// --pipeline 1 (default): one frame at a time, as the reference's process() loop.
+// --pipeline D >= 2: the component keeps up to D frames on the GPU behind its SOURCE through the STREAMING resident
+// engine (oat_tracker_stream_*, chunks of D/2 frames: one fused launch + one tail-server launch per chunk).  A frame
+// goes back to the SOURCE as soon as its pixels are the tracker's -- copied into its HBM (H2D from page-locked shm,
+// D2D from a device frame), or at once when the SINK declared its frames persistent (a static test image, a clip
+// preloaded into HBM: read in place, no copy at all) -- and its position is published later, in order, one token at
+// a time, every Sample intact.  The SOURCE and the SINK both see the reference's lock-step protocol (one token in
+// flight per edge); what changes is that the host does nothing per frame but move tokens.  This is the GPU-aware
 // counterpart of putting an `oat buffer` (src/buffer/FrameBuffer.cpp:56-116) in front of a slow component.
 class FusedTracker : public PositionDetector {
 public:
@@ -266,7 +269,7 @@ public:
     {
         auto o = HSVOptions::options();
         o.push_back({"adaptation-coeff", 'A', true, "framefilt mog's adaptation coefficient, 0 to 1.0. Default 0."});
-        o.push_back({"pipeline", 'p', true, "Frames kept in flight on the GPU (1 = synchronous; positions lag by pipeline-1 frames)."});
+        o.push_back({"pipeline", 'p', true, "Frames kept in flight on the GPU, 1 to 64 (1 = synchronous; positions lag by up to pipeline-1 frames)."});
         return o;
     }
     void applyConfiguration(const config::VariableMap &vm, const config::OptionTable &t) override
@@ -274,16 +277,14 @@ public:
         o_.apply(vm, t);
         config::getNumericValue<double>(vm, t, "adaptation-coeff", learning_coeff_, 0.0, 1.0);
         config::getNumericValue<int>(vm, t, "gpu-index", gpu_index_, 0, 1 << 20);
-        config::getNumericValue<int>(vm, t, "pipeline", depth_, 1, 32);
+        config::getNumericValue<int>(vm, t, "pipeline", depth_, 1, 64);
     }
 
 protected:
-    void setup() override { gpu::ck(oat_tracker_create(ctx_->h, (int)in_.rows, (int)in_.cols, nullptr, depth_, &trk_)); }
+    void setup() override { gpu::ck(oat_tracker_create(ctx_->h, (int)in_.rows, (int)in_.cols, nullptr, depth_ < 2 ? 1 : depth_, &trk_)); }
     void detectPosition(const uint8_t *, Position2D &) override {}  // (process() below drives the tracker itself)
-    void publish_oldest()
+    void publish(const oat_detection &d)
     {
-        oat_detection d;
-        gpu::ck(oat_tracker_collect(trk_, &d));
         Position2D internal_pos("");
         internal_pos.set_sample(samples_.front());  // propagate tick / usec (PositionDetector.cpp:80)
         samples_.pop_front();
@@ -292,22 +293,71 @@ protected:
         *shared_position_ = internal_pos;  // everything but the label (Position2D.h:84-105)
         position_sink_.post();
     }
-    int process() override
+    const uint8_t *source_pixels() const
     {
-        if (frame_source_.wait() == NodeState::END) {
-            while (!samples_.empty() && !quit) publish_oldest();  // drain: every frame that went in comes out
-            return 1;
-        }
+        // the frame goes to the GPU straight from where the SOURCE keeps it (page-locked shm or device memory)
+        return src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) + frame_source_.header()->device_offset
+                        : static_cast<const uint8_t *>(frame_source_.pixels());
+    }
+    int process_one_at_a_time()
+    {
+        if (frame_source_.wait() == NodeState::END) return 1;
         if (frame_source_.header()->memory != src_memory_)
             throw std::runtime_error("SOURCE frame memory kind changed after connect()");
-        // the frame goes to the GPU straight from where the SOURCE keeps it (page-locked shm or device memory)
-        const uint8_t *pixels = src_dev_ ? static_cast<const uint8_t *>(src_dev_->p) + frame_source_.header()->device_offset
-                                         : static_cast<const uint8_t *>(frame_source_.pixels());
-        gpu::ck(oat_tracker_submit(trk_, pixels, in_.cols * 3, learning_coeff_, &o_.p, nullptr, 0));
+        gpu::ck(oat_tracker_submit(trk_, source_pixels(), in_.cols * 3, learning_coeff_, &o_.p, nullptr, 0));
         samples_.push_back(frame_source_.retrieve()->sample());
         gpu::ck(oat_tracker_wait_ingest(trk_));
         frame_source_.post();
-        if ((int)samples_.size() >= depth_) publish_oldest();
+        oat_detection d;
+        gpu::ck(oat_tracker_collect(trk_, &d));
+        publish(d);
+        return 0;
+    }
+    void publish_finished(bool block)
+    {
+        oat_detection d[64];
+        size_t got = 0;
+        gpu::ck(oat_tracker_stream_poll(trk_, d, nullptr, 64, block ? 1 : 0, &got));
+        clk_.lap(4);
+        for (size_t i = 0; i < got && !quit; ++i) publish(d[i]);
+        clk_.lap(5);
+    }
+    int process() override
+    {
+        if (depth_ < 2) return process_one_at_a_time();
+        // 1. a frame, if the SOURCE has one (block only when nothing is outstanding: there is nothing else to do)
+        NodeState state;
+        bool have;
+        clk_.start();
+        if (samples_.empty()) {
+            state = frame_source_.wait();
+            have = true;
+        } else {
+            have = frame_source_.try_wait(&state);
+        }
+        clk_.lap(0);
+        if (state == NodeState::END) {
+            while (!samples_.empty() && !quit) publish_finished(true);  // drain: every frame that went in comes out
+            clk_.report(name_);
+            return 1;
+        }
+        if (have) {
+            if (frame_source_.header()->memory != src_memory_)
+                throw std::runtime_error("SOURCE frame memory kind changed after connect()");
+            const bool in_place = src_dev_ && frame_source_.header()->persistent;
+            gpu::ck(oat_tracker_stream_push(trk_, source_pixels(), in_.cols * 3, learning_coeff_, &o_.p, in_place ? 0u : OAT_STREAM_COPY));
+            samples_.push_back(frame_source_.retrieve()->sample());
+            clk_.lap(1);
+            if (!in_place) gpu::ck(oat_tracker_stream_wait_ingest(trk_));
+            frame_source_.post();
+            clk_.lap(2);
+            ++clk_.n;
+        } else {
+            gpu::ck(oat_tracker_stream_flush(trk_, 0));  // nothing waiting: the GPU gets what has been gathered so far
+            clk_.lap(3);
+        }
+        // 2. the positions of whatever has finished
+        publish_finished(false);
         return 0;
     }
 
@@ -317,6 +367,7 @@ private:
     int depth_{1};
     std::deque<Sample> samples_;  // Samples of the frames in flight, oldest first
     oat_tracker *trk_{nullptr};
+    StageClock<6> clk_{"source wait/poll", "push", "ingest + post", "flush", "poll results", "publish"};
 };
 
 }  // namespace oat

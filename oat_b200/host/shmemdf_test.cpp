@@ -348,8 +348,28 @@ static int dump_frames(const std::string &addr)
     return 0;
 }
 
+// helper mode for transport-rate measurements: take tokens from ADDR without touching the pixels until the SINK leaves
+static int count_frames(const std::string &addr)
+{
+    Source<Frame> src;
+    src.touch(addr);
+    if (src.connect() != SourceState::CONNECTED) return 2;
+    uint64_t n = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        if (src.wait() == NodeState::END) break;
+        if (n == 0) t0 = std::chrono::steady_clock::now();
+        src.post();
+        ++n;
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << n << " tokens, " << (n > 1 ? 1e6 * sec / (double)(n - 1) : 0.0) << " us per token" << std::endl;
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 2 && std::string(argv[1]) == "count-frames") return count_frames(argv[2]);
     if (argc > 3 && std::string(argv[1]) == "emit-positions") return emit_positions(argv[2], std::atoi(argv[3]));
     if (argc > 2 && std::string(argv[1]) == "dump-frames") return dump_frames(argv[2]);
     test_node();

@@ -340,3 +340,120 @@ def test_clip_engine_many_blobs_are_labelled_on_the_device(ctx):
     assert st["replays"] <= 1, st               # (the first frame's whole-image blob goes frame by frame and is replayed)
     a.close()
     b.close()
+
+
+# ---- streaming use of the engine (oat_tracker_stream_*): what `oat posidet track --pipeline` drives ----------------
+def _stream_all(trk, frames, copy, flush_every=None, poll_every=3, pitch=None):
+    """Push every frame (flush / poll on a schedule), then drain; returns the detections in order."""
+    got = []
+    for i, f in enumerate(frames):
+        trk.stream_push(f, copy=copy, pitch=pitch)
+        if copy:
+            trk.stream_wait_ingest()
+        if flush_every and (i + 1) % flush_every == 0:
+            trk.stream_flush()
+        if poll_every and (i + 1) % poll_every == 0:
+            got += trk.stream_poll()
+    while sum(trk.stream_pending()) > 0:
+        got += trk.stream_poll(block=True)
+    return [_det(d) for d in got]
+
+
+@pytest.mark.parametrize("shape", [(120, 160), (480, 640), (100, 1000)])
+@pytest.mark.parametrize("lr", [0.0, 0.02])
+@pytest.mark.parametrize("ring,flush_every", [(2, None), (8, None), (8, 1), (64, 5), (64, None)])
+def test_stream_equals_frame_by_frame(ctx, shape, lr, ring, flush_every):
+    """Device frames read in place: full chunks, short chunks (flush after every frame / every 5), polls in between --
+    detections and the whole GMM state equal the synchronous path's."""
+    rows, cols = shape
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    n = 75
+    pitch = None if (cols * 3) % 16 == 0 else (cols * 3 + 15) // 16 * 16  # (in place: the engine wants 16-byte aligned rows)
+    bufs = _frames(ctx, rows, cols, 1000, n, pitch=pitch)
+    a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=ring)
+    got = _stream_all(a, bufs, copy=False, flush_every=flush_every, pitch=pitch)
+    assert a.tail_stats()["clip_frames"] == n - 1, "the resident engine did not take the stream"
+    b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
+    want = []
+    for f in bufs:  # the per-frame path, one frame in flight
+        b.submit(f, pitch=pitch)
+        want.append(_det(b.collect()))
+    assert got == want
+    _state_equal(a, b)
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("source", ["host", "pinned", "device"])
+@pytest.mark.parametrize("cols", [160, 1000])
+def test_stream_with_staged_frames(ctx, source, cols):
+    """OAT_STREAM_COPY: ONE buffer is overwritten with the next frame as soon as wait_ingest returns (what a lock-step
+    SOURCE does with its shared frame) -- pageable host, pinned host and device memory."""
+    rows = 120
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    n = 50
+    frames = [oracle.synth_frame(rows, cols, 7, t) for t in range(n)]
+    a = oat_b200.Tracker(ctx, rows, cols, 0.02, hp, ring_depth=8)
+    if source == "host":
+        shared = np.empty((rows, cols, 3), np.uint8)
+    elif source == "pinned":
+        pin = oat_b200.PinnedArray((rows, cols, 3))
+        shared = pin.array
+    else:
+        shared = ctx.alloc(rows * cols * 3)
+    got = []
+    for t in range(n):
+        if source == "device":
+            shared.upload(frames[t])
+        else:
+            shared[...] = frames[t]
+        a.stream_push(shared, copy=True)
+        a.stream_wait_ingest()
+        if t % 2:
+            a.stream_flush()
+        got += a.stream_poll()
+    while sum(a.stream_pending()) > 0:
+        got += a.stream_poll(block=True)
+    b = oat_b200.Tracker(ctx, rows, cols, 0.02, hp)
+    want = [_det(b.track(f)[0]) for f in frames]
+    assert [_det(d) for d in got] == want
+    _state_equal(a, b)
+    a.close()
+    b.close()
+
+
+def test_stream_mixed_parameters_and_positions(ctx):
+    """A learning rate that changes mid-stream closes the chunk; with a position filter attached poll returns the
+    filtered positions, equal to the per-frame path's; the other entry points refuse while frames are in flight."""
+    rows, cols = 240, 320
+    hp = oat_b200.HsvParams.make(**HSV_BAND)
+    n = 40
+    bufs = _frames(ctx, rows, cols, 1000, n)
+    lrs = [0.02 if t < 17 else 0.05 if t < 30 else 0.0 for t in range(n)]
+    a = oat_b200.Tracker(ctx, rows, cols, 0.02, hp, ring_depth=16)
+    fa = oat_b200.PositionFilter(ctx, 1, kalman=dict(dt=0.02, timeout=1.0, sigma_accel=5.0, sigma_noise=1.0))
+    a.attach_posfilt(fa)
+    dets, poss = [], []
+    for t in range(n):
+        a.stream_push(bufs[t], learning_rate=lrs[t])
+        if t == 5:
+            with pytest.raises(oat_b200.OatError):
+                a.submit(bufs[t])
+        d, p = a.stream_poll(positions=True)
+        dets += d
+        poss += p
+    while sum(a.stream_pending()) > 0:
+        d, p = a.stream_poll(block=True, positions=True)
+        dets += d
+        poss += p
+    b = oat_b200.Tracker(ctx, rows, cols, 0.02, hp)
+    fb = oat_b200.PositionFilter(ctx, 1, kalman=dict(dt=0.02, timeout=1.0, sigma_accel=5.0, sigma_noise=1.0))
+    b.attach_posfilt(fb)
+    for t in range(n):
+        b.submit(bufs[t], learning_rate=lrs[t])
+        d, p = b.collect_position()
+        assert _det(dets[t]) == _det(d)
+        assert (poss[t].position_valid, poss[t].x, poss[t].y, poss[t].vx, poss[t].vy) == (p.position_valid, p.x, p.y, p.vx, p.vy)
+    _state_equal(a, b)
+    a.close()
+    b.close()

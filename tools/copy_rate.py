@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Copy-engine rates that decide how frames are staged (diagnostic, cuda-python): linear vs strided H2D from pinned
+memory, strided D2D re-pitch, and the host cost of issuing each.  usage: copy_rate.py"""
+import time
+
+from cuda.bindings import runtime as rt
+
+
+def ck(r):
+    if isinstance(r, tuple):
+        err, *rest = r
+        assert err == rt.cudaError_t.cudaSuccess, err
+        return rest[0] if len(rest) == 1 else rest
+    assert r == rt.cudaError_t.cudaSuccess, r
+
+
+def timed(stream, fn, n=200):
+    e0, e1 = ck(rt.cudaEventCreate()), ck(rt.cudaEventCreate())
+    for _ in range(10):
+        fn()
+    ck(rt.cudaStreamSynchronize(stream))
+    ck(rt.cudaEventRecord(e0, stream))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    host = (time.perf_counter() - t0) / n
+    ck(rt.cudaEventRecord(e1, stream))
+    ck(rt.cudaStreamSynchronize(stream))
+    ms = ck(rt.cudaEventElapsedTime(e0, e1))
+    return ms * 1e3 / n, host * 1e6
+
+
+ck(rt.cudaSetDevice(0))
+stream = ck(rt.cudaStreamCreate())
+K = rt.cudaMemcpyKind
+for name, rows, cols in (("1mp", 1000, 1000), ("1080p", 1080, 1920), ("1000x1080p-ragged", 1080, 1000)):
+    rb = 3 * cols
+    tight = (rb + 15) // 16 * 16
+    h = ck(rt.cudaMallocHost(rb * rows))
+    d_raw = ck(rt.cudaMalloc(rb * rows))
+    d_al = ck(rt.cudaMalloc(tight * rows))
+    res = {}
+    res["H2D linear"] = timed(stream, lambda: ck(rt.cudaMemcpyAsync(d_raw, h, rb * rows, K.cudaMemcpyHostToDevice, stream)))
+    res["H2D strided (pitch %d -> %d)" % (rb, tight)] = timed(stream, lambda: ck(rt.cudaMemcpy2DAsync(d_al, tight, h, rb, rb, rows, K.cudaMemcpyHostToDevice, stream)))
+    res["D2D linear"] = timed(stream, lambda: ck(rt.cudaMemcpyAsync(d_al, d_raw, rb * rows, K.cudaMemcpyDeviceToDevice, stream)))
+    res["D2D strided (pitch %d -> %d)" % (rb, tight)] = timed(stream, lambda: ck(rt.cudaMemcpy2DAsync(d_al, tight, d_raw, rb, rb, rows, K.cudaMemcpyDeviceToDevice, stream)))
+    print(f"{name}: {rows} x {cols} x 3 = {rb * rows / 1e6:.2f} MB")
+    for k, (dev_us, host_us) in res.items():
+        print(f"   {k:38s} {dev_us:8.2f} us on the device ({rb * rows / dev_us / 1e3:7.1f} GB/s), {host_us:6.2f} us of host time per call")
+    ck(rt.cudaFreeHost(h))
+    ck(rt.cudaFree(d_raw))
+    ck(rt.cudaFree(d_al))

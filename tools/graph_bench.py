@@ -47,7 +47,7 @@ def run(tag, image, n, consumers, device, last_is_position):
         t0 = time.perf_counter()
         try:
             serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", names["raw"], "-f", image, "-n", str(n)] +
-                                   (["--device"] if device else []), capture_output=True, text=True, timeout=90)
+                                   (["--device"] if device else []), capture_output=True, text=True, timeout=90, env=env)
         except subprocess.TimeoutExpired:
             # say who is still there and what they wrote before giving up on this graph
             state = []
@@ -67,12 +67,18 @@ def run(tag, image, n, consumers, device, last_is_position):
             sock.wait(timeout=120)
             sock_out.seek(0)
             npos = len([ln for ln in sock_out.read().splitlines() if ln.strip()])
-        stages = []
+        stages, ends = [], []
         for p in procs:
             _, se = p.communicate(timeout=120)
             assert p.returncode == 0, (p.args, se)
             stages += [ln for ln in se.splitlines() if "per frame (us)" in ln]
-        return {"frames": n, "wall_s": wall, "fps": n / wall, "positions": npos, "stages": stages}
+            ends += [float(ln.rsplit(" ", 1)[1]) for ln in se.splitlines() if "end of stream at" in ln]
+        # steady state: from the server's first frame to the moment the last token left the last component (the
+        # server's own start-up -- for --device its CUDA context -- and the components' teardown are not in it)
+        started = [float(ln.rsplit(" ", 1)[1]) for ln in serve.stderr.splitlines() if "serving started at" in ln]
+        steady = max(ends) - started[0] if ends and started else None
+        return {"frames": n, "wall_s": wall, "fps": n / wall, "steady_s": steady, "steady_fps": n / steady if steady else None,
+                "positions": npos, "stages": stages}
     finally:
         for p in procs:
             if p.poll() is None:
@@ -86,7 +92,8 @@ def main():
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     res = {"protocol": "N static frames from `oat-frameserve test`, free-running, through real shm; fps = N / wall time of the frame server "
-                       "(test/perf/results.md:12-18); consumers started 3 s earlier",
+                       "process (test/perf/results.md:12-18: `time oat frameserve test ...`; with --device that includes creating its CUDA "
+                       "context); steady_fps = N / (first frame served -> last token out of the last component); consumers started 3 s earlier",
            "reference_published": {"framefilt mog, cv::cuda MOG, GTX 970 (results.md:34-37)": 573.0,
                                    "framefilt mog, CPU MOG2, i7-5600U (results.md:91-95)": 75.7,
                                    "posidet hsv, GTX 970 box CPU path (results.md:55-58)": 214.0}}
@@ -107,12 +114,16 @@ def main():
             r[f"track_{k}"] = run(f"{wl}t{k}", img, args.frames, lambda n: [["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01"] + HSV], dev, True)
             r[f"track_pipeline8_{k}"] = run(f"{wl}p{k}", img, args.frames, lambda n: [
                 ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "8"] + HSV], dev, True)
+            # the streaming resident engine behind the lock-step SOURCE: chunks of 32 frames, long enough a run to see its rate
+            r[f"track_pipeline64_{k}"] = run(f"{wl}q{k}", img, args.frames * (20 if dev else 4), lambda n: [
+                ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "64"] + HSV], dev, True)
         res[wl] = r
         for k, v in r.items():
             if "error" in v:
                 print(f"{wl:6s} {k:24s} FAILED: {v}", flush=True)
             else:
-                print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps  ({v['frames']} frames in {v['wall_s']:.3f} s, positions {v['positions']})", flush=True)
+                print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps by the protocol's clock ({v['frames']} frames, `time oat-frameserve` {v['wall_s']:.3f} s), "
+                      f"{v['steady_fps'] or 0:10.1f} fps steady (first frame served -> last token out, {v['steady_s'] or 0:.4f} s), positions {v['positions']}", flush=True)
                 for ln in v["stages"]:
                     print("         " + ln, flush=True)
     # frameserve alone (no listener), the protocol's own overhead
