@@ -255,8 +255,9 @@ def load_traffic(workload, alpha):
 
 
 def multi_blob_frames(rows, cols, nblobs, nframes):
-    """A busy scene for the detect tail: the stream's static background + `nblobs` discs of the target colour on a
-    jittered grid (different every frame).  Host numpy arrays."""
+    """A busy scene for the detect tail: the stream's static background + `nblobs` discs of the target colour, one per
+    cell of a grid, each wandering over its whole cell from frame to frame (a pixel is covered ~7 % of the time, so an
+    adapting MOG model keeps calling the discs foreground however long the stream runs).  Host numpy arrays."""
     import numpy as np
 
     import oracle
@@ -264,10 +265,10 @@ def multi_blob_frames(rows, cols, nblobs, nframes):
     bg = oracle.synth_frame(rows, cols, SEED, 0)
     gx = max(1, int(round((nblobs * cols / rows) ** 0.5)))
     gy = (nblobs + gx - 1) // gx
-    r = max(3, min(rows // (3 * gy), cols // (3 * gx), rows // 40))
-    yy, xx = np.mgrid[0:rows, 0:cols]
+    cw, ch = cols // gx, rows // gy
+    r = max(3, min(ch // 6, cw // 6, rows // 40))
+    yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
     out = []
-    rng = np.random.default_rng(5)
     for t in range(nframes):
         f = bg.copy()
         k = 0
@@ -275,10 +276,11 @@ def multi_blob_frames(rows, cols, nblobs, nframes):
             for i in range(gx):
                 if k >= nblobs:
                     break
-                cx = int((i + 0.5) * cols / gx + rng.integers(-r, r + 1))
-                cy = int((j + 0.5) * rows / gy + rng.integers(-r, r + 1))
                 rr = r - (k % 3)
-                f[(xx - cx) ** 2 + (yy - cy) ** 2 <= rr * rr] = (40, 220, 60)
+                cx = i * cw + r + (t * 37 + k * 11) % max(1, cw - 2 * r)
+                cy = j * ch + r + (t * 23 + k * 7) % max(1, ch - 2 * r)
+                win = f[cy - r:cy + r + 1, cx - r:cx + r + 1]
+                win[xx ** 2 + yy ** 2 <= rr * rr] = (40, 220, 60)
                 k += 1
         out.append(f)
     return [bg] + out
@@ -511,7 +513,7 @@ def run_b200(args):
         try:
             import numpy as np
 
-            host = multi_blob_frames(rows, cols, 60, 6)
+            host = multi_blob_frames(rows, cols, 60, 24)
             mb = []
             for f in host:
                 b_ = ctx.alloc(fbytes)

@@ -8,7 +8,7 @@ timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N
 echo "reference arm rc=$?"; cut -c1-600 gpurun_out/${T}_scale_ref_n$N.json; tail -n 3 gpurun_out/${T}_scale_ref_n$N.err
 python - <<P
 import json
-d = json.load(open("gpurun_out/${T}_scale_n$N.json"))
+d = json.loads(open("gpurun_out/${T}_scale_n$N.json").read().splitlines()[-1])
 for k in ("value", "ms_per_step_per_rank", "e2e", "multi_stream", "config4_8x4k_per_gpu", "host"):
     print(k, d.get(k))
 print("roofline", {k: d["roofline"][k] for k in ("frac", "kernel_ms", "achieved")})
