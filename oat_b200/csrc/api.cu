@@ -394,8 +394,8 @@ static int copy_frame_in(cudaStream_t s, DevBuf &stage, DevBuf *raw, const void 
             CKRET(repitch(s, stage.p, rowbytes * rows, src, rowbytes * rows, rowbytes * rows, 1));  // one long row
         else
             CKRET(repitch(s, stage.p, tight, src, pitch, rowbytes, rows));
-    } else if (pitch == rowbytes && tight == rowbytes) {  // contiguous frame: one linear DMA
-        CK(cudaMemcpyAsync(stage.p, src, rowbytes * rows, cudaMemcpyHostToDevice, s));
+    } else if (pitch == tight) {  // same pitch on both sides (tight frames of 16-byte-multiple rows included): one linear DMA
+        CK(cudaMemcpyAsync(stage.p, src, pitch * (size_t)(rows - 1) + rowbytes, cudaMemcpyHostToDevice, s));
     } else if (raw && pitch == rowbytes) {
         CKRET(raw->ensure(rowbytes * rows));
         CK(cudaMemcpyAsync(raw->p, src, rowbytes * rows, cudaMemcpyHostToDevice, s));
@@ -2549,9 +2549,15 @@ static int stream_launch_gathered(oat_tracker *t, bool block)
         CKRET(stream_retire_oldest(t));
     }
     if (st->staged_any && st->copy_pending) {
-        // (on the host, so that nothing but the previous fused kernel precedes this launch on the compute stream)
-        CK(cudaEventSynchronize(st->copied));
-        st->copy_pending = false;
+        if (cudaEventQuery(st->copied) == cudaSuccess) {
+            st->copy_pending = false;  // every staged frame has arrived: nothing but the previous fused kernel precedes this launch
+        } else {
+            // the last staged frame is still on its way (a host-fed stream: the launch is issued in the copy's shadow):
+            // the compute stream waits for it, and the launch orders itself behind the whole previous grid, not tile by tile
+            cudaGetLastError();
+            CK(cudaStreamWaitEvent(t->ctx->stream, st->copied, 0));
+            t->ctx->chain_uid = 0;
+        }
     }
     size_t taken = 0;
     CKRET(st->eng.launch(st->gathered.data(), st->gathered.size(), st->pitch, st->lr, &st->p, &taken));

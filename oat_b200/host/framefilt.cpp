@@ -68,11 +68,13 @@ protected:
     // FrameFilter::process (FrameFilter.cpp:59-98), with the heap copies replaced by DMA
     // OAT_B200_TIMING=1: where a frame's time goes in this component (printed at end of stream)
     StageClock<5> clk_{"wait source", "ingest", "filter", "wait sink", "egress"};
+    TokenClock out_clk_;
     int process() override
     {
         clk_.start();
         if (frame_source_.wait() == NodeState::END) {
             clk_.report(name_);
+            out_clk_.report(name_);
             return 1;
         }
         clk_.lap(0);
@@ -100,6 +102,7 @@ protected:
         frame_sink_.post();
         clk_.lap(4);
         ++clk_.n;
+        out_clk_.tick();
         return 0;
     }
     virtual PixelColor outputColor(PixelColor in) const { return in; }

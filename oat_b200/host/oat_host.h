@@ -16,6 +16,7 @@
 // handle (DEVICE).
 #pragma once
 #include <fcntl.h>
+#include <sched.h>
 #include <semaphore.h>
 #include <signal.h>
 #include <sys/mman.h>
@@ -269,15 +270,17 @@ inline void packPosition(const Position2D &p, char out[Position2D::NPY_DTYPE_BYT
 enum class NodeState : int { END = -1, UNDEFINED = 0, SINK_BOUND = 1, ERROR = 2 };
 
 namespace detail {
-// A token hand-off between two running components takes a few hundred nanoseconds when the waiter is still looking
-// and 5-10 us of futex wake-up when it has gone to sleep -- at the tens of thousands of tokens per second a GPU
-// component sustains that is the whole budget.  So every barrier wait spins first (OAT_B200_SPIN_US, default
-// 200 us; 0 = sleep at once, as the reference's interprocess semaphores effectively do) and only then blocks.
+// A token hand-off between two running components takes a few hundred nanoseconds when the waiter is still looking;
+// once it has gone to sleep it costs a futex wake-up plus the core's way out of its idle state -- measured on the B200
+// hosts at up to a millisecond, i.e. a graph whose frame period is just above the spin budget runs five times slower
+// than one just below it.  So every barrier wait spins first (OAT_B200_SPIN_US, default 2000 us: a core stays busy
+// while tokens flow at more than ~500 per second and sleeps between the frames of a camera; 0 = sleep at once, as
+// the reference's interprocess semaphores do) and only then blocks.
 inline int spin_budget_us()
 {
     static const int v = [] {
         const char *e = getenv("OAT_B200_SPIN_US");
-        return e ? atoi(e) : 200;
+        return e ? atoi(e) : 2000;
     }();
     return v;
 }
@@ -294,14 +297,19 @@ inline bool sem_spin(sem_t *s)
     if (sem_trywait(s) == 0) return true;
     const int budget = spin_budget_us();
     if (budget <= 0) return false;
-    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(budget);
-    do {
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto until = t0 + std::chrono::microseconds(budget), polite = t0 + std::chrono::microseconds(20);
+    for (;;) {
         for (int i = 0; i < 32; ++i) {
             if (sem_trywait(s) == 0) return true;
             cpu_relax();
         }
-    } while (std::chrono::steady_clock::now() < until);
-    return false;
+        const auto now = std::chrono::steady_clock::now();
+        if (now >= until) return false;
+        // the process we are waiting for may be runnable on THIS core: after 20 us give it the chance every round
+        // (returns at once when nothing else is runnable here)
+        if (now >= polite) sched_yield();
+    }
 }
 inline bool sem_timedwait_ms(sem_t *s, int ms)
 {
@@ -826,6 +834,32 @@ struct StageClock {
         }
         snprintf(buf, sizeof buf, " over %llu frames\n", (unsigned long long)n);
         fputs((line + buf).c_str(), stderr);
+    }
+};
+
+// OAT_B200_TIMING=1: wall-clock time at which the 1st, 10th, 100th, ... and the last token left a component, so that a
+// harness can take a rate that excludes start-up (the first frame pays for model allocation, lazy module loading and
+// the GPU's clock ramp: anything from 10 ms to a second).
+struct TokenClock {
+    bool on = getenv("OAT_B200_TIMING") != nullptr;
+    uint64_t n = 0, next = 1;
+    std::string marks;
+    double last = 0.0;
+    void tick()
+    {
+        if (!on) return;
+        ++n;
+        last = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
+        if (n == next) {
+            char buf[64];
+            snprintf(buf, sizeof buf, " %llu:%.6f", (unsigned long long)n, last);
+            marks += buf;
+            next *= 10;
+        }
+    }
+    void report(const std::string &who) const
+    {
+        if (on && n) fprintf(stderr, "%s: tokens out at:%s last(%llu):%.6f\n", who.c_str(), marks.c_str(), (unsigned long long)n, last);
     }
 };
 

@@ -333,7 +333,13 @@ protected:
             state = frame_source_.wait();
             have = true;
         } else {
+            // frames are outstanding: look for a token for a few microseconds (a running SINK answers a post() within
+            // one), but do not sleep on it -- there are chunks to launch and positions to publish meanwhile
             have = frame_source_.try_wait(&state);
+            for (int spin = 0; !have && state != NodeState::END && spin < 48; ++spin) {
+                detail::cpu_relax();
+                have = frame_source_.try_wait(&state);
+            }
         }
         clk_.lap(0);
         if (state == NodeState::END) {
@@ -348,7 +354,12 @@ protected:
             gpu::ck(oat_tracker_stream_push(trk_, source_pixels(), in_.cols * 3, learning_coeff_, &o_.p, in_place ? 0u : OAT_STREAM_COPY));
             samples_.push_back(frame_source_.retrieve()->sample());
             clk_.lap(1);
-            if (!in_place) gpu::ck(oat_tracker_stream_wait_ingest(trk_));
+            if (!in_place) {
+                // the frame is on its way into the tracker's memory: launch what has been gathered in the copy's shadow
+                // (if a chunk slot is free -- otherwise the GPU is the bottleneck and chunks grow), then hand it back
+                gpu::ck(oat_tracker_stream_flush(trk_, 0));
+                gpu::ck(oat_tracker_stream_wait_ingest(trk_));
+            }
             frame_source_.post();
             clk_.lap(2);
             ++clk_.n;

@@ -46,10 +46,12 @@ int main(int argc, char *argv[])
         source.touch(argv[2]);
         if (source.connect() != SourceState::CONNECTED) return 0;
         Position2D p("");
+        TokenClock out_clk;
         while (!quit) {
             if (source.wait() == NodeState::END) break;
             p = *source.retrieve();
             source.post();
+            out_clk.tick();
             if (npy.is_open()) {
                 char rec[Position2D::NPY_DTYPE_BYTES];
                 packPosition(p, rec);
@@ -59,6 +61,7 @@ int main(int argc, char *argv[])
                 std::cout << serializePosition(p) << "\n" << std::flush;
             }
         }
+        out_clk.report("posisock[" + std::string(argv[2]) + "]");
         if (npy.is_open()) {  // emplaceNumpyShape
             const std::string n = std::to_string(nrec);
             if (n.size() <= 10) {

@@ -259,6 +259,59 @@ static void test_frames()
 }
 
 // frameserve (separate process) -> Source<Frame>: every frame of the synthetic stream arrives bit-exact, in order
+// the additions the GPU components rely on: Source::try_wait, the persistent tag, Sink::end_and_linger
+static void test_nonblocking_and_persistent()
+{
+    const std::string addr = "oatb200test_nb";
+    scrub(addr);
+    {
+        Sink<Frame> sink;
+        sink.bind(addr, 4 * 4 * 3, false);
+        Frame shared = sink.retrieve(4, 4, 3, PIX_BGR);
+        sink.set_persistent(true);
+        sink.announce();
+        Source<Frame> src;
+        src.touch(addr);
+        NodeState st = NodeState::UNDEFINED;
+        CHECK_THROWS(src.try_wait(&st));  // not connected yet
+        CHECK(src.connect(PIX_BGR) == SourceState::CONNECTED);
+        CHECK(src.header()->persistent == 1u);
+        CHECK(!src.try_wait(&st) && st == NodeState::SINK_BOUND);  // nothing published yet: no token, no blocking
+        sink.wait();
+        shared.incrementSampleCount();
+        sink.post();
+        CHECK(src.try_wait(&st) && st == NodeState::SINK_BOUND);  // the token is there
+        CHECK_THROWS(src.try_wait(&st));                          // post() is required first
+        CHECK(src.retrieve()->sample().count() == 1);
+        src.post();
+        CHECK(!src.try_wait(&st));
+        // end_and_linger: END is flagged at once, the SINK stays until the SOURCE has detached
+        auto gone = std::async(std::launch::async, [&] {
+            const auto t0 = std::chrono::steady_clock::now();
+            sink.end_and_linger(2000);
+            return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        CHECK(!src.try_wait(&st) && st == NodeState::END);
+        CHECK(gone.wait_for(std::chrono::milliseconds(0)) != std::future_status::ready);  // still lingering: a SOURCE is attached
+    }
+    scrub(addr);
+    {
+        Sink<Frame> sink;
+        sink.bind(addr, 4 * 4 * 3);
+        sink.retrieve(4, 4, 3, PIX_BGR);
+        auto src = std::make_unique<Source<Frame>>();
+        src->touch(addr);
+        CHECK(src->connect() == SourceState::CONNECTED);
+        CHECK(src->header()->persistent == 0u);  // the default: frames are the SINK's again after post()
+        auto gone = std::async(std::launch::async, [&] { sink.end_and_linger(5000); return true; });
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        src.reset();  // the SOURCE detaches: the SINK may leave
+        CHECK(gone.wait_for(std::chrono::milliseconds(1000)) == std::future_status::ready);
+    }
+    scrub(addr);
+}
+
 static void test_pipeline(const std::string &frameserve)
 {
     const std::string addr = "oatb200test_pipe";
@@ -378,6 +431,7 @@ int main(int argc, char **argv)
     test_tokens();
     test_concurrency();
     test_frames();
+    test_nonblocking_and_persistent();
     if (argc > 1) test_pipeline(argv[1]);
     scrub(node_addr);
     std::cout << "shmemdf_test: " << checks << " checks, " << failures << " failures\n";

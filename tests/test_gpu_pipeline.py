@@ -302,3 +302,34 @@ def test_buffer_component_in_front_of_the_tracker(tmp_path, device_sink):
             if p.poll() is None:
                 p.kill()
         subprocess.run([os.path.join(BIN, "oat-clean")] + names, capture_output=True)
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("shape", [(240, 320), (250, 1000)])
+def test_streaming_tracker_behind_a_free_running_clip(tmp_path, device, shape):
+    """`frameserve file` WITHOUT --fps (free-running, as the reference's perf protocol runs its server) -> posidet track
+    --pipeline 64: the component drives the streaming resident engine (chunks of up to 32 frames; with --device the clip
+    is persistent in HBM and read in place, from shm every frame is staged H2D; 1000 columns: rows that are not a
+    multiple of 16 bytes are re-pitched on the device).  Every frame comes out once, in order, with its own Sample,
+    and every position equals the oracle's."""
+    rows, cols = shape
+    n = 150
+    path = tmp_path / "clip.npy"
+    _write_clip(path, rows, cols, n)
+    trk = oracle.Tracker(rows, cols)
+    hp = oracle.HsvParams(**BAND)
+    want = [trk.track(oracle.synth_frame(rows, cols, 1000, t), 0.05, hp)[0] for t in range(n)]
+
+    def nodes(nm):
+        return [["oat-posidet", "track", nm[0], nm[3], "-A", "0.05", "--pipeline", "64"] + HSV_ARGS]
+
+    got = run_graph(f"strm{rows}" + ("d" if device else "h"), nodes, serve_args=(("--device",) if device else ()),
+                    server=lambda raw: ["file", raw, "-f", str(path)])
+    assert [p["tick"] for p in got] == list(range(1, n + 1))
+    n_valid = 0
+    for t, (p, o) in enumerate(zip(got, want)):
+        assert p["pos_ok"] == bool(o.position_valid), t
+        if o.position_valid:
+            n_valid += 1
+            assert abs(p["pos_xy"][0] - o.x) < 1e-4 and abs(p["pos_xy"][1] - o.y) < 1e-4, (t, p, o.x, o.y)
+    assert n_valid >= n - 2

@@ -3,6 +3,8 @@ the fused kernel + ONE launch of the tail server per chunk of frames, frame-to-f
 the device.  Everything it produces -- detections, filtered positions, the whole GMM state -- must be bit-identical
 to the frame-by-frame synchronous path (which tests/test_gpu_tracker.py pins to the oracle), for every geometry
 class, for frames smaller than one CTA's pipeline, across chunk and launch boundaries, and over long runs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -142,7 +144,7 @@ def test_clip_engine_soak_1080p(ctx):
     """The benchmark's own configuration, long: 2000 frames 1080p, -a 0.01, chunks of 32 frames (62 chunk boundaries,
     every one of them overlapped tile by tile with its predecessor) against the synchronous frame-by-frame path:
     every detection and the whole GMM state bit-identical."""
-    rows, cols, lr, n = 1080, 1920, 0.01, 2000
+    rows, cols, lr, n = 1080, 1920, 0.01, int(os.environ.get("OAT_SOAK_FRAMES", "2000"))  # (shortened under compute-sanitizer)
     hp = oat_b200.HsvParams.make(**HSV_BAND)
     R = 24
     bufs = _frames(ctx, rows, cols, 1000, R + 1)
@@ -297,7 +299,7 @@ def test_clip_engine_close_dependencies_stress(ctx, shape):
     release (an unfenced flag store behind completed bulk stores fails here about once in 30 clips).  Repeated
     clips, whole-state comparison against the synchronous path."""
     rows, cols = shape
-    lr, n, reps = 0.05, 160, 12
+    lr, n, reps = 0.05, 160, int(os.environ.get("OAT_STRESS_REPS", "12"))  # (fewer under compute-sanitizer)
     hp = oat_b200.HsvParams.make(**HSV_BAND)
     R = 16
     bufs = _frames(ctx, rows, cols, 1000, R + 1)

@@ -39,7 +39,8 @@ def run(tag, image, n, consumers, device, last_is_position):
         sock = None
         sock_out = open(f"/tmp/oatb200_graph_bench/{tag}.positions", "w+")  # (a pipe would fill up and stall the graph)
         if last_is_position:
-            sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names["pos"]], stdout=sock_out, text=True)
+            sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", names["pos"]], stdout=sock_out, stderr=subprocess.PIPE, text=True,
+                                    env=dict(os.environ, OAT_B200_TIMING="1"))
         env = dict(os.environ, OAT_B200_TIMING="1")
         for argv in consumers(names):
             procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env))
@@ -63,22 +64,33 @@ def run(tag, image, n, consumers, device, last_is_position):
         wall = time.perf_counter() - t0
         assert serve.returncode == 0, serve.stderr
         npos = None
+        marks = None  # token times of the LAST component of the graph
         if sock is not None:
-            sock.wait(timeout=120)
+            _, se = sock.communicate(timeout=120)
             sock_out.seek(0)
             npos = len([ln for ln in sock_out.read().splitlines() if ln.strip()])
+            marks = [ln for ln in se.splitlines() if "tokens out at:" in ln]
         stages, ends = [], []
         for p in procs:
             _, se = p.communicate(timeout=120)
             assert p.returncode == 0, (p.args, se)
             stages += [ln for ln in se.splitlines() if "per frame (us)" in ln]
             ends += [float(ln.rsplit(" ", 1)[1]) for ln in se.splitlines() if "end of stream at" in ln]
+            if marks is None:
+                marks = [ln for ln in se.splitlines() if "tokens out at:" in ln]
+        # the rate once the graph is warm: from the 100th token out of the last component to its last one
+        warm = None
+        if marks:
+            tk = dict((k, float(v)) for k, v in (w.replace("last(", "").replace(")", "").split(":") for w in marks[0].split("tokens out at:")[1].split()))
+            nl = max(int(k) for k in tk)
+            if "100" in tk and nl > 100 and tk[str(nl)] > tk["100"]:
+                warm = (nl - 100) / (tk[str(nl)] - tk["100"])
         # steady state: from the server's first frame to the moment the last token left the last component (the
         # server's own start-up -- for --device its CUDA context -- and the components' teardown are not in it)
         started = [float(ln.rsplit(" ", 1)[1]) for ln in serve.stderr.splitlines() if "serving started at" in ln]
         steady = max(ends) - started[0] if ends and started else None
         return {"frames": n, "wall_s": wall, "fps": n / wall, "steady_s": steady, "steady_fps": n / steady if steady else None,
-                "positions": npos, "stages": stages}
+                "warm_fps": warm, "positions": npos, "stages": stages}
     finally:
         for p in procs:
             if p.poll() is None:
@@ -93,7 +105,9 @@ def main():
     args = ap.parse_args()
     res = {"protocol": "N static frames from `oat-frameserve test`, free-running, through real shm; fps = N / wall time of the frame server "
                        "process (test/perf/results.md:12-18: `time oat frameserve test ...`; with --device that includes creating its CUDA "
-                       "context); steady_fps = N / (first frame served -> last token out of the last component); consumers started 3 s earlier",
+                       "context); steady_fps = N / (first frame served -> last token out of the last component); warm_fps = rate between the 100th and "
+                       "the last token out of the last component (the first frames pay for model allocation, lazy module loading and the GPU's "
+                       "clock ramp: 10 ms to 1 s from run to run); consumers started 3 s earlier",
            "reference_published": {"framefilt mog, cv::cuda MOG, GTX 970 (results.md:34-37)": 573.0,
                                    "framefilt mog, CPU MOG2, i7-5600U (results.md:91-95)": 75.7,
                                    "posidet hsv, GTX 970 box CPU path (results.md:55-58)": 214.0}}
@@ -115,7 +129,7 @@ def main():
             r[f"track_pipeline8_{k}"] = run(f"{wl}p{k}", img, args.frames, lambda n: [
                 ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "8"] + HSV], dev, True)
             # the streaming resident engine behind the lock-step SOURCE: chunks of 32 frames, long enough a run to see its rate
-            r[f"track_pipeline64_{k}"] = run(f"{wl}q{k}", img, args.frames * (20 if dev else 4), lambda n: [
+            r[f"track_pipeline64_{k}"] = run(f"{wl}q{k}", img, args.frames * 20, lambda n: [
                 ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "64"] + HSV], dev, True)
         res[wl] = r
         for k, v in r.items():
@@ -123,7 +137,8 @@ def main():
                 print(f"{wl:6s} {k:24s} FAILED: {v}", flush=True)
             else:
                 print(f"{wl:6s} {k:24s} {v['fps']:10.1f} fps by the protocol's clock ({v['frames']} frames, `time oat-frameserve` {v['wall_s']:.3f} s), "
-                      f"{v['steady_fps'] or 0:10.1f} fps steady (first frame served -> last token out, {v['steady_s'] or 0:.4f} s), positions {v['positions']}", flush=True)
+                      f"{v['steady_fps'] or 0:10.1f} fps first frame served -> last token out ({v['steady_s'] or 0:.4f} s), "
+                      f"{v['warm_fps'] or 0:10.1f} fps WARM (100th -> last token out of the last component), positions {v['positions']}", flush=True)
                 for ln in v["stages"]:
                     print("         " + ln, flush=True)
     # frameserve alone (no listener), the protocol's own overhead
