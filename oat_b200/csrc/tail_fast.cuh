@@ -30,7 +30,7 @@ struct TailResult {
     uint32_t nodes;      // run-table entries the mask needed (diagnostic / sizing)
     uint32_t slow_groups;  // fused kernel's census: 4-pixel groups that left its fast path in this frame
     uint32_t pad;
-    uint32_t cyc[8];     // SM-clock stamps of the labelling CTA (diagnostic): start, ticket, staged, counted, filled, merged, filled holes, end
+    uint32_t cyc[8];     // SM-clock stamps of the labelling CTA (diagnostic): start, ticket, extents staged, runs counted, mask staged + run table filled, merged, holes filled, end
 };
 
 struct FastArgs;
@@ -51,6 +51,8 @@ struct FastArgs {
     int smem_bytes;          // dynamic shared memory per CTA
     int max_comps;
     unsigned int *slow_in;   // or NULL: the fused kernel's slow-path census of this frame (read into the result, re-armed)
+    int in_place_ok;         // nobody reads `out` after the labelling (no thresh egress): a mask too large to be staged beside
+                             // its run table may be read -- and have its holes filled -- where it is
 };
 
 // the frame's result: device copy (epilogues, replays read it) and, when asked for, the pinned-host mirror the
@@ -156,7 +158,7 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     const int H = ymax - ymin + 1;
     const int C = a.max_comps;
     // ---- 0. stage row extents, then the bounding region of the mask ---------------------------
-    // layout: ext[H] (int2) | offF[H+1] offB[H+1] (u32) | acc[3*C] (u64) | M[H*Wd] (u32) | node arrays
+    // layout: ext[H] (int2) | offF[H+1] offB[H+1] (u32) | acc[3*C] (u64) | [M[H*Wd] (u32): the staged mask] | node arrays
     size_t used = 0;
     int2 *ext = reinterpret_cast<int2 *>(smem);
     used += (size_t)H * 8;
@@ -204,37 +206,8 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     __syncthreads();
     const int jmin = s_xmin >> 5, jmax = s_xmax >> 5, Wd = jmax - jmin + 1;
     const size_t RW = (size_t)H * Wd;
-    uint32_t *Ms = reinterpret_cast<uint32_t *>(smem + used);
-    uint32_t *Gs = Ms;  // holes are OR-ed into the same words once the merges (the last readers of the bare mask) are done
-    used += RW * 4;
-    const long long avail = (long long)a.smem_bytes - (long long)used;
-    const int N = avail > 0 ? (int)(avail / 12) : 0;  // start,end,row,comp: u16 x4 + parent u32 = 12 B
-    if (N < 16) {
-        if (final && tid == 0) {
-            r.status = TAIL_OVERFLOW;
-            store_result(a, r);
-        }
-        return false;
-    }
-    uint32_t *parent = reinterpret_cast<uint32_t *>(smem + used);
-    uint16_t *nstart = reinterpret_cast<uint16_t *>(parent + N);
-    uint16_t *nend = nstart + N;
-    uint16_t *nrow = nend + N;
-    uint16_t *ncomp = nrow + N;
-    for (size_t t = tid; t < RW; t += NT) {
-        const int y = (int)(t / Wd), j = jmin + (int)(t % Wd);
-        const uint32_t w = __ldcg(a.out + (size_t)(ymin + y) * g.wpr + j);
-        Ms[t] = w;
-    }
-    for (int c = tid; c < 3 * C; c += NT) acc[c] = 0ull;
-    __syncthreads();
     r.cyc[2] = (uint32_t)clock64();
-    const bool vol = __isGlobal(smem) != 0;
-    RegionView M{Ms, ymin, ymax, jmin, jmax, Wd, vol};
-    RegionView G{Gs, ymin, ymax, jmin, jmax, Wd, vol};
-
-    r.cyc[3] = (uint32_t)clock64();
-    // ---- 2. exclusive scan over rows (one warp, chunked) ---------------------------------------
+    // ---- 1. exclusive scan over rows (one warp, chunked): the run counts size the table --------
     if (warp == 0) {
         uint32_t baseF = 0, baseB = 0;
         for (int y0 = 0; y0 < H; y0 += 32) {
@@ -266,13 +239,40 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     __syncthreads();
     const uint32_t nF = s_nF, nB = s_nB;
     r.nodes = nF + nB + 1;
-    if (nF + nB + 1 > (uint32_t)N) {
+    r.cyc[3] = (uint32_t)clock64();
+    // ---- 2. working memory: the run table (start,end,row,comp: u16 x4 + parent u32 = 12 B per run) and, if it fits
+    //         beside it, a staged copy of the mask's bounding region.  A region too large for that (many blobs spread
+    //         over the frame: the region is the frame) is read where the bands left it -- streaming reads through L2,
+    //         while everything the union-find chases stays in this memory
+    const size_t need_nodes = ((size_t)nF + nB + 1) * 12 + 16;
+    const bool staged = used + RW * 4 + need_nodes <= (size_t)a.smem_bytes;
+    if (!staged && !(a.in_place_ok && used + need_nodes <= (size_t)a.smem_bytes)) {
         if (final && tid == 0) {
             r.status = TAIL_OVERFLOW;
             store_result(a, r);
         }
         return false;
     }
+    uint32_t *Ms = staged ? reinterpret_cast<uint32_t *>(smem + used) : a.out + (size_t)ymin * g.wpr + jmin;
+    uint32_t *Gs = Ms;  // holes are OR-ed into the same words once the merges (the last readers of the bare mask) are done
+    const int Ws = staged ? Wd : g.wpr;  // row stride of Ms / Gs in words
+    if (staged) used += RW * 4;
+    const int N = (int)(((size_t)a.smem_bytes - used) / 12);
+    uint32_t *parent = reinterpret_cast<uint32_t *>(smem + used);
+    uint16_t *nstart = reinterpret_cast<uint16_t *>(parent + N);
+    uint16_t *nend = nstart + N;
+    uint16_t *nrow = nend + N;
+    uint16_t *ncomp = nrow + N;
+    if (staged)
+        for (size_t t = tid; t < RW; t += NT) {
+            const int y = (int)(t / Wd), j = jmin + (int)(t % Wd);
+            Ms[t] = __ldcg(a.out + (size_t)(ymin + y) * g.wpr + j);
+        }
+    for (int c = tid; c < 3 * C; c += NT) acc[c] = 0ull;
+    __syncthreads();
+    const bool vol = !staged || __isGlobal(smem) != 0;
+    RegionView M{Ms, ymin, ymax, jmin, jmax, Ws, vol};
+    RegionView G{Gs, ymin, ymax, jmin, jmax, Ws, vol};
     // node ids: 0 = EXT, 1..nF foreground runs (raster order), nF+1..nF+nB candidate background runs
     // ---- 3. fill the run table: G lanes per row (G = region width in words rounded up to a power of two,
     //         so a narrow blob puts 32/G rows in flight per warp), one word per lane, segmented warp scans ----
@@ -409,7 +409,7 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
         }
         suf_union(P, id, lo);  // nend[lo] == s - 1
         if (lo + 1 < hi0) suf_union(P, id, lo + 1);  // nstart[lo + 1] == e + 1
-        for (int j = s >> 5; j <= (e >> 5); ++j) atomicOr(Gs + (size_t)(y - ymin) * Wd + (j - jmin), range_mask(j, s, e));
+        for (int j = s >> 5; j <= (e >> 5); ++j) atomicOr(Gs + (size_t)(y - ymin) * Ws + (j - jmin), range_mask(j, s, e));
     }
     __syncthreads();
     r.cyc[6] = (uint32_t)clock64();

@@ -315,33 +315,73 @@ def test_clip_engine_close_dependencies_stress(ctx, shape):
     b.close()
 
 
-def test_clip_engine_many_blobs_are_labelled_on_the_device(ctx):
-    """~60 blobs spread over the frame: the mask's bounding region is the whole frame and its run table outgrows the
-    labelling CTA's shared memory.  The tail server labels such frames a second time in its global-memory scratch area
-    -- on the device, no host replay -- with the same result as the synchronous path (which replays through the
-    unbounded multi-kernel tail)."""
-    import bench
+def _blob_scene(rows, cols, nblobs, nframes, seed=1000):
+    """Background + `nblobs` shapes of the target colour wandering over the cells of a grid: discs, rings (a hole that must
+    join its contour) and rings with a disc inside (a contour inside a hole: its own external contour)."""
+    bg = oracle.synth_frame(rows, cols, seed, 0)
+    gx = max(1, int(round((nblobs * cols / rows) ** 0.5)))
+    gy = (nblobs + gx - 1) // gx
+    cw, ch = cols // gx, rows // gy
+    r = max(4, min(ch // 5, cw // 5, rows // 30))
+    yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
+    d2 = xx ** 2 + yy ** 2
+    out = [bg]
+    for t in range(nframes):
+        f = bg.copy()
+        for k in range(nblobs):
+            i, j = k % gx, k // gx
+            cx = i * cw + r + (t * 37 + k * 11) % max(1, cw - 2 * r)
+            cy = j * ch + r + (t * 23 + k * 7) % max(1, ch - 2 * r)
+            win = f[cy - r:cy + r + 1, cx - r:cx + r + 1]
+            keep = win.copy()
+            shape = d2 <= (r - k % 3) ** 2
+            if k % 3 == 1:
+                shape &= d2 >= (r // 2) ** 2                      # ring
+            elif k % 3 == 2:
+                shape &= (d2 >= (r // 2) ** 2) | (d2 <= (r // 4) ** 2)  # ring with a disc inside its hole
+            win[shape] = (40, 220, 60)
+            win[~shape] = keep[~shape]
+        out.append(f)
+    return out
 
+
+@pytest.mark.parametrize("nblobs", [8, 60, 200])
+def test_clip_engine_many_blobs_are_labelled_on_the_device(ctx, nblobs):
+    """Blobs spread over the frame: the mask's bounding region is the whole frame (259 KB at 1080p), far more than the
+    labelling CTA's shared memory.  8 and 60 blobs: the run table still fits there, the mask is read -- and its holes
+    filled -- IN PLACE; 200 blobs: table and contour count outgrow shared memory, the tail server labels the frame a
+    second time in its global-memory scratch area.  Either way on the device, no host replay, and the same result as the
+    synchronous path (which replays through the unbounded multi-kernel tail)."""
     rows, cols, lr = 1080, 1920, 0.01
     hp = oat_b200.HsvParams.make(**HSV_BAND)
-    host = bench.multi_blob_frames(rows, cols, 60, 5)
+    host = _blob_scene(rows, cols, nblobs, 7)
     bufs = []
     for f in host:
         b = ctx.alloc(rows * cols * 3)
         b.upload(f)
         bufs.append(b)
-    seq = [bufs[0]] + [bufs[1 + i % 5] for i in range(40)]
+    seq = [bufs[0]] + [bufs[1 + i % 7] for i in range(40)]
     a = oat_b200.Tracker(ctx, rows, cols, lr, hp, ring_depth=16)
     got = [_det(d) for d in a.run_clip(seq)]
     st = a.tail_stats()
     b = oat_b200.Tracker(ctx, rows, cols, lr, hp)
     want = [_det(b.track(f)[0]) for f in seq]
     assert got == want
-    assert want[-1][1] >= 50, want[-1]          # the scene really has that many contours
+    assert want[-1][1] >= nblobs - nblobs // 8, want[-1]   # the scene really has that many contours (rings count once)
     assert st["clip_frames"] == 40
     assert st["replays"] <= 1, st               # (the first frame's whole-image blob goes frame by frame and is replayed)
+    # and against the oracle on the last frames' masks: the tail's contour semantics (holes, nested contours)
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(**HSV_BAND)
+    for t, f in enumerate([host[0]] + [host[1 + i % 7] for i in range(3)]):
+        o, _ = orc.track(f, lr, op)
+        d = got[t]
+        assert bool(d[0]) == bool(o.position_valid) and d[1] == o.n_components, (t, d, o.n_components)
+        assert abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
     a.close()
     b.close()
+    for x in bufs:
+        x.free()
 
 
 # ---- streaming use of the engine (oat_tracker_stream_*): what `oat posidet track --pipeline` drives ----------------

@@ -39,7 +39,7 @@ for nb in args.blobs:
     dt = time.perf_counter() - t0
     s = trk.tail_stats()
     cyc = s["cyc"]
-    names = ["ticket", "staged", "counted", "filled", "merged", "holes", "end"]
+    names = ["ticket", "extents", "counted", "staged+filled", "merged", "holes", "end"]
     deltas = [((cyc[i + 1] - cyc[i]) & 0xffffffff) / 1965.0 for i in range(7)]
     print(f"{nb:4d} blobs: {args.frames / dt:9.0f} frames/s ({1e6 * dt / args.frames:6.1f} us/frame); last frame: {d.n_components} components, "
           f"{s['nodes']} run-table entries, status {s['status']}, replays {s['replays']}; labelling CTA (us): "
