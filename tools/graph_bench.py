@@ -102,7 +102,30 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--out", default="")
+    ap.add_argument("--mps", action="store_true", help="run the graphs under the CUDA MPS daemon (the processes of a graph share the GPU "
+                    "concurrently instead of time-slicing it between their contexts)")
+    ap.add_argument("--only", default="", help="comma-separated graph name prefixes to run (default: all)")
     args = ap.parse_args()
+    mps = None
+    if args.mps:
+        os.makedirs("/tmp/oatb200_mps/log", exist_ok=True)
+        os.environ["CUDA_MPS_PIPE_DIRECTORY"] = "/tmp/oatb200_mps"
+        os.environ["CUDA_MPS_LOG_DIRECTORY"] = "/tmp/oatb200_mps/log"
+        mps = subprocess.run(["nvidia-cuda-mps-control", "-d"], capture_output=True, text=True, timeout=30)
+        print("MPS daemon:", mps.returncode, mps.stdout.strip(), mps.stderr.strip(), flush=True)
+    try:
+        _main(args)
+    finally:
+        if args.mps:
+            subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", capture_output=True, text=True, timeout=30)
+
+
+def _main(args):
+    want = [w for w in args.only.split(",") if w]
+
+    def sel(name):
+        return not want or any(name.startswith(w) for w in want)
+
     res = {"protocol": "N static frames from `oat-frameserve test`, free-running, through real shm; fps = N / wall time of the frame server "
                        "process (test/perf/results.md:12-18: `time oat frameserve test ...`; with --device that includes creating its CUDA "
                        "context); steady_fps = N / (first frame served -> last token out of the last component); warm_fps = rate between the 100th and "
@@ -120,16 +143,21 @@ def main():
         for dev in (False, True):
             k = "device" if dev else "host"
             ds = ["--device-sink"] if dev else []
-            r[f"mog_{k}"] = run(f"{wl}m{k}", img, args.frames, lambda n: [["oat-framefilt", "mog", n["raw"], n["filt"], "-a", "0.01"] + ds], dev, False)
-            r[f"chain_{k}"] = run(f"{wl}c{k}", img, args.frames, lambda n: [
+            if sel("mog"):
+                r[f"mog_{k}"] = run(f"{wl}m{k}", img, args.frames, lambda n: [["oat-framefilt", "mog", n["raw"], n["filt"], "-a", "0.01"] + ds], dev, False)
+            if sel("chain"):
+                r[f"chain_{k}"] = run(f"{wl}c{k}", img, args.frames, lambda n: [
                 ["oat-posidet", "hsv", n["hsv"], n["pos"]] + HSV,
                 ["oat-framefilt", "col", n["filt"], n["hsv"], "-C", "HSV"] + ds,
                 ["oat-framefilt", "mog", n["raw"], n["filt"], "-a", "0.01"] + ds], dev, True)
-            r[f"track_{k}"] = run(f"{wl}t{k}", img, args.frames, lambda n: [["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01"] + HSV], dev, True)
-            r[f"track_pipeline8_{k}"] = run(f"{wl}p{k}", img, args.frames, lambda n: [
+            if sel("track_" + k):
+                r[f"track_{k}"] = run(f"{wl}t{k}", img, args.frames, lambda n: [["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01"] + HSV], dev, True)
+            if sel("track_pipeline8"):
+                r[f"track_pipeline8_{k}"] = run(f"{wl}p{k}", img, args.frames, lambda n: [
                 ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "8"] + HSV], dev, True)
             # the streaming resident engine behind the lock-step SOURCE: chunks of 32 frames, long enough a run to see its rate
-            r[f"track_pipeline64_{k}"] = run(f"{wl}q{k}", img, args.frames * 20, lambda n: [
+            if sel("track_pipeline64"):
+                r[f"track_pipeline64_{k}"] = run(f"{wl}q{k}", img, args.frames * 20, lambda n: [
                 ["oat-posidet", "track", n["raw"], n["pos"], "-A", "0.01", "--pipeline", "64"] + HSV], dev, True)
         res[wl] = r
         for k, v in r.items():
