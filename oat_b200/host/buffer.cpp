@@ -58,6 +58,7 @@ protected:
         if (source_.connect() != SourceState::CONNECTED) return false;
         in_ = source_.parameters();
         src_memory_ = source_.header()->memory;
+        require_same_device(source_.header(), gpu_index_, name());
         if (src_memory_ == FrameMemory::DEVICE)
             src_dev_.reset(new gpu::IpcImport(*push_ctx_, source_.header()->ipc_handle));
         else

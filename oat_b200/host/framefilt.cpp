@@ -47,6 +47,7 @@ protected:
         out_bytes_ = out_bytes;
         // SOURCE side: a DEVICE frame is imported through its IPC handle (device -> device hand-off);
         // a host frame's mapping is page-locked once (HOST_PINNED) so the per-frame copy is plain DMA
+        require_same_device(frame_source_.header(), gpu_index_, name());
         if (frame_source_.header()->memory == FrameMemory::DEVICE)
             src_dev_.reset(new gpu::IpcImport(*ctx_, frame_source_.header()->ipc_handle));
         else

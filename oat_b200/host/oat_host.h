@@ -517,6 +517,16 @@ struct SharedFrameHeader {
                                    // as it has read offset and Sample, and read the pixels in place later
 };
 
+// a DEVICE frame can only be taken over by a component running on the GPU that holds it (CUDA IPC maps the
+// exporter's allocation on the same device); say so instead of failing inside cudaIpcOpenMemHandle
+inline void require_same_device(const SharedFrameHeader *h, int gpu_index, const std::string &who)
+{
+    if (h->memory == FrameMemory::DEVICE && h->device_index != gpu_index)
+        throw std::runtime_error(who + ": the SOURCE publishes frames in the memory of GPU " + std::to_string(h->device_index) +
+                                 ", this component runs on GPU " + std::to_string(gpu_index) + " (use --gpu-index " +
+                                 std::to_string(h->device_index) + ").");
+}
+
 // ---- lib/shmemdf/Sink.h -------------------------------------------------------------------------------
 template <typename T>
 class SinkBase {

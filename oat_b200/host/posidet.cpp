@@ -34,6 +34,7 @@ protected:
         in_ = frame_source_.parameters();
         position_sink_.bind(position_sink_address_, position_sink_address_);
         shared_position_ = position_sink_.retrieve();
+        require_same_device(frame_source_.header(), gpu_index_, name());
         if (frame_source_.header()->memory == FrameMemory::DEVICE)  // device -> device hand-off
             src_dev_.reset(new gpu::IpcImport(*ctx_, frame_source_.header()->ipc_handle));
         else

@@ -401,6 +401,29 @@ static int dump_frames(const std::string &addr)
     return 0;
 }
 
+// helper mode for the process-graph tests: block until every ADDR has at least N SOURCEs attached (a SINK only waits
+// for SOURCEs that have touched its node, Sink.h:93-116, so a server started too early serves into the void);
+// returns 0 when they have, 3 after TIMEOUT seconds
+static int wait_sources(int n, int timeout_s, const std::vector<std::string> &addrs)
+{
+    const auto until = std::chrono::steady_clock::now() + std::chrono::seconds(timeout_s);
+    for (const auto &addr : addrs) {
+        for (;;) {
+            bool ok = false;
+            try {
+                Shmem shm;
+                shm.open(addr + "_node", sizeof(Node), Shmem::OPEN_ONLY);
+                const Node *node = reinterpret_cast<const Node *>(shm.base());
+                ok = shm.bytes() >= sizeof(Node) && node->ready() && (int)node->source_ref_count() >= n;
+            } catch (const std::exception &) {}  // not there yet
+            if (ok) break;
+            if (std::chrono::steady_clock::now() >= until) return 3;
+            usleep(2000);
+        }
+    }
+    return 0;
+}
+
 // helper mode for transport-rate measurements: take tokens from ADDR without touching the pixels until the SINK leaves
 static int count_frames(const std::string &addr)
 {
@@ -425,6 +448,8 @@ int main(int argc, char **argv)
     if (argc > 2 && std::string(argv[1]) == "count-frames") return count_frames(argv[2]);
     if (argc > 3 && std::string(argv[1]) == "emit-positions") return emit_positions(argv[2], std::atoi(argv[3]));
     if (argc > 2 && std::string(argv[1]) == "dump-frames") return dump_frames(argv[2]);
+    if (argc > 4 && std::string(argv[1]) == "wait-sources")
+        return wait_sources(std::atoi(argv[2]), std::atoi(argv[3]), std::vector<std::string>(argv + 4, argv + argc));
     test_node();
     test_sink();
     test_source();

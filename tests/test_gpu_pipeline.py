@@ -9,11 +9,11 @@ PositionCout + serializePosition) are compared with the CPU oracle on the same s
 import json
 import os
 import subprocess
-import time
 
 import pytest
 
 import oracle
+from graph_util import wait_sources
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -33,6 +33,13 @@ def oracle_positions(lr):
     return out
 
 
+def used_addresses(names, argvs):
+    """the addresses of `names` the graph uses (the last one is the socket's): each needs its SOURCE attached before
+    frames flow"""
+    flat = [a for argv in argvs for a in argv]
+    return [n for n in names if n in flat or n == names[-1]]
+
+
 def run_graph(tag, nodes, serve_args=(), rows=ROWS, cols=COLS, n=N, server=None):
     """nodes: list of argv lists; consumers are started first, the frame server last (examples/*/*.sh).
     server: None = `frameserve synth`, else a function (raw address) -> argv of the frame server."""
@@ -44,7 +51,7 @@ def run_graph(tag, nodes, serve_args=(), rows=ROWS, cols=COLS, n=N, server=None)
         for argv in nodes(names):
             procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                                           text=True))
-        time.sleep(0.5)
+        wait_sources(*used_addresses(names, nodes(names)))
         if server is None:
             serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", names[0], "--rows", str(rows), "--cols", str(cols),
                                       "--num-samples", str(n), "--fps", "100"] + list(serve_args))
@@ -137,7 +144,7 @@ def test_hsv_requires_hsv_source():
     subprocess.run([os.path.join(BIN, "oat-clean"), name, name + "_pos"], capture_output=True)
     det = subprocess.Popen([os.path.join(BIN, "oat-posidet"), "hsv", name, name + "_pos"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                            text=True)
-    time.sleep(0.3)
+    wait_sources(name)
     serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", name, "--rows", "60", "--cols", "80", "--num-samples", "3"])
     so, se = det.communicate(timeout=60)
     serve.wait(timeout=30)
@@ -164,8 +171,8 @@ def test_two_colour_graph_with_kalman_and_mean():
         sock = subprocess.Popen([os.path.join(BIN, "oat-posisock"), "std", pos], stdout=subprocess.PIPE, text=True)
         for argv in argvs:
             procs.append(subprocess.Popen([os.path.join(BIN, argv[0])] + argv[1:], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-            time.sleep(0.3)
-        time.sleep(0.5)
+        wait_sources(raw, n=2)
+        wait_sources(pa, pb, ka, kb, pos)
         serve = subprocess.Popen([os.path.join(BIN, "oat-frameserve"), "synth", raw, "--rows", str(ROWS), "--cols", str(COLS),
                                   "--num-samples", str(N), "--fps", "100"])
         out, _ = sock.communicate(timeout=120)
@@ -223,7 +230,7 @@ def test_frameserve_test_through_mog_component(tmp_path):
     reader = subprocess.Popen([os.path.join(BIN, "shmemdf_test"), "dump-frames", names[1]], stdout=subprocess.PIPE, text=True)
     mog = subprocess.Popen([os.path.join(BIN, "oat-framefilt"), "mog", names[0], names[1], "-a", "0.0"], stdout=subprocess.DEVNULL,
                            stderr=subprocess.PIPE, text=True)
-    time.sleep(1.0)
+    wait_sources(*names)
     serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "test", names[0], "-f", str(path), "-n", "5"], capture_output=True, text=True,
                            timeout=120)
     assert serve.returncode == 0, serve.stderr
@@ -287,7 +294,7 @@ def test_buffer_component_in_front_of_the_tracker(tmp_path, device_sink):
                                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
         procs.append(subprocess.Popen([os.path.join(BIN, "oat-buffer"), "frame", names[0], names[1], "--capacity", "32"] +
                                       (["--device-sink"] if device_sink else []), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
-        time.sleep(1.0)
+        wait_sources(*names)
         serve = subprocess.run([os.path.join(BIN, "oat-frameserve"), "file", names[0], "-f", str(path), "-r", "100"], capture_output=True,
                                text=True, timeout=120)
         assert serve.returncode == 0, serve.stderr

@@ -7,6 +7,8 @@ import subprocess
 
 import pytest
 
+from graph_util import wait_sources
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "oat_b200", "bin")
 
@@ -170,6 +172,7 @@ def test_frameserve_test_serves_a_static_image(host_bin, tmp_path, fmt):
     addr = f"oatb200test_tf_{fmt.replace('-', '_')}"
     subprocess.run([os.path.join(host_bin, "oat-clean"), addr], capture_output=True)
     reader = subprocess.Popen([os.path.join(host_bin, "shmemdf_test"), "dump-frames", addr], stdout=subprocess.PIPE, text=True)
+    wait_sources(addr)
     serve = run([os.path.join(host_bin, "oat-frameserve"), "test", addr, "-f", str(path), "-n", str(n), "-r", "500"] + args)
     out, _ = reader.communicate(timeout=60)
     assert serve.returncode == 0, serve.stderr

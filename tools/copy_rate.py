@@ -50,3 +50,33 @@ for name, rows, cols in (("1mp", 1000, 1000), ("1080p", 1080, 1920), ("1000x1080
     ck(rt.cudaFreeHost(h))
     ck(rt.cudaFree(d_raw))
     ck(rt.cudaFree(d_al))
+
+# two copy streams: does a second DMA stream hide the per-copy start-up gaps of back-to-back H2D copies?
+rows, cols = 1080, 1920
+nb = rows * cols * 3
+hs = [ck(rt.cudaMallocHost(nb)) for _ in range(4)]
+ds = [ck(rt.cudaMalloc(nb)) for _ in range(4)]
+s2 = ck(rt.cudaStreamCreate())
+for label, streams in (("one stream", [stream]), ("two streams, frames alternating", [stream, s2])):
+    e0, e1 = ck(rt.cudaEventCreate()), ck(rt.cudaEventCreate())
+    for st in streams:
+        ck(rt.cudaStreamSynchronize(st))
+    n = 400
+    t0 = time.perf_counter()
+    for i in range(n):
+        ck(rt.cudaMemcpyAsync(ds[i % 4], hs[i % 4], nb, K.cudaMemcpyHostToDevice, streams[i % len(streams)]))
+    for st in streams:
+        ck(rt.cudaStreamSynchronize(st))
+    dt = time.perf_counter() - t0
+    print(f"1080p H2D, {label}: {n * nb / dt / 1e9:6.1f} GB/s ({1e6 * dt / n:6.1f} us per frame)")
+for label, parts in (("halves on two streams", 2),):
+    n = 400
+    t0 = time.perf_counter()
+    for i in range(n):
+        for k in range(parts):
+            off = k * (nb // parts)
+            ck(rt.cudaMemcpyAsync(ds[i % 4] + off, hs[i % 4] + off, nb // parts, K.cudaMemcpyHostToDevice, [stream, s2][k]))
+    ck(rt.cudaStreamSynchronize(stream))
+    ck(rt.cudaStreamSynchronize(s2))
+    dt = time.perf_counter() - t0
+    print(f"1080p H2D, {label}: {n * nb / dt / 1e9:6.1f} GB/s ({1e6 * dt / n:6.1f} us per frame)")
