@@ -360,7 +360,7 @@ int oat_tracker_submit_fused_only(oat_tracker *t, const uint8_t *bgr_in, size_t 
                                   double learning_rate, const oat_hsv_params *p);
 /* Diagnostic: the detect tail of the most recently collected frame. out[15] = { status (0 = the
  * one-launch tail sufficed, 1 = replayed through the unbounded path), run-table entries needed,
- * replays so far, one-launch tail used, 8 SM-clock stamps of its labelling CTA, frames run on the generic fused
+ * replays so far, one-launch tail used (bit 0; bit 1: run table pre-labelled by the bands), 8 SM-clock stamps of its labelling CTA, frames run on the generic fused
  * kernel so far (adaptive kernel choice), 4-pixel groups that left the fused kernel's fast path in that frame,
  * frames served by the resident clip engine so far }. */
 int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out);

@@ -774,8 +774,8 @@ class Tracker:
         a = (C.c_uint32 * 15)()
         _ck(lib().oat_tracker_tail_stats(self._h, a))
         v = list(a)
-        return {"status": v[0], "nodes": v[1], "replays": v[2], "fast": v[3], "cyc": v[4:12], "generic_frames": v[12],
-                "slow_groups": v[13], "clip_frames": v[14]}
+        return {"status": v[0], "nodes": v[1], "replays": v[2], "fast": v[3] & 1, "prelabelled": (v[3] >> 1) & 1, "cyc": v[4:12],
+                "generic_frames": v[12], "slow_groups": v[13], "clip_frames": v[14]}
 
     @staticmethod
     def run_clips(trackers, frames, learning_rate=None, fused_only=False, pitch=None):

@@ -137,6 +137,8 @@ struct oat_ctx {
     // development switches, read once at creation: OAT_B200_NO_PIPE / _NO_FAST_TAIL / _NO_OVERLAP force the generic
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
+    bool no_prelabel = false;  // OAT_B200_NO_PRELABEL (A/B switch): the labelling CTA extracts every run table itself
+    bool force_prelabel = false;  // OAT_B200_FORCE_PRELABEL (tests): ... and never, whatever the size of the mask
     cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
     // Work scheduler of the resident fused kernel (mog_pipe.cuh): every launch draws its (frame, tile) items from
     // one counter of this ring (slot = launch number % NSLOTS; counter and exit ticket are re-armed by the
@@ -213,6 +215,8 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->num_sms = prop.multiProcessorCount;
     c->no_pipe = getenv("OAT_B200_NO_PIPE") != nullptr;
     c->no_fast_tail = getenv("OAT_B200_NO_FAST_TAIL") != nullptr;
+    c->no_prelabel = getenv("OAT_B200_NO_PRELABEL") != nullptr;
+    c->force_prelabel = getenv("OAT_B200_FORCE_PRELABEL") != nullptr;
     c->no_overlap = getenv("OAT_B200_NO_OVERLAP") != nullptr;
     c->pdl = getenv("OAT_B200_NO_PDL") == nullptr;
     c->no_chain = getenv("OAT_B200_NO_CHAIN") != nullptr;
@@ -1059,6 +1063,28 @@ struct FastBufs {
     int2 *rowcnt = nullptr;      // per-row run counts
     int *bbox = nullptr;         // ymin, ymax
     unsigned int *ticket = nullptr;
+    // band pre-labelling pool of the resident tail server (tail_fast.cuh: band_prelabel), allocated on first use
+    uint2 *pool_runs = nullptr;
+    uint4 *pool_sums = nullptr;
+    uint4 *pool_agg = nullptr;
+    uint4 *band_hdr = nullptr;
+    unsigned int *pool_alloc = nullptr;
+    int pool_cap = 0;
+    int ensure_pool(int rows, int nbands)
+    {
+        if (pool_runs) return OAT_OK;
+        // 16 runs per row on average before a frame falls back to the in-place extraction (a 1080p frame of 200 blobs
+        // has ~14 k): 40 bytes per run
+        const int cap = std::min(std::max(rows * 16, 8192), 1 << 20);
+        CK(cudaMalloc(&pool_runs, (size_t)cap * sizeof(uint2)));
+        CK(cudaMalloc(&pool_sums, (size_t)cap * sizeof(uint4)));
+        CK(cudaMalloc(&pool_agg, (size_t)cap * sizeof(uint4)));
+        CK(cudaMalloc(&band_hdr, (size_t)nbands * sizeof(uint4)));
+        CK(cudaMalloc(&pool_alloc, sizeof(unsigned int)));
+        CK(cudaMemset(pool_alloc, 0, sizeof(unsigned int)));
+        pool_cap = cap;
+        return OAT_OK;
+    }
     int create(size_t nwords, int rows)
     {
         CK(cudaMalloc(&di, nwords * 4));
@@ -1078,6 +1104,11 @@ struct FastBufs {
         cudaFree(rowcnt);
         cudaFree(bbox);
         cudaFree(ticket);
+        cudaFree(pool_runs);
+        cudaFree(pool_sums);
+        cudaFree(pool_agg);
+        cudaFree(band_hdr);
+        cudaFree(pool_alloc);
         *this = FastBufs();
     }
 };
@@ -1163,7 +1194,7 @@ struct Tail {
             }
             fast_smem_set = 200 * 1024;
         }
-        FastArgs fa;
+        FastArgs fa{};  // (no band pool: the per-frame launch labels from the mask)
         fa.in = src;
         fa.out = b.di;
         fa.ke = ke;
@@ -2206,6 +2237,10 @@ struct ClipEngine {
         const bool full = (long long)ntiles * (long long)(cnt * S) >= (long long)pipe_grid_full(c, reserved);
         bool chain_launch = c->pdl && !c->no_chain && c->chain_uid != 0 && full;
         for (int s = 0; s < S; ++s) chain_launch = chain_launch && trk[s]->m.flags_current;
+        // the band pre-labelling pools of the slots this chunk uses (first use of a slot only; before any bookkeeping moves)
+        if (!fused_only && !c->no_prelabel && R == 32)
+            for (size_t i = 0; i < cnt; ++i)
+                for (int s = 0; s < S; ++s) CKRET(trk[s]->ring[(size_t)h * chunkF + i].fb.ensure_pool(g.rows, div_up(g.rows, R)));
         FusedArgs a{};
         bool seen[64] = {};  // (n_trackers <= 64)
         for (size_t i = 0; i < cnt; ++i)
@@ -2252,6 +2287,16 @@ struct ClipEngine {
                     fa.max_comps = t->tail.fast_comps;
                     fa.slow_in = sl.d_slow;
                     fa.in_place_ok = 1;  // (the engine has no thresh egress: nobody reads the slot's mask after the labelling)
+                    fa.pool_runs = nullptr;
+                    if (sl.fb.pool_runs && !c->no_prelabel && R == 32) {
+                        fa.pool_runs = sl.fb.pool_runs;
+                        fa.pool_sums = sl.fb.pool_sums;
+                        fa.pool_agg = sl.fb.pool_agg;
+                        fa.band_hdr = sl.fb.band_hdr;
+                        fa.pool_alloc = sl.fb.pool_alloc;
+                        fa.pool_cap = sl.fb.pool_cap;
+                        fa.force_pre = c->force_prelabel ? 1 : 0;
+                    }
                     tf.done_count = sl.d_done;
                     tf.done_target = sl.done_total;
                     tf.pad = 0;
@@ -2775,7 +2820,7 @@ extern "C" int oat_tracker_tail_stats(oat_tracker *t, uint32_t *out /* [15]: sta
     out[0] = (uint32_t)s.h_res->status;
     out[1] = s.h_res->nodes;
     out[2] = (uint32_t)t->replays;
-    out[3] = s.fast ? 1u : 0u;
+    out[3] = (s.fast ? 1u : 0u) | (s.h_res->pad ? 2u : 0u);  // bit 1: the run table came pre-labelled from the bands
     for (int i = 0; i < 8; ++i) out[4 + i] = s.h_res->cyc[i];
     out[14] = (uint32_t)t->clip_frames;      // frames served by the resident clip engine (one launch per chunk)
     out[12] = (uint32_t)t->generic_frames;  // frames that ran the generic fused kernel (adaptive choice)

@@ -499,3 +499,102 @@ def test_stream_mixed_parameters_and_positions(ctx):
     _state_equal(a, b)
     a.close()
     b.close()
+
+
+# ---- band pre-labelling (tail_fast.cuh: band_prelabel): the run table of a busy mask arrives merged inside every band ----
+def _structure_scene(rows, cols, nframes, seed):
+    """Frames whose target-coloured pixels form structures that stress everything a band cannot decide alone: worms and
+    rings that cross band borders (rows that are multiples of 32), U shapes whose inside reaches the exterior only
+    through another band, holes with islands, nested rings, speckle (many short runs), shapes on the frame border."""
+    rng = np.random.default_rng(seed)
+    bg = oracle.synth_frame(rows, cols, 1000, 0)
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    out = [bg]
+    dens = max(1, min(6, rows * cols // 25000))  # (a frame that is mostly foreground leaves the resident engine: keep it sparse)
+    for t in range(nframes):
+        m = np.zeros((rows, cols), bool)
+        for _ in range(dens):  # rings and nested rings, any size, clipped by the frame
+            cy, cx, r = rng.integers(0, rows), rng.integers(0, cols), rng.integers(6, max(8, rows // 3))
+            d2 = (yy - cy) ** 2 + (xx - cx) ** 2
+            w = rng.integers(1, 4)
+            m |= (d2 <= r * r) & (d2 >= (r - w) ** 2)
+            if rng.integers(2):
+                m |= d2 <= (r // 3) ** 2
+            if rng.integers(2):
+                m |= (d2 <= (r // 2) ** 2) & (d2 >= (r // 2 - 1) ** 2)
+        for _ in range(dens):  # U / C shapes: a frame of a rectangle with one side open
+            y0, x0 = rng.integers(0, rows - 8), rng.integers(0, cols - 8)
+            h, w = rng.integers(6, max(8, rows // 2)), rng.integers(6, max(8, cols // 3))
+            y1, x1 = min(rows - 1, y0 + h), min(cols - 1, x0 + w)
+            box = np.zeros((rows, cols), bool)
+            box[y0:y1 + 1, x0:x1 + 1] = True
+            box[y0 + 2:y1 - 1, x0 + 2:x1 - 1] = False
+            side = rng.integers(4)
+            if side == 0:
+                box[y0:y0 + 2, x0 + 3:x1 - 2] = False
+            elif side == 1:
+                box[y1 - 1:y1 + 1, x0 + 3:x1 - 2] = False
+            elif side == 2:
+                box[y0 + 3:y1 - 2, x0:x0 + 2] = False
+            else:
+                box[y0 + 3:y1 - 2, x1 - 1:x1 + 1] = False
+            m |= box
+        for _ in range(max(1, dens - 2)):  # worms
+            y, x = int(rng.integers(0, rows)), int(rng.integers(0, cols))
+            for _ in range(rows // 2):
+                m[max(0, y - 1):y + 1, max(0, x - 1):x + 1] = True
+                y = int(np.clip(y + rng.integers(-2, 3), 0, rows - 1))
+                x = int(np.clip(x + rng.integers(-2, 3), 0, cols - 1))
+        ph, pw = (40, 60) if dens > 2 else (12, 20)
+        py, px = rng.integers(0, max(1, rows - ph)), rng.integers(0, max(1, cols - pw))  # a speckled patch
+        m[py:py + ph, px:px + pw] |= rng.random(m[py:py + ph, px:px + pw].shape) < 0.3
+        if t % 3 == 0:  # something on every frame border
+            m[0, cols // 4:cols // 2] = True
+            m[rows - 1, cols // 3:cols // 2] = True
+            m[rows // 4:rows // 2, 0] = True
+            m[rows // 3:rows // 2, cols - 1] = True
+        f = bg.copy()
+        f[m] = (40, 220, 60)
+        out.append(f)
+    return out
+
+
+@pytest.mark.parametrize("shape", [(96, 128), (250, 332), (480, 640), (1080, 1920)])
+@pytest.mark.parametrize("dilate", [0, 3])
+def test_prelabelled_bands_equal_the_synchronous_tail(shape, dilate):
+    """The tail server with the bands' pre-labelled pool forced on (a private context: the switch is read when it is
+    created) against the synchronous per-frame path, which labels from the mask; then against the oracle's contours."""
+    rows, cols = shape
+    lr, n = 0.01, 12
+    os.environ["OAT_B200_FORCE_PRELABEL"] = "1"
+    try:
+        c2 = oat_b200.Context(0)
+    finally:
+        del os.environ["OAT_B200_FORCE_PRELABEL"]
+    hp = oat_b200.HsvParams.make(dilate=dilate, **HSV_BAND)
+    host = _structure_scene(rows, cols, n, seed=rows + dilate)
+    bufs = []
+    for f in host:
+        b = c2.alloc(rows * cols * 3)
+        b.upload(f)
+        bufs.append(b)
+    a = oat_b200.Tracker(c2, rows, cols, lr, hp, ring_depth=8)
+    got = [_det(d) for d in a.run_clip(bufs)]
+    st = a.tail_stats()
+    b = oat_b200.Tracker(c2, rows, cols, lr, hp)
+    want = [_det(b.track(f)[0]) for f in bufs]
+    assert got == want
+    assert st["generic_frames"] <= 1 and st["clip_frames"] == n, st   # (the scene stayed on the resident engine ...)
+    assert st["prelabelled"] == 1 and st["status"] == 0, st           # (... and its last frame took the bands' table)
+    orc = oracle.Tracker(rows, cols)
+    op = oracle.HsvParams(dilate=dilate, **HSV_BAND)
+    for t in range(4 if rows > 500 else n + 1):
+        o, _ = orc.track(host[t], lr, op)
+        d = got[t]
+        assert bool(d[0]) == bool(o.position_valid) and d[1] == o.n_components, (t, d, o.n_components)
+        assert abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
+    a.close()
+    b.close()
+    for x in bufs:
+        x.free()
+    c2.close()

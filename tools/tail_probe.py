@@ -44,6 +44,19 @@ for nb in args.blobs:
     print(f"{nb:4d} blobs: {args.frames / dt:9.0f} frames/s ({1e6 * dt / args.frames:6.1f} us/frame); last frame: {d.n_components} components, "
           f"{s['nodes']} run-table entries, status {s['status']}, replays {s['replays']}; labelling CTA (us): "
           + ", ".join(f"{n} {v:.1f}" for n, v in zip(names, deltas)) + f"  total {sum(deltas):.1f}")
+    # the same clip through the fused kernel alone (no detect tail): what the tail is being measured against
+    trk2 = oat_b200.Tracker(ctx, rows, cols, 0.01, hp, ring_depth=64)
+    trk2.submit(bufs[0])
+    trk2.collect()
+    oat_b200.Tracker.run_clips([trk2], clip, fused_only=True)
+    ctx.sync()
+    t0 = time.perf_counter()
+    oat_b200.Tracker.run_clips([trk2], clip, fused_only=True)
+    ctx.sync()
+    dt2 = time.perf_counter() - t0
+    print(f"            fused kernel alone on this scene: {args.frames / dt2:9.0f} frames/s ({1e6 * dt2 / args.frames:6.1f} us/frame), "
+          f"mean live modes {trk2.live_modes() / (rows * cols):.3f}")
+    trk2.close()
     trk.close()
     for b in bufs:
         b.free()
