@@ -139,6 +139,7 @@ struct oat_ctx {
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
     bool no_prelabel = false;  // OAT_B200_NO_PRELABEL (A/B switch): the labelling CTA extracts every run table itself
     bool force_prelabel = false;  // OAT_B200_FORCE_PRELABEL (tests): ... and never, whatever the size of the mask
+    double heavy_tail_at = 10000.0;  // run-table entries per frame from which the tail server gets twice its share (OAT_B200_HEAVY_TAIL_AT)
     cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
     // Work scheduler of the resident fused kernel (mog_pipe.cuh): every launch draws its (frame, tile) items from
     // one counter of this ring (slot = launch number % NSLOTS; counter and exit ticket are re-armed by the
@@ -217,6 +218,7 @@ extern "C" int oat_ctx_create(int device_index, oat_ctx **out)
     c->no_fast_tail = getenv("OAT_B200_NO_FAST_TAIL") != nullptr;
     c->no_prelabel = getenv("OAT_B200_NO_PRELABEL") != nullptr;
     c->force_prelabel = getenv("OAT_B200_FORCE_PRELABEL") != nullptr;
+    if (const char *e = getenv("OAT_B200_HEAVY_TAIL_AT")) c->heavy_tail_at = atof(e);
     c->no_overlap = getenv("OAT_B200_NO_OVERLAP") != nullptr;
     c->pdl = getenv("OAT_B200_NO_PDL") == nullptr;
     c->no_chain = getenv("OAT_B200_NO_CHAIN") != nullptr;
@@ -1073,9 +1075,9 @@ struct FastBufs {
     int ensure_pool(int rows, int nbands)
     {
         if (pool_runs) return OAT_OK;
-        // 16 runs per row on average before a frame falls back to the in-place extraction (a 1080p frame of 200 blobs
-        // has ~14 k): 40 bytes per run
-        const int cap = std::min(std::max(rows * 16, 8192), 1 << 20);
+        // 32 runs per row on average before a frame falls back to the in-place extraction (a 1080p frame of 200 blobs
+        // has ~14 k): 40 bytes per run, 1.4 MB per ring slot at 1080p -- allocated for streams whose masks are busy only
+        const int cap = std::min(std::max(rows * 32, 8192), 1 << 20);
         CK(cudaMalloc(&pool_runs, (size_t)cap * sizeof(uint2)));
         CK(cudaMalloc(&pool_sums, (size_t)cap * sizeof(uint4)));
         CK(cudaMalloc(&pool_agg, (size_t)cap * sizeof(uint4)));
@@ -2221,16 +2223,17 @@ struct ClipEngine {
         if (cnt == 0) return OAT_OK;
         CKRET(half[h].ensure(chunkF * (size_t)S));
         // The tail server's share of the machine follows the masks: a tracking stream (a blob or a few: ~100 run-table
-        // entries per frame) keeps 24 of the 296 CTA slots busy at most; a scene of dozens of blobs makes every band
-        // and every labelling several times as long, and the tail -- not the HBM-bound fused kernel -- sets the frame
-        // rate: it then gets twice the slots (measured at 60 blobs per 1080p frame: 23 k -> 34 k frames/s; on a
-        // single-blob stream the same split costs 5 %).
+        // entries per frame) keeps 24 of the 296 CTA slots busy at most, and so does a scene of dozens of blobs now that
+        // the bands pre-label their rows (60 blobs per 1080p frame, 6.5 k entries: 36.7 k frames/s on 24 slots, 31.0 k on
+        // 48 -- the fused kernel misses the slots more than the tail needs them).  From ~10 k entries per frame (200 blobs:
+        // 14 k) the tail, not the HBM-bound fused kernel, sets the frame rate and gets twice the slots (27.3 k against
+        // 25.8 k frames/s).
         for (int s = 0; s < S; ++s) {
-            if (trk[s]->tail_load > 2000.0) heavy_tail = true;
+            if (trk[s]->tail_load > c->heavy_tail_at) heavy_tail = true;
         }
         if (heavy_tail) {
             bool all_light = true;
-            for (int s = 0; s < S; ++s) all_light = all_light && trk[s]->tail_load < 1000.0;
+            for (int s = 0; s < S; ++s) all_light = all_light && trk[s]->tail_load < 0.5 * c->heavy_tail_at;
             if (all_light) heavy_tail = false;
         }
         const int reserved = fused_only ? 0 : (heavy_tail ? 2 : 1) * (int)PIPE_RESERVED_CTAS_CFG;
@@ -2238,9 +2241,13 @@ struct ClipEngine {
         bool chain_launch = c->pdl && !c->no_chain && c->chain_uid != 0 && full;
         for (int s = 0; s < S; ++s) chain_launch = chain_launch && trk[s]->m.flags_current;
         // the band pre-labelling pools of the slots this chunk uses (first use of a slot only; before any bookkeeping moves)
+        // (a tracking mask -- a blob or a few, ~100 runs -- is labelled from a staged copy in a few us: the bands'
+        // pre-labelling would only lengthen every band by as much)
         if (!fused_only && !c->no_prelabel && R == 32)
             for (size_t i = 0; i < cnt; ++i)
-                for (int s = 0; s < S; ++s) CKRET(trk[s]->ring[(size_t)h * chunkF + i].fb.ensure_pool(g.rows, div_up(g.rows, R)));
+                for (int s = 0; s < S; ++s)
+                    if (trk[s]->tail_load > 300.0 || c->force_prelabel)
+                        CKRET(trk[s]->ring[(size_t)h * chunkF + i].fb.ensure_pool(g.rows, div_up(g.rows, R)));
         FusedArgs a{};
         bool seen[64] = {};  // (n_trackers <= 64)
         for (size_t i = 0; i < cnt; ++i)
@@ -2287,8 +2294,14 @@ struct ClipEngine {
                     fa.max_comps = t->tail.fast_comps;
                     fa.slow_in = sl.d_slow;
                     fa.in_place_ok = 1;  // (the engine has no thresh egress: nobody reads the slot's mask after the labelling)
-                    fa.pool_runs = nullptr;
-                    if (sl.fb.pool_runs && !c->no_prelabel && R == 32) {
+                    fa.pool_runs = nullptr;  // (h_tf is reused from chunk to chunk: every field is set every time)
+                    fa.pool_sums = nullptr;
+                    fa.pool_agg = nullptr;
+                    fa.band_hdr = nullptr;
+                    fa.pool_alloc = nullptr;
+                    fa.pool_cap = 0;
+                    fa.force_pre = 0;
+                    if (sl.fb.pool_runs && !c->no_prelabel && R == 32 && (t->tail_load > 300.0 || c->force_prelabel)) {
                         fa.pool_runs = sl.fb.pool_runs;
                         fa.pool_sums = sl.fb.pool_sums;
                         fa.pool_agg = sl.fb.pool_agg;

@@ -240,15 +240,25 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     __syncthreads();
     {
         int xmin = INT_MAX, xmax = -1;
-        for (int y = tid; y < H; y += NT) {
-            const int2 e = __ldcg(a.rowext + ymin + y);
-            ext[y] = e;
-            const int2 cnt = __ldcg(a.rowcnt + ymin + y);  // run counts, made by the CTA that produced the row
-            offF[y] = (uint32_t)cnt.x;
-            offB[y] = (uint32_t)cnt.y;
-            if (e.y >= 0) {
-                xmin = min(xmin, e.x);
-                xmax = max(xmax, e.y);
+        for (int yb = tid; yb < H; yb += 4 * NT) {  // (four rows per thread in flight: a tall region is a few L2 round trips, not H / NT)
+            int2 e[4], cnt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int y = yb + u * NT;
+                e[u] = y < H ? __ldcg(a.rowext + ymin + y) : make_int2(INT_MAX, -1);
+                cnt[u] = y < H ? __ldcg(a.rowcnt + ymin + y) : make_int2(0, 0);  // run counts, made by the CTA that produced the row
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int y = yb + u * NT;
+                if (y >= H) continue;
+                ext[y] = e[u];
+                offF[y] = (uint32_t)cnt[u].x;
+                offB[y] = (uint32_t)cnt[u].y;
+                if (e[u].y >= 0) {
+                    xmin = min(xmin, e[u].x);
+                    xmax = max(xmax, e[u].y);
+                }
             }
         }
         xmin = __reduce_min_sync(0xffffffffu, xmin);
@@ -262,8 +272,67 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     const int jmin = s_xmin >> 5, jmax = s_xmax >> 5, Wd = jmax - jmin + 1;
     const size_t RW = (size_t)H * Wd;
     r.cyc[2] = (uint32_t)clock64();
-    // ---- 1. exclusive scan over rows (one warp, chunked): the run counts size the table --------
-    if (warp == 0) {
+    // ---- 1. exclusive scan over rows: the run counts size the table.  Chunks of 32 rows, a warp each; then the chunk
+    //         totals (one warp); then every row adds its chunk's base.  (More than 128 chunks: one warp walks them.) ----
+    __shared__ uint32_t s_ctF[128], s_ctB[128];
+    const int nchunks = (H + 31) >> 5;
+    if (nchunks <= 128) {
+        for (int ck = warp; ck < nchunks; ck += nwarps) {
+            const int y = 32 * ck + lane;
+            const uint32_t vf = y < H ? offF[y] : 0u, vb = y < H ? offB[y] : 0u;
+            uint32_t sf = vf, sb = vb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tf = __shfl_up_sync(0xffffffffu, sf, d), tb = __shfl_up_sync(0xffffffffu, sb, d);
+                if (lane >= d) {
+                    sf += tf;
+                    sb += tb;
+                }
+            }
+            if (y < H) {
+                offF[y] = sf - vf;
+                offB[y] = sb - vb;
+            }
+            if (lane == 31) {
+                s_ctF[ck] = sf;
+                s_ctB[ck] = sb;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t baseF = 0, baseB = 0;
+            for (int c0 = 0; c0 < nchunks; c0 += 32) {
+                const int ck = c0 + lane;
+                const uint32_t vf = ck < nchunks ? s_ctF[ck] : 0u, vb = ck < nchunks ? s_ctB[ck] : 0u;
+                uint32_t sf = vf, sb = vb;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t tf = __shfl_up_sync(0xffffffffu, sf, d), tb = __shfl_up_sync(0xffffffffu, sb, d);
+                    if (lane >= d) {
+                        sf += tf;
+                        sb += tb;
+                    }
+                }
+                if (ck < nchunks) {
+                    s_ctF[ck] = baseF + sf - vf;
+                    s_ctB[ck] = baseB + sb - vb;
+                }
+                baseF += __shfl_sync(0xffffffffu, sf, 31);
+                baseB += __shfl_sync(0xffffffffu, sb, 31);
+            }
+            if (lane == 0) {
+                offF[H] = baseF;
+                offB[H] = baseB;
+                s_nF = baseF;
+                s_nB = baseB;
+            }
+        }
+        __syncthreads();
+        for (int y = tid; y < H; y += NT) {
+            offF[y] += s_ctF[y >> 5];
+            offB[y] += s_ctB[y >> 5];
+        }
+    } else if (warp == 0) {
         uint32_t baseF = 0, baseB = 0;
         for (int y0 = 0; y0 < H; y0 += 32) {
             const int y = y0 + lane;
@@ -534,12 +603,12 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
     if (pre) {
         // rows inside a band were merged by the band: only its first and its last row have a neighbour it did not see
         // (a warp per such row: the work is where the rows are, not spread over every run of the table)
-        for (int q = warp; q < 2 * nbd; q += nwarps) {
+        for (int q = tid >> 3; q < 2 * nbd; q += NT >> 3) {  // (eight lanes per row: a row of a busy mask has about that many runs)
             const int b = b0 + (q >> 1);
             const int y = (q & 1) ? min(b * Rb + Rb - 1, g.rows - 1) : b * Rb;
             if (y < ymin || y > ymax || ((q & 1) && Rb == 1)) continue;
-            for (uint32_t id = 1 + offF[y - ymin] + lane; id < 1 + offF[y - ymin + 1]; id += 32) merge_run(id);
-            for (uint32_t id = 1 + nF + offB[y - ymin] + lane; id < 1 + nF + offB[y - ymin + 1]; id += 32) merge_run(id);
+            const uint32_t f0 = offF[y - ymin], nf = offF[y - ymin + 1] - f0, c0 = offB[y - ymin], nc = offB[y - ymin + 1] - c0;
+            for (uint32_t i = (uint32_t)(tid & 7); i < nf + nc; i += 8) merge_run(i < nf ? 1 + f0 + i : 1 + nF + c0 + (i - nf));
         }
     } else {
         for (uint32_t id = 1 + tid; id <= nF + nB; id += NT) merge_run(id);
@@ -652,13 +721,15 @@ __device__ bool tail_label_phase(const FastArgs &a, uint8_t *smem, const int ymi
             atomicAdd(acc + C + c, t10);
             atomicAdd(acc + 2 * C + c, t01);
         };
-        // (a) a warp per band-last row, four lanes per run
-        for (int b = b0 + warp; b <= b1; b += nwarps) {
+        // (a) eight lanes per band-last row, four lanes per run, folded with shuffles (warp-uniform trip counts)
+        for (int bq = b0 + (warp << 2); bq <= b1; bq += nwarps << 2) {
+            const int b = bq + (lane >> 3);
             const int y = b * Rb + Rb - 1;
-            if (y < ymin || y > ymax || y >= g.rows - 1) continue;
-            const uint32_t lo = 1 + offF[y - ymin], hi = 1 + offF[y - ymin + 1];
-            for (uint32_t i = lo; i < hi; i += 8) {  // (warp-uniform trip count)
-                const uint32_t id = i + (uint32_t)(lane >> 2);
+            const bool rowok = b <= b1 && y >= ymin && y <= ymax && y < g.rows - 1;
+            const uint32_t lo = rowok ? 1 + offF[y - ymin] : 0u, hi = rowok ? 1 + offF[y - ymin + 1] : 0u;
+            const uint32_t trips = __reduce_max_sync(0xffffffffu, (hi - lo + 1u) >> 1);
+            for (uint32_t it = 0; it < trips; ++it) {
+                const uint32_t id = lo + 2u * it + (uint32_t)((lane & 7) >> 2);
                 unsigned long long t00 = 0, t10 = 0, t01 = 0;
                 if (id < hi) run_cell_sums(G_at, y, (int)nstart[id], (int)nend[id], (nstart[id] >> 5) + (lane & 3), 4, t00, t10, t01);
 #pragma unroll
@@ -1255,20 +1326,22 @@ __global__ void __launch_bounds__(256, TAIL_STREAM_MINBLOCKS_CFG) tail_stream_ke
             tail_band<true>(s_tf.a, s_band, sm);
             __threadfence();
             __syncthreads();
+            // two independent round trips, two threads: this band is done / the next band to work on.  (If this CTA turns
+            // out to be the frame's finisher every band had been claimed already: its draw is >= nbands, as it must be.)
             if (threadIdx.x == 0) {
                 s_last = (atomicAdd(band_done + f, 1u) == (unsigned)nbands - 1u);
-                if (s_last) {
-                    __threadfence();
-                    s_ymin = atomicExch(s_tf.a.bbox, INT_MAX);  // read + reset for the slot's next frame
-                    s_ymax = atomicExch(s_tf.a.bbox + 1, -1);
-                    if (s_tf.a.pool_alloc) *s_tf.a.pool_alloc = 0u;  // (every band of the frame has drawn its share)
-                }
-                s_band = s_last ? nbands : (int)atomicAdd(band_ctr + f, 1u);
+                if (s_last) __threadfence();
             }
+            if (threadIdx.x == 32) s_band = (int)atomicAdd(band_ctr + f, 1u);
             __syncthreads();
             if (s_last) {
                 __shared__ uint32_t s_slow;
-                if (threadIdx.x == 0) s_slow = s_tf.a.slow_in ? atomicExch(s_tf.a.slow_in, 0u) : 0u;  // the frame's census, re-armed
+                // the frame's bounding rows and the fused kernel's census, read and re-armed for the slot's next frame
+                // (likewise independent: one thread each)
+                if (threadIdx.x == 0) s_ymin = atomicExch(s_tf.a.bbox, INT_MAX);
+                if (threadIdx.x == 32) s_ymax = atomicExch(s_tf.a.bbox + 1, -1);
+                if (threadIdx.x == 64) s_slow = s_tf.a.slow_in ? atomicExch(s_tf.a.slow_in, 0u) : 0u;
+                if (threadIdx.x == 96 && s_tf.a.pool_alloc) *s_tf.a.pool_alloc = 0u;  // (every band of the frame has drawn its share)
                 __syncthreads();
                 // label in shared memory; a mask whose tables do not fit (many blobs, noise) is labelled again by this
                 // CTA in its global-memory scratch area -- slower, but on the device and beside the other CTAs' frames,

@@ -559,7 +559,7 @@ def _structure_scene(rows, cols, nframes, seed):
     return out
 
 
-@pytest.mark.parametrize("shape", [(96, 128), (250, 332), (480, 640), (1080, 1920)])
+@pytest.mark.parametrize("shape", [(96, 128), (250, 336), (480, 640), (1080, 1920)])
 @pytest.mark.parametrize("dilate", [0, 3])
 def test_prelabelled_bands_equal_the_synchronous_tail(shape, dilate):
     """The tail server with the bands' pre-labelled pool forced on (a private context: the switch is read when it is
