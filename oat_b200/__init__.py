@@ -710,13 +710,19 @@ class Tracker:
         _ck(lib().oat_tracker_collect(self._h, C.byref(d)))
         return d
 
-    def run_clip(self, frames, depth=4, learning_rate=None, positions=False, pitch=None):
+    def run_clip(self, frames, depth=4, learning_rate=None, positions=False, pitch=None, out=None):
         """frames: device buffers / arrays of one clip -> list of Detection (and of Position with a filter attached).
         Device-resident frames go through the resident engine (one launch per chunk of frames), anything else
-        through the natively looped submit/collect pipeline (oat_tracker_run_clip)."""
+        through the natively looped submit/collect pipeline (oat_tracker_run_clip).
+        out: a caller-owned (Detection * n)() the detections are written to and that is returned as it is -- nothing is
+        allocated or converted per frame on the Python side (what a measurement loop wants)."""
         lr = self.learning_coeff if learning_rate is None else learning_rate
         ptrs = frames if isinstance(frames, C.Array) else frame_pointers(frames)
         n = len(ptrs)
+        if out is not None:
+            assert len(out) >= n and not positions
+            _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, pitch or self.cols * 3, lr, C.byref(self.hsv), depth, out, None))
+            return out
         out = (Detection * n)()
         pos = (Position * n)() if positions else None
         _ck(lib().oat_tracker_run_clip(self._h, ptrs, n, pitch or self.cols * 3, lr, C.byref(self.hsv), depth, out, pos))

@@ -1072,20 +1072,24 @@ struct FastBufs {
     uint4 *band_hdr = nullptr;
     unsigned int *pool_alloc = nullptr;
     int pool_cap = 0;
-    int ensure_pool(int rows, int nbands)
+    // (the engine carves the pools of all ring slots of a tracker out of ONE allocation: oat_tracker::pool_block)
+    // 32 runs per row on average before a frame falls back to the in-place extraction (a 1080p frame of 200 blobs
+    // has ~14 k): 40 bytes per run, 1.4 MB per ring slot at 1080p -- allocated for streams whose masks are busy only
+    static int pool_cap_for(int rows) { return std::min(std::max(rows * 32, 8192), 1 << 20); }
+    static size_t pool_bytes(int rows, int nbands)
     {
-        if (pool_runs) return OAT_OK;
-        // 32 runs per row on average before a frame falls back to the in-place extraction (a 1080p frame of 200 blobs
-        // has ~14 k): 40 bytes per run, 1.4 MB per ring slot at 1080p -- allocated for streams whose masks are busy only
-        const int cap = std::min(std::max(rows * 32, 8192), 1 << 20);
-        CK(cudaMalloc(&pool_runs, (size_t)cap * sizeof(uint2)));
-        CK(cudaMalloc(&pool_sums, (size_t)cap * sizeof(uint4)));
-        CK(cudaMalloc(&pool_agg, (size_t)cap * sizeof(uint4)));
-        CK(cudaMalloc(&band_hdr, (size_t)nbands * sizeof(uint4)));
-        CK(cudaMalloc(&pool_alloc, sizeof(unsigned int)));
-        CK(cudaMemset(pool_alloc, 0, sizeof(unsigned int)));
-        pool_cap = cap;
-        return OAT_OK;
+        const size_t cap = (size_t)pool_cap_for(rows);
+        return cap * (sizeof(uint2) + 2 * sizeof(uint4)) + (((size_t)nbands * sizeof(uint4) + 255) & ~(size_t)255) + 256;
+    }
+    void set_pool(uint8_t *block, int rows, int nbands)  // block: pool_bytes(rows, nbands) of zeroed device memory, 256-byte aligned
+    {
+        const size_t cap = (size_t)pool_cap_for(rows);
+        pool_sums = reinterpret_cast<uint4 *>(block);
+        pool_agg = pool_sums + cap;
+        pool_runs = reinterpret_cast<uint2 *>(pool_agg + cap);
+        band_hdr = reinterpret_cast<uint4 *>(block + cap * (sizeof(uint2) + 2 * sizeof(uint4)));
+        pool_alloc = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(band_hdr) + (((size_t)nbands * sizeof(uint4) + 255) & ~(size_t)255));
+        pool_cap = (int)cap;
     }
     int create(size_t nwords, int rows)
     {
@@ -1106,12 +1110,7 @@ struct FastBufs {
         cudaFree(rowcnt);
         cudaFree(bbox);
         cudaFree(ticket);
-        cudaFree(pool_runs);
-        cudaFree(pool_sums);
-        cudaFree(pool_agg);
-        cudaFree(band_hdr);
-        cudaFree(pool_alloc);
-        *this = FastBufs();
+        *this = FastBufs();  // (the pool belongs to the tracker: oat_tracker::pool_block)
     }
 };
 
@@ -1763,6 +1762,7 @@ struct oat_tracker {
     size_t last_slot = 0;            // ring slot of the most recently collected frame (oat_tracker_tail_stats)
     uint64_t clip_frames = 0;        // frames that went through the resident clip engine
     double tail_load = 0.0;          // moving estimate of the run-table entries a frame's mask needs (sizes the tail server's share)
+    void *pool_block = nullptr;      // band pre-labelling pools of every ring slot (allocated when the stream's masks get busy)
     struct StreamState *stream = nullptr;  // oat_tracker_stream_*: the resident engine kept alive between calls
 };
 static bool stream_busy(const oat_tracker *t);
@@ -1840,6 +1840,7 @@ extern "C" int oat_tracker_destroy(oat_tracker *t)
         if (s.d_pos) cudaFree(s.d_pos);
         if (s.h_pos) cudaFreeHost(s.h_pos);
     }
+    if (t->pool_block) cudaFree(t->pool_block);
     if (t->pf) t->pf->attached = 0;
     for (auto &pr : t->prof_pending) {
         cudaEventDestroy(pr.first);
@@ -2244,10 +2245,15 @@ struct ClipEngine {
         // (a tracking mask -- a blob or a few, ~100 runs -- is labelled from a staged copy in a few us: the bands'
         // pre-labelling would only lengthen every band by as much)
         if (!fused_only && !c->no_prelabel && R == 32)
-            for (size_t i = 0; i < cnt; ++i)
-                for (int s = 0; s < S; ++s)
-                    if (trk[s]->tail_load > 300.0 || c->force_prelabel)
-                        CKRET(trk[s]->ring[(size_t)h * chunkF + i].fb.ensure_pool(g.rows, div_up(g.rows, R)));
+            for (int s = 0; s < S; ++s)
+                if ((trk[s]->tail_load > 300.0 || c->force_prelabel) && !trk[s]->pool_block) {
+                    // one allocation for the pools of every ring slot of the stream, the first time its masks are busy
+                    const size_t per = (FastBufs::pool_bytes(g.rows, div_up(g.rows, R)) + 255) & ~(size_t)255;
+                    CK(cudaMalloc(&trk[s]->pool_block, per * trk[s]->ring.size()));
+                    CK(cudaMemset(trk[s]->pool_block, 0, per * trk[s]->ring.size()));
+                    for (size_t k = 0; k < trk[s]->ring.size(); ++k)
+                        trk[s]->ring[k].fb.set_pool((uint8_t *)trk[s]->pool_block + k * per, g.rows, div_up(g.rows, R));
+                }
         FusedArgs a{};
         bool seen[64] = {};  // (n_trackers <= 64)
         for (size_t i = 0; i < cnt; ++i)

@@ -42,8 +42,8 @@ namespace oat {
 #ifndef PIPE_RESERVED_CTAS_CFG
 #define PIPE_RESERVED_CTAS_CFG 24
 #endif
-#ifndef PIPE_PUBLISH_BATCH_CFG
-#define PIPE_PUBLISH_BATCH_CFG 2   // finished tiles published per release fence (storer lane)
+#ifndef PIPE_STORERS_CFG
+#define PIPE_STORERS_CFG 2   // storer lanes per CTA (each in a warp of its own), taking the CTA's tiles in turn
 #endif
 #ifndef PIPE_TAIL_GRID_CFG
 #define PIPE_TAIL_GRID_CFG 24   // CTAs of the resident tail server: one beside the single fused CTA of a reserved SM
@@ -55,10 +55,11 @@ namespace oat {
 #define PIPE_MINBLOCKS_CFG 2
 #endif
 constexpr int PIPE_CTHREADS = PIPE_CTHREADS_CFG;    // compute threads (8 warps), 4 pixels each
-constexpr int PIPE_THREADS = PIPE_CTHREADS + 64;     // + a loader warp (bulk loads) and a storer warp (write-back + publication)
+constexpr int PIPE_STORERS = PIPE_STORERS_CFG;
+constexpr int PIPE_THREADS = PIPE_CTHREADS + 32 + 32 * PIPE_STORERS;  // + a loader warp (bulk loads) and the storer warps (write-back + publication)
 constexpr int PIPE_TILE = PIPE_CTHREADS * 4;        // pixels per tile
 constexpr int PIPE_STAGES = PIPE_STAGES_CFG;
-constexpr int PIPE_PUBLISH_BATCH = PIPE_PUBLISH_BATCH_CFG;
+static_assert(PIPE_STORERS >= 1 && PIPE_STORERS <= PIPE_STAGES_CFG, "every storer lane needs a stage to work on");
 #ifndef PIPE_CTAS_PER_SM_CFG
 #define PIPE_CTAS_PER_SM_CFG PIPE_MINBLOCKS_CFG
 #endif
@@ -441,8 +442,8 @@ __device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, u
 // The resident fused kernel.
 //
 // Roles inside a CTA: PIPE_CTHREADS compute threads, a LOADER lane (draws work, waits for the tile's previous
-// frame, issues the bulk loads) and a STORER lane (writes finished tiles back with bulk stores and publishes
-// them), each in a warp of its own, around a ring of PIPE_STAGES stages:
+// frame, issues the bulk loads) and PIPE_STORERS STORER lanes (write finished tiles back with bulk stores and publish
+// them, taking the CTA's tiles in turn), each in a warp of its own, around a ring of PIPE_STAGES stages:
 //
 //     loader --full[s]--> compute warps --done[s]--> storer --freed[s]--> loader
 //
@@ -450,18 +451,15 @@ __device__ __forceinline__ void slow_pixel(const StreamArgs &pa, float *state, u
 // that reads it next -- a release/acquire pair at GPU scope, correct under the PTX memory model:
 //   writer   compute warps' direct stores (modes >= 1)  --mbarrier done[s] (release.cta / acquire.cta)-->  storer lane;
 //            the tile's bulk stores are COMPLETE (cp.async.bulk.wait_group, not .read);
-//            fence.acq_rel.gpu  (cumulative: covers what the storer lane observed through the mbarrier) -- ONE fence
-//            for a batch of PIPE_PUBLISH_BATCH retired tiles;
-//            st.relaxed.gpu tile_seq[tile]  (+ red.add done_count for the tail server) for every tile of the batch
+//            fence.acq_rel.gpu  (cumulative: covers what the storer lane observed through the mbarrier);
+//            st.relaxed.gpu tile_seq[tile]  (+ red.add done_count for the tail server)
 //   reader   loader lane: ld.acquire.gpu tile_seq[tile] == seq_expect;  fence.proxy.async.global;  bulk loads;
 //            the compute warps' own ld.global.cg follow the mbarrier full[s] the loads complete on.
 // The release fence is a MEMBAR.GPU: a round trip through a memory system that this kernel keeps saturated.  It
-// lives in the storer lane, where it delays nothing but the next write-back, and one fence publishes a batch of
-// tiles.  (Fence per tile: 0.71 of the HBM peak with one lane doing loads and stores, 0.83 with it in the storer
-// lane; NO fence -- flags behind the mere completion of the bulk stores -- reaches 0.95-0.99 but is wrong: see the
-// storer lane.  As built: profiles/.)
-// The storer publishes a batch when it is full, or after a bounded wait if no further tile arrives -- so a tile is
-// never withheld from a CTA that waits for it.
+// lives in the storer lanes, where it delays nothing but that lane's next write-back -- and with two lanes the other
+// lane's write-back goes on beside it.  (One lane doing loads and stores, fence per tile: 0.71 of the HBM peak; one
+// storer lane: 0.83 per tile, 0.95 with one fence per 2 tiles; NO fence -- flags behind the mere completion of the
+// bulk stores -- reaches 0.97-0.99 but is wrong: see the storer lanes.  As built: profiles/.)
 //
 // LINEAR: cols % 32 == 0 and every image pitch is tight, so a pixel's byte offsets are plain multiples of its
 // padded index (one bulk copy brings a tile's BGR bytes).  Otherwise the loader lane issues one bulk copy
@@ -482,7 +480,9 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
     __shared__ __align__(8) uint64_t freed[PIPE_STAGES];  // stage written back (its bulk stores have read it)
     const FusedArgs &a = pa.f;
     const int tid = threadIdx.x;
-    const bool is_loader = (tid == PIPE_CTHREADS), is_storer = (tid == PIPE_CTHREADS + 32);
+    const bool is_loader = (tid == PIPE_CTHREADS);
+    const bool is_storer = (tid >= PIPE_CTHREADS + 32) && ((tid & 31) == 0);  // lane 0 of every storer warp
+    const int storer_x = (tid - PIPE_CTHREADS - 32) >> 5;                       // which one: it takes the stage uses x, x + PIPE_STORERS, ...
     // let the next launch on this stream (programmatic dependent launch) become resident as CTAs of
     // this one retire; it either parks in griddepcontrol.wait below or orders itself tile by tile
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -636,7 +636,14 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
                 // the stage's previous tile has been written back
                 if (li >= PIPE_STAGES) mbar_wait(&freed[s], (uint32_t)(li / PIPE_STAGES - 1) & 1u);
                 if (nxt.tile < 0) {
-                    hdr_of(s)[HDR_TILE] = 0xffffffffu;
+                    // End marker: one for every storer lane, in the stage uses li .. li + PIPE_STORERS - 1 (each lane owns
+                    // every PIPE_STORERS-th use).  All of them are written before the compute warps are released, which
+                    // pass them on together.
+#pragma unroll
+                    for (int k = 1; k < PIPE_STORERS; ++k)
+                        if (li + k >= PIPE_STAGES) mbar_wait(&freed[(li + k) % PIPE_STAGES], (uint32_t)((li + k) / PIPE_STAGES - 1) & 1u);
+#pragma unroll
+                    for (int k = 0; k < PIPE_STORERS; ++k) hdr_of((li + k) % PIPE_STAGES)[HDR_TILE] = 0xffffffffu;
                     mbar_arrive(&full[s]);  // completes the phase: the compute warps read the marker, pass it on and stop
                     break;
                 }
@@ -664,13 +671,17 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
             return;
         }
         if (!is_storer) return;
-        // ---- storer lane ---------------------------------------------------------------------------
-        // Finished tiles whose publication is still owed (at most PIPE_PUBLISH_BATCH): ONE release fence publishes the
-        // whole batch.  A MEMBAR.GPU is a round trip through a memory system this kernel keeps saturated (~1.5 us, most
-        // of a tile period): paid per tile it makes this lane the bottleneck (0.83 instead of 0.95 of the HBM peak at
-        // 1080p), and it cannot be dropped -- without it a reader that has seen the flag can still see a stale plane of
-        // the tile (observed on 640x480 frames, where consecutive frames of a stream are in flight together).
-        constexpr int NB = PIPE_PUBLISH_BATCH;
+        // ---- storer lanes --------------------------------------------------------------------------
+        // PIPE_STORERS lanes take the CTA's finished tiles in turn.  Each writes its tile back, hands the stage to the
+        // loader as soon as the bulk stores have READ it, and then publishes: waits until the stores are COMPLETE,
+        // fence.acq_rel.gpu, flag.  A MEMBAR.GPU is a round trip through a memory system this kernel keeps saturated
+        // (~1.5 us, most of a tile period): in ONE lane, paid per tile, it makes the lane the bottleneck (0.83 instead of
+        // 0.95 of the HBM peak at 1080p) and has to be shared by a batch of tiles (NB = 2: 0.95; the second tile of a
+        // batch is withheld from its waiter for a tile period); with two lanes every tile is published as soon as its
+        // own stores have landed, and the fence of one lane runs beside the write-back of the other.  It cannot be
+        // dropped -- without it a reader that has seen the flag can still see a stale plane of the tile (observed on
+        // 640x480 frames, where consecutive frames of a stream are in flight together).
+        constexpr int NB = PIPE_STORERS == 1 ? 2 : 1;
         unsigned int *pend_tseq[NB], *pend_done[NB];
         uint32_t pend_tile[NB], pend_seq[NB];
         int npend = 0;
@@ -688,17 +699,15 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
                 }
             npend = 0;
         };
-        for (int si = 0;; ++si) {
+        for (int si = storer_x;; si += PIPE_STORERS) {
             const int s = si % PIPE_STAGES;
             const uint32_t par = (uint32_t)(si / PIPE_STAGES) & 1u;
             volatile uint32_t *h = hdr_of(s);
             uint8_t *st = stage_mem + (size_t)s * PIPE_STAGE_BYTES;
-            // the next tile normally arrives within a tile period; if it does not, somebody may be waiting for the
-            // tile this lane still owes: publish it, then wait for as long as it takes
-            if (!mbar_try_wait_ns(&done[s], par, 4000u)) {
-                publish_pending();
-                mbar_wait(&done[s], par);
-            }
+            // (one lane) the next tile normally arrives within a tile period; if it does not, somebody may be waiting
+            // for the tile this lane still owes: publish it, then wait for as long as it takes
+            if (NB > 1 && !mbar_try_wait_ns(&done[s], par, 4000u)) publish_pending();
+            mbar_wait(&done[s], par);
             const int tile = (int)h[HDR_TILE];
             if (tile < 0) break;
             // 1. a full batch of retired tiles (the youngest has had a whole tile period for its bulk stores): publish it
@@ -750,13 +759,15 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
             // 3. hand the stage back as soon as its stores have READ it
             bulk_wait_read<0>();
             mbar_arrive(&freed[s]);
+            // 4. (several lanes) publish the tile as soon as its stores have landed: the other lane has the next one
+            if (NB == 1) publish_pending();
         }
         publish_pending();
         bulk_wait_all<0>();  // shared memory must outlive the last bulk stores
-        // (the loader lane has drawn its last number before it passed the end marker on)
-        // the last CTA to leave re-arms the scheduler slot for its next user (a launch the host starts only
-        // after this one has said so) and tells the host
-        if (atomicAdd(pa.exit_ticket, 1u) == gridDim.x - 1u) {
+        // (the loader lane has drawn its last number before it passed the end markers on)
+        // the last storer lane of the last CTA to leave re-arms the scheduler slot for its next user (a launch the host
+        // starts only after this one has said so) and tells the host
+        if (atomicAdd(pa.exit_ticket, 1u) == gridDim.x * (unsigned)PIPE_STORERS - 1u) {
             *pa.work_counter = 0u;
             *pa.exit_ticket = 0u;
             __threadfence_system();
@@ -790,7 +801,10 @@ __global__ void PIPE_KERNEL_BOUNDS mog_stream_kernel(const __grid_constant__ Str
 
         const int tile = (int)h[HDR_TILE];
         if (tile < 0) {
-            mbar_arrive(&done[s]);  // the storer lane reads the marker too
+            // every storer lane reads a marker of its own: this stage's and the next stages' (written by the loader
+            // lane before it released this one; those stages' previous tiles are long done)
+#pragma unroll
+            for (int k = 0; k < PIPE_STORERS; ++k) mbar_arrive(&done[(s + k) % PIPE_STAGES]);
             break;
         }
         size_t pidx;

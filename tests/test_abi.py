@@ -77,19 +77,22 @@ def test_product_never_imports_the_oracle():
 
 class _ResidentModel:
     """A transcription of the resident fused kernel's scheduling protocol (oat_b200/csrc/mog_pipe.cuh,
-    mog_stream_kernel): every CTA has a LOADER lane, compute warps and a STORER lane around a ring of `stages`
+    mog_stream_kernel): every CTA has a LOADER lane, compute warps and `storers` STORER lanes around a ring of `stages`
     stages (loader --full--> compute --done--> storer --freed--> loader); work items (frame, tile) are drawn from
     one counter (the first `stages` of a CTA in one draw, then one at a time); a tile of frame f+1 of a model may
-    only be loaded once the same tile of the model's previous frame has been PUBLISHED.  The storer publishes
-    retired tiles in batches (one release fence per batch): when a batch is full, or -- if the next tile does not
-    arrive in time -- while it waits.
+    only be loaded once the same tile of the model's previous frame has been PUBLISHED.  Storer lane x owns the stage
+    uses x, x + storers, ...; it frees the stage first and publishes afterwards -- one lane: in batches (one release
+    fence per batch), when a batch is full or, if the next tile does not arrive in time, while it waits; several lanes:
+    every tile on its own, before the lane looks at its next one.  The end of the queue is marked in `storers`
+    consecutive stage uses, one marker per lane, written together.
     The model is stepped by an adversarial (random) scheduler; it checks that every item is processed exactly
     once, that no load ever precedes the publication it depends on, and that the protocol cannot deadlock --
     including frames smaller than one CTA's ring, where the loader waits for a tile that still sits in its own
     CTA's stages."""
 
-    def __init__(self, nframes, ntiles, grid, stages, models, rng, batch=2):
-        self.nf, self.nt, self.grid, self.S, self.rng, self.P = nframes, ntiles, grid, stages, rng, batch
+    def __init__(self, nframes, ntiles, grid, stages, models, rng, batch=2, storers=1):
+        self.nf, self.nt, self.grid, self.S, self.rng, self.P, self.NS = nframes, ntiles, grid, stages, rng, batch, storers
+        assert storers <= stages
         self.total = nframes * ntiles
         self.model_of = [f % models for f in range(nframes)]      # frames of `models` streams interleaved
         self.prev = {}                                            # frame -> previous frame of the same model
@@ -105,8 +108,8 @@ class _ResidentModel:
 
     def _new_cta(self):
         # stage state: None (free) -> item (loaded) -> computed flag -> stored (free again)
-        return {"stage": [None] * self.S, "computed": [False] * self.S, "li": 0, "si": 0, "ci": 0, "pend": [],
-                "nxt": None, "batch": None, "ldone": False, "cdone": False, "sdone": False}
+        return {"stage": [None] * self.S, "li": 0, "si": list(range(self.NS)), "ci": 0, "pend": [[] for _ in range(self.NS)],
+                "nxt": None, "batch": None, "ldone": False, "cdone": False, "sdone": [False] * self.NS}
 
     def _item(self, g):
         return "END" if g >= self.total else (g // self.nt, g % self.nt)
@@ -122,6 +125,11 @@ class _ResidentModel:
         self.counter += 1
         return g
 
+    def _freed(self, c, use):
+        """mbar_wait(freed[use % S]) for the stage's previous tenant: use - S has been written back by its storer lane"""
+        prev = use - self.S
+        return prev < 0 or c["si"][prev % self.NS] > prev
+
     def step_loader(self, c):
         S = self.S
         if c["ldone"]:
@@ -131,20 +139,23 @@ class _ResidentModel:
             c["nxt"] = self._item(self.counter)
             self.counter += S
             return True
-        s = c["li"] % S
-        if c["li"] - c["si"] >= S:
-            return False  # mbar_wait(freed[s]): only this CTA's own storer lane is waited for
+        if not self._freed(c, c["li"]):
+            return False  # only this CTA's own storer lanes are waited for
         if c["nxt"] == "END":
-            c["stage"][s] = "END"
-            c["li"] += 1
+            if not all(self._freed(c, c["li"] + k) for k in range(1, self.NS)):
+                return False
+            for k in range(self.NS):  # one marker per storer lane, all written before the compute warps are released
+                assert c["stage"][(c["li"] + k) % S] is None
+                c["stage"][(c["li"] + k) % S] = "END"
+            c["li"] += self.NS
             c["ldone"] = True
             return True
         if not self._ready(c["nxt"]):
             return False  # spins on the tile's flag
         it = c["nxt"]
         self.loaded.append(it)
-        c["stage"][s] = it
-        c["computed"][s] = False
+        assert c["stage"][c["li"] % S] is None
+        c["stage"][c["li"] % S] = it
         c["nxt"] = self._item(self._draw(c))
         c["li"] += 1
         return True
@@ -155,46 +166,52 @@ class _ResidentModel:
         s = c["ci"] % self.S
         if c["stage"][s] == "END":
             c["cdone"] = True
-            c["computed"][s] = True  # passes the marker on to the storer
-            c["ci"] += 1
+            c["ci"] += self.NS  # passes every lane's marker on
             return True
-        c["computed"][s] = True
         c["ci"] += 1
         return True
 
-    def step_storer(self, c):
-        if c["sdone"]:
+    def step_storer(self, c, x=None):
+        if x is None:
+            x = self.rng.randrange(self.NS)
+        if c["sdone"][x]:
             return False
-        s = c["si"] % self.S
-        if c["si"] >= c["ci"]:  # done[s] has not completed: after the bounded wait, publish what is owed
-            if c["pend"]:
-                self.published.update(c["pend"])
-                c["pend"] = []
+        pend = c["pend"][x]
+        if self.NS > 1 and pend:  # several lanes: the tile just written back is published before anything else
+            self.published.update(pend)
+            pend.clear()
+            return True
+        si = c["si"][x]
+        s = si % self.S
+        if si >= c["ci"]:  # done[s] has not completed: (one lane) after the bounded wait, publish what is owed
+            if pend:
+                self.published.update(pend)
+                pend.clear()
                 return True
             return False
         if c["stage"][s] == "END":
-            self.published.update(c["pend"])
-            c["pend"] = []
-            c["sdone"] = True
+            self.published.update(pend)
+            pend.clear()
+            c["sdone"][x] = True
             self.exited += 1
             return True
-        if len(c["pend"]) == self.P:  # a full batch: one fence publishes it
-            self.published.update(c["pend"])
-            c["pend"] = []
-        c["pend"].append(c["stage"][s])
+        if len(pend) == self.P:  # a full batch: one fence publishes it
+            self.published.update(pend)
+            pend.clear()
+        pend.append(c["stage"][s])
         c["stage"][s] = None
-        c["si"] += 1
+        c["si"][x] = si + self.NS
         return True
 
     def run(self, max_steps=10_000_000):
         steps = 0
-        while self.exited < self.grid:
+        while self.exited < self.grid * self.NS:
             order = list(range(self.grid))
             self.rng.shuffle(order)
             progressed = False
             for b in order:
                 c = self.ctas[b]
-                acts = [self.step_loader, self.step_compute, self.step_storer]
+                acts = [self.step_loader, self.step_compute] + [lambda cc, x=x: self.step_storer(cc, x) for x in range(self.NS)]
                 self.rng.shuffle(acts)
                 for act in acts:
                     if self.rng.random() < 0.7:  # an adversarial scheduler: some actors simply do not run this round
@@ -202,7 +219,9 @@ class _ResidentModel:
             if not progressed:
                 # nobody moved in a randomised round: give everybody a deterministic chance before calling it a deadlock
                 for c in self.ctas:
-                    progressed |= self.step_loader(c) | self.step_compute(c) | self.step_storer(c)
+                    progressed |= self.step_loader(c) | self.step_compute(c)
+                    for x in range(self.NS):
+                        progressed |= self.step_storer(c, x)
                 assert progressed, "deadlock: no CTA can make progress"
             steps += 1
             assert steps < max_steps
@@ -217,7 +236,7 @@ def test_resident_scheduler_protocol_model():
     cases = [(1, 1, 1, 1), (1, 7, 3, 1), (4, 5, 8, 1), (6, 2, 8, 2), (8, 13, 5, 1), (16, 3, 7, 4), (5, 40, 6, 1),
              (12, 9, 4, 3), (3, 1, 5, 1), (20, 2, 3, 2), (9, 1, 1, 1), (30, 2, 1, 1), (10, 4, 2, 2), (64, 75, 16, 1)]
     for nframes, ntiles, grid, models in cases:
-        for S, P in ((3, 1), (4, 2), (2, 3), (4, 4)):
-            m = _ResidentModel(nframes, ntiles, grid, S, models, rng, batch=P).run()
+        for S, P, NS in ((3, 1, 1), (4, 2, 1), (2, 3, 1), (4, 4, 1), (4, 1, 2), (3, 1, 2), (2, 1, 2), (4, 1, 3)):  # (shipped: 4 stages, 2 lanes)
+            m = _ResidentModel(nframes, ntiles, grid, S, models, rng, batch=P, storers=NS).run()
             assert sorted(m.loaded) == [(f, t) for f in range(nframes) for t in range(ntiles)], (nframes, ntiles, grid)
             assert len(m.published) == nframes * ntiles

@@ -10,6 +10,7 @@ timeout -k 10 300 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_benc
 timeout -k 10 600 python bench.py --workload 4k --steps 600 > gpurun_out/${TAG}_bench_4k.json 2> gpurun_out/${TAG}_bench_4k.err
 timeout -k 10 300 python bench.py --alpha 0 --steps 1000 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_bench_1080p_a0.json 2> gpurun_out/${TAG}_bench_1080p_a0.err
 timeout -k 10 300 python bench.py --workload 1mp --steps 1000 --no-extras > gpurun_out/${TAG}_bench_1mp.json 2> gpurun_out/${TAG}_bench_1mp.err
+timeout -k 10 300 python bench.py --workload 1mp-tight --steps 1000 --no-extras --no-cpu-baseline > gpurun_out/${TAG}_bench_1mp_tight.json 2> gpurun_out/${TAG}_bench_1mp_tight.err
 timeout -k 10 300 python bench.py --impl reference --steps 100 --warmup 10 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 kill $SMI
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 64 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_ncu_launches.log 2>&1
@@ -19,6 +20,6 @@ timeout -k 10 600 ncu --set full --clock-control none --import-source on -k rege
 timeout -k 10 200 python tools/hostrate.py 1080p > gpurun_out/${TAG}_hostrate.log 2>&1
 timeout -k 10 200 python tools/clip_rate.py 1080p > gpurun_out/${TAG}_clip_rate.txt 2>&1
 timeout -k 10 200 python tools/clip_rate.py 4k >> gpurun_out/${TAG}_clip_rate.txt 2>&1
-for f in 1080p 1080p_20steps 4k 1080p_a0 1mp reference; do echo "== $f"; cat gpurun_out/${TAG}_bench_$f.json | cut -c1-400; done
+for f in 1080p 1080p_20steps 4k 1080p_a0 1mp 1mp_tight reference; do echo "== $f"; cat gpurun_out/${TAG}_bench_$f.json | cut -c1-400; done
 cat gpurun_out/${TAG}_hostrate.log gpurun_out/${TAG}_clip_rate.txt
-tail -3 gpurun_out/${TAG}_ncu_fused_1080p.log gpurun_out/${TAG}_ncu_tail_1080p.log
+tail -n 3 gpurun_out/${TAG}_ncu_fused_1080p.log; tail -n 3 gpurun_out/${TAG}_ncu_tail_1080p.log
