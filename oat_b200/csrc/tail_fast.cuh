@@ -836,16 +836,17 @@ __device__ __forceinline__ void band_prelabel(const FastArgs &a, const int band,
     __syncthreads();
     const uint32_t nF = sb_offF[32], nB = sb_offB[32], n = nF + nB;
     if (n == 0) return;  // (the labelling CTA only asks bands that have runs)
-    // table: parent u32 | start, end u16 | row u8 | band-local sums of the roots 3 x u32 (native shared-memory atomics;
+    // table: parent u32 (x2) | start, end u16 | row u8 | band-local sums of the roots 3 x u32 (native shared-memory atomics;
     // a band-local contour of a frame of up to 4096 x 4096 stays below 2^32: 6 * 32 rows * sum of x, cols * 32 * (6 y + 3))
-    const size_t need = (size_t)(n + 1) * (4 + 2 + 2 + 1) + 16 + (size_t)(nF + 1) * 12;
+    const size_t need = (size_t)(n + 1) * (4 + 4 + 2 + 2 + 1) + 16 + (size_t)(nF + 1) * 12;
     if (need > work_bytes || g.cols > 4096 || g.rows > 4096 || n >= 65535u) {  // (16-bit band-local ids)
         if (tid == 0) a.band_hdr[band] = make_uint4(0u, nF, nB, 0u);
         return;
     }
     uint32_t *agg = reinterpret_cast<uint32_t *>(work);  // [3][nF + 1]
     uint32_t *par = agg + (size_t)3 * (nF + 1);
-    uint16_t *st = reinterpret_cast<uint16_t *>(par + n + 1);
+    uint32_t *par2 = par + n + 1;  // second copy for the pointer jumping
+    uint16_t *st = reinterpret_cast<uint16_t *>(par2 + n + 1);
     uint16_t *en = st + n + 1;
     uint8_t *rw = reinterpret_cast<uint8_t *>(en + n + 1);
     for (uint32_t i = tid; i < 3u * (nF + 1u); i += NT) agg[i] = 0u;
@@ -960,13 +961,13 @@ __device__ __forceinline__ void band_prelabel(const FastArgs &a, const int band,
     }
     __syncthreads();
     // ---- publish: runs with their band-local root, per-run moment sums, per-root sums ----
-    // the direct links left chains (a run -> the run above it -> ...): five rounds of pointer jumping bring a depth of
-    // 32 down to 1; whatever unions of several branches left deeper is walked by the plain finds below
-    for (int it = 0; it < 5; ++it) {
-        for (uint32_t id = 1 + tid; id <= n; id += NT) {
-            const uint32_t pp = P[id], gp = P[pp];
-            if (gp != pp) P[id] = gp;
-        }
+    // the direct links left chains (a run -> the run above it -> ...): rounds of pointer jumping bring a depth of
+    // 32 (64) down to 1; whatever unions of several branches left deeper is walked by the plain finds below
+    // (between two copies of the parent array: no round reads what it writes; six rounds, so the result is back in `par`)
+    for (int it = 0; it < 6; ++it) {
+        const uint32_t *src = (it & 1) ? par2 : par;
+        uint32_t *dst = (it & 1) ? par : par2;
+        for (uint32_t id = tid; id <= n; id += NT) dst[id] = src[src[id]];
         __syncthreads();
     }
     const unsigned int base = sb_base;
