@@ -68,6 +68,8 @@ int oat_ctx_create(int device_index, oat_ctx **out);
 int oat_ctx_destroy(oat_ctx *ctx);
 /* Block until everything queued through this context has finished. */
 int oat_ctx_sync(oat_ctx *ctx);
+/* Polls instead: *idle = 1 when everything given to the context's compute stream so far has finished. */
+int oat_ctx_idle(oat_ctx *ctx, int *idle);
 /* The cudaStream_t (as void*) the synchronous entry points launch on; lets a harness time
  * with CUDA events on the launching stream. */
 void *oat_ctx_stream(oat_ctx *ctx);
@@ -390,6 +392,15 @@ int oat_ipc_open(oat_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
 int oat_ipc_close(oat_ctx *ctx, void *dev_ptr);
 /* Copy between any two of {device, pinned, pageable}; synchronous. */
 int oat_memcpy(oat_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* The same, asynchronous, on one of the context's two copy lanes (0: ingest, 1: egress; each a stream of its own, so
+ * a frame on its way back to the host overlaps the next one on its way up and the kernels between them).  An egress
+ * copy is ordered behind everything the context's compute stream was given before the call (it reads what the kernels
+ * produce); an ingest copy is ordered behind nothing but the lane's earlier copies -- its destination must not be in
+ * use by work still in flight (double-buffer it).  oat_memcpy_wait returns once the lane's copies have landed;
+ * oat_memcpy_done polls (*done = 1: nothing in flight on the lane). */
+int oat_memcpy_async(oat_ctx *ctx, int lane, void *dst, const void *src, size_t bytes);
+int oat_memcpy_wait(oat_ctx *ctx, int lane);
+int oat_memcpy_done(oat_ctx *ctx, int lane, int *done);
 /* L2 flush for benchmarking: overwrites an internal buffer larger than L2. */
 int oat_flush_l2(oat_ctx *ctx);
 

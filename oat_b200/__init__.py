@@ -197,6 +197,10 @@ _SIGS = {
     "oat_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "oat_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "oat_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "oat_ctx_idle": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "oat_memcpy_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "oat_memcpy_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "oat_memcpy_done": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "oat_flush_l2": (C.c_int, [C.c_void_p]),
 }
 

@@ -157,6 +157,9 @@ struct oat_ctx {
     bool no_chain = false, no_mirror = false, no_track = false, no_clip = false, relaxed_publish = false, fence_always = false;
     uint64_t pipe_launches = 0;
     cudaStream_t aux = nullptr;  // small host-synchronous uploads (frame descriptors of a clip)
+    cudaStream_t lane[2] = {nullptr, nullptr};      // oat_memcpy_async: ingest / egress copies of a host component
+    cudaEvent_t lane_done[2] = {nullptr, nullptr};  // ... the lane's latest copy
+    cudaEvent_t lane_after = nullptr;               // ... what the compute stream had been given when a copy was enqueued
     ClipHalf clip[2];            // two chunks of the resident clip engine in flight
     const void *clip_owner = nullptr;  // the tracker whose stream (oat_tracker_stream_*) holds chunks in flight, if any
     DevBuf tail_scratch[2];      // per chunk in flight: one global-memory labelling area per CTA of the tail server
@@ -303,6 +306,11 @@ static void ctx_free(oat_ctx *c)
     if (c->aux) {
         cudaStreamSynchronize(c->aux);
         cudaStreamDestroy(c->aux);
+        for (int l = 0; l < 2; ++l) {
+            if (c->lane[l]) cudaStreamDestroy(c->lane[l]);
+            if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
+        }
+        if (c->lane_after) cudaEventDestroy(c->lane_after);
     }
     if (c->slow_count) cudaFree(c->slow_count);
     cudaStreamDestroy(c->stream);
@@ -310,6 +318,15 @@ static void ctx_free(oat_ctx *c)
     delete c;
 }
 
+extern "C" int oat_ctx_idle(oat_ctx *c, int *idle)
+{
+    CKRET(bind(c));
+    REQUIRE(idle, "oat_ctx_idle: null argument");
+    const cudaError_t e = cudaStreamQuery(c->stream);
+    if (e != cudaSuccess && e != cudaErrorNotReady) CK(e);
+    *idle = (e == cudaSuccess) ? 1 : 0;
+    return OAT_OK;
+}
 extern "C" int oat_ctx_sync(oat_ctx *c)
 {
     CKRET(bind(c));
@@ -2962,6 +2979,43 @@ extern "C" int oat_memcpy(oat_ctx *c, void *dst, const void *src, size_t bytes)
     REQUIRE(dst && src, "oat_memcpy: null pointer");
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return OAT_OK;
+}
+extern "C" int oat_memcpy_async(oat_ctx *c, int lane, void *dst, const void *src, size_t bytes)
+{
+    CKRET(bind(c));
+    REQUIRE(dst && src, "oat_memcpy_async: null pointer");
+    REQUIRE(lane == 0 || lane == 1, "oat_memcpy_async: lane must be 0 (ingest) or 1 (egress)");
+    if (!c->lane[lane]) {
+        CK(cudaStreamCreateWithFlags(&c->lane[lane], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->lane_done[lane], cudaEventDisableTiming));
+    }
+    if (lane == 1) {  // egress: the copy reads what the compute stream produces
+        if (!c->lane_after) CK(cudaEventCreateWithFlags(&c->lane_after, cudaEventDisableTiming));
+        CK(cudaEventRecord(c->lane_after, c->stream));
+        CK(cudaStreamWaitEvent(c->lane[lane], c->lane_after, 0));
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->lane[lane]));
+    CK(cudaEventRecord(c->lane_done[lane], c->lane[lane]));
+    return OAT_OK;
+}
+extern "C" int oat_memcpy_wait(oat_ctx *c, int lane)
+{
+    CKRET(bind(c));
+    REQUIRE(lane == 0 || lane == 1, "oat_memcpy_wait: lane must be 0 or 1");
+    if (c->lane[lane]) CK(cudaEventSynchronize(c->lane_done[lane]));
+    return OAT_OK;
+}
+extern "C" int oat_memcpy_done(oat_ctx *c, int lane, int *done)
+{
+    CKRET(bind(c));
+    REQUIRE(done && (lane == 0 || lane == 1), "oat_memcpy_done: bad argument");
+    *done = 1;
+    if (c->lane[lane]) {
+        const cudaError_t e = cudaEventQuery(c->lane_done[lane]);
+        if (e == cudaErrorNotReady) *done = 0;
+        else CK(e);
+    }
     return OAT_OK;
 }
 extern "C" int oat_flush_l2(oat_ctx *c)

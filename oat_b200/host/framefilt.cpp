@@ -44,6 +44,7 @@ protected:
         shared_frame_ = frame_sink_.retrieve(in_.rows, in_.cols, color_bytes(out_color), out_color);
         d_in_.reset(new gpu::DeviceBuffer(*ctx_, in_.bytes));
         d_out_.reset(new gpu::DeviceBuffer(*ctx_, out_bytes));
+        if (!device_sink_) d_out2_.reset(new gpu::DeviceBuffer(*ctx_, out_bytes));
         out_bytes_ = out_bytes;
         // SOURCE side: a DEVICE frame is imported through its IPC handle (device -> device hand-off);
         // a host frame's mapping is page-locked once (HOST_PINNED) so the per-frame copy is plain DMA
@@ -70,10 +71,42 @@ protected:
     // OAT_B200_TIMING=1: where a frame's time goes in this component (printed at end of stream)
     StageClock<5> clk_{"wait source", "ingest", "filter", "wait sink", "egress"};
     TokenClock out_clk_;
+    // Host-memory SINK: the copy of frame t back into shared memory runs on the egress lane while the component
+    // already waits for, ingests and filters frame t+1 (done one after the other a frame pays H2D + filter + D2H).
+    // Frame t is published as soon as its copy has landed -- at the latest when the filter of frame t+1 is done, and
+    // at once if no further frame is waiting: a slow SOURCE sees no added latency.  (A third stage -- the next frame
+    // coming up while this one is filtered -- was measured and dropped: on the B200 hosts H2D and D2H in flight
+    // together share ~60 GB/s, so two copies per frame bound the rate either way, profiles/README.md.)
+    bool egress_pending_{false};
+    Sample egress_sample_;
+    int out_k_{0};
+    void finish_egress()
+    {
+        gpu::ck(oat_memcpy_wait(ctx_->h, 1));
+        shared_frame_.sample() = egress_sample_;  // filters never advance time
+        frame_sink_.post();
+        egress_pending_ = false;
+        out_clk_.tick();
+    }
     int process() override
     {
         clk_.start();
-        if (frame_source_.wait() == NodeState::END) {
+        bool have = false;
+        while (egress_pending_) {  // the next frame, or the end of the copy: whichever comes first
+            NodeState st;
+            if (frame_source_.try_wait(&st)) {
+                have = true;
+                break;
+            }
+            int done = 0;
+            gpu::ck(oat_memcpy_done(ctx_->h, 1, &done));
+            if (done || st == NodeState::END || quit) {
+                finish_egress();
+                break;
+            }
+            detail::cpu_relax();
+        }
+        if (!have && frame_source_.wait() == NodeState::END) {
             clk_.report(name_);
             out_clk_.report(name_);
             return 1;
@@ -92,18 +125,23 @@ protected:
             clk_.lap(3);
             filter(d_in_->u8(), d_out_->u8());
             clk_.lap(2);
+            shared_frame_.sample() = sample;  // filters never advance time
+            frame_sink_.post();
+            out_clk_.tick();
         } else {
-            filter(d_in_->u8(), d_out_->u8());
+            gpu::DeviceBuffer &out = out_k_ ? *d_out2_ : *d_out_;  // (the previous frame may still be leaving the other one)
+            filter(d_in_->u8(), out.u8());
             clk_.lap(2);
+            if (egress_pending_) finish_egress();
             frame_sink_.wait();
             clk_.lap(3);
-            gpu::ck(oat_memcpy(ctx_->h, frame_sink_.pixels(), d_out_->p, out_bytes_));
+            gpu::ck(oat_memcpy_async(ctx_->h, 1, frame_sink_.pixels(), out.p, out_bytes_));
+            egress_pending_ = true;
+            egress_sample_ = sample;
+            out_k_ ^= 1;
         }
-        shared_frame_.sample() = sample;  // filters never advance time
-        frame_sink_.post();
         clk_.lap(4);
         ++clk_.n;
-        out_clk_.tick();
         return 0;
     }
     virtual PixelColor outputColor(PixelColor in) const { return in; }
@@ -124,7 +162,7 @@ protected:
     std::unique_ptr<gpu::Context> ctx_;
     std::unique_ptr<gpu::HostRegistration> src_pin_, dst_pin_;
     std::unique_ptr<gpu::IpcImport> src_dev_;
-    std::unique_ptr<gpu::DeviceBuffer> d_in_, d_out_;
+    std::unique_ptr<gpu::DeviceBuffer> d_in_, d_out_, d_out2_;
 
 public:
     void set_device_sink(bool v) { device_sink_ = v; }

@@ -593,6 +593,15 @@ def test_prelabelled_bands_equal_the_synchronous_tail(shape, dilate):
         d = got[t]
         assert bool(d[0]) == bool(o.position_valid) and d[1] == o.n_components, (t, d, o.n_components)
         assert abs(d[2] - o.x) <= TOL and abs(d[3] - o.y) <= TOL and abs(d[4] - o.area) <= TOL
+    # ... and against OpenCV itself where the box has it: findContours(RETR_EXTERNAL) + moments on every frame
+    from oracle import cv2ref
+    if cv2ref.available():
+        pipe = cv2ref.Pipeline(lr, dilate=dilate, **HSV_BAND)
+        for t, f in enumerate(host):
+            valid, x, y, area = pipe.step(f)
+            d = got[t]
+            assert bool(d[0]) == bool(valid), t
+            assert abs(d[2] - x) <= TOL and abs(d[3] - y) <= TOL and abs(d[4] - area) <= TOL, (t, d, x, y, area)
     a.close()
     b.close()
     for x in bufs:

@@ -80,3 +80,20 @@ for label, parts in (("halves on two streams", 2),):
     ck(rt.cudaStreamSynchronize(s2))
     dt = time.perf_counter() - t0
     print(f"1080p H2D, {label}: {n * nb / dt / 1e9:6.1f} GB/s ({1e6 * dt / n:6.1f} us per frame)")
+
+# both directions at once (a frame filter moves every frame up AND down): do H2D and D2H in flight together each get the link?
+hs2 = [ck(rt.cudaMallocHost(nb)) for _ in range(4)]
+for label, up, down in (("H2D alone", True, False), ("D2H alone", False, True), ("H2D + D2H together", True, True)):
+    ck(rt.cudaStreamSynchronize(stream))
+    ck(rt.cudaStreamSynchronize(s2))
+    n = 400
+    t0 = time.perf_counter()
+    for i in range(n):
+        if up:
+            ck(rt.cudaMemcpyAsync(ds[i % 4], hs[i % 4], nb, K.cudaMemcpyHostToDevice, stream))
+        if down:
+            ck(rt.cudaMemcpyAsync(hs2[i % 4], ds[(i + 2) % 4], nb, K.cudaMemcpyDeviceToHost, s2))
+    ck(rt.cudaStreamSynchronize(stream))
+    ck(rt.cudaStreamSynchronize(s2))
+    dt = time.perf_counter() - t0
+    print(f"1080p {label}: {n * nb * (int(up) + int(down)) / dt / 1e9:6.1f} GB/s in total ({1e6 * dt / n:6.1f} us per frame)")
