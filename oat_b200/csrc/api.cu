@@ -84,7 +84,7 @@ struct ProfRec {  // one bracketed launch of the resident fused kernel (oat_ctx_
 struct ClipHalf {
     FrameDesc *h_desc = nullptr, *d_desc = nullptr;
     TailFrame *h_tf = nullptr, *d_tf = nullptr;
-    unsigned int *d_ctr = nullptr;  // band counters of the tail server, 2 per frame
+    unsigned int *d_ctr = nullptr;  // band counters of the tail server, 2 per frame, + its exit ticket
     size_t cap = 0;
     cudaEvent_t done = nullptr;
     int ensure(size_t n)
@@ -96,7 +96,9 @@ struct ClipHalf {
         CK(cudaHostAlloc(&h_tf, n * sizeof(TailFrame), cudaHostAllocDefault));
         CK(cudaMalloc(&d_desc, n * sizeof(FrameDesc)));
         CK(cudaMalloc(&d_tf, n * sizeof(TailFrame)));
-        CK(cudaMalloc(&d_ctr, 2 * n * sizeof(unsigned int)));
+        // (zeroed once: the tail server's last CTA to leave re-arms the counters of its launch and the ticket behind them)
+        CK(cudaMalloc(&d_ctr, (2 * n + 1) * sizeof(unsigned int)));
+        CK(cudaMemset(d_ctr, 0, (2 * n + 1) * sizeof(unsigned int)));
         cap = n;
         return OAT_OK;
     }
@@ -2174,6 +2176,7 @@ struct ClipEngine {
     double wait_ns = 0.0;
     bool frames_known_device = false;  // the stream checks every frame when it is pushed
     bool heavy_tail = false;           // the masks of these streams are busy: the tail server gets twice its usual share
+    TailQueue tail_queue;              // kernel-parameter image of a short queue of tail descriptors
 
     void init(oat_ctx *ctx, oat_tracker *const *trackers, int n_trackers, bool fused)
     {
@@ -2374,8 +2377,10 @@ struct ClipEngine {
         c->chain_uid = full ? t0->m.uid : 0;
         if (!fused_only) {
             cudaStream_t ts = c->tail[c->tail_rr++ % oat_ctx::NTAIL];
-            CK(cudaMemcpyAsync(half[h].d_tf, half[h].h_tf, nitems * sizeof(TailFrame), cudaMemcpyHostToDevice, ts));
-            CK(cudaMemsetAsync(half[h].d_ctr, 0, 2 * nitems * sizeof(unsigned int), ts));
+            // a short queue of tail descriptors travels in the kernel parameters, like the fused kernel's (one driver call
+            // less per chunk; the band counters need none either: the kernel leaves them re-armed)
+            const bool inline_tf = nitems <= (size_t)TAIL_INLINE_DESCS;
+            if (!inline_tf) CK(cudaMemcpyAsync(half[h].d_tf, half[h].h_tf, nitems * sizeof(TailFrame), cudaMemcpyHostToDevice, ts));
             const int nbands = div_up(g.rows, R);
             // (more CTAs than one frame has bands is useful: they work on different frames of the queue at the same time)
             const int gridT = std::max(1, std::min(nbands * (int)nitems, (heavy_tail ? 2 : 1) * (int)PIPE_TAIL_GRID_CFG));
@@ -2384,7 +2389,9 @@ struct ClipEngine {
                 scratch = (uint8_t *)c->tail_scratch[h].p;
             else
                 cudaGetLastError();  // no scratch: overflowing masks are replayed by the host
-            tail_stream_kernel<<<gridT, 256, tail_smem, ts>>>(half[h].d_tf, (int)nitems, half[h].d_ctr, half[h].d_ctr + nitems, scratch,
+            if (inline_tf) memcpy(tail_queue.inl, half[h].h_tf, nitems * sizeof(TailFrame));
+            tail_stream_kernel<<<gridT, 256, tail_smem, ts>>>(inline_tf ? nullptr : half[h].d_tf, tail_queue, (int)nitems, half[h].d_ctr,
+                                                              half[h].d_ctr + nitems, half[h].d_ctr + 2 * half[h].cap, scratch,
                                                               (int)scratch_bytes, scratch_comps);
             ++c->launches;
             CK(cudaGetLastError());

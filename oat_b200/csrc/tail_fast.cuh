@@ -1286,12 +1286,22 @@ struct TailFrame {
     unsigned int pad;
 };
 
+// Up to TAIL_INLINE_DESCS frames travel in the kernel parameters (no copy to enqueue in front of the launch).
+constexpr int TAIL_INLINE_DESCS = 32;
+struct TailQueue {
+    TailFrame inl[TAIL_INLINE_DESCS];
+};
+static_assert(sizeof(TailQueue) + 128 <= 32764, "kernel parameters are limited to 32764 bytes (CUDA 12.1+, sm_70+)");
+static_assert(sizeof(TailFrame) % 4 == 0, "TailFrame is copied word by word");
+
 #ifndef TAIL_STREAM_MINBLOCKS_CFG
 #define TAIL_STREAM_MINBLOCKS_CFG 2  // its CTAs sit beside ONE fused CTA on a reserved SM: registers are not what limits them
 #endif
-__global__ void __launch_bounds__(256, TAIL_STREAM_MINBLOCKS_CFG) tail_stream_kernel(const TailFrame *frames, const int nframes,
-                                                             unsigned int *band_ctr /* [nframes], zeroed */,
-                                                             unsigned int *band_done /* [nframes], zeroed */,
+__global__ void __launch_bounds__(256, TAIL_STREAM_MINBLOCKS_CFG) tail_stream_kernel(const TailFrame *frames /* or NULL: q.inl */,
+                                                             const __grid_constant__ TailQueue q, const int nframes,
+                                                             unsigned int *band_ctr /* [nframes], zero when the launch starts */,
+                                                             unsigned int *band_done /* [nframes], likewise */,
+                                                             unsigned int *exit_ticket /* likewise: the last CTA to leave re-arms all three */,
                                                              uint8_t *scratch /* or NULL: gridDim.x areas of scratch_bytes */,
                                                              const int scratch_bytes, const int scratch_comps)
 {
@@ -1302,8 +1312,11 @@ __global__ void __launch_bounds__(256, TAIL_STREAM_MINBLOCKS_CFG) tail_stream_ke
     __shared__ int s_ymin, s_ymax;
     for (int f = 0; f < nframes; ++f) {
         __syncthreads();  // the previous frame's use of s_tf / s_band is over
-        for (int i = threadIdx.x; i < (int)(sizeof(TailFrame) / 4); i += blockDim.x)
-            reinterpret_cast<uint32_t *>(&s_tf)[i] = reinterpret_cast<const uint32_t *>(frames + f)[i];
+        {
+            const TailFrame *src = frames ? frames + f : &q.inl[f];
+            for (int i = threadIdx.x; i < (int)(sizeof(TailFrame) / 4); i += blockDim.x)
+                reinterpret_cast<uint32_t *>(&s_tf)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+        }
         __syncthreads();
         const int nbands = (s_tf.a.g.rows + s_tf.a.R - 1) / s_tf.a.R;
         if (threadIdx.x == 0) {
@@ -1358,6 +1371,21 @@ __global__ void __launch_bounds__(256, TAIL_STREAM_MINBLOCKS_CFG) tail_stream_ke
                 if (threadIdx.x == 0) s_last = false;
             }
         }
+    }
+    // the last CTA to leave re-arms the launch's counters for the next user of this half of the ring (a launch the host
+    // starts only after this one has completed), so no memset has to be enqueued in front of a launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(exit_ticket, 1u) == gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (s_last) {
+        for (int i = threadIdx.x; i < nframes; i += blockDim.x) {
+            band_ctr[i] = 0u;
+            band_done[i] = 0u;
+        }
+        if (threadIdx.x == 0) *exit_ticket = 0u;
     }
 }
 

@@ -2,7 +2,7 @@
 # bench.py under torchrun exactly as the driver launches it.  usage: gpu_scale.sh <tag> <N>   (gpurun --gpus N)
 T=${1:-r02}; N=${2:-2}
 mkdir -p gpurun_out
-timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 2000 --warmup 50 > gpurun_out/${T}_scale_n$N.json 2> gpurun_out/${T}_scale_n$N.err
+timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${STEPS:-2000} --warmup ${WARMUP:-50} > gpurun_out/${T}_scale_n$N.json 2> gpurun_out/${T}_scale_n$N.err
 echo "own arm rc=$?"; cut -c1-600 gpurun_out/${T}_scale_n$N.json; tail -n 3 gpurun_out/${T}_scale_n$N.err
 timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus $N --steps 100 --warmup 10 > gpurun_out/${T}_scale_ref_n$N.json 2> gpurun_out/${T}_scale_ref_n$N.err
 echo "reference arm rc=$?"; cut -c1-600 gpurun_out/${T}_scale_ref_n$N.json; tail -n 3 gpurun_out/${T}_scale_ref_n$N.err
