@@ -13,6 +13,8 @@
 #include <chrono>
 #include <atomic>
 #include <new>
+#include <map>
+#include <mutex>
 #include <string>
 #include <deque>
 #include <vector>
@@ -378,8 +380,23 @@ extern "C" int oat_ctx_profile_resident_read(oat_ctx *c, double *total_ms, uint6
 
 // ---- pointer classification + staging ------------------------------------------------------
 enum MemKind { MEM_PAGEABLE, MEM_PINNED, MEM_DEVICE };
+// Device allocations handed out by oat_alloc_device (frames a host component or a benchmark keeps in HBM): a pointer
+// into one of them is device memory without asking the driver -- cudaPointerGetAttributes is a driver call per frame
+// on the enqueue path, and driver calls are what gets slow when several processes drive their GPUs at once.
+static std::mutex g_dev_mu;
+static std::map<uintptr_t, size_t> g_dev_ranges;
+static bool known_device_ptr(const void *p)
+{
+    const uintptr_t a = (uintptr_t)p;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    auto it = g_dev_ranges.upper_bound(a);
+    if (it == g_dev_ranges.begin()) return false;
+    --it;
+    return a - it->first < it->second;
+}
 static MemKind mem_kind(const void *p)
 {
+    if (known_device_ptr(p)) return MEM_DEVICE;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
@@ -2925,12 +2942,22 @@ extern "C" int oat_alloc_device(oat_ctx *c, size_t bytes, void **out)
     CKRET(bind(c));
     REQUIRE(out && bytes > 0, "oat_alloc_device: bad arguments");
     CK(cudaMalloc(out, bytes));
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        g_dev_ranges[(uintptr_t)*out] = bytes;
+    }
     return OAT_OK;
 }
 extern "C" int oat_free_device(oat_ctx *c, void *p)
 {
     CKRET(bind(c));
-    if (p) CK(cudaFree(p));
+    if (p) {
+        {
+            std::lock_guard<std::mutex> lk(g_dev_mu);
+            g_dev_ranges.erase((uintptr_t)p);
+        }
+        CK(cudaFree(p));
+    }
     return OAT_OK;
 }
 extern "C" int oat_alloc_pinned(size_t bytes, void **out)
