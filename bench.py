@@ -28,6 +28,12 @@ largest-blob centroid) -- the unit BASELINE.json's metric counts.  Measurements 
 
 N > 1 (torchrun): one independent stream per rank/GPU, no data-path collective ("weak" scaling);
 the job time is the max over ranks.  Prints ONE JSON line on rank 0.
+
+Timed region of `value`: W warm-up steps, barrier + synchronize, ONE more untimed chunk of 32 steps, then exactly K
+steps between a CUDA-event pair on the library's stream, barrier + synchronize.  The extra chunk is there because a
+barrier leaves the GPU idle until the slowest rank has arrived, and a 20-step region (0.3 ms) that starts on a GPU
+just back from idling measures the wake-up: 17.1 us per step at N = 2 against 15.3 us with the chunk and 15.1 us at
+N = 1, on every rank alike (OAT_BENCH_NO_REWARM=1 leaves it out; DESIGN.md 6, config.timing in the JSON line).
 """
 from __future__ import annotations
 
@@ -387,6 +393,14 @@ def run_b200(args):
     clip = make_clip(K, W) if native else None
     run_value(4 * CHUNK, WU, make_clip(4 * CHUNK, WU) if native else None)  # (untimed) the GPU is busy right up to the barrier
     barrier()
+    # A barrier leaves every GPU idle until the slowest rank has arrived (milliseconds at N > 1), and what follows an
+    # idle GPU starts slowly: measured at N = 2, 20 steps, 17.1 us per step right after the barrier, 18.1 us after
+    # 2 ms more of idling, 15.1 us when the GPU is busy up to the start (N = 1, where the barrier is immediate).  A
+    # 20-step region is 0.3 ms, so that wake-up would be a tenth of it.  One more untimed chunk of warm-up steps runs
+    # between the barrier and the timed steps: every rank does the same, at the same time, and the events bracket
+    # exactly the K timed steps.
+    if os.environ.get("OAT_BENCH_NO_REWARM") is None:
+        run_value(CHUNK, WU + 4 * CHUNK, make_clip(CHUNK, WU + 4 * CHUNK) if native else None)
     ctx.clip_host_stats()
     launches0 = ctx.kernel_launches
     cpu0 = time.process_time()
@@ -664,6 +678,12 @@ def run_b200(args):
                 "loop": (f"oat_tracker_run_clip: resident engine, chunks of {CHUNK} frames, one fused-kernel launch + one tail-server launch per chunk, "
                          "no host work per frame" if native else "submit/collect called per frame from this script"),
                 "parallelism": f"{world} independent stream(s), one per GPU, no collective",
+                "timing": (f"{W} warm-up steps (topped up to {WU}), barrier + synchronize, one more untimed chunk of {CHUNK} steps "
+                           "(a GPU that idled in the barrier starts slowly: DESIGN.md 6), then exactly the timed steps between one "
+                           "CUDA-event pair per rank, barrier + synchronize, max over ranks"
+                           if os.environ.get("OAT_BENCH_NO_REWARM") is None else
+                           f"{W} warm-up steps (topped up to {WU}), barrier + synchronize, the timed steps between one CUDA-event pair per rank, "
+                           "barrier + synchronize, max over ranks"),
             },
             "roofline": {
                 "bound": "hbm",
