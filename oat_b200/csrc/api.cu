@@ -142,7 +142,7 @@ struct oat_ctx {
     // fused kernel / the multi-launch tail / single-stream execution (A-B measurements; results are identical)
     bool no_pipe = false, no_fast_tail = false, no_overlap = false, pdl = true;
     bool no_prelabel = false;  // OAT_B200_NO_PRELABEL (A/B switch): the labelling CTA extracts every run table itself
-    bool force_prelabel = false;  // OAT_B200_FORCE_PRELABEL (tests): ... and never, whatever the size of the mask
+    bool force_prelabel = false;  // OAT_B200_FORCE_PRELABEL (tests): the bands' tables are used whatever the size of the mask
     double heavy_tail_at = 10000.0;  // run-table entries per frame from which the tail server gets twice its share (OAT_B200_HEAVY_TAIL_AT)
     cudaStream_t post = nullptr;  // position epilogues (Kalman/mean), strictly in frame order
     // Work scheduler of the resident fused kernel (mog_pipe.cuh): every launch draws its (frame, tile) items from

@@ -15,8 +15,13 @@
 //
 // The run table is bounded by the shared-memory budget.  A mask that does not fit (more runs or
 // contours than the table holds: the first frame's whole-image blob, heavy noise) makes the
-// kernel report TAIL_OVERFLOW; the host then replays the frame through the unbounded
+// per-frame kernel report TAIL_OVERFLOW; the host then replays the frame through the unbounded
 // global-memory path of tail.cuh.  Results are identical either way.
+//
+// tail_stream_kernel is the RESIDENT form: one launch serves the tails of a whole queue of frames as the
+// fused kernel (mog_pipe.cuh) publishes their masks.  For busy masks its band CTAs pre-label their own rows
+// (band_prelabel) and the labelling CTA only merges across band borders; a table that outgrows shared memory
+// is labelled in a global-memory scratch area on the device.
 #pragma once
 #include "tail.cuh"
 

@@ -240,3 +240,56 @@ def test_resident_scheduler_protocol_model():
             m = _ResidentModel(nframes, ntiles, grid, S, models, rng, batch=P, storers=NS).run()
             assert sorted(m.loaded) == [(f, t) for f in range(nframes) for t in range(ntiles)], (nframes, ntiles, grid)
             assert len(m.published) == nframes * ntiles
+
+
+def test_doubling_window_model():
+    """The band morphology's horizontal pass (oat_b200/csrc/tail_fast.cuh: hwin_or) ORs a k-wide window by doubling on the
+    96 bits prev:cur:next of a word instead of one shift per window position.  A transcription of it against the
+    definition -- bit x of the result = OR over [x - k/2, x - k/2 + k - 1] (cv::dilate's anchor, MORPH_RECT) -- for every
+    k the fast path takes (1..32), random sparse and dense words; erosion is the same on the complement."""
+    import random
+
+    M64 = (1 << 64) - 1
+
+    def hwin_or(prev, cur, nxt, k):
+        lo, hi = (prev | (cur << 32)) & M64, nxt
+
+        def shr_or(sft):
+            nonlocal lo, hi
+            nlo, nhi = ((lo >> sft) | (hi << (64 - sft))) & M64, hi >> sft
+            lo |= nlo
+            hi |= nhi
+
+        w = 1
+        while 2 * w <= k:
+            shr_or(w)
+            w <<= 1
+        if w < k:
+            shr_or(k - w)
+        sft = 32 - k // 2
+        return ((lo >> sft) | (hi << (64 - sft))) & 0xFFFFFFFF
+
+    def window(prev, cur, nxt, k):
+        P = prev | (cur << 32) | (nxt << 64)
+        out = 0
+        for x in range(32):
+            if any((P >> (32 + x + d)) & 1 for d in range(-(k // 2), k - k // 2)):
+                out |= 1 << x
+        return out
+
+    rng = random.Random(7)
+    for k in range(1, 33):
+        for density in (1, 2, 4):
+            for _ in range(60):
+                p, c, n = (rng.getrandbits(32) & rng.getrandbits(32) if density > 1 else rng.getrandbits(32) for _ in range(3))
+                if density == 4:
+                    p, c, n = p & rng.getrandbits(32), c & rng.getrandbits(32), n & rng.getrandbits(32)
+                assert hwin_or(p, c, n, k) == window(p, c, n, k), (k, p, c, n)
+                # erosion: complement in, complement out (all three words inside the image)
+                e = ~hwin_or(~p & 0xFFFFFFFF, ~c & 0xFFFFFFFF, ~n & 0xFFFFFFFF, k) & 0xFFFFFFFF
+                P = p | (c << 32) | (n << 64)
+                want = 0
+                for x in range(32):
+                    if all((P >> (32 + x + d)) & 1 for d in range(-(k // 2), k - k // 2)):
+                        want |= 1 << x
+                assert e == want, (k, p, c, n)
