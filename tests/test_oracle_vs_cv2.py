@@ -259,3 +259,28 @@ def test_difference_detector_restatement_matches_cv2():
             assert bool(got.position_valid) == bool(want[0]), (k, t)
             if want[0]:
                 assert abs(got.x - want[1]) < 1e-9 and abs(got.y - want[2]) < 1e-9 and abs(got.area - want[3]) < 1e-9, (k, t)
+
+
+@pytest.mark.parametrize("shape", [(40, 64), (64, 96), (100, 131)])
+def test_external_contours_on_structure_scenes(shape):
+    """The geometries the band pre-labelling tests use on the GPU (tests/test_tail_model.py: rings, rings with a disc
+    inside, U shapes, worms, speckle, shapes on the frame border): the oracle's contours against cv2's, so that what
+    those tests compare with is pinned on exactly such masks."""
+    from test_tail_model import _scene
+
+    rows, cols = shape
+    rng = np.random.default_rng(rows + cols)
+    for trial in range(20):
+        m = _scene(rng, rows, cols).astype(np.uint8) * 255
+        if not m.any():
+            continue
+        want = cv2_contour_list(m)
+        got = oracle.external_contours(m)
+        assert [g[0] for g in got] == [w[0] for w in want][::-1], trial
+        for g, w in zip(got, want[::-1]):
+            assert abs(g[2] - w[1]) < 1e-9 and abs(g[3] - w[2]) < 1e-6 and abs(g[4] - w[3]) < 1e-6, trial
+        o = oracle.sift_contours(m)
+        valid, x, y, area = cv2ref.sift_contours(m)
+        assert bool(o.position_valid) == valid and abs(o.area - area) < 1e-9, trial
+        if valid:
+            assert abs(o.x - x) < 1e-9 and abs(o.y - y) < 1e-9, trial
